@@ -1,0 +1,236 @@
+/*
+ * psi_b200.h -- C-ABI of libpsi_b200.so: the B200-native fully-sensitive seed
+ * finding path of PSI (cartoonist/psi) behind plain pointers and sizes.
+ *
+ * The reference has no FFI layer: its boundary for this path is the C++
+ * template class psi::SeedFinder as driven by find_seeds() of the CLI
+ * (reference src/psikt.cpp:83-212).  Every entry point below names the
+ * reference interface it stands behind (file:line relative to the reference
+ * tree).  The C++17 mirror of that class lives in psi_b200/include/psi/ and
+ * calls only these functions; INTEGRATION.md shows the binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every function returns PSI_B200_OK (0) or a negative error code; the
+ *     message is available from psi_b200_last_error() (per context) or
+ *     psi_b200_global_error() (for calls without a context);
+ *   - no exceptions, no STL, no torch types cross this boundary;
+ *   - host pointers are caller-owned and only read/written during the call;
+ *   - one context per GPU, calls on one context are serialised by the caller;
+ *   - all graph arrays are indexed by node RANK (0-based position in the
+ *     reference graph's rank order, i.e. gum rank - 1);
+ *   - there is NO CPU fallback: device entry points fail with
+ *     PSI_B200_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PSI_B200_H
+#define PSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSI_B200_OK            0
+#define PSI_B200_ERR_ARG      -1   /* invalid argument (reference: std::runtime_error) */
+#define PSI_B200_ERR_CUDA     -2   /* CUDA runtime / no device */
+#define PSI_B200_ERR_NOMEM    -3
+#define PSI_B200_ERR_IO       -4   /* reference: `false` from load/save calls */
+#define PSI_B200_ERR_STATE    -5   /* call order (e.g. seeds_all before submit_chunk) */
+#define PSI_B200_ERR_OVERFLOW -6   /* device buffer exhausted after regrow attempts */
+
+#define PSI_B200_MAX_SEED_LEN 32   /* a seed is one 2-bit packed 64-bit word */
+
+/* ===================================================================== *
+ *  Host side: graph, reads, genome-wide paths (no GPU needed)
+ * ===================================================================== */
+
+/* Flattened sequence graph; stands behind gum::SeqGraph<Succinct> as loaded by
+ * gum::util::load(graph, file, sort=true) (src/psikt.cpp:249-251).  Node
+ * ranks, internal ids and out-edge order reproduce gum's. */
+typedef struct psi_b200_graph psi_b200_graph;
+
+typedef struct {
+  uint64_t        n_nodes;
+  uint64_t        n_edges;
+  uint64_t        n_bases;
+  uint64_t        n_paths;     /* embedded (reference) paths */
+  const uint64_t* seq_start;   /* n_nodes+1 */
+  const char*     seq;         /* n_bases, ASCII */
+  const uint64_t* row_ptr;     /* n_nodes+1 */
+  const uint32_t* col;         /* n_edges successor ranks */
+  const uint64_t* internal_id; /* n_nodes: gum Succinct id written by psikt (src/psikt.cpp:172-181) */
+  const uint64_t* coord_id;    /* n_nodes: external id, graph.coordinate_id(id) */
+} psi_b200_graph_view;
+
+/* gum::util::load(graph, fname, sort) for GFA1 (S/L/P) and GFA2 (S/E/O)
+ * (gum/gfa_utils.hpp:541-554). */
+int  psi_b200_graph_load_gfa(const char* path, int sort, psi_b200_graph** out);
+/* Build from flat arrays (synthetic graphs).  ids[] are external ids; when
+ * sort != 0 ranks are re-ordered exactly like the GFA loader would.  Embedded
+ * paths: n_paths, path_ptr[n_paths+1], path_nodes = indices into the INPUT
+ * node order. */
+int  psi_b200_graph_from_arrays(uint64_t n_nodes, const uint64_t* ids,
+                                const uint64_t* seq_start, const char* seq,
+                                const uint64_t* row_ptr, const uint32_t* col,
+                                uint64_t n_paths, const uint64_t* path_ptr,
+                                const uint32_t* path_nodes, int sort,
+                                psi_b200_graph** out);
+void psi_b200_graph_free(psi_b200_graph* g);
+int  psi_b200_graph_get_view(const psi_b200_graph* g, psi_b200_graph_view* view);
+/* Embedded path i: name and node ranks (gum for_each_path / path(id)). */
+int  psi_b200_graph_path(const psi_b200_graph* g, uint64_t i, const char** name,
+                         const uint32_t** nodes, uint64_t* n_nodes);
+/* Write the graph as GFA1 (used to hand synthetic graphs to the reference). */
+int  psi_b200_graph_write_gfa(const psi_b200_graph* g, const char* path);
+
+/* Genome-wide path selection; stands behind SeedFinder::pick_paths
+ * (seed_finder.hpp:1138-1167) + Haplotyper / least_covered_adjacent
+ * (graph_iter.hpp:537-1005, graph.hpp:216-287).  For every embedded path of the
+ * graph, n walks are started at its first node and extended to a sink, always
+ * taking a least-covered successor; ties are broken by a seeded xorshift (the
+ * reference uses std::random_device, so its paths differ run to run; the seed
+ * SET does not depend on the choice).  Fails with PSI_B200_ERR_ARG
+ * when the graph embeds no path (seed_finder.hpp:1145-1147). */
+typedef struct psi_b200_pathset psi_b200_pathset;
+typedef struct {
+  uint64_t        n_paths;
+  const uint64_t* path_ptr;   /* n_paths+1 */
+  const uint32_t* nodes;      /* node ranks */
+  const uint32_t* head_off;   /* n_paths: bases trimmed from first node */
+  const uint32_t* tail_trim;  /* n_paths: bases trimmed from last node */
+} psi_b200_pathset_view;
+int  psi_b200_pick_paths(const psi_b200_graph* g, unsigned n, int patched,
+                         unsigned context, uint64_t seed, psi_b200_pathset** out);
+void psi_b200_pathset_free(psi_b200_pathset* p);
+int  psi_b200_pathset_get_view(const psi_b200_pathset* p, psi_b200_pathset_view* view);
+
+/* Read chunking; stands behind readRecords(Records&, SeqStreamIn&, n)
+ * (sequence.hpp:1608-1624) over kseq++: FASTQ/FASTA, plain or gzip. */
+typedef struct psi_b200_reader psi_b200_reader;
+typedef struct {
+  uint64_t        n_reads;
+  uint64_t        first_read_id; /* Records::rec_offset = records read before (sequence.hpp:1616) */
+  const uint64_t* read_ptr;      /* n_reads+1 */
+  const char*     bases;
+  const uint64_t* name_ptr;      /* n_reads+1 */
+  const char*     names;
+} psi_b200_chunk_view;
+int  psi_b200_reader_open(const char* path, psi_b200_reader** out);
+/* Loads up to max_reads records (0 = all) into the reader's (pinned when a GPU
+ * is present) chunk buffer.  view->n_reads == 0 at end of input. */
+int  psi_b200_reader_next(psi_b200_reader* r, uint64_t max_reads, psi_b200_chunk_view* view);
+void psi_b200_reader_close(psi_b200_reader* r);
+
+const char* psi_b200_global_error(void);
+
+/* ===================================================================== *
+ *  Device side: one context per GPU
+ * ===================================================================== */
+
+typedef struct psi_b200_ctx psi_b200_ctx;
+
+/* SeedFinder(graph, seed_len, ...) (seed_finder.hpp:930-942); seed_len <= 32. */
+int  psi_b200_create(int device, unsigned seed_len, psi_b200_ctx** out);
+void psi_b200_destroy(psi_b200_ctx* ctx);
+const char* psi_b200_last_error(const psi_b200_ctx* ctx);
+/* Run all work of this context on the given cudaStream_t (default: a private
+ * non-blocking stream). */
+int  psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream);
+int  psi_b200_sync(psi_b200_ctx* ctx);
+
+/* The graph the finder borrows (seed_finder.hpp:1747), flattened: CSR
+ * adjacency + concatenated labels (gum layout graph_traits_succinct.hpp:27-57,
+ * accessors digraph_succinct.hpp:595-610,722-731, seqgraph_succinct.hpp:194-199).
+ * node_id[r] is the id reported in seed records. */
+int  psi_b200_set_graph(psi_b200_ctx* ctx, uint64_t n_nodes,
+                        const uint64_t* seq_start, const char* seq,
+                        const uint64_t* row_ptr, const uint32_t* col,
+                        const uint64_t* node_id);
+
+/* index_paths() -> PathIndex::create_index (seed_finder.hpp:1169-1176,
+ * pathindex.hpp:235-243, fmindex.hpp:257-271): builds the GPU-resident path
+ * index (distinct (k-mer, locus) pairs of all path windows, bucketised hash)
+ * from the picked paths. */
+int  psi_b200_set_paths(psi_b200_ctx* ctx, uint64_t n_paths,
+                        const uint64_t* path_ptr, const uint32_t* path_nodes,
+                        const uint32_t* head_off, const uint32_t* tail_trim);
+
+/* add_uncovered_loci(step) (seed_finder.hpp:1481-1541): starting loci = graph
+ * positions with at least one k-walk whose (k-mer, locus) is not in the path
+ * index.  Computed on the device. */
+int  psi_b200_find_loci(psi_b200_ctx* ctx, unsigned step, uint64_t* n_loci);
+/* get_starting_loci() (seed_finder.hpp:957) / loci load (:1637-1679). */
+int  psi_b200_get_loci(psi_b200_ctx* ctx, uint32_t* node_rank, uint32_t* offset,
+                       uint64_t cap, uint64_t* n_loci);
+int  psi_b200_set_loci(psi_b200_ctx* ctx, uint64_t n_loci,
+                       const uint32_t* node_rank, const uint32_t* offset);
+
+/* get_seeds(seeds, chunk, distance) + index_reads(seeds)
+ * (seed_finder.hpp:1089-1109, sequence.hpp:1688-1745): uploads one read chunk,
+ * packs its seeds (offsets 0,d,2d,.. while off+k <= len) into 2-bit k-mers and
+ * prepares the device read index.  distance == 0 means seed_len
+ * (src/psikt.cpp:469).  Asynchronous on the context's stream. */
+int  psi_b200_submit_chunk(psi_b200_ctx* ctx, uint64_t n_reads,
+                           const uint64_t* read_ptr, const char* bases,
+                           uint64_t first_read_id, unsigned distance);
+/* Same with read_ptr/bases already resident in device memory. */
+int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
+                                  const uint64_t* d_read_ptr, const char* d_bases,
+                                  uint64_t n_bases, uint64_t first_read_id,
+                                  unsigned distance);
+
+#define PSI_B200_ON_PATHS   1u   /* seeds_on_paths  (seed_finder.hpp:1426-1457) */
+#define PSI_B200_OFF_PATHS  2u   /* seeds_off_paths (seed_finder.hpp:1703-1722) */
+#define PSI_B200_ALL        3u   /* seeds_all       (seed_finder.hpp:1724-1732) */
+#define PSI_B200_SORTED     4u   /* additionally sort records canonically on the device */
+#define PSI_B200_NO_RESOLVE 8u   /* keep compact device records only (benchmark of the probe alone) */
+
+/* Finds the seeds of the submitted chunk.  The result is the SET of hits
+ * (each (read, offset, node, offset) once), resident in device
+ * memory; *n_hits is its size (synchronises the stream). */
+int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
+
+/* Copies the records of the last seeds_all to the host in the reference
+ * CLI's byte layout (src/psikt.cpp:172-181, seed.hpp:32-46): per hit 4 x u64
+ * {node_id, node_offset, read_id, read_offset}. */
+int  psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits);
+/* Device pointer to the same records (valid until the next seeds_all). */
+int  psi_b200_fetch_device(psi_b200_ctx* ctx, const uint64_t** d_hits, uint64_t* n_hits);
+
+/* Pinned host memory for chunk / result buffers. */
+int  psi_b200_host_alloc(void** p, size_t bytes);
+void psi_b200_host_free(void* p);
+
+/* SeedFinderStats counters / timers (seed_finder.hpp:50-726) for the last chunk
+ * and index build; times are CUDA-event milliseconds on the context's stream. */
+typedef struct {
+  uint64_t n_nodes, n_edges, n_bases;
+  uint64_t n_path_bases;       /* indexed path text length */
+  uint64_t n_index_entries;    /* distinct (k-mer, locus) pairs */
+  uint64_t n_index_kmers;      /* distinct k-mers */
+  uint64_t index_bytes;        /* device bytes of the path index */
+  uint64_t index_buckets;      /* 32-byte buckets */
+  uint32_t index_slot_bytes;   /* 8 or 16 */
+  uint32_t reserved0;
+  uint64_t n_loci;
+  uint64_t n_reads, n_seeds;   /* last chunk */
+  uint64_t n_hits_on, n_hits_off, n_hits;
+  uint64_t n_walks;            /* k-walks completed by the off-path kernel */
+  uint64_t n_on_probe_sectors; /* 32-byte buckets read by the on-path probe (diagnostic builds) */
+  float ms_index_build, ms_find_loci;
+  float ms_h2d, ms_pack, ms_read_index, ms_on, ms_off, ms_resolve, ms_sort, ms_d2h;
+  uint32_t launches;           /* kernels of this library launched since create / reset */
+  uint32_t reserved1;
+} psi_b200_counters_t;
+int  psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out);
+int  psi_b200_reset_counters(psi_b200_ctx* ctx);
+
+/* Library build info: "psi_b200 <version> sm_100a". */
+const char* psi_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSI_B200_H */

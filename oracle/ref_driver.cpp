@@ -1,0 +1,217 @@
+/**
+ *  oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, not product code.
+ *
+ *  A thin driver around the UNMODIFIED reference headers under /root/reference.
+ *  It does what `find_seeds` in the reference CLI does (src/psikt.cpp:83-212):
+ *
+ *      SeedFinder(graph, k) -> create_path_index(n, patched, context, step)
+ *      loop { readRecords; get_seeds; index_reads; seeds_all(write_callback) }
+ *
+ *  minus spdlog / protobuf / SeqAn ArgumentParser (not buildable in this image),
+ *  with GFA as the graph format (gum::util::load(graph, file, sort=true),
+ *  src/psikt.cpp:249-251).  It is compiled in place by oracle/Makefile into
+ *  oracle/_ref/psi_ref_driver; no reference source is copied into this repo.
+ *
+ *  Outputs:
+ *    --out FILE    canonical seed set: sorted unique tuples
+ *                  (read_id, read_offset, coordinate(external) node id, node_offset),
+ *                  4 x u64 LE each.
+ *    --raw FILE    the reference CLI's byte format (src/psikt.cpp:172-181):
+ *                  per hit node_id(internal), node_offset, read_id, read_offset
+ *                  as native size_t, in emission order (multiset, path dependent).
+ *    --nodes FILE  per rank (1..n): internal id, coordinate id, label length (3 x u64).
+ *    --loci FILE   starting loci: internal id, offset (2 x u64).
+ *  and one JSON line on stdout with counts and timings.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <array>
+#include <algorithm>
+#include <chrono>
+#include <functional>
+#include <unordered_set>
+
+#include <psi/seed_finder.hpp>
+#include <psi/sequence.hpp>
+#include <gum/graph.hpp>
+#include <gum/io_utils.hpp>
+#include <kseq++/seqio.hpp>
+
+using namespace psi;
+
+struct Args {
+  std::string gfa, fastq, out, raw, nodes, loci;
+  unsigned k = 0, d = 0, n = 0, context = 0, step = 1;
+  unsigned long chunk = 0, first_read = 0, max_reads = 0;
+  bool patched = true;
+  bool on_only = false, off_only = false;
+};
+
+static double now_s()
+{
+  using namespace std::chrono;
+  return duration< double >( steady_clock::now().time_since_epoch() ).count();
+}
+
+static void write_u64s( std::FILE* f, const uint64_t* p, size_t n )
+{
+  if ( std::fwrite( p, sizeof( uint64_t ), n, f ) != n ) { std::perror( "fwrite" ); std::exit( 3 ); }
+}
+
+int main( int argc, char** argv )
+{
+  Args a;
+  for ( int i = 1; i < argc; ++i ) {
+    std::string s = argv[i];
+    auto next = [&]() -> std::string { if ( i + 1 >= argc ) { std::fprintf( stderr, "missing value for %s\n", s.c_str() ); std::exit( 2 ); } return argv[++i]; };
+    if ( s == "--gfa" ) a.gfa = next();
+    else if ( s == "--fastq" ) a.fastq = next();
+    else if ( s == "--out" ) a.out = next();
+    else if ( s == "--raw" ) a.raw = next();
+    else if ( s == "--nodes" ) a.nodes = next();
+    else if ( s == "--loci" ) a.loci = next();
+    else if ( s == "-k" ) a.k = std::stoul( next() );
+    else if ( s == "-d" ) a.d = std::stoul( next() );
+    else if ( s == "-n" ) a.n = std::stoul( next() );
+    else if ( s == "-t" ) a.context = std::stoul( next() );
+    else if ( s == "-e" ) a.step = std::stoul( next() );
+    else if ( s == "-c" ) a.chunk = std::stoul( next() );
+    else if ( s == "--first-read" ) a.first_read = std::stoul( next() );
+    else if ( s == "--max-reads" ) a.max_reads = std::stoul( next() );
+    else if ( s == "-P" ) a.patched = false;
+    else if ( s == "--on-only" ) a.on_only = true;
+    else if ( s == "--off-only" ) a.off_only = true;
+    else { std::fprintf( stderr, "unknown option %s\n", s.c_str() ); return 2; }
+  }
+  if ( a.gfa.empty() || a.k == 0 ) {
+    std::fprintf( stderr, "usage: psi_ref_driver --gfa G [--fastq F] -k K [-d D] [-n N] [-P] [-t CTX] [-e STEP] [-c CHUNK]\n"
+                          "       [--first-read I] [--max-reads M] [--out F] [--raw F] [--nodes F] [--loci F]\n" );
+    return 2;
+  }
+  if ( a.d == 0 ) a.d = a.k;  /* src/psikt.cpp:469 */
+
+  typedef gum::SeqGraph< gum::Succinct > graph_type;
+  typedef Dna5QStringSet<> readsstringset_type;
+  typedef SeedFinderTraits< gum::Succinct, readsstringset_type, seqan2::IndexWotd<>, InMemory > traits_type;
+  typedef SeedFinder< NoStats, traits_type > finder_type;
+  typedef typename finder_type::traverser_type traverser_type;
+
+  double t0 = now_s();
+  graph_type graph;
+  gum::util::load( graph, a.gfa, true );
+  double t_load = now_s() - t0;
+
+  if ( !a.nodes.empty() ) {
+    std::FILE* f = std::fopen( a.nodes.c_str(), "wb" );
+    graph.for_each_node( [&]( auto rank, auto id ) {
+      uint64_t rec[3] = { (uint64_t)id, (uint64_t)graph.coordinate_id( id ), (uint64_t)graph.node_length( id ) };
+      (void)rank;
+      write_u64s( f, rec, 3 );
+      return true;
+    } );
+    std::fclose( f );
+  }
+
+  finder_type finder( graph, a.k );
+  t0 = now_s();
+  if ( a.n != 0 ) {
+    finder.create_path_index( a.n, a.patched, a.context, a.step );
+  }
+  double t_index = now_s() - t0;
+
+  if ( !a.loci.empty() ) {
+    std::FILE* f = std::fopen( a.loci.c_str(), "wb" );
+    for ( auto const& l : finder.get_starting_loci() ) {
+      uint64_t rec[2] = { (uint64_t)l.node_id(), (uint64_t)l.offset() };
+      write_u64s( f, rec, 2 );
+    }
+    std::fclose( f );
+  }
+
+  unsigned long long raw_on = 0, raw_off = 0;
+  std::vector< std::array< uint64_t, 4 > > hits;
+  std::FILE* rawf = a.raw.empty() ? nullptr : std::fopen( a.raw.c_str(), "wb" );
+  bool keep = !a.out.empty();
+  bool in_off = false;
+
+  std::function< void( typename traverser_type::output_type const& ) > cb =
+    [&]( typename traverser_type::output_type const& h ) {
+      if ( in_off ) ++raw_off; else ++raw_on;
+      if ( rawf ) {
+        uint64_t rec[4] = { (uint64_t)h.node_id, (uint64_t)h.node_offset, (uint64_t)h.read_id, (uint64_t)h.read_offset };
+        write_u64s( rawf, rec, 4 );
+      }
+      if ( keep ) {
+        hits.push_back( { (uint64_t)h.read_id, (uint64_t)h.read_offset,
+                          (uint64_t)graph.coordinate_id( h.node_id ), (uint64_t)h.node_offset } );
+      }
+    };
+
+  double t_seeding = 0, t_on = 0, t_off = 0;
+  unsigned long n_reads = 0, n_seeds = 0, n_chunks = 0;
+  if ( !a.fastq.empty() ) {
+    klibpp::SeqStreamIn iss( a.fastq.c_str() );
+    if ( !iss ) { std::fprintf( stderr, "cannot open %s\n", a.fastq.c_str() ); return 2; }
+    /* Skip to the first read of this shard; read ids stay global (sequence.hpp:1616). */
+    {
+      klibpp::KSeq rec;
+      for ( unsigned long s = 0; s < a.first_read; ++s ) if ( !( iss >> rec ) ) break;
+    }
+    auto chunk = finder.create_readrecord();
+    auto seeds = finder.create_readrecord();
+    auto traverser = finder.create_traverser();
+    while ( true ) {
+      unsigned long want = a.chunk;
+      if ( a.max_reads != 0 ) {
+        unsigned long left = a.max_reads - n_reads;
+        if ( left == 0 ) break;
+        if ( want == 0 || want > left ) want = left;
+      }
+      if ( !readRecords( chunk, iss, want ) ) break;
+      n_reads += length( chunk );
+      ++n_chunks;
+      t0 = now_s();
+      finder.get_seeds( seeds, chunk, a.d );
+      auto seeds_index = finder.index_reads( seeds );
+      t_seeding += now_s() - t0;
+      n_seeds += length( seeds );
+      if ( !a.off_only ) {
+        t0 = now_s();
+        in_off = false;
+        finder.seeds_on_paths( seeds, seeds_index, cb );
+        t_on += now_s() - t0;
+      }
+      if ( !a.on_only ) {
+        t0 = now_s();
+        in_off = true;
+        finder.setup_traverser( traverser, seeds, seeds_index );
+        finder.seeds_off_paths( traverser, cb );
+        t_off += now_s() - t0;
+      }
+    }
+  }
+  if ( rawf ) std::fclose( rawf );
+
+  size_t n_unique = 0;
+  if ( keep ) {
+    std::sort( hits.begin(), hits.end() );
+    hits.erase( std::unique( hits.begin(), hits.end() ), hits.end() );
+    n_unique = hits.size();
+    std::FILE* f = std::fopen( a.out.c_str(), "wb" );
+    if ( !f ) { std::perror( "open out" ); return 3; }
+    if ( !hits.empty() ) write_u64s( f, &hits[0][0], hits.size() * 4 );
+    std::fclose( f );
+  }
+
+  std::printf( "{\"impl\": \"reference\", \"nodes\": %lu, \"loci\": %lu, \"loci_nodes\": %lu, \"reads\": %lu, \"query_seeds\": %lu, "
+               "\"chunks\": %lu, \"raw_on\": %llu, \"raw_off\": %llu, \"unique\": %lu, "
+               "\"t_load\": %.6f, \"t_index\": %.6f, \"t_seeding\": %.6f, \"t_on\": %.6f, \"t_off\": %.6f}\n",
+               (unsigned long)graph.get_node_count(), (unsigned long)finder.get_starting_loci().size(),
+               (unsigned long)finder.get_nof_uniq_nodes(), n_reads, n_seeds, n_chunks, raw_on, raw_off,
+               (unsigned long)n_unique, t_load, t_index, t_seeding, t_on, t_off );
+  return 0;
+}

@@ -1,0 +1,382 @@
+"""ctypes binding of libpsi_b200.so (include/psi_b200.h).
+
+This is plumbing for tests/ and bench.py: numpy arrays in, numpy arrays out.
+The product is the shared library; nothing here computes anything, and there is
+no CPU fallback -- if the library (or a GPU, for the device entry points) is
+missing, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libpsi_b200.so"
+
+OK = 0
+ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5, -6
+ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE = 1, 2, 3, 4, 8
+
+# every symbol include/psi_b200.h declares
+SYMBOLS = [
+    "psi_b200_graph_load_gfa", "psi_b200_graph_from_arrays", "psi_b200_graph_free",
+    "psi_b200_graph_get_view", "psi_b200_graph_path", "psi_b200_graph_write_gfa",
+    "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
+    "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
+    "psi_b200_global_error",
+    "psi_b200_create", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync",
+    "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
+    "psi_b200_submit_chunk", "psi_b200_submit_chunk_device", "psi_b200_seeds_all",
+    "psi_b200_fetch", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
+    "psi_b200_counters", "psi_b200_reset_counters", "psi_b200_version",
+]
+
+
+class PsiError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"psi_b200 error {code}: {msg}")
+        self.code = code
+
+
+class GraphView(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("n_bases", C.c_uint64), ("n_paths", C.c_uint64),
+                ("seq_start", C.POINTER(C.c_uint64)), ("seq", C.POINTER(C.c_char)),
+                ("row_ptr", C.POINTER(C.c_uint64)), ("col", C.POINTER(C.c_uint32)),
+                ("internal_id", C.POINTER(C.c_uint64)), ("coord_id", C.POINTER(C.c_uint64))]
+
+
+class PathSetView(C.Structure):
+    _fields_ = [("n_paths", C.c_uint64), ("path_ptr", C.POINTER(C.c_uint64)), ("nodes", C.POINTER(C.c_uint32)),
+                ("head_off", C.POINTER(C.c_uint32)), ("tail_trim", C.POINTER(C.c_uint32))]
+
+
+class ChunkView(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("first_read_id", C.c_uint64),
+                ("read_ptr", C.POINTER(C.c_uint64)), ("bases", C.POINTER(C.c_char)),
+                ("name_ptr", C.POINTER(C.c_uint64)), ("names", C.POINTER(C.c_char))]
+
+
+class Counters(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("n_bases", C.c_uint64),
+                ("n_path_bases", C.c_uint64), ("n_index_entries", C.c_uint64), ("n_index_kmers", C.c_uint64),
+                ("index_bytes", C.c_uint64), ("index_buckets", C.c_uint64),
+                ("index_slot_bytes", C.c_uint32), ("reserved0", C.c_uint32),
+                ("n_loci", C.c_uint64), ("n_reads", C.c_uint64), ("n_seeds", C.c_uint64),
+                ("n_hits_on", C.c_uint64), ("n_hits_off", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_walks", C.c_uint64), ("n_on_probe_sectors", C.c_uint64),
+                ("ms_index_build", C.c_float), ("ms_find_loci", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_read_index", C.c_float), ("ms_on", C.c_float),
+                ("ms_off", C.c_float), ("ms_resolve", C.c_float), ("ms_sort", C.c_float), ("ms_d2h", C.c_float),
+                ("launches", C.c_uint32), ("reserved1", C.c_uint32)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libpsi_b200.so (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PsiError(ERR_IO, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(os.fspath(LIB_PATH))
+    u64p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p
+    L.psi_b200_version.restype = C.c_char_p
+    L.psi_b200_global_error.restype = C.c_char_p
+    L.psi_b200_last_error.restype = C.c_char_p
+    L.psi_b200_last_error.argtypes = [vp]
+    L.psi_b200_graph_load_gfa.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.psi_b200_graph_from_arrays.argtypes = [C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]
+    L.psi_b200_graph_free.argtypes = [vp]
+    L.psi_b200_graph_free.restype = None
+    L.psi_b200_graph_get_view.argtypes = [vp, C.POINTER(GraphView)]
+    L.psi_b200_graph_path.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(u32p), u64p]
+    L.psi_b200_graph_write_gfa.argtypes = [vp, C.c_char_p]
+    L.psi_b200_pick_paths.argtypes = [vp, C.c_uint, C.c_int, C.c_uint, C.c_uint64, C.POINTER(vp)]
+    L.psi_b200_pathset_free.argtypes = [vp]
+    L.psi_b200_pathset_free.restype = None
+    L.psi_b200_pathset_get_view.argtypes = [vp, C.POINTER(PathSetView)]
+    L.psi_b200_reader_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.psi_b200_reader_next.argtypes = [vp, C.c_uint64, C.POINTER(ChunkView)]
+    L.psi_b200_reader_close.argtypes = [vp]
+    L.psi_b200_reader_close.restype = None
+    L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
+    L.psi_b200_destroy.argtypes = [vp]
+    L.psi_b200_destroy.restype = None
+    L.psi_b200_set_stream.argtypes = [vp, vp]
+    L.psi_b200_sync.argtypes = [vp]
+    L.psi_b200_set_graph.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp]
+    L.psi_b200_set_paths.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
+    L.psi_b200_find_loci.argtypes = [vp, C.c_uint, u64p]
+    L.psi_b200_get_loci.argtypes = [vp, vp, vp, C.c_uint64, u64p]
+    L.psi_b200_set_loci.argtypes = [vp, C.c_uint64, vp, vp]
+    L.psi_b200_submit_chunk.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint]
+    L.psi_b200_submit_chunk_device.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, C.c_uint]
+    L.psi_b200_seeds_all.argtypes = [vp, C.c_uint, u64p]
+    L.psi_b200_fetch.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.psi_b200_fetch_device.argtypes = [vp, C.POINTER(vp), u64p]
+    L.psi_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.psi_b200_host_free.argtypes = [vp]
+    L.psi_b200_host_free.restype = None
+    L.psi_b200_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.psi_b200_reset_counters.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int, ctx=None):
+    if rc != OK:
+        L = lib()
+        msg = L.psi_b200_last_error(ctx) if ctx else L.psi_b200_global_error()
+        raise PsiError(rc, (msg or b"").decode())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype) if dtype != np.uint8 else \
+        np.frombuffer(C.string_at(ptr, n), dtype=np.uint8)
+
+
+class Graph:
+    """Flattened sequence graph (host).  Arrays are numpy copies of the library's."""
+
+    def __init__(self, handle):
+        self._h = handle
+        v = GraphView()
+        _check(lib().psi_b200_graph_get_view(handle, C.byref(v)))
+        n = v.n_nodes
+        self.n_nodes, self.n_edges, self.n_bases, self.n_paths = n, v.n_edges, v.n_bases, v.n_paths
+        self.seq_start = np.ctypeslib.as_array(v.seq_start, shape=(n + 1,)).copy()
+        self.row_ptr = np.ctypeslib.as_array(v.row_ptr, shape=(n + 1,)).copy()
+        self.col = np.ctypeslib.as_array(v.col, shape=(max(v.n_edges, 1),))[: v.n_edges].copy() \
+            if v.n_edges else np.zeros(0, np.uint32)
+        self.seq = np.frombuffer(C.string_at(v.seq, v.n_bases), dtype=np.uint8).copy()
+        self.internal_id = np.ctypeslib.as_array(v.internal_id, shape=(n,)).copy()
+        self.coord_id = np.ctypeslib.as_array(v.coord_id, shape=(n,)).copy()
+
+    @classmethod
+    def load_gfa(cls, path, sort=True) -> "Graph":
+        h = C.c_void_p()
+        _check(lib().psi_b200_graph_load_gfa(os.fspath(path).encode(), int(sort), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, ids, seq_start, seq, row_ptr, col, path_ptr=None, path_nodes=None, sort=False) -> "Graph":
+        ids = np.ascontiguousarray(ids, np.uint64)
+        seq_start = np.ascontiguousarray(seq_start, np.uint64)
+        seq = np.ascontiguousarray(seq, np.uint8)
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        n_paths = 0
+        if path_ptr is not None:
+            path_ptr = np.ascontiguousarray(path_ptr, np.uint64)
+            path_nodes = np.ascontiguousarray(path_nodes, np.uint32)
+            n_paths = len(path_ptr) - 1
+        h = C.c_void_p()
+        _check(lib().psi_b200_graph_from_arrays(len(ids), _ptr(ids), _ptr(seq_start), _ptr(seq), _ptr(row_ptr),
+                                                _ptr(col), n_paths, _ptr(path_ptr), _ptr(path_nodes), int(sort),
+                                                C.byref(h)))
+        return cls(h)
+
+    def path(self, i):
+        name, nodes, n = C.c_char_p(), C.POINTER(C.c_uint32)(), C.c_uint64()
+        _check(lib().psi_b200_graph_path(self._h, i, C.byref(name), C.byref(nodes), C.byref(n)))
+        return name.value.decode(), np.ctypeslib.as_array(nodes, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def write_gfa(self, path):
+        _check(lib().psi_b200_graph_write_gfa(self._h, os.fspath(path).encode()))
+
+    def pick_paths(self, n, patched=True, context=0, seed=1) -> "PathSet":
+        h = C.c_void_p()
+        _check(lib().psi_b200_pick_paths(self._h, n, int(patched), context, seed, C.byref(h)))
+        return PathSet(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().psi_b200_graph_free(self._h)
+            self._h = None
+
+
+class PathSet:
+    def __init__(self, handle=None, path_ptr=None, nodes=None, head_off=None, tail_trim=None):
+        self._h = handle
+        if handle is not None:
+            v = PathSetView()
+            _check(lib().psi_b200_pathset_get_view(handle, C.byref(v)))
+            n = v.n_paths
+            self.path_ptr = np.ctypeslib.as_array(v.path_ptr, shape=(n + 1,)).copy()
+            ne = int(self.path_ptr[-1])
+            self.nodes = np.ctypeslib.as_array(v.nodes, shape=(ne,)).copy() if ne else np.zeros(0, np.uint32)
+            self.head_off = np.ctypeslib.as_array(v.head_off, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+            self.tail_trim = np.ctypeslib.as_array(v.tail_trim, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        else:
+            self.path_ptr = np.ascontiguousarray(path_ptr, np.uint64)
+            self.nodes = np.ascontiguousarray(nodes, np.uint32)
+            n = len(self.path_ptr) - 1
+            self.head_off = np.zeros(n, np.uint32) if head_off is None else np.ascontiguousarray(head_off, np.uint32)
+            self.tail_trim = np.zeros(n, np.uint32) if tail_trim is None else np.ascontiguousarray(tail_trim, np.uint32)
+
+    @property
+    def n_paths(self):
+        return len(self.path_ptr) - 1
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().psi_b200_pathset_free(self._h)
+            self._h = None
+
+
+class Reader:
+    """FASTQ/FASTA chunk reader (readRecords, reference sequence.hpp:1608-1624)."""
+
+    def __init__(self, path):
+        self._h = C.c_void_p()
+        _check(lib().psi_b200_reader_open(os.fspath(path).encode(), C.byref(self._h)))
+
+    def next(self, max_reads=0):
+        """Returns (first_read_id, read_ptr[u64 n+1], bases[u8], names) or None at end of input."""
+        v = ChunkView()
+        _check(lib().psi_b200_reader_next(self._h, max_reads, C.byref(v)))
+        if v.n_reads == 0:
+            return None
+        n = v.n_reads
+        read_ptr = np.ctypeslib.as_array(v.read_ptr, shape=(n + 1,)).copy()
+        bases = np.frombuffer(C.string_at(v.bases, int(read_ptr[-1])), dtype=np.uint8).copy()
+        name_ptr = np.ctypeslib.as_array(v.name_ptr, shape=(n + 1,)).copy()
+        names_raw = C.string_at(v.names, int(name_ptr[-1]))
+        names = [names_raw[name_ptr[i]:name_ptr[i + 1]].decode() for i in range(n)]
+        return v.first_read_id, read_ptr, bases, names
+
+    def close(self):
+        if self._h:
+            lib().psi_b200_reader_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class Context:
+    """One GPU context (psi_b200_ctx)."""
+
+    def __init__(self, seed_len: int, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().psi_b200_create(device, seed_len, C.byref(self._h)))
+        self.k = seed_len
+
+    def _ck(self, rc):
+        _check(rc, self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().psi_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(lib().psi_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(lib().psi_b200_sync(self._h))
+
+    def set_graph(self, g: Graph, ids="internal"):
+        node_id = g.internal_id if ids == "internal" else g.coord_id
+        self._keep = (g.seq_start, g.seq, g.row_ptr, g.col, node_id)
+        self._ck(lib().psi_b200_set_graph(self._h, g.n_nodes, _ptr(g.seq_start), _ptr(g.seq), _ptr(g.row_ptr),
+                                          _ptr(g.col), _ptr(node_id)))
+
+    def set_paths(self, p: PathSet):
+        self._ck(lib().psi_b200_set_paths(self._h, p.n_paths, _ptr(p.path_ptr), _ptr(p.nodes), _ptr(p.head_off),
+                                          _ptr(p.tail_trim)))
+
+    def find_loci(self, step=1) -> int:
+        n = C.c_uint64()
+        self._ck(lib().psi_b200_find_loci(self._h, step, C.byref(n)))
+        return n.value
+
+    def get_loci(self):
+        n = C.c_uint64()
+        self._ck(lib().psi_b200_get_loci(self._h, None, None, 0, C.byref(n)))
+        node = np.zeros(n.value, np.uint32)
+        off = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(lib().psi_b200_get_loci(self._h, _ptr(node), _ptr(off), n.value, C.byref(n)))
+        return node, off
+
+    def set_loci(self, node, off):
+        node = np.ascontiguousarray(node, np.uint32)
+        off = np.ascontiguousarray(off, np.uint32)
+        self._ck(lib().psi_b200_set_loci(self._h, len(node), _ptr(node), _ptr(off)))
+
+    def submit_chunk(self, read_ptr, bases, first_read_id=0, distance=0):
+        read_ptr = np.ascontiguousarray(read_ptr, np.uint64)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        self._chunk_keep = (read_ptr, bases)
+        self._ck(lib().psi_b200_submit_chunk(self._h, len(read_ptr) - 1, _ptr(read_ptr), _ptr(bases), first_read_id,
+                                             distance))
+
+    def submit_chunk_ptr(self, n_reads, read_ptr_addr, bases_addr, first_read_id=0, distance=0):
+        """Host pointers given as integers (e.g. pinned torch tensors)."""
+        self._ck(lib().psi_b200_submit_chunk(self._h, n_reads, C.c_void_p(read_ptr_addr), C.c_void_p(bases_addr),
+                                             first_read_id, distance))
+
+    def submit_chunk_device(self, n_reads, d_read_ptr, d_bases, n_bases, first_read_id=0, distance=0):
+        self._ck(lib().psi_b200_submit_chunk_device(self._h, n_reads, C.c_void_p(d_read_ptr), C.c_void_p(d_bases),
+                                                    n_bases, first_read_id, distance))
+
+    def seeds_all(self, flags=ALL) -> int:
+        n = C.c_uint64()
+        self._ck(lib().psi_b200_seeds_all(self._h, flags, C.byref(n)))
+        return n.value
+
+    def fetch(self, n=None) -> np.ndarray:
+        """(n, 4) u64 records {node_id, node_offset, read_id, read_offset} (reference src/psikt.cpp:172-181)."""
+        cnt = C.c_uint64()
+        self._ck(lib().psi_b200_fetch(self._h, None, 0, C.byref(cnt)))
+        n = cnt.value if n is None else min(n, cnt.value)
+        out = np.zeros((n, 4), np.uint64)
+        if n:
+            self._ck(lib().psi_b200_fetch(self._h, _ptr(out), n, C.byref(cnt)))
+        return out
+
+    def fetch_into(self, addr: int, cap: int) -> int:
+        cnt = C.c_uint64()
+        self._ck(lib().psi_b200_fetch(self._h, C.c_void_p(addr), cap, C.byref(cnt)))
+        return cnt.value
+
+    def fetch_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(lib().psi_b200_fetch_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counters(self) -> dict:
+        c = Counters()
+        self._ck(lib().psi_b200_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._ck(lib().psi_b200_reset_counters(self._h))
+
+
+def canonical(records: np.ndarray) -> np.ndarray:
+    """Reference-CLI records {node, node_off, read, read_off} -> the canonical seed
+    set: unique rows (read_id, read_offset, node_id, node_offset), sorted."""
+    if records.size == 0:
+        return np.zeros((0, 4), np.uint64)
+    t = np.ascontiguousarray(records.reshape(-1, 4)[:, [2, 3, 0, 1]])
+    return np.unique(t, axis=0)

@@ -1,0 +1,356 @@
+// capi.cu -- the extern "C" surface of libpsi_b200.so (include/psi_b200.h).
+// Every entry point converts C++ exceptions into error codes; nothing else
+// happens here.
+#include <cstring>
+#include <exception>
+#include <new>
+#include <string>
+
+#include "../../include/psi_b200.h"
+#include "device/engine.hpp"
+#include "flat_graph.hpp"
+#include "paths.hpp"
+#include "reads.hpp"
+
+using namespace psi_b200;
+
+struct psi_b200_graph { FlatGraph g; };
+struct psi_b200_pathset { PathSet p; };
+struct psi_b200_reader { ChunkReader* r; };
+struct psi_b200_ctx { Ctx* c; };
+
+namespace {
+
+thread_local std::string g_error;
+
+int translate(std::string& err)
+{
+  try { throw; }
+  catch (const ArgError& e) { err = e.what(); return PSI_B200_ERR_ARG; }
+  catch (const StateError& e) { err = e.what(); return PSI_B200_ERR_STATE; }
+  catch (const CudaError& e) { err = e.what(); return PSI_B200_ERR_CUDA; }
+  catch (const OverflowError& e) { err = e.what(); return PSI_B200_ERR_OVERFLOW; }
+  catch (const std::bad_alloc&) { err = "out of host memory"; return PSI_B200_ERR_NOMEM; }
+  catch (const std::exception& e) { err = e.what(); return PSI_B200_ERR_ARG; }
+  catch (...) { err = "unknown error"; return PSI_B200_ERR_ARG; }
+}
+
+#define HOST_GUARD(body)                         \
+  try { body; return PSI_B200_OK; }              \
+  catch (...) { return translate(g_error); }
+
+#define CTX_GUARD(ctx, body)                                        \
+  if (!(ctx) || !(ctx)->c) { g_error = "null context"; return PSI_B200_ERR_ARG; } \
+  try { body; return PSI_B200_OK; }                                 \
+  catch (...) { return translate((ctx)->c->error); }
+
+}  // namespace
+
+extern "C" {
+
+const char* psi_b200_version(void) { return "psi_b200 0.1.0 sm_100a"; }
+const char* psi_b200_global_error(void) { return g_error.c_str(); }
+
+/* ------------------------------------------------------------ graph -- */
+
+int psi_b200_graph_load_gfa(const char* path, int sort, psi_b200_graph** out)
+{
+  if (!path || !out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  psi_b200_graph* g = nullptr;
+  try {
+    g = new psi_b200_graph();
+    load_gfa(path, sort != 0, g->g);
+    *out = g;
+    return PSI_B200_OK;
+  }
+  catch (...) {
+    delete g;
+    int rc = translate(g_error);
+    return rc == PSI_B200_ERR_ARG && g_error.find("could not open") != std::string::npos ? PSI_B200_ERR_IO : rc;
+  }
+}
+
+int psi_b200_graph_from_arrays(uint64_t n_nodes, const uint64_t* ids, const uint64_t* seq_start, const char* seq,
+                               const uint64_t* row_ptr, const uint32_t* col, uint64_t n_paths,
+                               const uint64_t* path_ptr, const uint32_t* path_nodes, int sort,
+                               psi_b200_graph** out)
+{
+  if (!out || !ids || !seq_start || !seq || !row_ptr) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  psi_b200_graph* g = nullptr;
+  try {
+    RawGraph raw;
+    raw.ids.assign(ids, ids + n_nodes);
+    raw.labels.resize(n_nodes);
+    for (uint64_t v = 0; v < n_nodes; ++v) raw.labels[v].assign(seq + seq_start[v], seq + seq_start[v + 1]);
+    raw.edges.reserve(row_ptr[n_nodes]);
+    for (uint64_t v = 0; v < n_nodes; ++v)
+      for (uint64_t e = row_ptr[v]; e < row_ptr[v + 1]; ++e) raw.edges.push_back({ (uint32_t)v, col[e], false });
+    for (uint64_t p = 0; p < n_paths; ++p) {
+      RawGraph::RawPath rp;
+      rp.name = "path" + std::to_string(p);
+      rp.nodes.assign(path_nodes + path_ptr[p], path_nodes + path_ptr[p + 1]);
+      raw.paths.push_back(std::move(rp));
+    }
+    g = new psi_b200_graph();
+    build_flat_graph(std::move(raw), sort != 0, g->g);
+    *out = g;
+    return PSI_B200_OK;
+  }
+  catch (...) { delete g; return translate(g_error); }
+}
+
+void psi_b200_graph_free(psi_b200_graph* g) { delete g; }
+
+int psi_b200_graph_get_view(const psi_b200_graph* g, psi_b200_graph_view* v)
+{
+  if (!g || !v) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  const FlatGraph& f = g->g;
+  v->n_nodes = f.node_count();
+  v->n_edges = f.edge_count();
+  v->n_bases = f.seq.size();
+  v->n_paths = f.paths.size();
+  v->seq_start = f.seq_start.data();
+  v->seq = f.seq.data();
+  v->row_ptr = f.row_ptr.data();
+  v->col = f.col.data();
+  v->internal_id = f.internal_id.data();
+  v->coord_id = f.coord_id.data();
+  return PSI_B200_OK;
+}
+
+int psi_b200_graph_path(const psi_b200_graph* g, uint64_t i, const char** name, const uint32_t** nodes, uint64_t* n_nodes)
+{
+  if (!g || i >= g->g.paths.size()) { g_error = "path index out of range"; return PSI_B200_ERR_ARG; }
+  if (name) *name = g->g.paths[i].name.c_str();
+  if (nodes) *nodes = g->g.paths[i].nodes.data();
+  if (n_nodes) *n_nodes = g->g.paths[i].nodes.size();
+  return PSI_B200_OK;
+}
+
+int psi_b200_graph_write_gfa(const psi_b200_graph* g, const char* path)
+{
+  if (!g || !path) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  try { write_gfa1(g->g, path); return PSI_B200_OK; }
+  catch (...) { translate(g_error); return PSI_B200_ERR_IO; }
+}
+
+/* ------------------------------------------------------------ paths -- */
+
+int psi_b200_pick_paths(const psi_b200_graph* g, unsigned n, int patched, unsigned context, uint64_t seed,
+                        psi_b200_pathset** out)
+{
+  if (!g || !out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  psi_b200_pathset* p = nullptr;
+  try {
+    p = new psi_b200_pathset();
+    pick_paths(g->g, n, patched != 0, context, seed, p->p);
+    *out = p;
+    return PSI_B200_OK;
+  }
+  catch (...) { delete p; return translate(g_error); }
+}
+
+void psi_b200_pathset_free(psi_b200_pathset* p) { delete p; }
+
+int psi_b200_pathset_get_view(const psi_b200_pathset* p, psi_b200_pathset_view* v)
+{
+  if (!p || !v) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  v->n_paths = p->p.size();
+  v->path_ptr = p->p.path_ptr.data();
+  v->nodes = p->p.nodes.data();
+  v->head_off = p->p.head_off.data();
+  v->tail_trim = p->p.tail_trim.data();
+  return PSI_B200_OK;
+}
+
+/* ------------------------------------------------------------ reads -- */
+
+int psi_b200_reader_open(const char* path, psi_b200_reader** out)
+{
+  if (!path || !out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  try {
+    ChunkReader* r = new ChunkReader(path);
+    *out = new psi_b200_reader{ r };
+    return PSI_B200_OK;
+  }
+  catch (...) { translate(g_error); return PSI_B200_ERR_IO; }
+}
+
+int psi_b200_reader_next(psi_b200_reader* r, uint64_t max_reads, psi_b200_chunk_view* v)
+{
+  if (!r || !r->r || !v) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  HOST_GUARD({
+    r->r->next(max_reads);
+    v->n_reads = r->r->n_reads();
+    v->first_read_id = r->r->first_read_id();
+    v->read_ptr = r->r->read_ptr();
+    v->bases = r->r->bases();
+    v->name_ptr = r->r->name_ptr();
+    v->names = r->r->names();
+  })
+}
+
+void psi_b200_reader_close(psi_b200_reader* r)
+{
+  if (!r) return;
+  delete r->r;
+  delete r;
+}
+
+/* ----------------------------------------------------------- device -- */
+
+int psi_b200_create(int device, unsigned seed_len, psi_b200_ctx** out)
+{
+  if (!out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  try {
+    Ctx* c = engine_create(device, seed_len);
+    *out = new psi_b200_ctx{ c };
+    return PSI_B200_OK;
+  }
+  catch (...) { return translate(g_error); }
+}
+
+void psi_b200_destroy(psi_b200_ctx* ctx)
+{
+  if (!ctx) return;
+  engine_destroy(ctx->c);
+  delete ctx;
+}
+
+const char* psi_b200_last_error(const psi_b200_ctx* ctx)
+{
+  if (!ctx || !ctx->c) return g_error.c_str();
+  return ctx->c->error.c_str();
+}
+
+int psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream)
+{
+  CTX_GUARD(ctx, {
+    Ctx& c = *ctx->c;
+    PSI_CUDA(cudaSetDevice(c.device));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.own_stream) { cudaStreamDestroy(c.stream); c.own_stream = false; }
+    c.stream = (cudaStream_t)cuda_stream;
+  })
+}
+
+int psi_b200_sync(psi_b200_ctx* ctx)
+{
+  CTX_GUARD(ctx, {
+    PSI_CUDA(cudaSetDevice(ctx->c->device));
+    PSI_CUDA(cudaStreamSynchronize(ctx->c->stream));
+  })
+}
+
+int psi_b200_set_graph(psi_b200_ctx* ctx, uint64_t n_nodes, const uint64_t* seq_start, const char* seq,
+                       const uint64_t* row_ptr, const uint32_t* col, const uint64_t* node_id)
+{
+  CTX_GUARD(ctx, engine_set_graph(*ctx->c, n_nodes, seq_start, seq, row_ptr, col, node_id))
+}
+
+int psi_b200_set_paths(psi_b200_ctx* ctx, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                       const uint32_t* head_off, const uint32_t* tail_trim)
+{
+  CTX_GUARD(ctx, engine_build_index(*ctx->c, n_paths, path_ptr, path_nodes, head_off, tail_trim))
+}
+
+int psi_b200_find_loci(psi_b200_ctx* ctx, unsigned step, uint64_t* n_loci)
+{
+  CTX_GUARD(ctx, {
+    engine_find_loci(*ctx->c, step);
+    if (n_loci) *n_loci = ctx->c->n_loci;
+  })
+}
+
+int psi_b200_get_loci(psi_b200_ctx* ctx, uint32_t* node_rank, uint32_t* offset, uint64_t cap, uint64_t* n_loci)
+{
+  CTX_GUARD(ctx, {
+    if (n_loci) *n_loci = ctx->c->n_loci;
+    if (cap) engine_get_loci(*ctx->c, node_rank, offset, cap);
+  })
+}
+
+int psi_b200_set_loci(psi_b200_ctx* ctx, uint64_t n_loci, const uint32_t* node_rank, const uint32_t* offset)
+{
+  CTX_GUARD(ctx, engine_set_loci(*ctx->c, n_loci, node_rank, offset))
+}
+
+int psi_b200_submit_chunk(psi_b200_ctx* ctx, uint64_t n_reads, const uint64_t* read_ptr, const char* bases,
+                          uint64_t first_read_id, unsigned distance)
+{
+  CTX_GUARD(ctx, engine_submit_chunk(*ctx->c, n_reads, read_ptr, bases, 0, first_read_id, distance, false))
+}
+
+int psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads, const uint64_t* d_read_ptr, const char* d_bases,
+                                 uint64_t n_bases, uint64_t first_read_id, unsigned distance)
+{
+  CTX_GUARD(ctx, engine_submit_chunk(*ctx->c, n_reads, d_read_ptr, d_bases, n_bases, first_read_id, distance, true))
+}
+
+int psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (!(flags & PSI_B200_ALL)) throw ArgError("seeds_all: neither ON_PATHS nor OFF_PATHS requested");
+    engine_seeds(*ctx->c, flags);
+    if (n_hits) *n_hits = ctx->c->n_hits;
+  })
+}
+
+int psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (n_hits) *n_hits = ctx->c->n_hits;
+    if (cap && !hits) throw ArgError("fetch: null buffer");
+    if (cap) engine_fetch(*ctx->c, hits, cap);
+  })
+}
+
+int psi_b200_fetch_device(psi_b200_ctx* ctx, const uint64_t** d_hits, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (!ctx->c->records_valid) throw StateError("fetch_device: no resolved seed records");
+    if (d_hits) *d_hits = ctx->c->records.p;
+    if (n_hits) *n_hits = ctx->c->n_hits;
+  })
+}
+
+int psi_b200_host_alloc(void** p, size_t bytes)
+{
+  if (!p) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { g_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); (void)cudaGetLastError(); *p = nullptr; return PSI_B200_ERR_CUDA; }
+  return PSI_B200_OK;
+}
+
+void psi_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out)
+{
+  CTX_GUARD(ctx, {
+    if (!out) throw ArgError("counters: null argument");
+    Ctx& c = *ctx->c;
+    PSI_CUDA(cudaSetDevice(c.device));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    c.counters.ms_h2d = PhaseTimer::timer_ms(c, T_H2D);
+    c.counters.ms_pack = PhaseTimer::timer_ms(c, T_PACK);
+    c.counters.ms_read_index = PhaseTimer::timer_ms(c, T_READ_INDEX);
+    c.counters.ms_on = PhaseTimer::timer_ms(c, T_ON);
+    c.counters.ms_off = PhaseTimer::timer_ms(c, T_OFF);
+    c.counters.ms_resolve = PhaseTimer::timer_ms(c, T_RESOLVE);
+    c.counters.ms_sort = PhaseTimer::timer_ms(c, T_SORT);
+    c.counters.ms_d2h = PhaseTimer::timer_ms(c, T_D2H);
+    *out = c.counters;
+  })
+}
+
+int psi_b200_reset_counters(psi_b200_ctx* ctx)
+{
+  CTX_GUARD(ctx, { ctx->c->counters.launches = 0; })
+}
+
+}  // extern "C"

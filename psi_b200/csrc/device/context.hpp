@@ -1,0 +1,157 @@
+// context.hpp -- per-GPU state of libpsi_b200 (host-side view).
+#ifndef PSI_B200_DEVICE_CONTEXT_HPP
+#define PSI_B200_DEVICE_CONTEXT_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../../include/psi_b200.h"
+#include "common.cuh"
+
+namespace psi_b200 {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct ArgError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct StateError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct OverflowError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define PSI_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      throw ::psi_b200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+// Grow-only device buffer.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // Ensure room for n elements; contents are NOT preserved on growth.
+  void ensure(size_t n, double slack = 1.0)
+  {
+    if (n <= cap) return;
+    size_t want = (size_t)((double)n * slack) + 16;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    PSI_CUDA(cudaMalloc((void**)&p, want * sizeof(T)));
+    cap = want;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+// Node record used by the graph walkers: one 16-byte load per visited node.
+struct alignas(16) NodeRec {
+  uint32_t seq_start;  // global position of the first base
+  uint32_t seq_len;
+  uint32_t edge_start; // into col[]
+  uint32_t outdeg;
+};
+
+// A compact hit: (seed index within the chunk, global graph position).
+struct alignas(8) Hit {
+  uint32_t seed;
+  uint32_t gpos;
+};
+
+struct HostTable {
+  dev::KmerTable view{};
+  DevBuf<char> slots;
+  DevBuf<dev::Slot16> stash;
+  DevBuf<uint32_t> stash_used;
+  uint64_t n_lines = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  unsigned k = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string error;
+  psi_b200_counters_t counters{};
+  cudaEvent_t ev[24]{};
+  int ev_state[12]{};   // 0 never recorded, 1 started, 2 start+stop recorded
+
+  // ---- graph ----
+  bool has_graph = false;
+  uint32_t n_nodes = 0, n_edges = 0;
+  uint64_t n_bases = 0;
+  bool graph_has_n = false;
+  DevBuf<NodeRec> node_rec;      // n_nodes + 1 (sentinel with seq_start = n_bases)
+  DevBuf<uint32_t> col;
+  DevBuf<uint64_t> seq2;         // 2-bit labels
+  DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
+  DevBuf<uint64_t> node_id;
+  DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
+  static constexpr uint32_t POS2NODE_SHIFT = 6;
+
+  // ---- path index ----
+  bool has_index = false;
+  HostTable index;
+  DevBuf<uint32_t> multi;        // [count, gpos...] runs of k-mers with several loci
+
+  // ---- starting loci ----
+  uint64_t n_loci = 0;
+  DevBuf<uint32_t> loci_node, loci_off;
+
+  // ---- current chunk ----
+  bool has_chunk = false;
+  bool chunk_indexed = false;
+  uint64_t n_reads = 0, n_read_bases = 0, first_read_id = 0, n_seeds_cap = 0;
+  unsigned distance = 0;
+  DevBuf<char> bases;            // owned copy for host submissions
+  DevBuf<uint64_t> read_ptr;
+  const char* d_bases = nullptr; // points to `bases` or to caller's device memory
+  const uint64_t* d_read_ptr = nullptr;
+  DevBuf<uint32_t> seed_first;   // n_reads + 1: first seed of each read (exclusive scan)
+  DevBuf<uint32_t> seed_read;    // per seed: local read index
+  DevBuf<uint64_t> seed_kmer;
+  DevBuf<uint32_t> seed_valid;   // bitmap
+  DevBuf<uint32_t> seed_next;    // chain links of the read index
+  HostTable read_index;
+  DevBuf<char> scan_tmp;
+  uint64_t* h_pinned = nullptr;  // small pinned scratch for async counter read-back
+
+  // ---- results ----
+  DevBuf<Hit> hits;              // compact, on-path first then off-path
+  DevBuf<unsigned long long> dedup;  // off-path (chain head, gpos) set
+  DevBuf<uint64_t> records;      // 4 x u64 per hit, reference layout
+  DevBuf<unsigned long long> dev_counters;  // see DC_* below
+  uint64_t n_hits = 0;
+  bool records_valid = false;
+  uint32_t spill_items = 4096;   // per-warp global spill of the walker
+  DevBuf<char> walk_spill;
+};
+
+// indices into Ctx::dev_counters
+enum {
+  DC_HITS = 0,        // compact hits appended
+  DC_WALKS = 1,       // completed k-walks (off-path kernel)
+  DC_ERR = 2,         // bit 0: walker stack overflow, bit 1: table overflow, bit 2: dedup overflow
+  DC_SECTORS = 3,     // sectors read by the on-path probe (diagnostic)
+  DC_WORK = 4,        // dynamic work counter of the walkers
+  DC_SEEDS = 5,       // total seeds of the chunk
+  DC_AUX = 6,
+  DC_AUX2 = 7,
+  DC_COUNT = 8
+};
+
+}  // namespace psi_b200
+#endif

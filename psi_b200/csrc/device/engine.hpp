@@ -1,0 +1,71 @@
+// engine.hpp -- host entry points of the device engine (one per C-ABI call).
+#ifndef PSI_B200_DEVICE_ENGINE_HPP
+#define PSI_B200_DEVICE_ENGINE_HPP
+
+#include "context.hpp"
+
+namespace psi_b200 {
+
+Ctx* engine_create(int device, unsigned seed_len);
+void engine_destroy(Ctx* ctx);
+
+void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const char* seq,
+                      const uint64_t* row_ptr, const uint32_t* col, const uint64_t* node_id);
+void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                        const uint32_t* head_off, const uint32_t* tail_trim);
+void engine_find_loci(Ctx& c, unsigned step);
+void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* off);
+void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap);
+void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, const char* bases,
+                         uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
+void engine_seeds(Ctx& c, unsigned flags);
+void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap);
+
+// ---- helpers shared by the .cu files ----
+
+// Size a KmerTable for n_keys distinct k-mers of 2k = kbits bits; allocates and
+// clears the slots.  max_inflate_bytes bounds how far the table may be grown
+// beyond its natural size to keep the compact 8-byte slot format.
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t max_inflate_bytes,
+                 uint64_t stash_slots);
+void table_clear(Ctx& c, HostTable& t);
+
+// CUDA-event timer slots (Ctx::ev holds a start/stop pair per slot)
+enum { T_INDEX = 0, T_LOCI = 1, T_H2D = 2, T_PACK = 3, T_READ_INDEX = 4, T_ON = 5, T_OFF = 6, T_RESOLVE = 7,
+       T_SORT = 8, T_D2H = 9, T_USER = 10, T_COUNT = 12 };
+
+struct PhaseTimer {
+  Ctx& c;
+  int i;
+  PhaseTimer(Ctx& ctx, int slot) : c(ctx), i(slot)
+  {
+    cudaEventRecord(c.ev[2 * i], c.stream);
+    c.ev_state[i] = 1;
+  }
+  void stop()
+  {
+    cudaEventRecord(c.ev[2 * i + 1], c.stream);
+    c.ev_state[i] = 2;
+  }
+  // valid after the stream has been synchronised
+  float ms() const { return timer_ms(c, i); }
+  static float timer_ms(Ctx& c, int i)
+  {
+    float v = 0;
+    if (c.ev_state[i] != 2) return 0.f;
+    if (cudaEventElapsedTime(&v, c.ev[2 * i], c.ev[2 * i + 1]) != cudaSuccess) { (void)cudaGetLastError(); return 0.f; }
+    return v;
+  }
+};
+
+inline unsigned grid_for(uint64_t items, unsigned block, unsigned items_per_thread = 1)
+{
+  uint64_t per_block = (uint64_t)block * items_per_thread;
+  uint64_t g = (items + per_block - 1) / per_block;
+  if (g == 0) g = 1;
+  if (g > 0x7fffffffull) g = 0x7fffffffull;
+  return (unsigned)g;
+}
+
+}  // namespace psi_b200
+#endif

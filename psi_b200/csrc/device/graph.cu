@@ -1,0 +1,205 @@
+// graph.cu -- context lifecycle, graph upload/flattening, table allocation.
+//
+// The graph crosses the C-ABI as CSR + concatenated ASCII labels (what gum's
+// node_sequence / for_each_edges_out expose, reference
+// gum/seqgraph_succinct.hpp:194-199, gum/digraph_succinct.hpp:595-610,722-731)
+// and is re-laid out for the walkers: one 16-byte NodeRec per node, 2-bit
+// labels, an N bitmap and a sampled position->node table.
+#include "engine.hpp"
+
+#include <cstring>
+#include <vector>
+
+namespace psi_b200 {
+
+using namespace dev;
+
+// One thread per 32-base word: ASCII -> 2-bit + N bitmap.
+__global__ void __launch_bounds__(256)
+pack_labels_kernel(const char* __restrict__ seq, uint64_t n_bases, uint64_t* __restrict__ seq2,
+                   uint32_t* __restrict__ nmask, unsigned long long* __restrict__ n_count)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t n_words = (n_bases + 31) >> 5;
+  if (w >= n_words) return;
+  const uint64_t b0 = w << 5;
+  uint64_t bits = 0;
+  uint32_t mask = 0;
+  const uint32_t cnt = (uint32_t)min((uint64_t)32, n_bases - b0);
+  for (uint32_t i = 0; i < cnt; ++i) {
+    const uint32_t c = base_code((unsigned char)seq[b0 + i]);
+    if (c > 3) mask |= 1u << i;
+    else bits |= (uint64_t)c << (2 * i);
+  }
+  seq2[w] = bits;
+  nmask[w] = mask;
+  if (mask) atomicAdd(n_count, (unsigned long long)__popc(mask));
+}
+
+// One thread per node: sampled position -> node table.
+__global__ void __launch_bounds__(256)
+pos2node_kernel(const NodeRec* __restrict__ rec, uint32_t n_nodes, uint32_t* __restrict__ pos2node, uint32_t shift)
+{
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_nodes) return;
+  const NodeRec r = rec[v];
+  if (r.seq_len == 0) return;
+  const uint64_t step = 1ull << shift;
+  uint64_t p = ((uint64_t)r.seq_start + step - 1) & ~(step - 1);
+  for (; p < (uint64_t)r.seq_start + r.seq_len; p += step) pos2node[p >> shift] = v;
+}
+
+Ctx* engine_create(int device, unsigned seed_len)
+{
+  if (seed_len == 0 || seed_len > PSI_B200_MAX_SEED_LEN)
+    throw ArgError("seed length must be in [1, 32]");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw CudaError(std::string("no CUDA device available (no CPU fallback exists): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) throw ArgError("invalid device ordinal");
+  PSI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PSI_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) throw CudaError("libpsi_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+  Ctx* c = new Ctx();
+  c->device = device;
+  c->k = seed_len;
+  c->sm_count = prop.multiProcessorCount;
+  PSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  for (auto& ev : c->ev) PSI_CUDA(cudaEventCreate(&ev));
+  c->dev_counters.ensure(DC_COUNT);
+  PSI_CUDA(cudaMemsetAsync(c->dev_counters.p, 0, DC_COUNT * sizeof(unsigned long long), c->stream));
+  PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, DC_COUNT * sizeof(uint64_t), cudaHostAllocDefault));
+  return c;
+}
+
+void engine_destroy(Ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const char* seq,
+                      const uint64_t* row_ptr, const uint32_t* col, const uint64_t* node_id)
+{
+  if (n_nodes == 0 || !seq_start || !seq || !row_ptr || !node_id) throw ArgError("set_graph: null or empty graph");
+  if (n_nodes >= 0xfffffff0ull) throw ArgError("set_graph: too many nodes");
+  const uint64_t n_bases = seq_start[n_nodes];
+  const uint64_t n_edges = row_ptr[n_nodes];
+  if (n_bases >= 0xfffffff0ull) throw ArgError("set_graph: graphs above 4 Gbp are not supported (32-bit loci)");
+  if (n_edges >= 0xfffffff0ull) throw ArgError("set_graph: too many edges");
+  if (n_edges && !col) throw ArgError("set_graph: null adjacency");
+  PSI_CUDA(cudaSetDevice(c.device));
+
+  std::vector<NodeRec> rec(n_nodes + 1);
+  for (uint64_t v = 0; v < n_nodes; ++v) {
+    if (seq_start[v + 1] < seq_start[v] || row_ptr[v + 1] < row_ptr[v]) throw ArgError("set_graph: offsets not monotone");
+    rec[v].seq_start = (uint32_t)seq_start[v];
+    rec[v].seq_len = (uint32_t)(seq_start[v + 1] - seq_start[v]);
+    rec[v].edge_start = (uint32_t)row_ptr[v];
+    rec[v].outdeg = (uint32_t)(row_ptr[v + 1] - row_ptr[v]);
+  }
+  rec[n_nodes] = NodeRec{ (uint32_t)n_bases, 0, (uint32_t)n_edges, 0 };
+  for (uint64_t e = 0; e < n_edges; ++e)
+    if (col[e] >= n_nodes) throw ArgError("set_graph: successor rank out of range");
+
+  c.n_nodes = (uint32_t)n_nodes;
+  c.n_edges = (uint32_t)n_edges;
+  c.n_bases = n_bases;
+  c.node_rec.ensure(n_nodes + 1);
+  c.col.ensure(n_edges + 1);
+  c.node_id.ensure(n_nodes);
+  const uint64_t n_words = (n_bases + 31) >> 5;
+  c.seq2.ensure(n_words + 2);
+  c.nmask.ensure(n_words + 2);
+  c.pos2node.ensure((n_bases >> Ctx::POS2NODE_SHIFT) + 2);
+
+  DevBuf<char> ascii;
+  ascii.ensure(n_bases + 1);
+  PSI_CUDA(cudaMemcpyAsync(ascii.p, seq, n_bases, cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(c.node_rec.p, rec.data(), (n_nodes + 1) * sizeof(NodeRec), cudaMemcpyHostToDevice, c.stream));
+  if (n_edges) PSI_CUDA(cudaMemcpyAsync(c.col.p, col, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(c.node_id.p, node_id, n_nodes * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.seq2.p, 0, (n_words + 2) * sizeof(uint64_t), c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.nmask.p, 0, (n_words + 2) * sizeof(uint32_t), c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.pos2node.p, 0, ((n_bases >> Ctx::POS2NODE_SHIFT) + 2) * sizeof(uint32_t), c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.dev_counters.p + DC_AUX, 0, sizeof(unsigned long long), c.stream));
+  if (n_words) {
+    pack_labels_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(ascii.p, n_bases, c.seq2.p, c.nmask.p,
+                                                                     c.dev_counters.p + DC_AUX);
+    ++c.counters.launches;
+  }
+  pos2node_kernel<<<grid_for(n_nodes, 256), 256, 0, c.stream>>>(c.node_rec.p, c.n_nodes, c.pos2node.p, Ctx::POS2NODE_SHIFT);
+  ++c.counters.launches;
+  PSI_CUDA(cudaGetLastError());
+  unsigned long long n_count = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_count, c.dev_counters.p + DC_AUX, sizeof(n_count), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.graph_has_n = n_count != 0;
+  c.has_graph = true;
+  c.has_index = false;
+  c.n_loci = 0;
+  c.counters.n_nodes = n_nodes;
+  c.counters.n_edges = n_edges;
+  c.counters.n_bases = n_bases;
+}
+
+// ------------------------------------------------------------- tables --
+
+static uint32_t ceil_log2(uint64_t x)
+{
+  uint32_t b = 0;
+  while ((1ull << b) < x) ++b;
+  return b;
+}
+
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t max_inflate_bytes,
+                 uint64_t stash_slots)
+{
+  // natural size: ~6 keys per 128-byte line for 8-byte slots (16 slots, load
+  // 0.39), ~3 per line for 16-byte slots (8 slots).
+  uint32_t lb8 = ceil_log2((n_keys + 5) / 6 + 1);
+  uint32_t lb16 = ceil_log2((n_keys + 2) / 3 + 1);
+  uint32_t fmt = 16, line_bits = lb16, rem_bits = 0;
+  if (kbits >= 2) {
+    uint32_t lb = lb8;
+    if (lb > kbits - 2) lb = kbits - 2;           // tiny k: one possible key per (line, bucket)
+    uint32_t need = kbits - 2 > 29 ? kbits - 2 - 29 : 0;  // remainder must fit 29 bits
+    if (lb < need && (128ull << need) <= max_inflate_bytes) lb = need;
+    if (kbits - 2 - lb <= 29) { fmt = 8; line_bits = lb; rem_bits = kbits - 2 - lb; }
+  }
+  if (fmt == 16 && line_bits > 63) throw ArgError("table too large");
+  const uint64_t n_lines = 1ull << line_bits;
+  t.n_lines = n_lines;
+  t.slots.ensure(n_lines * 128);
+  uint64_t ss = 1024;
+  while (ss < stash_slots) ss <<= 1;
+  t.stash.ensure(ss);
+  t.stash_used.ensure(1);
+  t.view.slots = t.slots.p;
+  t.view.stash = t.stash.p;
+  t.view.stash_used = t.stash_used.p;
+  t.view.line_bits = line_bits;
+  t.view.kbits = kbits;
+  t.view.rem_bits = rem_bits;
+  t.view.fmt = fmt;
+  t.view.stash_mask = (uint32_t)(ss - 1);
+  t.view.stash_nonempty = 1;  // until the build has been checked
+  table_clear(c, t);
+}
+
+void table_clear(Ctx& c, HostTable& t)
+{
+  PSI_CUDA(cudaMemsetAsync(t.slots.p, 0xff, t.n_lines * 128, c.stream));
+  PSI_CUDA(cudaMemsetAsync(t.stash.p, 0xff, ((size_t)t.view.stash_mask + 1) * sizeof(Slot16), c.stream));
+  PSI_CUDA(cudaMemsetAsync(t.stash_used.p, 0, sizeof(uint32_t), c.stream));
+}
+
+}  // namespace psi_b200

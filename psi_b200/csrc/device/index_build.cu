@@ -1,0 +1,489 @@
+// index_build.cu -- GPU construction of the path index and of the starting loci.
+//
+// Path index: stands behind PathIndex::create_index + psi::FMIndex (reference
+// include/psi/pathindex.hpp:235-243, fmindex.hpp:257-271), which build
+// csa_wt<wt_huff<>,32,64> over rev(path_0)$rev(path_1)$...  The only queries
+// the seed-finding path ever makes against it are "all occurrences of a k-mer"
+// with fixed k (index_iter.hpp:808-852), each mapped to the (node, offset) of
+// the occurrence's first base (pathindex.hpp:378-416).  The device index
+// therefore stores exactly that relation: the distinct (k-mer, locus) pairs of
+// all k-windows of all paths, in a bucketised hash keyed by the k-mer.
+//
+// Starting loci: stands behind SeedFinder::add_uncovered_loci
+// (seed_finder.hpp:1481-1541).  A locus is kept iff some k-walk starting there
+// spells a k-mer w with (w, locus) absent from the path index -- then, and only
+// then, seeds_on_paths cannot report every hit at this locus.
+#include "engine.hpp"
+#include "walker.cuh"
+
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+namespace psi_b200 {
+
+using namespace dev;
+
+// ------------------------------------------------------ path k-windows --
+
+struct PathsView {
+  const uint64_t* path_ptr;    // n_paths + 1
+  const uint32_t* nodes;       // entries
+  const uint32_t* head_off;    // may be null
+  const uint32_t* tail_trim;   // may be null
+  uint32_t n_paths;
+};
+
+__device__ __forceinline__ uint32_t path_of_entry(const PathsView& p, uint64_t e)
+{
+  uint32_t lo = 0, hi = p.n_paths;  // path_ptr[lo] <= e < path_ptr[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(p.path_ptr + mid) <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// One warp per path entry (a node visit); lanes stride over the offsets inside
+// the node.  For every offset the k-window that starts there is gathered along
+// the PATH's successors.  count_only: just count valid windows.
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(256)
+path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t n_entries,
+                    uint64_t* __restrict__ out_kmer, uint32_t* __restrict__ out_gpos,
+                    unsigned long long* __restrict__ out_count)
+{
+  const uint32_t lane = lane_id();
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long local_count = 0;
+  for (uint64_t e = warp0; e < n_entries; e += n_warps) {
+    const uint32_t pi = path_of_entry(p, e);
+    const uint64_t pbeg = __ldg(p.path_ptr + pi), pend = __ldg(p.path_ptr + pi + 1);
+    const uint32_t head = p.head_off ? __ldg(p.head_off + pi) : 0;
+    const uint32_t tail = p.tail_trim ? __ldg(p.tail_trim + pi) : 0;
+    const uint32_t node = __ldg(p.nodes + e);
+    const NodeRec r = g.rec[node];
+    const uint32_t from = (e == pbeg) ? head : 0;
+    uint32_t to = r.seq_len;
+    if (e + 1 == pend) to = tail < to ? to - tail : 0;
+    for (uint32_t o0 = from; o0 < to; o0 += 32) {   // warp-uniform bounds
+      const uint32_t o = o0 + lane;
+      bool ok = o < to;
+      uint64_t kmer = 0;
+      if (ok) {
+        uint32_t depth = 0, off = o;
+        uint64_t ce = e;
+        NodeRec cr = r;
+        uint32_t cto = to;
+        while (true) {
+          const uint32_t avail = cto > off ? cto - off : 0;
+          const uint32_t want = k - depth;
+          const uint32_t take = avail < want ? avail : want;
+          if (take) {
+            const uint64_t pos = (uint64_t)cr.seq_start + off;
+            if (g.has_n && extract_nmask(g.nmask, pos, take)) { ok = false; break; }
+            kmer |= extract_bases(g.seq2, pos, take) << (2u * depth);
+            depth += take;
+          }
+          if (depth == k) break;
+          if (++ce == pend) { ok = false; break; }   // window runs off the path
+          cr = g.rec[__ldg(p.nodes + ce)];
+          off = 0;
+          cto = cr.seq_len;
+          if (ce + 1 == pend) cto = tail < cto ? cto - tail : 0;
+        }
+      }
+      if (COUNT_ONLY) local_count += ok;
+      else {
+        const uint64_t slot = warp_reserve(out_count, ok ? 1u : 0u);
+        if (ok) { out_kmer[slot] = kmer; out_gpos[slot] = r.seq_start + o; }
+      }
+    }
+  }
+  if (COUNT_ONLY) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, d);
+    if (lane == 0 && local_count) atomicAdd(out_count, local_count);
+  }
+}
+
+// ------------------------------------------- unique pairs and k-mer runs --
+
+// flag[i] = 1 iff pair i differs from pair i-1 (pairs sorted by (kmer, gpos)).
+__global__ void __launch_bounds__(256)
+flag_unique_pairs_kernel(const uint64_t* __restrict__ kmer, const uint32_t* __restrict__ gpos, uint64_t n,
+                         uint32_t* __restrict__ flag)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flag[i] = (i == 0 || kmer[i] != kmer[i - 1] || gpos[i] != gpos[i - 1]) ? 1u : 0u;
+}
+
+// Scatter unique pairs: dst index = exclusive scan of flag.
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const uint64_t* __restrict__ kmer, const uint32_t* __restrict__ gpos,
+                     const uint32_t* __restrict__ flag, const uint32_t* __restrict__ scan, uint64_t n,
+                     uint64_t* __restrict__ ukmer, uint32_t* __restrict__ ugpos)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  ukmer[scan[i]] = kmer[i];
+  ugpos[scan[i]] = gpos[i];
+}
+
+// head[i] = 1 iff unique pair i starts a new k-mer run.
+__global__ void __launch_bounds__(256)
+flag_run_heads_kernel(const uint64_t* __restrict__ ukmer, uint64_t n, uint32_t* __restrict__ head)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  head[i] = (i == 0 || ukmer[i] != ukmer[i - 1]) ? 1u : 0u;
+}
+
+// run_start[run id] = i for every run head (run id = exclusive scan of head).
+__global__ void __launch_bounds__(256)
+scatter_run_starts_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ scan, uint64_t n,
+                          uint32_t n_runs, uint32_t* __restrict__ run_start)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) run_start[n_runs] = (uint32_t)n;
+  if (i >= n || !head[i]) return;
+  run_start[scan[i]] = (uint32_t)i;
+}
+
+// words each run needs in the multi array: 0 for single-locus k-mers, else 1 + count
+__global__ void __launch_bounds__(256)
+run_multi_words_kernel(const uint32_t* __restrict__ run_start, uint32_t n_runs, uint32_t* __restrict__ words)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const uint32_t len = run_start[r + 1] - run_start[r];
+  words[r] = len > 1 ? len + 1 : 0;
+}
+
+// One thread per distinct k-mer: write its locus list (if several) and insert
+// it into the table.
+template <int FMT>
+__global__ void __launch_bounds__(256)
+insert_runs_kernel(KmerTable t, const uint64_t* __restrict__ ukmer, const uint32_t* __restrict__ ugpos,
+                   const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ multi_off,
+                   uint32_t n_runs, uint32_t* __restrict__ multi, unsigned long long* __restrict__ err_flag)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const uint32_t b = run_start[r], e = run_start[r + 1];
+  const uint64_t kmer = ukmer[b];
+  uint32_t payload, flags;
+  if (e - b == 1) { payload = ugpos[b]; flags = 0; }
+  else {
+    const uint32_t m = multi_off[r];
+    multi[m] = e - b;
+    for (uint32_t i = b; i < e; ++i) multi[m + 1 + (i - b)] = ugpos[i];
+    payload = m;
+    flags = 1;
+  }
+  uint32_t prev;
+  if (!table_insert<FMT>(t, kmer, payload, flags, false, prev)) atomicOr(err_flag, 2ull);
+}
+
+// ------------------------------------------------------------ host side --
+
+static void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, uint64_t n)
+{
+  size_t tmp = 0;
+  PSI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int64_t)n, c.stream));
+  c.scan_tmp.ensure(tmp);
+  PSI_CUDA(cub::DeviceScan::ExclusiveSum(c.scan_tmp.p, tmp, in, out, (int64_t)n, c.stream));
+  c.counters.launches += 2;
+}
+
+void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                        const uint32_t* head_off, const uint32_t* tail_trim)
+{
+  if (!c.has_graph) throw StateError("set_paths: no graph");
+  PSI_CUDA(cudaSetDevice(c.device));
+  c.has_index = false;
+  c.counters.n_path_bases = c.counters.n_index_entries = c.counters.n_index_kmers = 0;
+  c.counters.index_bytes = c.counters.index_buckets = 0;
+  c.counters.ms_index_build = 0;
+  if (n_paths == 0) return;
+  if (!path_ptr || !path_nodes) throw ArgError("set_paths: null arrays");
+  if (n_paths >= 0x7fffffffull) throw ArgError("set_paths: too many paths");
+  const uint64_t n_entries = path_ptr[n_paths];
+  for (uint64_t e = 0; e < n_entries; ++e)
+    if (path_nodes[e] >= c.n_nodes) throw ArgError("set_paths: node rank out of range");
+
+  PhaseTimer timer(c, T_INDEX);
+  DevBuf<uint64_t> d_path_ptr;
+  DevBuf<uint32_t> d_nodes, d_head, d_tail;
+  d_path_ptr.ensure(n_paths + 1);
+  d_nodes.ensure(n_entries + 1);
+  PSI_CUDA(cudaMemcpyAsync(d_path_ptr.p, path_ptr, (n_paths + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+  if (n_entries) PSI_CUDA(cudaMemcpyAsync(d_nodes.p, path_nodes, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+  PathsView pv{ d_path_ptr.p, d_nodes.p, nullptr, nullptr, (uint32_t)n_paths };
+  if (head_off) {
+    d_head.ensure(n_paths);
+    PSI_CUDA(cudaMemcpyAsync(d_head.p, head_off, n_paths * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    pv.head_off = d_head.p;
+  }
+  if (tail_trim) {
+    d_tail.ensure(n_paths);
+    PSI_CUDA(cudaMemcpyAsync(d_tail.p, tail_trim, n_paths * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    pv.tail_trim = d_tail.p;
+  }
+  const GraphView g = make_graph_view(c);
+  unsigned long long* d_cnt = c.dev_counters.p + DC_AUX;
+  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
+  PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+  PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+
+  // pass 1: count valid windows
+  const unsigned wgrid = (unsigned)std::min<uint64_t>((n_entries + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
+  path_windows_kernel<true><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, nullptr, nullptr, d_cnt);
+  ++c.counters.launches;
+  unsigned long long n_pairs = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  if (n_pairs >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows (index them in several contexts)");
+  c.counters.n_path_bases = n_pairs;
+  if (n_pairs == 0) {  // paths shorter than k: empty index
+    table_alloc(c, c.index, 1, 2 * c.k, 1ull << 30, 1024);
+    c.index.view.stash_nonempty = 0;
+    c.multi.ensure(2);
+    c.has_index = true;
+    timer.stop();
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    c.counters.ms_index_build = timer.ms();
+    return;
+  }
+
+  // pass 2: emit (kmer, gpos)
+  DevBuf<uint64_t> kmer_a, kmer_b;
+  DevBuf<uint32_t> gpos_a, gpos_b;
+  kmer_a.ensure(n_pairs); kmer_b.ensure(n_pairs);
+  gpos_a.ensure(n_pairs); gpos_b.ensure(n_pairs);
+  PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+  path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, kmer_a.p, gpos_a.p, d_cnt);
+  ++c.counters.launches;
+
+  // sort by (kmer, gpos): LSD = stable sort by gpos, then stable sort by kmer
+  {
+    size_t tmp1 = 0, tmp2 = 0;
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n_pairs, 0, 32, c.stream));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n_pairs, 0, (int)(2 * c.k), c.stream));
+    DevBuf<char> tmp;
+    tmp.ensure(std::max(tmp1, tmp2));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n_pairs, 0, 32, c.stream));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n_pairs, 0, (int)(2 * c.k), c.stream));
+    c.counters.launches += 12;
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  // sorted pairs are now in (kmer_a, gpos_a)
+
+  // unique pairs
+  DevBuf<uint32_t> flag, scan;
+  flag.ensure(n_pairs + 1); scan.ensure(n_pairs + 1);
+  flag_unique_pairs_kernel<<<grid_for(n_pairs, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, n_pairs, flag.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaMemsetAsync(flag.p + n_pairs, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, flag.p, scan.p, n_pairs + 1);
+  uint32_t n_unique = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_unique, scan.p + n_pairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  compact_pairs_kernel<<<grid_for(n_pairs, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, flag.p, scan.p, n_pairs, kmer_b.p, gpos_b.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  // unique pairs are in (kmer_b, gpos_b)[0, n_unique)
+
+  // k-mer runs
+  flag_run_heads_kernel<<<grid_for(n_unique, 256), 256, 0, c.stream>>>(kmer_b.p, n_unique, flag.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaMemsetAsync(flag.p + n_unique, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, flag.p, scan.p, (uint64_t)n_unique + 1);
+  uint32_t n_runs = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_runs, scan.p + n_unique, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  DevBuf<uint32_t> run_start, words, multi_off;
+  run_start.ensure((uint64_t)n_runs + 2); words.ensure((uint64_t)n_runs + 2); multi_off.ensure((uint64_t)n_runs + 2);
+  scatter_run_starts_kernel<<<grid_for(n_unique, 256), 256, 0, c.stream>>>(flag.p, scan.p, n_unique, n_runs, run_start.p);
+  run_multi_words_kernel<<<grid_for(n_runs, 256), 256, 0, c.stream>>>(run_start.p, n_runs, words.p);
+  c.counters.launches += 2;
+  PSI_CUDA(cudaMemsetAsync(words.p + n_runs, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, words.p, multi_off.p, (uint64_t)n_runs + 1);
+  uint32_t multi_words = 0;
+  PSI_CUDA(cudaMemcpyAsync(&multi_words, multi_off.p + n_runs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.multi.ensure((uint64_t)multi_words + 2);
+
+  // table
+  table_alloc(c, c.index, n_runs, 2 * c.k, 1ull << 30, (uint64_t)n_runs / 512 + 1024);
+  if (c.index.view.fmt == 8)
+    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.multi.p, d_err);
+  else
+    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.multi.p, d_err);
+  ++c.counters.launches;
+  PSI_CUDA(cudaGetLastError());
+  unsigned long long err = 0;
+  uint32_t stash_used = 0;
+  PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(&stash_used, c.index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  timer.stop();
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  if (err & 2ull) throw OverflowError("path index: hash stash exhausted");
+  c.index.view.stash_nonempty = stash_used ? 1u : 0u;
+  c.has_index = true;
+  c.counters.ms_index_build = timer.ms();
+  c.counters.n_index_entries = n_unique;
+  c.counters.n_index_kmers = n_runs;
+  c.counters.index_buckets = c.index.n_lines * 4;
+  c.counters.index_bytes = c.index.n_lines * 128 + ((uint64_t)multi_words + 2) * 4 +
+                           ((uint64_t)c.index.view.stash_mask + 1) * sizeof(Slot16);
+  c.counters.index_slot_bytes = c.index.view.fmt;
+}
+
+// -------------------------------------------------------- starting loci --
+
+struct AllLociSource {
+  GraphView g;
+  uint32_t step;
+  __device__ bool init(uint64_t idx, WalkItem& it) const
+  {
+    const uint32_t pos = (uint32_t)idx;
+    const uint32_t v = node_of_pos(g, pos);
+    const uint32_t off = pos - __ldg(&g.rec[v].seq_start);
+    if (step > 1 && off % step) return false;
+    it.kmer = 0; it.origin = pos; it.node = v; it.off = off; it.depth = 0;
+    return true;
+  }
+};
+
+struct UncoveredSink {
+  KmerTable t;
+  const uint32_t* multi;
+  uint32_t* flags;   // bitmap over global positions
+  uint32_t has_index;
+  __device__ bool skip(uint32_t origin) const
+  {
+    return (((volatile const uint32_t*)flags)[origin >> 5] >> (origin & 31u)) & 1u;
+  }
+  __device__ void complete(uint64_t kmer, uint32_t origin)
+  {
+    if (!has_index || !index_contains(t, multi, kmer, origin)) atomicOr(flags + (origin >> 5), 1u << (origin & 31u));
+  }
+  __device__ void finish() {}
+};
+
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+find_loci_kernel(GraphView g, uint32_t k, uint32_t step, KmerTable t, const uint32_t* multi, uint32_t has_index,
+                 uint32_t* flags, unsigned long long* work, WalkItem* spill, uint32_t spill_items,
+                 unsigned long long* err)
+{
+  __shared__ WalkItem smem[WALK_WARPS * WALK_SMEM_ITEMS];
+  AllLociSource src{ g, step };
+  UncoveredSink sink{ t, multi, flags, has_index };
+  walk_all(g, k, g.n_bases, work, smem, spill, spill_items, err, src, sink);
+}
+
+__global__ void __launch_bounds__(256)
+popc_words_kernel(const uint32_t* __restrict__ flags, uint64_t n_words, uint32_t* __restrict__ cnt)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n_words) cnt[w] = __popc(flags[w]);
+}
+
+__global__ void __launch_bounds__(256)
+emit_loci_kernel(GraphView g, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
+                 uint64_t n_words, uint32_t* __restrict__ loci_node, uint32_t* __restrict__ loci_off)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t m = flags[w];
+  uint32_t dst = scan[w];
+  while (m) {
+    const uint32_t b = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t pos = (uint32_t)(w << 5) + b;
+    const uint32_t v = node_of_pos(g, pos);
+    loci_node[dst] = v;
+    loci_off[dst] = pos - g.rec[v].seq_start;
+    ++dst;
+  }
+}
+
+void engine_find_loci(Ctx& c, unsigned step)
+{
+  if (!c.has_graph) throw StateError("find_loci: no graph");
+  PSI_CUDA(cudaSetDevice(c.device));
+  if (step == 0) step = 1;
+  PhaseTimer timer(c, T_LOCI);
+  const uint64_t n_words = (c.n_bases + 31) >> 5;
+  DevBuf<uint32_t> flags, cnt, scan;
+  flags.ensure(n_words + 1); cnt.ensure(n_words + 1); scan.ensure(n_words + 1);
+  const GraphView g = make_graph_view(c);
+  const unsigned grid = (unsigned)c.sm_count * 8;
+  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
+  unsigned long long* d_work = c.dev_counters.p + DC_WORK;
+  while (true) {
+    PSI_CUDA(cudaMemsetAsync(flags.p, 0, (n_words + 1) * sizeof(uint32_t), c.stream));
+    PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+    PSI_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), c.stream));
+    c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
+    find_loci_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, step, c.index.view, c.multi.p, c.has_index ? 1u : 0u,
+                                                            flags.p, d_work, (WalkItem*)c.walk_spill.p, c.spill_items, d_err);
+    ++c.counters.launches;
+    PSI_CUDA(cudaGetLastError());
+    unsigned long long err = 0;
+    PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    if (!(err & 1ull)) break;
+    if (c.spill_items >= (1u << 20)) throw OverflowError("find_loci: walk frontier exceeds 2^20 states per warp");
+    c.spill_items *= 4;  // frontier overflow: retry with a larger spill area
+  }
+  popc_words_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(flags.p, n_words, cnt.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaMemsetAsync(cnt.p + n_words, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, cnt.p, scan.p, n_words + 1);
+  uint32_t n_loci = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_loci, scan.p + n_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.loci_node.ensure((uint64_t)n_loci + 1);
+  c.loci_off.ensure((uint64_t)n_loci + 1);
+  if (n_loci) {
+    emit_loci_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(g, flags.p, scan.p, n_words, c.loci_node.p, c.loci_off.p);
+    ++c.counters.launches;
+  }
+  timer.stop();
+  PSI_CUDA(cudaGetLastError());
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.n_loci = n_loci;
+  c.counters.n_loci = n_loci;
+  c.counters.ms_find_loci = timer.ms();
+}
+
+void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* off)
+{
+  if (!c.has_graph) throw StateError("set_loci: no graph");
+  if (n && (!node || !off)) throw ArgError("set_loci: null arrays");
+  PSI_CUDA(cudaSetDevice(c.device));
+  c.loci_node.ensure(n + 1);
+  c.loci_off.ensure(n + 1);
+  if (n) {
+    PSI_CUDA(cudaMemcpyAsync(c.loci_node.p, node, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(c.loci_off.p, off, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+  }
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.n_loci = n;
+  c.counters.n_loci = n;
+}
+
+void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap)
+{
+  PSI_CUDA(cudaSetDevice(c.device));
+  const uint64_t n = c.n_loci < cap ? c.n_loci : cap;
+  if (n && node) PSI_CUDA(cudaMemcpyAsync(node, c.loci_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  if (n && off) PSI_CUDA(cudaMemcpyAsync(off, c.loci_off.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace psi_b200

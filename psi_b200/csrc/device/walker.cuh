@@ -1,0 +1,182 @@
+// walker.cuh -- warp-cooperative enumeration of all k-long forward walks of
+// the graph that start at a set of loci.
+//
+// Stands behind TraverserBFS::{run,filter,compute,advance} of the reference
+// (include/psi/traverser_bfs.hpp:71-161): a state walks the label of its node,
+// 'N' kills it (:124), at the node end it fans out over EVERY out-edge (link
+// type ignored, forward strand only, :146-160), a node without successors kills
+// it (:140-143), and at depth k the walk is reported together with its START
+// locus (:96-110).  The reference keeps the frontier in a std::vector of states
+// per locus and descends a suffix tree of the read seeds base by base; here
+//   - a warp owns a LIFO frontier of packed states in shared memory (spilling to
+//     a private global region), pops up to 32 states per round (one per lane),
+//     extends each to its node end with 2-bit word extraction, and pushes the
+//     children of all lanes with one warp prefix sum over the out-degrees;
+//   - starting loci are claimed 32 at a time from a global counter whenever the
+//     frontier runs low, so lanes stay busy across loci with few walks;
+//   - the match against the read seeds is one hash probe of the packed k-mer at
+//     depth k (exact-match formulation) instead of k tree descents.
+#ifndef PSI_B200_DEVICE_WALKER_CUH
+#define PSI_B200_DEVICE_WALKER_CUH
+
+#include "common.cuh"
+#include "context.hpp"
+
+namespace psi_b200 {
+namespace dev {
+
+struct alignas(8) WalkItem {
+  uint64_t kmer;
+  uint32_t origin;  // global position of the start locus
+  uint32_t node;
+  uint32_t off;
+  uint32_t depth;
+};
+
+struct GraphView {
+  const NodeRec* rec;
+  const uint32_t* col;
+  const uint64_t* seq2;
+  const uint32_t* nmask;
+  const uint32_t* pos2node;
+  uint32_t n_nodes;
+  uint32_t pos2node_shift;
+  uint64_t n_bases;
+  uint32_t has_n;
+};
+
+inline GraphView make_graph_view(const Ctx& c)
+{
+  GraphView g;
+  g.rec = c.node_rec.p;
+  g.col = c.col.p;
+  g.seq2 = c.seq2.p;
+  g.nmask = c.nmask.p;
+  g.pos2node = c.pos2node.p;
+  g.n_nodes = c.n_nodes;
+  g.pos2node_shift = Ctx::POS2NODE_SHIFT;
+  g.n_bases = c.n_bases;
+  g.has_n = c.graph_has_n ? 1u : 0u;
+  return g;
+}
+
+// node containing global position g
+__device__ __forceinline__ uint32_t node_of_pos(const GraphView& g, uint32_t pos)
+{
+  uint32_t v = __ldg(g.pos2node + (pos >> g.pos2node_shift));
+  while (__ldg(&g.rec[v + 1].seq_start) <= pos) ++v;
+  return v;
+}
+
+constexpr int WALK_WARPS = 4;          // warps per CTA
+constexpr int WALK_SMEM_ITEMS = 96;    // frontier slots per warp in shared memory
+
+struct WalkStack {
+  WalkItem* smem;      // this warp's shared slots
+  WalkItem* spill;     // this warp's global slots
+  uint32_t spill_items;
+  __device__ __forceinline__ WalkItem& at(uint32_t i) const
+  {
+    return i < (uint32_t)WALK_SMEM_ITEMS ? smem[i] : spill[i - WALK_SMEM_ITEMS];
+  }
+};
+
+// Source: yields the initial state of work item `idx` (false = nothing to do).
+// Sink:   skip(origin) -> drop a state early; complete(kmer, origin) at depth k.
+template <class Source, class Sink>
+__device__ void walk_all(const GraphView& g, uint32_t k, uint64_t n_items, unsigned long long* work_counter,
+                         WalkItem* smem_all, WalkItem* spill_all, uint32_t spill_items,
+                         unsigned long long* err_flag, Source& source, Sink& sink)
+{
+  const uint32_t lane = lane_id();
+  const uint32_t warp_in_cta = threadIdx.x >> 5;
+  const uint64_t warp_global = (uint64_t)blockIdx.x * WALK_WARPS + warp_in_cta;
+  WalkStack st{ smem_all + warp_in_cta * WALK_SMEM_ITEMS, spill_all + warp_global * spill_items, spill_items };
+  const uint32_t capacity = WALK_SMEM_ITEMS + spill_items;
+
+  uint32_t top = 0;
+  bool more = true;
+  while (true) {
+    // ---- refill from the work queue ----
+    if (top < 32 && more) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(work_counter, 32ull);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= n_items) more = false;
+      else {
+        WalkItem it;
+        const uint64_t idx = base + lane;
+        const bool ok = idx < n_items && source.init(idx, it);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) st.at(top + __popc(m & ((1u << lane) - 1u))) = it;
+        top += __popc(m);
+        __syncwarp();
+        if (top < 32) continue;  // try to fill a whole round first
+      }
+    }
+    if (top == 0) break;
+
+    // ---- pop one state per lane ----
+    const uint32_t n = top < 32 ? top : 32;
+    bool alive = lane < n;
+    WalkItem it;
+    if (alive) it = st.at(top - 1 - lane);
+    top -= n;
+    __syncwarp();
+
+    uint32_t n_children = 0;
+    NodeRec r{ 0, 0, 0, 0 };
+    if (alive && sink.skip(it.origin)) alive = false;
+    if (alive) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(g.rec + it.node));
+      r.seq_start = raw.x; r.seq_len = raw.y; r.edge_start = raw.z; r.outdeg = raw.w;
+      const uint32_t avail = r.seq_len - it.off;
+      const uint32_t want = k - it.depth;
+      const uint32_t take = avail < want ? avail : want;
+      if (take) {
+        const uint64_t p = (uint64_t)r.seq_start + it.off;
+        if (g.has_n && extract_nmask(g.nmask, p, take)) alive = false;
+        else {
+          it.kmer |= extract_bases(g.seq2, p, take) << (2u * it.depth);
+          it.depth += take;
+        }
+      }
+      if (alive) {
+        if (it.depth == k) { sink.complete(it.kmer, it.origin); alive = false; }
+        else n_children = r.outdeg;  // node end reached; 0 successors kills the state
+      }
+    }
+
+    // ---- push the children of all lanes ----
+    uint32_t incl = n_children;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (uint32_t)d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      if (top + total > capacity) {
+        if (lane == 0) atomicOr(err_flag, 1ull);
+        break;  // result is invalid; the host retries with a larger spill area
+      }
+      uint32_t dst = top + incl - n_children;
+      for (uint32_t c = 0; c < n_children; ++c) {
+        WalkItem ch;
+        ch.kmer = it.kmer;
+        ch.origin = it.origin;
+        ch.node = __ldg(g.col + r.edge_start + c);
+        ch.off = 0;
+        ch.depth = it.depth;
+        st.at(dst + c) = ch;
+      }
+      top += total;
+    }
+    __syncwarp();
+  }
+  sink.finish();
+}
+
+}  // namespace dev
+}  // namespace psi_b200
+#endif
