@@ -1,0 +1,21 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "tests"):
+    if os.fspath(p) not in sys.path:
+        sys.path.insert(0, os.fspath(p))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the shared libraries once per session (cheap no-op when up to date)."""
+    import __graft_entry__ as ge
+    ge.build()

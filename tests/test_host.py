@@ -1,0 +1,115 @@
+"""Host-side logic and the C-ABI surface, CPU only (no compute calls)."""
+import ctypes as C
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+from psi_b200 import capi
+
+
+def test_library_exports_every_declared_symbol():
+    header = (util.ROOT / "include" / "psi_b200.h").read_text()
+    declared = set(re.findall(r"\b(psi_b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"psi_b200_graph", "psi_b200_ctx"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    L = capi.lib()
+    for s in declared:
+        assert hasattr(L, s), f"{s} is declared in include/psi_b200.h but not exported"
+    assert L.psi_b200_version().decode().endswith("sm_100a")
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.PsiError) as e:
+        capi.Context(12, 0)
+    assert e.value.code == capi.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    for p in (util.ROOT / "psi_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".cpp", ".hpp", ".h") and p.is_file():
+            txt = p.read_text()
+            assert "oracle" not in txt.lower(), f"{p} mentions the oracle"
+
+
+def test_reader_fasta_fastq_gz_and_chunking(tmp_path):
+    fq = tmp_path / "r.fastq"
+    fq.write_text("@a desc\nACGT\n+\nIIII\n@b\nGGCCA\n+\nIIIII\n@c\nTT\n+\nII\n")
+    r = capi.Reader(fq)
+    first, rp, bases, names = r.next(2)
+    assert (first, rp.tolist(), bases.tobytes(), names) == (0, [0, 4, 9], b"ACGTGGCCA", ["a", "b"])
+    first, rp, bases, names = r.next(2)
+    assert (first, rp.tolist(), bases.tobytes(), names) == (2, [0, 2], b"TT", ["c"])   # global ids (sequence.hpp:1616)
+    assert r.next(2) is None
+    fa = tmp_path / "r.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        f.write(">x\nACGT\nACG\n>y\nTTTT\n")
+    first, rp, bases, names = capi.Reader(fa).next(0)
+    assert (rp.tolist(), bases.tobytes(), names) == ([0, 7, 11], b"ACGTACGTTTT", ["x", "y"])
+    with pytest.raises(capi.PsiError) as e:
+        capi.Reader(tmp_path / "missing.fq")
+    assert e.value.code == capi.ERR_IO
+
+
+def test_gfa1_and_gfa2_load_the_same_graph(tmp_path):
+    g2 = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    p = tmp_path / "x1.gfa"
+    g2.write_gfa(p)
+    g1 = capi.Graph.load_gfa(p)
+    for a in ("seq_start", "seq", "row_ptr", "col", "internal_id", "coord_id"):
+        assert np.array_equal(getattr(g1, a), getattr(g2, a)), a
+    assert g1.path(0)[1].tolist() == g2.path(0)[1].tolist()
+
+
+def test_from_arrays_matches_loader():
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/multi.gfa.gz")
+    # shuffle the nodes, rebuild from arrays with sort=True: same graph
+    perm = np.random.default_rng(3).permutation(g.n_nodes)
+    inv = np.argsort(perm)
+    lens = (g.seq_start[1:] - g.seq_start[:-1])[perm]
+    seq_start = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    seq = np.concatenate([g.seq[int(g.seq_start[v]):int(g.seq_start[v + 1])] for v in perm])
+    deg = (g.row_ptr[1:] - g.row_ptr[:-1])[perm]
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.uint64)
+    col = np.concatenate([inv[g.col[int(g.row_ptr[v]):int(g.row_ptr[v + 1])]] for v in perm]).astype(np.uint32)
+    paths = [g.path(i)[1] for i in range(g.n_paths)]
+    path_ptr = np.concatenate([[0], np.cumsum([len(p) for p in paths])]).astype(np.uint64)
+    path_nodes = np.concatenate([inv[p] for p in paths]).astype(np.uint32)
+    h = capi.Graph.from_arrays(g.coord_id[perm], seq_start, seq, row_ptr, col, path_ptr, path_nodes, sort=True)
+    for a in ("seq_start", "seq", "row_ptr", "col", "internal_id", "coord_id"):
+        assert np.array_equal(getattr(h, a), getattr(g, a)), a
+
+
+@pytest.mark.parametrize("name,n", [("tiny", 4), ("x", 16), ("multi", 4), ("m", 8)])
+def test_pick_paths_are_walks_from_each_region_start(name, n):
+    g = capi.Graph.load_gfa(util.GOLDEN / f"inputs/{name}.gfa.gz")
+    ps = g.pick_paths(n, seed=11)
+    assert ps.n_paths == n * g.n_paths
+    succ = [set(g.col[int(g.row_ptr[v]):int(g.row_ptr[v + 1])].tolist()) for v in range(g.n_nodes)]
+    for i in range(ps.n_paths):
+        nodes = ps.nodes[int(ps.path_ptr[i]):int(ps.path_ptr[i + 1])]
+        region = g.path(i // n)[1]
+        assert nodes[0] == region[0]
+        assert all(int(b) in succ[int(a)] for a, b in zip(nodes[:-1], nodes[1:]))
+        assert len(succ[int(nodes[-1])]) == 0           # ends in a sink
+    # seeded: reproducible; different seeds give different haplotypes on a variant-dense graph
+    ps2 = g.pick_paths(n, seed=11)
+    assert np.array_equal(ps.nodes, ps2.nodes)
+    if name == "m":
+        assert not np.array_equal(ps.nodes, g.pick_paths(n, seed=12).nodes)
+
+
+def test_pick_paths_requires_an_embedded_path(tmp_path):
+    p = tmp_path / "nopath.gfa"
+    p.write_text("S\t1\tACGT\nS\t2\tGG\nL\t1\t+\t2\t+\t0M\n")
+    g = capi.Graph.load_gfa(p)
+    with pytest.raises(capi.PsiError) as e:       # reference seed_finder.hpp:1145-1147 throws
+        g.pick_paths(2)
+    assert e.value.code == capi.ERR_ARG

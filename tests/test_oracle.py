@@ -1,0 +1,183 @@
+"""The CPU restatement (oracle/psi_oracle.c) pinned against
+  * the reference's own known-answer tests, and
+  * golden seed sets produced by the unmodified reference (tests/golden/make_golden.py).
+CPU only."""
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle_py as orc
+from psi_b200 import capi
+
+G = util.golden_index()
+CASES = {c["name"]: c for c in G["cases"]}
+
+
+def load_case(c):
+    g = capi.Graph.load_gfa(util.GOLDEN / c["gfa"])
+    rp, bases = util.read_fasta(util.GOLDEN / c["reads"])
+    return g, rp, bases
+
+
+# ---- reference test/src/test_indexiter.cpp:131-402 (hit counts of kmer_exact_matches) ----
+
+SET5_A = ["TGCAGTATAGTCGTCGCACGCCTTCTGGCCGCTGGCGGCAGTACAGGATCCTCTTGCTCACAGT"
+          "GTAGGGCCCTCTTGCTCCCGGTGTGACGGCTGGCGTGCAGCTGGCTCCCCCGCTGGCAGCTGGGGACACTGACGGGCCC"
+          "TCTTGCTCCCCTACTGGCCGCCTCCTGCACCAATTAAAGTCGGAGCACCGGTTACGC",
+          "TGCAGTATAGTCGTCGCACGCCTTCTGGCCGCTGGCGGCAGTACAGGATCCTCTTGCTCACAGT"
+          "GTAGGGCCCTCTTGCTCCCGGTGTGACGGCTGGCGTGCAGCTGGCTCCCCCGCTCGCAGGTGGCGACACAAACGGGCCC"
+          "TCTTGCTCCCCTACTGGCCGCCTCCTGCACCAATTAAAGTCGGAGCACCGGTTACGC"]
+SET5_B = ["CATTGCAGAGCCCTCTTGCTCACAGTGTAGTGGCAGCACGCCCGCCTCCTGGCAGCTAGGGACA"
+          "GTGCCAGGCCCTCTTGCTCCAAGTGTAGTGGCAGCTGGCTCCCCCGCTGGCAGCTGGGGACACTGACGGGCCCTCTTGC"
+          "TTGCAGT",
+          "TAGGGCAACTGCAGGGCTATCTTGCTTACAGTGGTGTCCAGCGCCCTCTGCTGGCGTCGGAGCA"
+          "TTGCAGGGCTCTCTTGCTCGCAGTGTAGTGGCGGCACGCCGCCTGCTGGCAGCTAGGGACATTGCAGAGCCCTCTTGCT"
+          "CACAGTG"]
+
+
+@pytest.mark.parametrize("s1,s2,k,expect", [
+    (["GATAGACTAGCCA", "GGGCGTAGCCA"], ["GGGCGTAGCCA"], 4, 11),                      # test_indexiter.cpp:182-185
+    (["CATATA"], ["ATATAC"], 3, 5),                                                   # :230-233
+    (["TAGGCTACCGATTTAAATAGGCACAC", "TAGGCTACGGATTTAAATCGGCACAC"],
+     ["GGATTTAAATA", "CGATTTAAATC", "GGATTTAAATC", "CGATTTAAATA"], 10, 8),            # :282-285
+    (["TAGGCTACCGATTNAAATAGGCACAC", "TAGGCTACGGATTNAAATCGGCACAC"],
+     ["GGATTNAAATA", "CGATTNAAATC", "GGATTNAAATC", "CGATTNAAATA"], 10, 0),            # :335-338 (fine iterators)
+    (SET5_A, SET5_B, 30, 21),                                                         # :394-397
+])
+def test_kmer_exact_matches_known_answers(s1, s2, k, expect):
+    assert orc.kmer_exact_matches(s1, s2, k) == expect
+    assert orc.kmer_exact_matches(s2, s1, k) == expect
+
+
+# ---- reference test/src/test_sequence.cpp:1194-1270 (increment_kmer) ----
+
+def test_increment_kmer_known_answers():
+    k = 20
+    assert orc.increment_kmer("A" * k, k - 1) == ("A" * 19 + "C", k - 1)
+    s, r = orc.increment_kmer("A" * k, 11)
+    assert r == 11
+    s, r = orc.increment_kmer(s, 16)
+    assert (s, r) == ("AAAAAAAAAAACAAAACAAA", 16)
+    assert orc.increment_kmer("A" * 10 + "T" * 10, 14) == ("AAAAAAAAACAAAAAAAAAA", 9)
+    s, r = orc.increment_kmer("T" * k, k - 1)
+    assert s == "A" * k and r == 2 ** 64 - 1
+
+
+# ---- reference test/src/test_sequence.cpp:1272-1427 (seeding + SeedMap id/offset) ----
+
+TRUTH_NONOVERLAP = ["CAAA", "TAAG", "AAAT", "AAGA", "TTTC", "TGGA", "ATAA", "TATT", "TTCC", "TGGT",
+                    "GTCC", "TGGT", "TGCT", "ATGT", "TGTT", "GGGC", "CTTT", "TTTC", "CTTC", "TTCC"]
+TRUTH_OVERLAP = ["CAAA", "AAAT", "AATA", "ATAA", "TAAG", "AAGA", "AGAT",
+                 "AAAT", "AATA", "ATAA", "TAAG", "AAGA", "AGAC", "GACT",
+                 "TTTC", "TTCT", "TCTG", "CTGG", "TGGA", "GGAG", "GAGT",
+                 "ATAA", "TAAT", "AATA", "ATAT", "TATT", "ATTC", "TTCC",
+                 "TTCC", "TCCT", "CCTG", "CTGG", "TGGT", "GGTT", "GTTG",
+                 "GTCC", "TCCT", "CCTG", "CTGG", "TGGT", "GGTT", "GTTG",
+                 "TGCT", "GCTA", "CTAT", "TATG", "ATGT", "TGTG", "GTGT",
+                 "TGTT", "GTTG", "TTGG", "TGGG", "GGGC", "GGCT", "GCTT",
+                 "CTTT", "TTTT", "TTTT", "TTTT", "TTTC", "TTCT", "TCTT",
+                 "CTTC", "TTCT", "TCTT", "CTTC", "TTCC", "TCCT", "CCTT"]
+
+
+@pytest.mark.parametrize("d,truth,per_read", [(4, TRUTH_NONOVERLAP, 2), (1, TRUTH_OVERLAP, 7)])
+def test_seeding_known_answers(d, truth, per_read):
+    rp, bases = util.read_fasta(util.GOLDEN / "inputs/reads_n10l10e0i0.fa")
+    reads = orc.OReads(rp, bases)
+    rid, off = orc.seeding(reads, 4, d)
+    assert len(rid) == len(truth)
+    for i, t in enumerate(truth):
+        s = int(rp[int(rid[i])]) + int(off[i])
+        assert bases[s:s + 4].tobytes().decode() == t
+        assert rid[i] == i // per_read                      # position_to_id
+        assert off[i] == (i % per_read) * d                 # position_to_offset of the seed's first base
+
+
+def test_seeding_short_reads_and_offset():
+    rp = np.array([0, 3, 13, 13, 20], np.uint64)
+    bases = np.frombuffer(b"ACG" + b"ACGTACGTAC" + b"" + b"ACGTACG", np.uint8)
+    rid, off = orc.seeding(orc.OReads(rp, bases, first_read_id=100), 4, 4)
+    assert rid.tolist() == [101, 101, 103] and off.tolist() == [0, 4, 0]
+
+
+# ---- reference test/src/test_traverser.cpp:81-96 ----
+
+def test_traverser_known_answers():
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    rp, bases = util.read_fasta(util.GOLDEN / "inputs/reads_n10l10e0i0.fa")
+    node, off = util.all_loci(g)
+    t, raw = orc.seeds_off_paths(orc.OGraph.of(g), node, off, orc.OReads(rp, bases), 10, 10)
+    truth = [(1, 0), (1, 1), (9, 4), (9, 17), (16, 0), (17, 0), (20, 0), (20, 31), (20, 38), (20, 38)]
+    assert t.tolist() == [[i, 0, n, o] for i, (n, o) in enumerate(truth)]
+
+
+# ---- loader parity with gum ----
+
+@pytest.mark.parametrize("name", ["tiny", "x", "multi", "m"])
+def test_loader_reproduces_gum_ranks_and_ids(name):
+    ref = np.load(util.GOLDEN / f"nodes_{name}.npy")
+    g = capi.Graph.load_gfa(util.GOLDEN / f"inputs/{name}.gfa.gz")
+    assert np.array_equal(ref[:, 0], g.internal_id)
+    assert np.array_equal(ref[:, 1], g.coord_id)
+    assert np.array_equal(ref[:, 2], g.seq_start[1:] - g.seq_start[:-1])
+    # closed form of SURVEY 8a-8
+    deg = (g.row_ptr[1:] - g.row_ptr[:-1]).astype(np.int64)
+    indeg = np.bincount(g.col, minlength=g.n_nodes).astype(np.int64)
+    ids = 1 + np.concatenate([[0], np.cumsum(5 + 3 * (deg + indeg))[:-1]])
+    assert np.array_equal(ids.astype(np.uint64), g.internal_id)
+
+
+# ---- golden seed sets of the compiled reference ----
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_closed_form_matches_reference_golden(name):
+    c = CASES[name]
+    if c["query_seeds"] > 200000:
+        pytest.skip("large case: covered on the GPU box and by test_big_golden_cpu")
+    g, rp, bases = load_case(c)
+    t, raw = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), c["k"], c["d"])
+    assert len(t) == c["count"]
+    assert util.md5_tuples(t) == c["md5"]
+
+
+def test_big_golden_cpu():
+    c = CASES["x_k20_d1"]
+    g, rp, bases = load_case(c)
+    t, raw = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), c["k"], c["d"])
+    assert len(t) == c["count"] and util.md5_tuples(t) == c["md5"]
+
+
+@pytest.mark.parametrize("name", ["x_k12", "m_k20", "fuzz_03", "fuzz_06", "fuzz_10", "multi_k32"])
+def test_hybrid_decomposition_equals_closed_form(name):
+    """seeds_on_paths(paths) U seeds_off_paths(uncovered loci) == closed form, with this
+    repo's own (seeded) path picker: the set does not depend on the paths."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    og, orr = orc.OGraph.of(g), orc.OReads(rp, bases)
+    ps = g.pick_paths(c["n_paths"], seed=7)
+    op = orc.OPaths(ps.path_ptr, ps.nodes, ps.head_off, ps.tail_trim)
+    ln, lo = orc.uncovered_loci(og, op, c["k"])
+    t_all, _ = orc.seeds_all(og, op, ln, lo, orr, c["k"], c["d"])
+    assert util.md5_tuples(t_all) == c["md5"]
+    t_on, _ = orc.seeds_on_paths(og, op, orr, c["k"], c["d"])
+    t_off, _ = orc.seeds_off_paths(og, ln, lo, orr, c["k"], c["d"])
+    union = np.unique(np.concatenate([t_on, t_off]), axis=0)
+    assert util.md5_tuples(union) == c["md5"]
+    # removing any uncovered locus loses nothing only if it carried no read hit; all loci are needed for coverage:
+    n_all, _ = util.all_loci(g)
+    assert len(ln) <= len(n_all)
+
+
+def test_chunking_does_not_change_the_set():
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    og = orc.OGraph.of(g)
+    parts = []
+    n = len(rp) - 1
+    for b in range(0, n, 2500):
+        e = min(n, b + 2500)
+        sub_ptr = rp[b:e + 1] - rp[b]
+        sub_bases = bases[int(rp[b]):int(rp[e])]
+        t, _ = orc.seeds_closed_form(og, orc.OReads(sub_ptr, sub_bases, first_read_id=b), c["k"], c["d"])
+        parts.append(t)
+    t = np.concatenate(parts)
+    assert util.md5_tuples(t) == c["md5"]   # disjoint read ranges: concatenation is already canonical
