@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s and seeds/s of fully-sensitive seed finding on the
+synthetic chr22-shape graph (BASELINE.json configs[1]), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]    # the reference's own CPU path (oracle/_ref)
+
+A step = one pass of the hot path (pack -> seeds_on_paths -> read index ->
+seeds_off_paths -> resolve) over one batch of 1 M synthetic 100 bp reads.
+  value : whole-job reads/s with the batch already resident in HBM
+  e2e   : same through the C-ABI with pinned HOST buffers, H2D of the reads and D2H of
+          the seed records inside the timed region
+  roofline : seeds_on_paths probe kernel, algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline : the unmodified reference (oracle/_ref/psi_ref_driver) on the host cores, bounded sample
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, os.fspath(ROOT))
+
+K = 20
+READ_LEN = 100
+READS_PER_BATCH = 1_000_000
+N_PATHS = 16
+N_BATCHES = 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------- clocks --
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.max_mhz = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------- workload --
+
+def build_graph(shape: str):
+    from bench_support import synth
+    from psi_b200 import capi
+    a = synth.graph_arrays(**synth.SHAPES[shape])
+    return capi.Graph.from_arrays(a["ids"], a["seq_start"], a["seq"], a["row_ptr"], a["col"], a["path_ptr"],
+                                  a["path_nodes"], sort=True)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------ reference (CPU) --
+
+def reference_run(n_reads_per_core=None, cores=None, shape="chr22_1_51", budget_s=8.0):
+    """The unmodified reference on the host cores: one psi_ref_driver process per core on
+    disjoint read ranges of one FASTA (the reference seed path is single-threaded).
+    Returns dict(value reads/s, cores, sample, seeds_per_s, seconds)."""
+    from bench_support import synth
+    from oracle import oracle_py as orc
+    if not orc.have_reference():
+        raise RuntimeError("oracle/_ref/psi_ref_driver missing")
+    cores = cores or max(1, (os.cpu_count() or 1))
+    cores = min(cores, 64)
+    g = build_graph(shape)
+    # calibrated so that one process takes roughly budget_s: ~6.7e3 reads/s/core measured in the survey on this shape
+    n_per = n_reads_per_core or max(2000, int(2500 * budget_s))
+    n_reads = n_per * cores
+    rp, bases = synth.reads(g, n_reads, READ_LEN, 1002)
+    td = tempfile.mkdtemp(prefix="psi_ref_")
+    gfa = os.path.join(td, "g.gfa")
+    fa = os.path.join(td, "r.fa")
+    g.write_gfa(gfa)
+    with open(fa, "wb") as f:
+        b = bases.reshape(n_reads, READ_LEN)
+        for i in range(n_reads):
+            f.write(b">r%d\n" % i)
+            f.write(b[i].tobytes())
+            f.write(b"\n")
+    procs = []
+    env = dict(os.environ, TMPDIR=td, OMP_PROC_BIND="false", OMP_NUM_THREADS="1")
+    for c in range(cores):
+        cmd = [os.fspath(orc.REF_DRIVER), "--gfa", gfa, "--fastq", fa, "-k", str(K), "-d", str(K), "-n", str(N_PATHS),
+               "--first-read", str(c * n_per), "--max-reads", str(n_per)]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env))
+    stats = []
+    for p in procs:
+        out, _ = p.communicate()
+        stats.append(json.loads(out.strip().splitlines()[-1]))
+    import shutil
+    shutil.rmtree(td, ignore_errors=True)
+    # timed region = seeding + seeds_on_paths + seeds_off_paths (index build excluded, as for the GPU arm)
+    t = max(s["t_seeding"] + s["t_on"] + s["t_off"] for s in stats)
+    reads = sum(s["reads"] for s in stats)
+    hits = sum(s["raw_on"] + s["raw_off"] for s in stats)
+    return {"value": reads / t, "unit": "reads/s", "cores": cores, "kind": "reference",
+            "sample": f"synthetic chr22-shape graph at 1/51 scale (1 Mbp backbone, 19 608 sites, {N_PATHS} paths), "
+                      f"{reads} x {READ_LEN} bp reads, k={K}: {cores} single-threaded reference processes on disjoint "
+                      f"read ranges; timed = seeding + seeds_on_paths + seeds_off_paths, max over processes",
+            "seconds": t, "raw_hits_per_s": hits / t, "t_index_s": max(s["t_index"] for s in stats)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = reference_run(budget_s=4.0)
+            if i >= args.warmup:
+                vals.append(r)
+        v = float(np.mean([x["value"] for x in vals]))
+        ms = float(np.mean([x["seconds"] for x in vals])) * 1e3
+        last = vals[-1]
+        line = {"impl": "reference", "metric": "reads/s (fully-sensitive seed finding, chr22-shape graph, k=20)",
+                "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64",
+                "data": "synthetic", "config": {"workload": "chr22-shape graph at 1/51 scale, bounded sample per step"},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": last["cores"], "kind": "reference",
+                                 "sample": last["sample"]},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    except Exception as e:  # the reference binary did not travel / cannot run
+        line = {"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------ GPU arm --
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from bench_support import synth
+    from psi_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t0 = time.time()
+    g = build_graph(args.shape)
+    ps = g.pick_paths(N_PATHS, seed=1)
+    ctx = capi.Context(K, local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_graph(g, ids="internal")
+    ctx.set_paths(ps)
+    n_loci = ctx.find_loci()
+    c0 = ctx.counters()
+    if rank == 0:
+        log(f"[bench] graph {g.n_nodes} nodes / {g.n_bases} bp; index {c0['n_index_kmers']} k-mers, "
+            f"{c0['index_bytes'] / 1e6:.0f} MB, slot {c0['index_slot_bytes']} B, build {c0['ms_index_build']:.0f} ms; "
+            f"{n_loci} starting loci in {c0['ms_find_loci']:.0f} ms; setup {time.time() - t0:.1f} s")
+
+    # distinct read batches per rank (weak scaling: every GPU processes its own shard of the read set)
+    n_reads = args.reads
+    batches_h, batches_d = [], []
+    for b in range(N_BATCHES):
+        rp, bases = synth.reads(g, n_reads, READ_LEN, 1002 + 1000 * rank + b)
+        hp = torch.from_numpy(rp.view(np.int64)).pin_memory()
+        hb = torch.from_numpy(bases).pin_memory()
+        batches_h.append((hp, hb))
+        batches_d.append((hp.to(dev), hb.to(dev)))
+    rec_host = torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory()   # room for the seed records
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        dp, db = batches_d[i % N_BATCHES]
+        ctx.submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
+        return ctx.seeds_all(capi.ALL)
+
+    def step_e2e(i):
+        hp, hb = batches_h[i % N_BATCHES]
+        ctx.submit_chunk_ptr(n_reads, hp.data_ptr(), hb.data_ptr(), rank * n_reads, K)
+        ctx.seeds_all(capi.ALL)
+        return ctx.fetch_into(rec_host.data_ptr(), rec_host.shape[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        ctx.reset_counters()
+        acc = {"ms_on": 0.0, "ms_off": 0.0, "ms_pack": 0.0, "ms_read_index": 0.0, "ms_resolve": 0.0, "ms_h2d": 0.0,
+               "ms_d2h": 0.0, "n_hits_on": 0, "n_hits": 0, "n_seeds": 0, "n_walks": 0}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hits = 0
+        for i in range(steps):
+            hits += step_fn(warmup + i)
+            c = ctx.counters()          # syncs the stream; per-kernel CUDA-event times of this step
+            for k_ in acc:
+                acc[k_] += c[k_]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.counters()["launches"]
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, hits, acc, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, hits_dev, acc, launches = timed(step_device, args.steps, args.warmup)
+    ms_e2e, hits_e2e, acc_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-shard counts and a hits-per-read histogram, gathered with NCCL (the only collective on this path)
+    tot = torch.tensor([n_reads * args.steps, acc["n_seeds"], hits_dev, acc["n_hits_on"], acc["n_walks"]],
+                       device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tot)
+    tot = tot.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        reads_total, seeds_total, hits_total, hits_on_total, walks_total = tot
+        value = reads_total / (ms_dev * 1e-3)
+        # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches:
+        # algorithmic bytes per launch = seeds x (8 B packed k-mer + 32 B one index bucket) + on-path hits x 8 B record
+        alg_bytes = (acc["n_seeds"] * 40 + acc["n_hits_on"] * 8) / args.steps
+        on_ms = acc["ms_on"] / args.steps
+        achieved = alg_bytes / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
+        per_step = {k_: acc[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_read_index", "ms_off", "ms_resolve")}
+        e2e_value = n_reads * args.steps * world / (ms_e2e * 1e-3)
+        hp, hb = batches_h[0]
+        line = {
+            "metric": "reads/s (fully-sensitive seed finding, chr22-shape graph, k=20)",
+            "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u64", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.shape}-shape graph ({g.n_bases} bp, {g.n_nodes} nodes, {N_PATHS} paths, "
+                                   f"{n_loci} starting loci), {n_reads} x {READ_LEN} bp reads per GPU per step, k={K}, d={K}",
+                       "l2": f"{N_BATCHES} distinct read batches cycled ({N_BATCHES * n_reads * READ_LEN / 1e6:.0f} MB) and a "
+                             f"{c0['index_bytes'] / 1e6:.0f} MB index: inputs larger than L2",
+                       "sharding": "reads sharded by rank, graph + index replicated, NCCL all-reduce of counts only"},
+            "seeds_per_s": hits_total / (ms_dev * 1e-3), "query_seeds_per_s": seeds_total / (ms_dev * 1e-3),
+            "kernel_ms_per_step": per_step,
+            "e2e": {"value": e2e_value, "unit": "reads/s",
+                    "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
+                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 32), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "seeds_on_paths_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms},
+            "clocks": clocks,
+            "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
+                      "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = reference_run(budget_s=8.0)
+                line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference",
+                                        "sample": f"unavailable: {type(e).__name__}: {e}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="psi_b200", choices=["psi_b200", "reference"])
+    ap.add_argument("--shape", default="chr22", help="bench_support.synth.SHAPES key")
+    ap.add_argument("--reads", type=int, default=READS_PER_BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "psi_b200" else args.warmup
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

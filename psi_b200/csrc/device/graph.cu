@@ -71,7 +71,7 @@ Ctx* engine_create(int device, unsigned seed_len)
   for (auto& ev : c->ev) PSI_CUDA(cudaEventCreate(&ev));
   c->dev_counters.ensure(DC_COUNT);
   PSI_CUDA(cudaMemsetAsync(c->dev_counters.p, 0, DC_COUNT * sizeof(unsigned long long), c->stream));
-  PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, DC_COUNT * sizeof(uint64_t), cudaHostAllocDefault));
+  PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, (2 * DC_COUNT + 8) * sizeof(uint64_t), cudaHostAllocDefault));
   return c;
 }
 

@@ -265,8 +265,11 @@ def test_error_behaviour():
     g = capi.Graph.load_gfa(util.GOLDEN / "inputs/tiny.gfa.gz")
     ctx.set_graph(g)
     with pytest.raises(capi.PsiError) as e:
-        ctx.fetch()
-    assert e.value.code in (capi.ERR_STATE, capi.OK) or True
+        ctx.fetch_device()       # no resolved records yet
+    assert e.value.code == capi.ERR_STATE
+    with pytest.raises(capi.PsiError) as e:
+        ctx.set_paths(capi.PathSet(path_ptr=[0, 1], nodes=[10 ** 6]))   # node rank out of range
+    assert e.value.code == capi.ERR_ARG
     ctx.close()
 
 
