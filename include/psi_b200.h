@@ -133,6 +133,15 @@ typedef struct psi_b200_ctx psi_b200_ctx;
 
 /* SeedFinder(graph, seed_len, ...) (seed_finder.hpp:930-942); seed_len <= 32. */
 int  psi_b200_create(int device, unsigned seed_len, psi_b200_ctx** out);
+/* A further pipeline on the same GPU that SHARES the parent's resident graph,
+ * path index and starting loci (one copy in HBM) and owns its stream, chunk
+ * and result buffers.  Stands behind the reference's "one finder, several
+ * threads, one chunk each" use (SeedFinderStats is keyed by thread id,
+ * seed_finder.hpp:386-399,486-493); with two pipelines the upload of chunk i+1
+ * overlaps the kernels and the download of chunk i.  The graph/paths/loci must
+ * be final before the first fork; set_paths/find_loci/set_loci on a shared
+ * index fail with PSI_B200_ERR_STATE.  Forks may outlive the parent. */
+int  psi_b200_fork(psi_b200_ctx* parent, psi_b200_ctx** out);
 void psi_b200_destroy(psi_b200_ctx* ctx);
 const char* psi_b200_last_error(const psi_b200_ctx* ctx);
 /* Run all work of this context on the given cudaStream_t (default: a private

@@ -27,7 +27,7 @@ SYMBOLS = [
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_global_error",
-    "psi_b200_create", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync",
+    "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
     "psi_b200_submit_chunk", "psi_b200_submit_chunk_device", "psi_b200_seeds_all",
     "psi_b200_fetch", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
     L.psi_b200_reader_close.argtypes = [vp]
     L.psi_b200_reader_close.restype = None
     L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
+    L.psi_b200_fork.argtypes = [vp, C.POINTER(vp)]
     L.psi_b200_destroy.argtypes = [vp]
     L.psi_b200_destroy.restype = None
     L.psi_b200_set_stream.argtypes = [vp, vp]
@@ -272,10 +273,19 @@ class Reader:
 class Context:
     """One GPU context (psi_b200_ctx)."""
 
-    def __init__(self, seed_len: int, device: int = 0):
+    def __init__(self, seed_len: int, device: int = 0, _handle=None):
         self._h = C.c_void_p()
-        _check(lib().psi_b200_create(device, seed_len, C.byref(self._h)))
+        if _handle is not None:
+            self._h = _handle
+        else:
+            _check(lib().psi_b200_create(device, seed_len, C.byref(self._h)))
         self.k = seed_len
+
+    def fork(self) -> "Context":
+        """A second pipeline sharing this context's resident graph / index / loci."""
+        h = C.c_void_p()
+        self._ck(lib().psi_b200_fork(self._h, C.byref(h)))
+        return Context(self.k, _handle=h)
 
     def _ck(self, rc):
         _check(rc, self._h)

@@ -215,6 +215,16 @@ int psi_b200_create(int device, unsigned seed_len, psi_b200_ctx** out)
   catch (...) { return translate(g_error); }
 }
 
+int psi_b200_fork(psi_b200_ctx* parent, psi_b200_ctx** out)
+{
+  if (!out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  CTX_GUARD(parent, {
+    Ctx* c = engine_fork(*parent->c);
+    *out = new psi_b200_ctx{ c };
+  })
+}
+
 void psi_b200_destroy(psi_b200_ctx* ctx)
 {
   if (!ctx) return;
@@ -263,14 +273,14 @@ int psi_b200_find_loci(psi_b200_ctx* ctx, unsigned step, uint64_t* n_loci)
 {
   CTX_GUARD(ctx, {
     engine_find_loci(*ctx->c, step);
-    if (n_loci) *n_loci = ctx->c->n_loci;
+    if (n_loci) *n_loci = ctx->c->sh->n_loci;
   })
 }
 
 int psi_b200_get_loci(psi_b200_ctx* ctx, uint32_t* node_rank, uint32_t* offset, uint64_t cap, uint64_t* n_loci)
 {
   CTX_GUARD(ctx, {
-    if (n_loci) *n_loci = ctx->c->n_loci;
+    if (n_loci) *n_loci = ctx->c->sh->n_loci;
     if (cap) engine_get_loci(*ctx->c, node_rank, offset, cap);
   })
 }

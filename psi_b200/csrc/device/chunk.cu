@@ -93,7 +93,7 @@ build_read_index_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, con
 void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, const char* bases,
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device)
 {
-  if (!c.has_graph) throw StateError("submit_chunk: no graph");
+  if (!c.sh->has_graph) throw StateError("submit_chunk: no graph");
   if (n_reads && (!read_ptr || !bases)) throw ArgError("submit_chunk: null arrays");
   if (n_reads >= 0x7fffffffull) throw ArgError("submit_chunk: more than 2^31 reads in one chunk");
   PSI_CUDA(cudaSetDevice(c.device));

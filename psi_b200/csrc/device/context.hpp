@@ -4,6 +4,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 
@@ -78,17 +79,10 @@ struct HostTable {
   uint64_t n_lines = 0;
 };
 
-struct Ctx {
-  int device = 0;
-  unsigned k = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  int sm_count = 148;
-  std::string error;
-  psi_b200_counters_t counters{};
-  cudaEvent_t ev[24]{};
-  int ev_state[12]{};   // 0 never recorded, 1 started, 2 start+stop recorded
-
+// Everything that is immutable once built -- the flattened graph, the path
+// index and the starting loci -- lives in one object that forked contexts share
+// (psi_b200_fork): one resident copy per GPU, any number of chunk pipelines.
+struct Shared {
   // ---- graph ----
   bool has_graph = false;
   uint32_t n_nodes = 0, n_edges = 0;
@@ -100,7 +94,6 @@ struct Ctx {
   DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
   DevBuf<uint64_t> node_id;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
-  static constexpr uint32_t POS2NODE_SHIFT = 6;
 
   // ---- path index ----
   bool has_index = false;
@@ -110,6 +103,21 @@ struct Ctx {
   // ---- starting loci ----
   uint64_t n_loci = 0;
   DevBuf<uint32_t> loci_node, loci_off;
+};
+
+struct Ctx {
+  int device = 0;
+  unsigned k = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::string error;
+  psi_b200_counters_t counters{};
+  cudaEvent_t ev[24]{};
+  int ev_state[12]{};   // 0 never recorded, 1 started, 2 start+stop recorded
+
+  std::shared_ptr<Shared> sh = std::make_shared<Shared>();
+  static constexpr uint32_t POS2NODE_SHIFT = 6;
 
   // ---- current chunk ----
   bool has_chunk = false;

@@ -7,6 +7,7 @@
 namespace psi_b200 {
 
 Ctx* engine_create(int device, unsigned seed_len);
+Ctx* engine_fork(Ctx& parent);
 void engine_destroy(Ctx* ctx);
 
 void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const char* seq,

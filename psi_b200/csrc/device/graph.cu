@@ -7,6 +7,7 @@
 // labels, an N bitmap and a sampled position->node table.
 #include "engine.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -68,10 +69,41 @@ Ctx* engine_create(int device, unsigned seed_len)
   c->sm_count = prop.multiProcessorCount;
   PSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
+  // Index probes are single random 32-byte sectors: ask L2 not to promote a miss to
+  // a wider DRAM fetch.  Override for experiments with PSI_B200_L2_FETCH=32|64|128|0
+  // (0 = leave the device default).
+  {
+    size_t gran = 32;
+    if (const char* e = std::getenv("PSI_B200_L2_FETCH")) gran = (size_t)std::strtoul(e, nullptr, 10);
+    if (gran == 32 || gran == 64 || gran == 128) {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) (void)cudaGetLastError();
+    }
+  }
   for (auto& ev : c->ev) PSI_CUDA(cudaEventCreate(&ev));
   c->dev_counters.ensure(DC_COUNT);
   PSI_CUDA(cudaMemsetAsync(c->dev_counters.p, 0, DC_COUNT * sizeof(unsigned long long), c->stream));
   PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, (2 * DC_COUNT + 8) * sizeof(uint64_t), cudaHostAllocDefault));
+  return c;
+}
+
+// A second pipeline on the same GPU: shares the resident graph, path index and
+// starting loci, owns its stream, chunk buffers and result buffers.  This is how
+// one SeedFinder is driven from several host threads on different chunks (the
+// reference's stats are thread-aware for exactly that use, seed_finder.hpp:386-399)
+// and how H2D of chunk i+1 overlaps the kernels and D2H of chunk i.
+Ctx* engine_fork(Ctx& parent)
+{
+  PSI_CUDA(cudaSetDevice(parent.device));
+  PSI_CUDA(cudaStreamSynchronize(parent.stream));
+  Ctx* c = engine_create(parent.device, parent.k);
+  c->sh = parent.sh;
+  const psi_b200_counters_t& pc = parent.counters;
+  c->counters.n_nodes = pc.n_nodes; c->counters.n_edges = pc.n_edges; c->counters.n_bases = pc.n_bases;
+  c->counters.n_path_bases = pc.n_path_bases; c->counters.n_index_entries = pc.n_index_entries;
+  c->counters.n_index_kmers = pc.n_index_kmers; c->counters.index_bytes = pc.index_bytes;
+  c->counters.index_buckets = pc.index_buckets; c->counters.index_slot_bytes = pc.index_slot_bytes;
+  c->counters.n_loci = pc.n_loci; c->counters.ms_index_build = pc.ms_index_build; c->counters.ms_find_loci = pc.ms_find_loci;
+  c->spill_items = parent.spill_items;
   return c;
 }
 
@@ -97,6 +129,7 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   if (n_edges >= 0xfffffff0ull) throw ArgError("set_graph: too many edges");
   if (n_edges && !col) throw ArgError("set_graph: null adjacency");
   PSI_CUDA(cudaSetDevice(c.device));
+  if (c.sh.use_count() > 1) c.sh = std::make_shared<Shared>();  // forks keep the graph they were given
 
   std::vector<NodeRec> rec(n_nodes + 1);
   for (uint64_t v = 0; v < n_nodes; ++v) {
@@ -110,42 +143,42 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   for (uint64_t e = 0; e < n_edges; ++e)
     if (col[e] >= n_nodes) throw ArgError("set_graph: successor rank out of range");
 
-  c.n_nodes = (uint32_t)n_nodes;
-  c.n_edges = (uint32_t)n_edges;
-  c.n_bases = n_bases;
-  c.node_rec.ensure(n_nodes + 1);
-  c.col.ensure(n_edges + 1);
-  c.node_id.ensure(n_nodes);
+  c.sh->n_nodes = (uint32_t)n_nodes;
+  c.sh->n_edges = (uint32_t)n_edges;
+  c.sh->n_bases = n_bases;
+  c.sh->node_rec.ensure(n_nodes + 1);
+  c.sh->col.ensure(n_edges + 1);
+  c.sh->node_id.ensure(n_nodes);
   const uint64_t n_words = (n_bases + 31) >> 5;
-  c.seq2.ensure(n_words + 2);
-  c.nmask.ensure(n_words + 2);
-  c.pos2node.ensure((n_bases >> Ctx::POS2NODE_SHIFT) + 2);
+  c.sh->seq2.ensure(n_words + 2);
+  c.sh->nmask.ensure(n_words + 2);
+  c.sh->pos2node.ensure((n_bases >> Ctx::POS2NODE_SHIFT) + 2);
 
   DevBuf<char> ascii;
   ascii.ensure(n_bases + 1);
   PSI_CUDA(cudaMemcpyAsync(ascii.p, seq, n_bases, cudaMemcpyHostToDevice, c.stream));
-  PSI_CUDA(cudaMemcpyAsync(c.node_rec.p, rec.data(), (n_nodes + 1) * sizeof(NodeRec), cudaMemcpyHostToDevice, c.stream));
-  if (n_edges) PSI_CUDA(cudaMemcpyAsync(c.col.p, col, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
-  PSI_CUDA(cudaMemcpyAsync(c.node_id.p, node_id, n_nodes * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
-  PSI_CUDA(cudaMemsetAsync(c.seq2.p, 0, (n_words + 2) * sizeof(uint64_t), c.stream));
-  PSI_CUDA(cudaMemsetAsync(c.nmask.p, 0, (n_words + 2) * sizeof(uint32_t), c.stream));
-  PSI_CUDA(cudaMemsetAsync(c.pos2node.p, 0, ((n_bases >> Ctx::POS2NODE_SHIFT) + 2) * sizeof(uint32_t), c.stream));
+  PSI_CUDA(cudaMemcpyAsync(c.sh->node_rec.p, rec.data(), (n_nodes + 1) * sizeof(NodeRec), cudaMemcpyHostToDevice, c.stream));
+  if (n_edges) PSI_CUDA(cudaMemcpyAsync(c.sh->col.p, col, n_edges * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(c.sh->node_id.p, node_id, n_nodes * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.sh->seq2.p, 0, (n_words + 2) * sizeof(uint64_t), c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.sh->nmask.p, 0, (n_words + 2) * sizeof(uint32_t), c.stream));
+  PSI_CUDA(cudaMemsetAsync(c.sh->pos2node.p, 0, ((n_bases >> Ctx::POS2NODE_SHIFT) + 2) * sizeof(uint32_t), c.stream));
   PSI_CUDA(cudaMemsetAsync(c.dev_counters.p + DC_AUX, 0, sizeof(unsigned long long), c.stream));
   if (n_words) {
-    pack_labels_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(ascii.p, n_bases, c.seq2.p, c.nmask.p,
+    pack_labels_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(ascii.p, n_bases, c.sh->seq2.p, c.sh->nmask.p,
                                                                      c.dev_counters.p + DC_AUX);
     ++c.counters.launches;
   }
-  pos2node_kernel<<<grid_for(n_nodes, 256), 256, 0, c.stream>>>(c.node_rec.p, c.n_nodes, c.pos2node.p, Ctx::POS2NODE_SHIFT);
+  pos2node_kernel<<<grid_for(n_nodes, 256), 256, 0, c.stream>>>(c.sh->node_rec.p, c.sh->n_nodes, c.sh->pos2node.p, Ctx::POS2NODE_SHIFT);
   ++c.counters.launches;
   PSI_CUDA(cudaGetLastError());
   unsigned long long n_count = 0;
   PSI_CUDA(cudaMemcpyAsync(&n_count, c.dev_counters.p + DC_AUX, sizeof(n_count), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.graph_has_n = n_count != 0;
-  c.has_graph = true;
-  c.has_index = false;
-  c.n_loci = 0;
+  c.sh->graph_has_n = n_count != 0;
+  c.sh->has_graph = true;
+  c.sh->has_index = false;
+  c.sh->n_loci = 0;
   c.counters.n_nodes = n_nodes;
   c.counters.n_edges = n_edges;
   c.counters.n_bases = n_bases;

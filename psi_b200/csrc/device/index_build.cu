@@ -202,9 +202,10 @@ static void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, uint64
 void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
                         const uint32_t* head_off, const uint32_t* tail_trim)
 {
-  if (!c.has_graph) throw StateError("set_paths: no graph");
+  if (!c.sh->has_graph) throw StateError("set_paths: no graph");
+  if (c.sh.use_count() > 1) throw StateError("set_paths: the index is shared with forked contexts");
   PSI_CUDA(cudaSetDevice(c.device));
-  c.has_index = false;
+  c.sh->has_index = false;
   c.counters.n_path_bases = c.counters.n_index_entries = c.counters.n_index_kmers = 0;
   c.counters.index_bytes = c.counters.index_buckets = 0;
   c.counters.ms_index_build = 0;
@@ -213,7 +214,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   if (n_paths >= 0x7fffffffull) throw ArgError("set_paths: too many paths");
   const uint64_t n_entries = path_ptr[n_paths];
   for (uint64_t e = 0; e < n_entries; ++e)
-    if (path_nodes[e] >= c.n_nodes) throw ArgError("set_paths: node rank out of range");
+    if (path_nodes[e] >= c.sh->n_nodes) throw ArgError("set_paths: node rank out of range");
 
   PhaseTimer timer(c, T_INDEX);
   DevBuf<uint64_t> d_path_ptr;
@@ -249,10 +250,10 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   if (n_pairs >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows (index them in several contexts)");
   c.counters.n_path_bases = n_pairs;
   if (n_pairs == 0) {  // paths shorter than k: empty index
-    table_alloc(c, c.index, 1, 2 * c.k, 1ull << 30, 1024);
-    c.index.view.stash_nonempty = 0;
-    c.multi.ensure(2);
-    c.has_index = true;
+    table_alloc(c, c.sh->index, 1, 2 * c.k, 1ull << 30, 1024);
+    c.sh->index.view.stash_nonempty = 0;
+    c.sh->multi.ensure(2);
+    c.sh->has_index = true;
     timer.stop();
     PSI_CUDA(cudaStreamSynchronize(c.stream));
     c.counters.ms_index_build = timer.ms();
@@ -314,32 +315,32 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   uint32_t multi_words = 0;
   PSI_CUDA(cudaMemcpyAsync(&multi_words, multi_off.p + n_runs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.multi.ensure((uint64_t)multi_words + 2);
+  c.sh->multi.ensure((uint64_t)multi_words + 2);
 
   // table
-  table_alloc(c, c.index, n_runs, 2 * c.k, 1ull << 30, (uint64_t)n_runs / 512 + 1024);
-  if (c.index.view.fmt == 8)
-    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.multi.p, d_err);
+  table_alloc(c, c.sh->index, n_runs, 2 * c.k, 1ull << 30, (uint64_t)n_runs / 512 + 1024);
+  if (c.sh->index.view.fmt == 8)
+    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.sh->index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.sh->multi.p, d_err);
   else
-    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.multi.p, d_err);
+    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.sh->index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.sh->multi.p, d_err);
   ++c.counters.launches;
   PSI_CUDA(cudaGetLastError());
   unsigned long long err = 0;
   uint32_t stash_used = 0;
   PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
-  PSI_CUDA(cudaMemcpyAsync(&stash_used, c.index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(&stash_used, c.sh->index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   timer.stop();
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   if (err & 2ull) throw OverflowError("path index: hash stash exhausted");
-  c.index.view.stash_nonempty = stash_used ? 1u : 0u;
-  c.has_index = true;
+  c.sh->index.view.stash_nonempty = stash_used ? 1u : 0u;
+  c.sh->has_index = true;
   c.counters.ms_index_build = timer.ms();
   c.counters.n_index_entries = n_unique;
   c.counters.n_index_kmers = n_runs;
-  c.counters.index_buckets = c.index.n_lines * 4;
-  c.counters.index_bytes = c.index.n_lines * 128 + ((uint64_t)multi_words + 2) * 4 +
-                           ((uint64_t)c.index.view.stash_mask + 1) * sizeof(Slot16);
-  c.counters.index_slot_bytes = c.index.view.fmt;
+  c.counters.index_buckets = c.sh->index.n_lines * 4;
+  c.counters.index_bytes = c.sh->index.n_lines * 128 + ((uint64_t)multi_words + 2) * 4 +
+                           ((uint64_t)c.sh->index.view.stash_mask + 1) * sizeof(Slot16);
+  c.counters.index_slot_bytes = c.sh->index.view.fmt;
 }
 
 // -------------------------------------------------------- starting loci --
@@ -413,11 +414,12 @@ emit_loci_kernel(GraphView g, const uint32_t* __restrict__ flags, const uint32_t
 
 void engine_find_loci(Ctx& c, unsigned step)
 {
-  if (!c.has_graph) throw StateError("find_loci: no graph");
+  if (!c.sh->has_graph) throw StateError("find_loci: no graph");
+  if (c.sh.use_count() > 1) throw StateError("find_loci: the index is shared with forked contexts");
   PSI_CUDA(cudaSetDevice(c.device));
   if (step == 0) step = 1;
   PhaseTimer timer(c, T_LOCI);
-  const uint64_t n_words = (c.n_bases + 31) >> 5;
+  const uint64_t n_words = (c.sh->n_bases + 31) >> 5;
   DevBuf<uint32_t> flags, cnt, scan;
   flags.ensure(n_words + 1); cnt.ensure(n_words + 1); scan.ensure(n_words + 1);
   const GraphView g = make_graph_view(c);
@@ -429,7 +431,7 @@ void engine_find_loci(Ctx& c, unsigned step)
     PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
     PSI_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), c.stream));
     c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
-    find_loci_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, step, c.index.view, c.multi.p, c.has_index ? 1u : 0u,
+    find_loci_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, step, c.sh->index.view, c.sh->multi.p, c.sh->has_index ? 1u : 0u,
                                                             flags.p, d_work, (WalkItem*)c.walk_spill.p, c.spill_items, d_err);
     ++c.counters.launches;
     PSI_CUDA(cudaGetLastError());
@@ -447,42 +449,43 @@ void engine_find_loci(Ctx& c, unsigned step)
   uint32_t n_loci = 0;
   PSI_CUDA(cudaMemcpyAsync(&n_loci, scan.p + n_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.loci_node.ensure((uint64_t)n_loci + 1);
-  c.loci_off.ensure((uint64_t)n_loci + 1);
+  c.sh->loci_node.ensure((uint64_t)n_loci + 1);
+  c.sh->loci_off.ensure((uint64_t)n_loci + 1);
   if (n_loci) {
-    emit_loci_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(g, flags.p, scan.p, n_words, c.loci_node.p, c.loci_off.p);
+    emit_loci_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(g, flags.p, scan.p, n_words, c.sh->loci_node.p, c.sh->loci_off.p);
     ++c.counters.launches;
   }
   timer.stop();
   PSI_CUDA(cudaGetLastError());
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.n_loci = n_loci;
+  c.sh->n_loci = n_loci;
   c.counters.n_loci = n_loci;
   c.counters.ms_find_loci = timer.ms();
 }
 
 void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* off)
 {
-  if (!c.has_graph) throw StateError("set_loci: no graph");
+  if (!c.sh->has_graph) throw StateError("set_loci: no graph");
+  if (c.sh.use_count() > 1) throw StateError("set_loci: the index is shared with forked contexts");
   if (n && (!node || !off)) throw ArgError("set_loci: null arrays");
   PSI_CUDA(cudaSetDevice(c.device));
-  c.loci_node.ensure(n + 1);
-  c.loci_off.ensure(n + 1);
+  c.sh->loci_node.ensure(n + 1);
+  c.sh->loci_off.ensure(n + 1);
   if (n) {
-    PSI_CUDA(cudaMemcpyAsync(c.loci_node.p, node, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
-    PSI_CUDA(cudaMemcpyAsync(c.loci_off.p, off, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(c.sh->loci_node.p, node, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(c.sh->loci_off.p, off, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
   }
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.n_loci = n;
+  c.sh->n_loci = n;
   c.counters.n_loci = n;
 }
 
 void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap)
 {
   PSI_CUDA(cudaSetDevice(c.device));
-  const uint64_t n = c.n_loci < cap ? c.n_loci : cap;
-  if (n && node) PSI_CUDA(cudaMemcpyAsync(node, c.loci_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-  if (n && off) PSI_CUDA(cudaMemcpyAsync(off, c.loci_off.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  const uint64_t n = c.sh->n_loci < cap ? c.sh->n_loci : cap;
+  if (n && node) PSI_CUDA(cudaMemcpyAsync(node, c.sh->loci_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  if (n && off) PSI_CUDA(cudaMemcpyAsync(off, c.sh->loci_off.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
 }
 

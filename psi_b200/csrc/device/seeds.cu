@@ -260,8 +260,8 @@ void engine_seeds(Ctx& c, unsigned flags)
 {
   if (!c.has_chunk) throw StateError("seeds_all: no read chunk submitted");
   PSI_CUDA(cudaSetDevice(c.device));
-  const bool do_on = (flags & PSI_B200_ON_PATHS) && c.has_index;
-  const bool do_off = (flags & PSI_B200_OFF_PATHS) && c.n_loci > 0;
+  const bool do_on = (flags & PSI_B200_ON_PATHS) && c.sh->has_index;
+  const bool do_off = (flags & PSI_B200_OFF_PATHS) && c.sh->n_loci > 0;
   const GraphView g = make_graph_view(c);
   unsigned long long* dc = c.dev_counters.p;
   c.records_valid = false;
@@ -280,11 +280,11 @@ void engine_seeds(Ctx& c, unsigned flags)
     if (do_on) {
       constexpr int ITEMS = 4;
       const unsigned grid = grid_for(c.n_seeds_cap, 256, ITEMS);
-      if (c.index.view.fmt == 8)
-        seeds_on_paths_kernel<8, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.index.view, c.multi.p, c.seed_kmer.p, c.seed_valid.p,
+      if (c.sh->index.view.fmt == 8)
+        seeds_on_paths_kernel<8, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.sh->index.view, c.sh->multi.p, c.seed_kmer.p, c.seed_valid.p,
                                                                          dc + DC_SEEDS, c.hits.p, hits_cap, dc + DC_HITS, dc + DC_SECTORS);
       else
-        seeds_on_paths_kernel<16, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.index.view, c.multi.p, c.seed_kmer.p, c.seed_valid.p,
+        seeds_on_paths_kernel<16, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.sh->index.view, c.sh->multi.p, c.seed_kmer.p, c.seed_valid.p,
                                                                           dc + DC_SEEDS, c.hits.p, hits_cap, dc + DC_HITS, dc + DC_SECTORS);
       ++c.counters.launches;
     }
@@ -302,9 +302,9 @@ void engine_seeds(Ctx& c, unsigned flags)
       sink.rt = c.read_index.view;
       sink.rt.stash_nonempty = 1;  // not known without a sync; probing an empty stash costs one load, and only for full lines
       sink.next = c.seed_next.p;
-      sink.pt = c.index.view;
-      sink.multi = c.multi.p;
-      sink.has_index = c.has_index ? 1u : 0u;
+      sink.pt = c.sh->index.view;
+      sink.multi = c.sh->multi.p;
+      sink.has_index = c.sh->has_index ? 1u : 0u;
       sink.dedup = c.dedup.p;
       sink.dedup_mask = dedup_slots - 1;
       sink.hits = c.hits.p;
@@ -313,7 +313,7 @@ void engine_seeds(Ctx& c, unsigned flags)
       sink.walk_count = dc + DC_WALKS;
       sink.err = dc + DC_ERR;
       sink.walks = 0;
-      seeds_off_paths_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, c.n_loci, c.loci_node.p, c.loci_off.p, sink,
+      seeds_off_paths_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, c.sh->n_loci, c.sh->loci_node.p, c.sh->loci_off.p, sink,
                                                                      dc + DC_WORK, (WalkItem*)c.walk_spill.p, c.spill_items);
       ++c.counters.launches;
       t_off.stop();
@@ -372,7 +372,7 @@ void engine_seeds(Ctx& c, unsigned flags)
     PhaseTimer t_res(c, T_RESOLVE);
     c.records.ensure(4 * std::max<uint64_t>(n_total, 1), 1.25);
     if (n_total) {
-      resolve_hits_kernel<<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, c.node_id.p, c.hits.p, n_total, c.seed_read.p,
+      resolve_hits_kernel<<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, c.sh->node_id.p, c.hits.p, n_total, c.seed_read.p,
                                                                       c.seed_first.p, c.distance, c.first_read_id, c.records.p);
       ++c.counters.launches;
     }

@@ -48,15 +48,15 @@ struct GraphView {
 inline GraphView make_graph_view(const Ctx& c)
 {
   GraphView g;
-  g.rec = c.node_rec.p;
-  g.col = c.col.p;
-  g.seq2 = c.seq2.p;
-  g.nmask = c.nmask.p;
-  g.pos2node = c.pos2node.p;
-  g.n_nodes = c.n_nodes;
+  g.rec = c.sh->node_rec.p;
+  g.col = c.sh->col.p;
+  g.seq2 = c.sh->seq2.p;
+  g.nmask = c.sh->nmask.p;
+  g.pos2node = c.sh->pos2node.p;
+  g.n_nodes = c.sh->n_nodes;
   g.pos2node_shift = Ctx::POS2NODE_SHIFT;
-  g.n_bases = c.n_bases;
-  g.has_n = c.graph_has_n ? 1u : 0u;
+  g.n_bases = c.sh->n_bases;
+  g.has_n = c.sh->graph_has_n ? 1u : 0u;
   return g;
 }
 

@@ -1,0 +1,553 @@
+// psi/seed_finder.hpp -- psi::SeedFinder over libpsi_b200 (B200, sm_100a).
+//
+// Mirror of the reference's API object for fully-sensitive seed finding
+// (reference include/psi/seed_finder.hpp:728-1788) for the calls its CLI makes
+// (src/psikt.cpp:83-212): same class and method names, argument meaning, error
+// behaviour and callback contract; underneath, every method is a call into the
+// C-ABI of include/psi_b200.h -- no algorithm lives in this header and there is
+// no CPU fallback (construction throws when no sm_100 device is usable).
+//
+//   reference method (seed_finder.hpp)            C-ABI call
+//   SeedFinder(graph, k, ...)          :930-942    psi_b200_create + psi_b200_set_graph
+//   pick_paths                         :1138-1167  psi_b200_pick_paths
+//   index_paths                        :1169-1176  psi_b200_set_paths
+//   add_uncovered_loci                 :1481-1541  psi_b200_find_loci / get_loci
+//   load_path_index/serialize_..       :1372-1413  pathset + loci files (own paths format, reference loci format)
+//   get_seeds + index_reads            :1089-1109  psi_b200_submit_chunk
+//   seeds_on_paths/off_paths/all       :1426-1457,1703-1743  psi_b200_seeds_all + psi_b200_fetch
+//
+// Differences that are deliberate: callbacks see every hit of the
+// seed SET exactly once (the reference repeats a locus once per covering path
+// and per walk); `gocc` is not tracked (0); the distance index, approximate
+// matching, MEM mode and a non-zero gocc threshold are outside this build and
+// throw std::runtime_error when requested.
+#ifndef PSI_B200_PSI_SEED_FINDER_HPP
+#define PSI_B200_PSI_SEED_FINDER_HPP
+
+#include <atomic>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../../include/psi_b200.h"
+#include "graph.hpp"
+#include "seed.hpp"
+#include "sequence.hpp"
+#include "stats.hpp"
+
+namespace seqan2 {
+template <typename T = void> struct IndexWotd {};
+template <typename T = void> struct IndexEsa {};
+}  // namespace seqan2
+
+namespace psi {
+
+struct BFS {};
+struct DFS {};
+struct Whole {};
+struct PerComponent {};
+template <typename, typename> class ExactMatching {};
+
+// Process-wide totals the CLI reports (reference traverser_base.hpp:108-244).
+struct TraverserStats {
+  static std::atomic<unsigned long long>& seeds_off_paths() { static std::atomic<unsigned long long> v{ 0 }; return v; }
+  static std::atomic<unsigned long long>& nof_godowns() { static std::atomic<unsigned long long> v{ 0 }; return v; }
+  static unsigned long long get_total_seeds_off_paths() { return seeds_off_paths().load(); }
+  // "godown" = one index descent per base in the reference; here one hash probe per completed k-walk
+  static unsigned long long get_total_nof_godowns() { return nof_godowns().load(); }
+};
+
+template <typename TGraphSpec = gum::Succinct, typename TReadsStringSet = Dna5QStringSet<>,
+          typename TReadsIndexSpec = seqan2::IndexWotd<>, typename TPathsStringSetSpec = InMemory,
+          typename TStrategy = BFS, template <typename, typename> class TMatchingTraits = ExactMatching>
+struct SeedFinderTraits {
+  typedef SeqGraph<TGraphSpec> graph_type;
+  typedef TReadsStringSet stringset_type;
+  typedef TReadsIndexSpec indexspec_type;
+  typedef TPathsStringSetSpec pathstrsetspec_type;
+  typedef TStrategy strategy_type;
+};
+
+template <typename TStatsSpec = NoStats, typename TTraits = SeedFinderTraits<>>
+class SeedFinder {
+ public:
+  typedef TTraits traits_type;
+  typedef typename traits_type::graph_type graph_type;
+  typedef typename graph_type::id_type id_type;
+  typedef typename graph_type::offset_type offset_type;
+  typedef typename graph_type::rank_type rank_type;
+  typedef Records<typename traits_type::stringset_type> readsrecord_type;
+  typedef Seed<> output_type;
+  typedef std::function<void(output_type const&)> callback_type;
+  // bulk form: n records of 4 x u64 {node_id, node_offset, read_id, read_offset}, the CLI's byte layout
+  typedef std::function<void(const uint64_t*, uint64_t)> records_callback_type;
+
+  // The device read index of one submitted chunk (the reference builds a lazy
+  // suffix tree here, seed_finder.hpp:1089-1097; the GPU hash is built lazily too).
+  struct readsindex_type {
+    uint64_t serial = 0;
+  };
+
+  // The graph traverser of seeds_off_paths (reference Traverser<...>::Type); the
+  // walk itself runs on the device, this object carries the per-thread pipeline.
+  class traverser_type {
+   public:
+    typedef Seed<> output_type;
+    typedef TraverserStats stats_type;
+    typedef typename traits_type::stringset_type stringset_type;
+    typedef readsindex_type index_type;
+    traverser_type(const graph_type* g, unsigned len) : graph_ptr(g), seed_len(len) {}
+    void set_reads(const readsrecord_type* r) { reads = r; }
+    void set_reads_index(readsindex_type* i) { reads_index = i; }
+    const graph_type* graph_ptr;
+    unsigned seed_len;
+    const readsrecord_type* reads = nullptr;
+    readsindex_type* reads_index = nullptr;
+  };
+
+  // Timers under the reference's names (seed_finder.hpp:427-456): "<finder id><name><thread id>".
+  class stats_type {
+   public:
+    typedef Timer timer_type;
+    explicit stats_type(const SeedFinder* f)
+    {
+      char buf[32];
+      std::snprintf(buf, sizeof buf, "%08llx", (unsigned long long)(reinterpret_cast<uintptr_t>(f) & 0xffffffffull));
+      id = buf;
+    }
+    Timer timeit_ts(const std::string& name) const { return Timer(id + name + get_thread_id()); }
+    Timer::period_type get_timer(const std::string& name) const { return Timer::get(id + name); }
+    Timer::period_type get_timer(const std::string& name, const std::string& tid) const { return Timer::get(id + name + tid); }
+    void set_timer(const std::string& name, double seconds) const { Timer::set(id + name + get_thread_id(), seconds); }
+    static void signal_handler(int) {}
+    std::string id;
+  };
+
+  /* ---- lifecycle ---- */
+  SeedFinder(const graph_type& g, unsigned int len, unsigned int gocc_thr = 0, unsigned int mxmem = 0,
+             unsigned char mismatches = 0, int device = -1)
+      : graph_ptr(&g), seed_len(len), seed_mismatches(mismatches),
+        gocc_threshold(gocc_thr != 0 ? gocc_thr : UINT_MAX), max_mem(mxmem != 0 ? mxmem : UINT_MAX),
+        stats_ptr(std::make_unique<stats_type>(this))
+  {
+    if (mismatches != 0) throw std::runtime_error("approximate seed matching is not implemented");
+    if (gocc_thr != 0) throw std::runtime_error("a seed genome occurrence threshold makes the seed set path dependent; not supported");
+    if (device < 0) {
+      const char* e = std::getenv("PSI_B200_DEVICE");
+      device = e ? std::atoi(e) : 0;
+    }
+    if (psi_b200_create(device, len, &ctx) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
+    upload_graph();
+  }
+  SeedFinder(const SeedFinder&) = delete;
+  SeedFinder& operator=(const SeedFinder&) = delete;
+  ~SeedFinder()
+  {
+    if (host_records) psi_b200_host_free(host_records);
+    if (pathset) psi_b200_pathset_free(pathset);
+    if (ctx) psi_b200_destroy(ctx);
+  }
+
+  /* ---- accessors ---- */
+  const graph_type* get_graph_ptr() const { return graph_ptr; }
+  const std::vector<Position<>>& get_starting_loci() const { return starting_loci; }
+  unsigned int get_seed_len() const { return seed_len; }
+  unsigned char get_seed_mismatches() const { return seed_mismatches; }
+  unsigned int get_gocc_threshold() const { return gocc_threshold; }
+  const stats_type& get_stats() const { return *stats_ptr; }
+  unsigned int get_context() const { return context_; }
+  psi_b200_ctx* get_device_context() const { return ctx; }
+  psi_b200_counters_t get_counters() const
+  {
+    psi_b200_counters_t c;
+    check(psi_b200_counters(ctx, &c));
+    return c;
+  }
+
+  /* ---- mutators ---- */
+  void set_starting_loci(std::vector<Position<>> loci)
+  {
+    starting_loci = std::move(loci);
+    push_loci();
+  }
+  void add_start(const Position<>& locus) { starting_loci.push_back(locus); loci_dirty = true; }
+  void add_start(id_type node_id, offset_type offset) { add_start(Position<>(node_id, offset)); }
+
+  readsrecord_type create_readrecord() const { return readsrecord_type(); }
+  traverser_type create_traverser() const { return traverser_type(graph_ptr, seed_len); }
+  void setup_traverser(traverser_type& t, readsrecord_type const& reads, readsindex_type& idx) const
+  {
+    t.set_reads(&reads);
+    t.set_reads_index(&idx);
+  }
+
+  /* ---- path index ---- */
+  void pick_paths(unsigned int n, bool patched = true, unsigned int context = 0,
+                  std::function<void(std::string const&, int)> callback = nullptr,
+                  std::function<void(std::string const&)> info = nullptr,
+                  std::function<void(std::string const&)> warn = nullptr)
+  {
+    if (n == 0) return;
+    if (graph_ptr->get_path_count() == 0) throw std::runtime_error("no reference path found in the input graph");
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("pick-paths");
+    context_ = set_context(context, patched, info, warn);
+    if (callback)
+      graph_ptr->for_each_path([&](rank_type, id_type pid) {
+        for (unsigned i = 0; i < n; ++i) callback(graph_ptr->path_name(pid), (int)i + 1);
+        return true;
+      });
+    if (pathset) { psi_b200_pathset_free(pathset); pathset = nullptr; }
+    uint64_t seed = 0x9e3779b97f4a7c15ull;
+    if (const char* e = std::getenv("PSI_B200_PATH_SEED")) seed = std::strtoull(e, nullptr, 10);
+    if (psi_b200_pick_paths(graph_ptr->handle(), n, patched ? 1 : 0, context_, seed, &pathset) != PSI_B200_OK)
+      throw std::runtime_error(psi_b200_global_error());
+  }
+
+  void index_paths()
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("index-paths");
+    if (!pathset) return;
+    psi_b200_pathset_view v;
+    if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
+    check(psi_b200_set_paths(ctx, v.n_paths, v.path_ptr, v.nodes, v.head_off, v.tail_trim));
+    has_index = v.n_paths != 0;
+  }
+
+  void add_uncovered_loci(unsigned int step = 1)
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("find-uncovered");
+    uint64_t n = 0;
+    check(psi_b200_find_loci(ctx, step, &n));
+    pull_loci(n);
+  }
+
+  template <typename TDIndexMode = PerComponent>
+  void create_path_index(unsigned int n, bool patched = true, unsigned int context = 0, unsigned int step_size = 1,
+                         unsigned int dmin = 0, unsigned int dmax = 0, TDIndexMode = {},
+                         std::function<void(std::string const&)> info = nullptr,
+                         std::function<void(std::string const&)> warn = nullptr)
+  {
+    std::function<void(std::string const&, int)> progress = nullptr;
+    if (info) progress = [&info](std::string const& name, int i) {
+      info("Selecting path " + std::to_string(i) + " of region " + name + "...");
+    };
+    pick_paths(n, patched, context, progress, info, warn);
+    if (info) info("Indexing the selected paths...");
+    index_paths();
+    if (info) info("Detecting uncovered loci...");
+    add_uncovered_loci(step_size);
+    if (info) info("Constructing distance index for pair distance queries...");
+    create_distance_index(dmin, dmax);
+  }
+
+  // files: <prefix>_paths.b200 (picked paths; the device index is rebuilt from them at load) and
+  // <prefix>_loci_e<step>l<k> in the reference's own byte format (seed_finder.hpp:884-892,1659-1679).
+  bool serialize_path_index(std::string const& fpath, unsigned int step_size = 1)
+  {
+    if (fpath.empty() || !pathset) return false;
+    {
+      [[maybe_unused]] auto timer = stats_ptr->timeit_ts("save-pindex");
+      psi_b200_pathset_view v;
+      if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) return false;
+      std::ofstream ofs(fpath + "_paths.b200", std::ofstream::binary);
+      if (!ofs) return false;
+      const uint64_t hdr[4] = { PATHS_MAGIC, context_, v.n_paths, v.path_ptr[v.n_paths] };
+      ofs.write(reinterpret_cast<const char*>(hdr), sizeof hdr);
+      ofs.write(reinterpret_cast<const char*>(v.path_ptr), (v.n_paths + 1) * sizeof(uint64_t));
+      // node ranks are stable for a given graph file (the load order is deterministic)
+      ofs.write(reinterpret_cast<const char*>(v.nodes), v.path_ptr[v.n_paths] * sizeof(uint32_t));
+      ofs.write(reinterpret_cast<const char*>(v.head_off), v.n_paths * sizeof(uint32_t));
+      ofs.write(reinterpret_cast<const char*>(v.tail_trim), v.n_paths * sizeof(uint32_t));
+      if (!ofs) return false;
+    }
+    return save_starts(fpath, seed_len, step_size);
+  }
+
+  bool load_path_index(std::string const& fpath, unsigned int context = 0, unsigned int step_size = 1,
+                       unsigned int dmin = 0, unsigned int dmax = 0)
+  {
+    if (fpath.empty()) return false;
+    {
+      [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-pindex");
+      std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary);
+      if (!ifs) return false;
+      uint64_t hdr[4];
+      ifs.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+      if (!ifs || hdr[0] != PATHS_MAGIC) return false;
+      std::vector<uint64_t> path_ptr(hdr[2] + 1);
+      std::vector<uint32_t> nodes(hdr[3]), head(hdr[2]), tail(hdr[2]);
+      ifs.read(reinterpret_cast<char*>(path_ptr.data()), path_ptr.size() * sizeof(uint64_t));
+      ifs.read(reinterpret_cast<char*>(nodes.data()), nodes.size() * sizeof(uint32_t));
+      ifs.read(reinterpret_cast<char*>(head.data()), head.size() * sizeof(uint32_t));
+      ifs.read(reinterpret_cast<char*>(tail.data()), tail.size() * sizeof(uint32_t));
+      if (!ifs || path_ptr.back() != nodes.size()) return false;
+      for (uint32_t r : nodes) if (r >= graph_ptr->get_node_count()) return false;
+      context_ = context ? context : (unsigned)hdr[1];
+      check(psi_b200_set_paths(ctx, hdr[2], path_ptr.data(), nodes.data(), head.data(), tail.data()));
+      has_index = hdr[2] != 0;
+    }
+    if (!open_starts(fpath, seed_len, step_size)) {
+      add_uncovered_loci(step_size);
+      save_starts(fpath, seed_len, step_size);
+    }
+    create_distance_index(dmin, dmax);
+    return true;
+  }
+
+  static std::string get_sloci_filepath(const std::string& prefix, unsigned int seed_len, unsigned int step_size)
+  {
+    return prefix + "_loci_e" + std::to_string(step_size) + "l" + std::to_string(seed_len);
+  }
+
+  bool open_starts(const std::string& prefix, unsigned int len, unsigned int step_size)
+  {
+    std::ifstream ifs(get_sloci_filepath(prefix, len, step_size), std::ifstream::binary);
+    if (!ifs) return false;
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-starts");
+    uint64_t n = 0;
+    ifs.read(reinterpret_cast<char*>(&n), sizeof n);
+    if (!ifs) return false;
+    std::unordered_map<int64_t, int64_t> by_coord;   // external id -> internal id
+    const psi_b200_graph_view& v = graph_ptr->view();
+    for (uint64_t r = 0; r < v.n_nodes; ++r) by_coord.emplace((int64_t)v.coord_id[r], (int64_t)v.internal_id[r]);
+    std::vector<Position<>> loci;
+    loci.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      int64_t id; uint64_t off;
+      ifs.read(reinterpret_cast<char*>(&id), sizeof id);
+      ifs.read(reinterpret_cast<char*>(&off), sizeof off);
+      if (!ifs) return false;
+      auto it = by_coord.find(id);
+      if (it == by_coord.end()) return false;
+      loci.emplace_back(it->second, off);
+    }
+    set_starting_loci(std::move(loci));
+    return true;
+  }
+
+  bool save_starts(const std::string& prefix, unsigned int len, unsigned int step_size)
+  {
+    std::ofstream ofs(get_sloci_filepath(prefix, len, step_size), std::ofstream::binary);
+    if (!ofs) return false;
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("save-starts");
+    const uint64_t n = starting_loci.size();
+    ofs.write(reinterpret_cast<const char*>(&n), sizeof n);
+    for (const auto& l : starting_loci) {   // external (coordinate) ids on disk, as the reference writes them
+      const int64_t id = graph_ptr->coordinate_id(l.node_id());
+      const uint64_t off = l.offset();
+      ofs.write(reinterpret_cast<const char*>(&id), sizeof id);
+      ofs.write(reinterpret_cast<const char*>(&off), sizeof off);
+    }
+    return (bool)ofs;
+  }
+
+  std::size_t get_nof_uniq_nodes()
+  {
+    std::unordered_set<id_type> set;
+    for (const auto& l : starting_loci) set.insert(l.node_id());
+    return set.size();
+  }
+
+  /* ---- per chunk ---- */
+  // seeding(): seeds at offsets 0, d, 2d, ... of every read (sequence.hpp:1688-1745).  Uploads the
+  // chunk and packs the seeds on the device; `seeds` becomes a view of `reads`.
+  template <typename T>
+  void get_seeds(readsrecord_type& seeds, readsrecord_type const& reads, T distance) const
+  {
+    auto timer = stats_ptr->timeit_ts("seeding");
+    seeds = reads;
+    seeds.seed_len = seed_len;
+    seeds.distance = distance ? (unsigned)distance : seed_len;
+    seeds.serial = ++serial;
+    check(psi_b200_submit_chunk(ctx, reads.n_reads, reads.read_ptr, reads.bases, reads.rec_offset, seeds.distance));
+    timer.stop();
+  }
+
+  readsindex_type index_reads(readsrecord_type const& seeds) const
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("index-reads");
+    return readsindex_type{ seeds.serial };
+  }
+
+  void seeds_on_paths(readsrecord_type const& seeds, readsindex_type& reads_index, callback_type callback) const
+  {
+    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
+    if (!has_index) return;
+    run(seeds, reads_index, PSI_B200_ON_PATHS, "seeds-on-paths", callback, nullptr);
+  }
+
+  void seeds_off_paths(traverser_type& traverser, callback_type callback) const
+  {
+    if (!traverser.reads || !traverser.reads_index) throw std::runtime_error("traverser is not set up (setup_traverser)");
+    sync_loci();
+    if (starting_loci.empty()) return;
+    run(*traverser.reads, *traverser.reads_index, PSI_B200_OFF_PATHS, "seeds-off-path", callback, nullptr);
+  }
+
+  void seeds_all(readsrecord_type const& seeds, readsindex_type& reads_index, traverser_type& traverser,
+                 callback_type callback) const
+  {
+    seeds_all(seeds, reads_index, traverser, callback, callback);
+  }
+
+  // callback1 receives the hits found on the indexed paths, callback2 the rest (seed_finder.hpp:1734-1743).
+  void seeds_all(readsrecord_type const& seeds, readsindex_type& reads_index, traverser_type& traverser,
+                 callback_type callback1, callback_type callback2) const
+  {
+    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
+    setup_traverser(traverser, seeds, reads_index);
+    sync_loci();
+    run(seeds, reads_index, PSI_B200_ALL, nullptr, callback1, callback2);
+  }
+
+  // Bulk variant used by the CLI: one call per chunk with all records in the output byte layout.
+  void seeds_all_records(readsrecord_type const& seeds, readsindex_type& reads_index, records_callback_type cb) const
+  {
+    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
+    sync_loci();
+    check_serial(seeds, reads_index);
+    uint64_t n = 0;
+    check(psi_b200_seeds_all(ctx, PSI_B200_ALL, &n));
+    fetch(n);
+    account();
+    if (cb) cb(host_records, n);
+  }
+
+ private:
+  static constexpr uint64_t PATHS_MAGIC = 0x3130736874617042ull;  // "Bpaths01"
+
+  void check(int rc) const
+  {
+    if (rc != PSI_B200_OK) throw std::runtime_error(psi_b200_last_error(ctx));
+  }
+
+  void upload_graph()
+  {
+    const psi_b200_graph_view& v = graph_ptr->view();
+    if (graph_ptr->get_node_count() == 0) throw std::runtime_error("empty graph");
+    check(psi_b200_set_graph(ctx, v.n_nodes, v.seq_start, v.seq, v.row_ptr, v.col, v.internal_id));
+  }
+
+  unsigned int set_context(unsigned int context, bool patched, std::function<void(std::string const&)> = nullptr,
+                           std::function<void(std::string const&)> warn = nullptr)
+  {
+    if (!patched) context = 0;
+    if (patched && context == 0) {
+      if (warn) warn("The context size cannot be zero for patching. Assuming the seed length as the context size...");
+      context = seed_len;
+    }
+    return context;
+  }
+
+  void create_distance_index(unsigned int dmin, unsigned int dmax)
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("index-distances");
+    if (dmin == 0 && dmax == 0) return;   // reference: no-op when dmin == 0 (seed_finder.hpp:1198)
+    throw std::runtime_error("the paired-end distance index is outside this build's scope (use -m 0 -M 0)");
+  }
+
+  void pull_loci(uint64_t n)
+  {
+    std::vector<uint32_t> node(n), off(n);
+    uint64_t got = 0;
+    check(psi_b200_get_loci(ctx, node.data(), off.data(), n, &got));
+    const psi_b200_graph_view& v = graph_ptr->view();
+    starting_loci.clear();
+    starting_loci.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) starting_loci.emplace_back((int64_t)v.internal_id[node[i]], off[i]);
+    loci_dirty = false;
+  }
+
+  void push_loci() const
+  {
+    std::vector<uint32_t> node(starting_loci.size()), off(starting_loci.size());
+    for (size_t i = 0; i < starting_loci.size(); ++i) {
+      node[i] = (uint32_t)(graph_ptr->id_to_rank(starting_loci[i].node_id()) - 1);
+      off[i] = (uint32_t)starting_loci[i].offset();
+    }
+    check(psi_b200_set_loci(ctx, node.size(), node.data(), off.data()));
+    loci_dirty = false;
+  }
+  void sync_loci() const { if (loci_dirty) push_loci(); }
+
+  void check_serial(readsrecord_type const& seeds, readsindex_type const& idx) const
+  {
+    if (seeds.serial == 0 || seeds.serial != serial || idx.serial != seeds.serial)
+      throw std::runtime_error("seeds do not belong to the chunk last given to get_seeds()");
+  }
+
+  void fetch(uint64_t n) const
+  {
+    if (n > host_cap) {
+      if (host_records) psi_b200_host_free(host_records);
+      host_cap = n + n / 4 + 1024;
+      void* p = nullptr;
+      if (psi_b200_host_alloc(&p, host_cap * 32) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
+      host_records = static_cast<uint64_t*>(p);
+    }
+    uint64_t got = 0;
+    if (n) check(psi_b200_fetch(ctx, host_records, n, &got));
+  }
+
+  void account() const
+  {
+    psi_b200_counters_t c;
+    check(psi_b200_counters(ctx, &c));
+    TraverserStats::seeds_off_paths() += c.n_hits_off;
+    TraverserStats::nof_godowns() += c.n_walks;
+    last_on = c.n_hits_on;
+    stats_ptr->set_timer("seeds-on-paths", (c.ms_on) * 1e-3);
+    stats_ptr->set_timer("seeds-off-paths", (c.ms_read_index + c.ms_off) * 1e-3);
+    stats_ptr->set_timer("seeds-off-path", (c.ms_read_index + c.ms_off) * 1e-3);
+    stats_ptr->set_timer("query-dindex", 0.0);
+  }
+
+  void run(readsrecord_type const& seeds, readsindex_type const& idx, unsigned flags, const char* timer_name,
+           const callback_type& cb1, const callback_type& cb2) const
+  {
+    check_serial(seeds, idx);
+    auto timer = timer_name ? std::make_unique<Timer>(stats_ptr->timeit_ts(timer_name)) : nullptr;
+    uint64_t n = 0;
+    check(psi_b200_seeds_all(ctx, flags, &n));
+    fetch(n);
+    account();
+    // records are on-path hits first, then off-path hits
+    Seed<> hit;
+    hit.match_len = seed_len;
+    hit.gocc = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t* r = host_records + 4 * i;
+      hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
+      const callback_type& cb = (cb2 && i >= last_on) ? cb2 : cb1;
+      if (cb) cb(hit);
+    }
+  }
+
+  const graph_type* graph_ptr;
+  std::vector<Position<>> starting_loci;
+  unsigned int seed_len;
+  unsigned char seed_mismatches;
+  unsigned int gocc_threshold;
+  unsigned int max_mem;
+  unsigned int context_ = 0;
+  std::unique_ptr<stats_type> stats_ptr;
+  psi_b200_ctx* ctx = nullptr;
+  psi_b200_pathset* pathset = nullptr;
+  bool has_index = false;
+  mutable bool loci_dirty = false;
+  mutable uint64_t serial = 0;
+  mutable uint64_t* host_records = nullptr;
+  mutable uint64_t host_cap = 0;
+  mutable uint64_t last_on = 0;
+};
+
+}  // namespace psi
+#endif

@@ -1,0 +1,107 @@
+// Test driver for the psi::SeedFinder mirror (psi_b200/include/psi/seed_finder.hpp): it makes the
+// calls find_seeds() of the reference CLI makes (reference src/psikt.cpp:83-212), once with
+// seeds_on_paths + seeds_off_paths and separate callbacks, once with seeds_all, and dumps the hits
+// as 4 x u64 {read_id, read_offset, node_id (coordinate), node_offset} for the python side to compare
+// with the oracle.  Usage: driver GFA READS K D N_PATHS CHUNK OUT_PREFIX
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../psi_b200/include/psi/seed_finder.hpp"
+
+using namespace psi;
+
+static void dump(const std::string& path, const std::vector<uint64_t>& v)
+{
+  std::FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) { std::perror("fopen"); std::exit(2); }
+  if (!v.empty() && std::fwrite(v.data(), 8, v.size(), f) != v.size()) { std::perror("fwrite"); std::exit(2); }
+  std::fclose(f);
+}
+
+template <typename F>
+static bool throws_runtime_error(F f, const std::string& needle)
+{
+  try { f(); }
+  catch (const std::runtime_error& e) { return std::string(e.what()).find(needle) != std::string::npos; }
+  return false;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc < 8) { std::fprintf(stderr, "usage: %s GFA READS K D N_PATHS CHUNK OUT_PREFIX\n", argv[0]); return 2; }
+  const std::string gfa = argv[1], reads_path = argv[2], out = argv[7];
+  const unsigned k = std::atoi(argv[3]), d = std::atoi(argv[4]), n_paths = std::atoi(argv[5]);
+  const unsigned long chunk_size = std::strtoul(argv[6], nullptr, 10);
+
+  typedef SeedFinderTraits<gum::Succinct, Dna5QStringSet<>, seqan2::IndexWotd<>, InMemory> traits_type;
+  typedef SeedFinder<NoStats, traits_type> finder_type;
+
+  gum::SeqGraph<gum::Succinct> graph;
+  gum::util::load(graph, gfa, true);
+  finder_type finder(graph, k);
+  std::vector<std::string> infos;
+  finder.create_path_index(n_paths, true, 0, 1, 0, 0, PerComponent{}, [&](std::string const& m) { infos.push_back(m); },
+                           [&](std::string const& m) { infos.push_back("W:" + m); });
+
+  std::vector<uint64_t> on, off, all1, all2;
+  auto push = [&graph](std::vector<uint64_t>& v) {
+    return [&v, &graph](Seed<> const& h) {
+      v.push_back(h.read_id); v.push_back(h.read_offset);
+      v.push_back((uint64_t)graph.coordinate_id((int64_t)h.node_id)); v.push_back(h.node_offset);
+    };
+  };
+  klibpp::SeqStreamIn iss(reads_path.c_str());
+  if (!iss) { std::fprintf(stderr, "cannot open reads\n"); return 2; }
+  auto chunk = finder.create_readrecord();
+  auto seeds = finder.create_readrecord();
+  auto traverser = finder.create_traverser();
+  unsigned long n_chunks = 0, n_reads = 0;
+  while (readRecords(chunk, iss, chunk_size)) {
+    ++n_chunks;
+    n_reads += length(chunk);
+    finder.get_seeds(seeds, chunk, d);
+    auto index = finder.index_reads(seeds);
+    finder.seeds_on_paths(seeds, index, push(on));
+    finder.setup_traverser(traverser, seeds, index);
+    finder.seeds_off_paths(traverser, push(off));
+    finder.seeds_all(seeds, index, traverser, push(all1), push(all2));
+  }
+  dump(out + ".on", on);
+  dump(out + ".off", off);
+  dump(out + ".all1", all1);
+  dump(out + ".all2", all2);
+
+  // starting loci as (coordinate id, offset)
+  std::vector<uint64_t> loci;
+  for (auto const& l : finder.get_starting_loci()) { loci.push_back((uint64_t)graph.coordinate_id(l.node_id())); loci.push_back(l.offset()); }
+  dump(out + ".loci", loci);
+
+  // error behaviour of the reference API
+  bool ok = true;
+  {  // patched with a context shorter than the seed: seeds_on_paths must throw (seed_finder.hpp:1434-1437)
+    finder_type f2(graph, k);
+    f2.create_path_index(1, true, k - 1);
+    klibpp::SeqStreamIn iss2(reads_path.c_str());
+    auto c2 = f2.create_readrecord();
+    auto s2 = f2.create_readrecord();
+    readRecords(c2, iss2, 10);
+    f2.get_seeds(s2, c2, d);
+    auto i2 = f2.index_reads(s2);
+    ok &= throws_runtime_error([&] { f2.seeds_on_paths(s2, i2, [](Seed<> const&) {}); }, "seed length should not be larger than context size");
+    // seeds of an older submission are rejected instead of silently using the newer chunk
+    auto s3 = f2.create_readrecord();
+    f2.get_seeds(s3, c2, d);
+    ok &= throws_runtime_error([&] { f2.seeds_all_records(s2, i2, nullptr); }, "do not belong");
+  }
+  ok &= throws_runtime_error([&] { finder_type f3(graph, 33); }, "seed length");
+  ok &= throws_runtime_error([&] { finder_type f4(graph, k, 0, 0, 1); }, "approximate");
+  ok &= throws_runtime_error([&] { finder_type f5(graph, k); f5.create_path_index(1, true, 0, 1, 100, 300); }, "distance index");
+  std::printf("{\"chunks\": %lu, \"reads\": %lu, \"loci\": %zu, \"uniq_nodes\": %zu, \"on\": %zu, \"off\": %zu, \"all1\": %zu, \"all2\": %zu, "
+              "\"infos\": %zu, \"errors_ok\": %s}\n",
+              n_chunks, n_reads, finder.get_starting_loci().size(), finder.get_nof_uniq_nodes(), on.size() / 4, off.size() / 4,
+              all1.size() / 4, all2.size() / 4, infos.size(), ok ? "true" : "false");
+  return ok ? 0 : 1;
+}

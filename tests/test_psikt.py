@@ -1,0 +1,205 @@
+"""The reference-facing C++ layer: psi::SeedFinder (psi_b200/include/psi/seed_finder.hpp) and the
+psikt CLI (psi_b200/src/psikt.cpp).  CPU tests cover option parsing, help text and the loud
+failure without a device; GPU tests drive the CLI and the API the way the reference's
+find_seeds() does (reference src/psikt.cpp:83-212) and compare bit-exactly with the goldens."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import util
+from psi_b200 import capi
+
+ROOT = util.ROOT
+PSIKT = ROOT / "psi_b200" / "bin" / "psikt"
+DRIVER_SRC = ROOT / "tests" / "cpp" / "seed_finder_driver.cpp"
+DRIVER = ROOT / "tests" / "cpp" / "build" / "seed_finder_driver"
+G = {c["name"]: c for c in util.golden_index()["cases"]}
+
+
+def run(cmd, **kw):
+    return subprocess.run([os.fspath(c) for c in cmd], capture_output=True, text=True, timeout=600, **kw)
+
+
+def build_driver():
+    if DRIVER.exists() and DRIVER.stat().st_mtime > DRIVER_SRC.stat().st_mtime:
+        return
+    DRIVER.parent.mkdir(exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", os.fspath(DRIVER), os.fspath(DRIVER_SRC),
+                    "-L" + os.fspath(ROOT / "psi_b200"), "-lpsi_b200", "-Wl,-rpath," + os.fspath(ROOT / "psi_b200")], check=True)
+
+
+def gunzip_to(src, dst):
+    import gzip
+    with gzip.open(src, "rb") as f, open(dst, "wb") as o:
+        o.write(f.read())
+    return dst
+
+
+# ------------------------------------------------------------------ CPU --
+
+def test_psikt_exists_and_help_lists_the_reference_option_table():
+    assert PSIKT.exists(), "psi_b200/bin/psikt missing: run __graft_entry__.build()"
+    r = run([PSIKT, "--help"])
+    assert r.returncode == 0
+    # reference src/psikt.cpp:306-435
+    for short, long_ in [("f", "fastq"), ("o", "output"), ("I", "path-index"), ("l", "seed-length"), ("c", "chunk-size"),
+                         ("e", "step-size"), ("d", "distance"), ("n", "path-num"), ("P", "no-patched"), ("t", "context"),
+                         ("r", "gocc-threshold"), ("E", "max-mem"), ("m", "min-insert-size"), ("M", "max-insert-size"),
+                         ("i", "index"), ("x", "index-only"), ("L", "log-file"), ("Q", "no-log-file"), ("q", "quiet"),
+                         ("C", "no-color"), ("D", "disable-log"), ("v", "verbose")]:
+        assert f"-{short}, --{long_}" in r.stdout, long_
+    assert "--dindex-mode" in r.stdout
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-l", "12", "g.gfa"], "--fastq is required"),
+    (["-f", "r.fq", "g.gfa"], "--seed-length is required"),
+    (["-f", "r.fq", "-l", "12"], "Not enough arguments"),
+    (["-f", "r.fq", "-l", "12", "a.gfa", "b.gfa"], "Too many arguments"),
+    (["-f", "r.fq", "-l", "twelve", "g.gfa"], "cannot be casted to integer"),
+    (["-f", "r.fq", "-l", "12", "g.txt"], "invalid file extension"),
+    (["-f", "r.txt", "-l", "12", "g.gfa"], "invalid file extension"),
+    (["-f", "r.fq", "-l", "12", "-i", "BWT", "g.gfa"], "Undefined index type"),
+    (["-f", "r.fq", "-l", "12", "--dindex-mode", "fast", "g.gfa"], "allowed values"),
+    (["-f", "r.fq", "-l", "12", "--bogus", "g.gfa"], "unknown option"),
+])
+def test_psikt_argument_errors_exit_1(args, msg):
+    r = run([PSIKT] + args)
+    assert r.returncode == 1
+    assert msg in r.stderr
+
+
+def test_psikt_missing_inputs_fail_with_the_reference_messages(tmp_path):
+    gfa = gunzip_to(util.GOLDEN / "inputs/tiny.gfa.gz", tmp_path / "tiny.gfa")
+    r = run([PSIKT, "-f", tmp_path / "nope.fq", "-l", "10", "-Q", "-q", "-o", tmp_path / "o", gfa])
+    assert r.returncode == 1 and "could not open file" in r.stderr
+    r = run([PSIKT, "-f", util.GOLDEN / "inputs/reads_n10l10e0i0.fa", "-l", "10", "-Q", "-q", "-o", tmp_path / "o", tmp_path / "missing.gfa"])
+    assert r.returncode == 1 and "could not open" in r.stderr
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="checks the failure mode of a box without a GPU")
+def test_psikt_fails_loudly_without_a_gpu(tmp_path):
+    gfa = gunzip_to(util.GOLDEN / "inputs/tiny.gfa.gz", tmp_path / "tiny.gfa")
+    r = run([PSIKT, "-f", util.GOLDEN / "inputs/reads_n10l10e0i0.fa", "-l", "10", "-n", "2", "-Q", "-q", "-o", tmp_path / "o", gfa])
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr
+
+
+def test_mirror_headers_compile_standalone(tmp_path):
+    """The SeedFinder mirror is host C++17 over the C-ABI only: it must compile with g++ alone."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "%s"\nint main() { return sizeof(psi::SeedFinder<>) > 0 ? 0 : 1; }\n'
+                   % os.fspath(ROOT / "psi_b200/include/psi/seed_finder.hpp"))
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", os.fspath(src)], check=True)
+
+
+# ------------------------------------------------------------------ GPU --
+
+def load_psikt_output(path, g):
+    rec = np.fromfile(path, dtype="<u8").reshape(-1, 4)
+    # psikt writes gum's internal ids: map back to the coordinate ids of the goldens
+    order = np.argsort(g.internal_id)
+    idx = order[np.searchsorted(g.internal_id[order], rec[:, 0])]
+    assert np.array_equal(g.internal_id[idx], rec[:, 0])
+    rec = rec.copy()
+    rec[:, 0] = g.coord_id[idx]
+    return rec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra", [("x_k12", []), ("x_k20_c1000", ["-c", "1000"]), ("multi_k32", ["-c", "2500"]),
+                                        ("x_k20_d1", []), ("m_k20", ["-P"])])
+def test_psikt_output_is_the_reference_seed_set(tmp_path, name, extra):
+    c = G[name]
+    gfa = gunzip_to(util.GOLDEN / c["gfa"], tmp_path / "g.gfa") if c["gfa"].endswith(".gz") else util.GOLDEN / c["gfa"]
+    reads = util.GOLDEN / c["reads"]
+    if not any(str(reads).endswith(e) for e in (".fa", ".fa.gz", ".fq", ".fq.gz", ".fasta", ".fastq")):
+        pytest.skip("reads extension")
+    out, log = tmp_path / "seeds.bin", tmp_path / "psi.log"
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-d", c["d"], "-n", c["n_paths"], "-o", out, "-L", log, "-q"] + extra + [gfa])
+    assert r.returncode == 0, r.stderr
+    g = capi.Graph.load_gfa(gfa)
+    rec = load_psikt_output(out, g)
+    got = capi.canonical(rec)
+    assert len(rec) == len(got) == c["count"], "psikt writes each hit of the set exactly once"
+    assert util.md5_tuples(got) == c["md5"]
+    text = log.read_text()
+    for line in ["Parameters:", "- Seed length: %d" % c["k"], "Loading input graph from file", "Number of starting loci (in ",
+                 "Finding seeds...", "Fetched ", "Seeding done in ", "Found seeds on paths in ", "Found seeds off paths in ",
+                 "Total number of seeds found: %d" % c["count"], "-> of which found off paths: ", "Total number of reads covered: ",
+                 "Total number of 'godown' operations: ", "All Timers"]:
+        assert line in text, line
+    covered = len(np.unique(got[:, 0]))
+    assert "Total number of reads covered: %d" % covered in text
+
+
+@pytest.mark.gpu
+def test_psikt_saved_path_index_is_reloaded(tmp_path):
+    c = G["x_k12"]
+    gfa = gunzip_to(util.GOLDEN / c["gfa"], tmp_path / "g.gfa")
+    reads = util.GOLDEN / c["reads"]
+    prefix = tmp_path / "idx"
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-n", "4", "-I", prefix, "-x", "-L", tmp_path / "a.log", "-q", "-o", tmp_path / "o0", gfa])
+    assert r.returncode == 0, r.stderr
+    assert "Skipping seed finding as requested" in (tmp_path / "a.log").read_text()
+    loci_file = Path(str(prefix) + "_loci_e1l%d" % c["k"])
+    assert Path(str(prefix) + "_paths.b200").exists() and loci_file.exists()
+    # the loci file has the reference's byte layout: u64 count, then {i64 coordinate id, u64 offset} (seed_finder.hpp:1659-1679)
+    raw = np.fromfile(loci_file, dtype="<u8")
+    assert raw[0] == (len(raw) - 1) // 2
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-I", prefix, "-L", tmp_path / "b.log", "-q", "-o", tmp_path / "o1", gfa])
+    assert r.returncode == 0, r.stderr
+    text = (tmp_path / "b.log").read_text()
+    assert "The path index has been found and loaded." in text
+    g = capi.Graph.load_gfa(gfa)
+    got = capi.canonical(load_psikt_output(tmp_path / "o1", g))
+    assert util.md5_tuples(got) == c["md5"]
+    # -n 0 and no index: nothing is found (src/psikt.cpp:121-123)
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-L", tmp_path / "c.log", "-q", "-o", tmp_path / "o2", gfa])
+    assert r.returncode == 0
+    assert os.path.getsize(tmp_path / "o2") == 0
+    assert "No path has been specified. Skipping path indexing..." in (tmp_path / "c.log").read_text()
+
+
+@pytest.mark.gpu
+def test_psikt_graph_without_embedded_path_is_an_error(tmp_path):
+    gfa = tmp_path / "nopath.gfa"
+    gfa.write_text("H\tVN:Z:1.0\nS\t1\tACGTACGTACGTAAACCCGGGTTT\nS\t2\tACGT\nL\t1\t+\t2\t+\t0M\n")
+    r = run([PSIKT, "-f", util.GOLDEN / "inputs/reads_n10l10e0i0.fa", "-l", "10", "-n", "2", "-Q", "-q", "-o", tmp_path / "o", gfa])
+    assert r.returncode == 1
+    assert "no reference path found in the input graph" in r.stderr      # seed_finder.hpp:1145-1147
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,chunk", [("x_k12", 0), ("m_k20", 700), ("fuzz_03", 150)])
+def test_seed_finder_api_matches_oracle(tmp_path, name, chunk):
+    from oracle import oracle_py as orc
+    build_driver()
+    c = G[name]
+    gfa = gunzip_to(util.GOLDEN / c["gfa"], tmp_path / "g.gfa") if c["gfa"].endswith(".gz") else util.GOLDEN / c["gfa"]
+    r = run([DRIVER, gfa, util.GOLDEN / c["reads"], c["k"], c["d"], c["n_paths"], chunk, tmp_path / "out"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["errors_ok"] and info["infos"] >= 4
+
+    def load(ext):
+        return np.fromfile(str(tmp_path / "out") + ext, dtype="<u8").reshape(-1, 4)
+    on, off, all1, all2 = load(".on"), load(".off"), load(".all1"), load(".all2")
+    for part in (on, off, all1, all2):
+        assert len(np.unique(part, axis=0)) == len(part), "callbacks see each hit once"
+    sep = np.unique(np.concatenate([on, off]), axis=0)
+    both = np.unique(np.concatenate([all1, all2]), axis=0)
+    assert len(sep) == len(on) + len(off) == c["count"]
+    assert util.md5_tuples(sep) == c["md5"] == util.md5_tuples(both)
+    # seeds_all hands the on-path hits to callback1 and the rest to callback2 (seed_finder.hpp:1734-1743)
+    assert np.array_equal(np.unique(on, axis=0), np.unique(all1, axis=0))
+    assert np.array_equal(np.unique(off, axis=0), np.unique(all2, axis=0))
+    g = capi.Graph.load_gfa(gfa)
+    loci = np.fromfile(str(tmp_path / "out") + ".loci", dtype="<u8").reshape(-1, 2)
+    assert info["loci"] == len(loci) and info["uniq_nodes"] == len(np.unique(loci[:, 0]))
+    assert set(loci[:, 0].tolist()) <= set(g.coord_id.tolist())
