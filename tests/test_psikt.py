@@ -22,7 +22,7 @@ G = {c["name"]: c for c in util.golden_index()["cases"]}
 
 
 def run(cmd, **kw):
-    return subprocess.run([os.fspath(c) for c in cmd], capture_output=True, text=True, timeout=600, **kw)
+    return subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=600, **kw)
 
 
 def build_driver():
