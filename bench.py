@@ -31,6 +31,11 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, os.fspath(ROOT))
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one seeds_on_paths launch on this workload from the
+# last `ncu --set full` capture (see profiles/); None until a capture of the current kernel exists.
+TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_SOURCE = None
+
 K = 20
 READ_LEN = 100
 READS_PER_BATCH = 1_000_000
@@ -207,6 +212,7 @@ def main_gpu(args):
     g = build_graph(args.shape)
     ps = g.pick_paths(N_PATHS, seed=1)
     ctx = capi.Context(K, local)
+    ctx.set_option("offpath_mode", args.offpath_mode)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_graph(g, ids="internal")
     ctx.set_paths(ps)
@@ -215,7 +221,8 @@ def main_gpu(args):
     if rank == 0:
         log(f"[bench] graph {g.n_nodes} nodes / {g.n_bases} bp; index {c0['n_index_kmers']} k-mers, "
             f"{c0['index_bytes'] / 1e6:.0f} MB, slot {c0['index_slot_bytes']} B, build {c0['ms_index_build']:.0f} ms; "
-            f"{n_loci} starting loci in {c0['ms_find_loci']:.0f} ms; setup {time.time() - t0:.1f} s")
+            f"{n_loci} starting loci, {c0['n_offpath_walks']} uncovered walks -> {c0['n_offpath_entries']} off-path entries "
+            f"(mode {c0['offpath_mode']}) in {c0['ms_find_loci']:.0f} ms; setup {time.time() - t0:.1f} s")
 
     # distinct read batches per rank (weak scaling: every GPU processes its own shard of the read set)
     n_reads = args.reads
@@ -226,7 +233,11 @@ def main_gpu(args):
         hb = torch.from_numpy(bases).pin_memory()
         batches_h.append((hp, hb))
         batches_d.append((hp.to(dev), hb.to(dev)))
-    rec_host = torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory()   # room for the seed records
+    # e2e runs two pipelines (the context and a fork sharing its resident index) from two host threads, so that
+    # the upload of one batch overlaps the kernels and the download of the previous one (PCIe is full duplex)
+    n_pipes = max(1, args.pipelines)
+    pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
+    rec_hosts = [torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory() for _ in range(n_pipes)]   # room for the seed records
     torch.cuda.synchronize()
 
     def step_device(i):
@@ -234,11 +245,47 @@ def main_gpu(args):
         ctx.submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
         return ctx.seeds_all(capi.ALL)
 
-    def step_e2e(i):
+    def step_e2e(i, p=0):
         hp, hb = batches_h[i % N_BATCHES]
-        ctx.submit_chunk_ptr(n_reads, hp.data_ptr(), hb.data_ptr(), rank * n_reads, K)
-        ctx.seeds_all(capi.ALL)
-        return ctx.fetch_into(rec_host.data_ptr(), rec_host.shape[0])
+        cx, rec_host = pipes[p], rec_hosts[p]
+        cx.submit_chunk_ptr(n_reads, hp.data_ptr(), hb.data_ptr(), rank * n_reads, K)
+        cx.seeds_all(capi.ALL)
+        return cx.fetch_into(rec_host.data_ptr(), rec_host.shape[0])
+
+    def timed_e2e(steps, warmup):
+        """K steps through the C-ABI with host buffers, round-robin over the pipelines, one host thread each."""
+        for i in range(warmup):
+            step_e2e(i, i % n_pipes)
+        barrier()
+        for cx in pipes:
+            cx.reset_counters()
+        hits = [0] * n_pipes
+        errors = []
+
+        def work(p):
+            try:
+                for i in range(p, steps, n_pipes):
+                    hits[p] += step_e2e(warmup + i, p)
+            except Exception as e:   # surfaced after join
+                errors.append(e)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        threads = [threading.Thread(target=work, args=(p,)) for p in range(n_pipes)]
+        e0.record()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()          # every step ended with a synchronous fetch: all device work is done
+        e1.record()
+        barrier()
+        if errors:
+            raise errors[0]
+        ms = e0.elapsed_time(e1)
+        launches = sum(cx.counters()["launches"] for cx in pipes)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, sum(hits), launches
 
     def barrier():
         if world > 1:
@@ -251,7 +298,7 @@ def main_gpu(args):
         barrier()
         ctx.reset_counters()
         acc = {"ms_on": 0.0, "ms_off": 0.0, "ms_pack": 0.0, "ms_read_index": 0.0, "ms_resolve": 0.0, "ms_h2d": 0.0,
-               "ms_d2h": 0.0, "n_hits_on": 0, "n_hits": 0, "n_seeds": 0, "n_walks": 0}
+               "ms_d2h": 0.0, "n_hits_on": 0, "n_hits": 0, "n_seeds": 0, "n_walks": 0, "n_on_probe_sectors": 0}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         hits = 0
@@ -274,7 +321,8 @@ def main_gpu(args):
     if rank == 0:
         sampler.start()
     ms_dev, hits_dev, acc, launches = timed(step_device, args.steps, args.warmup)
-    ms_e2e, hits_e2e, acc_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    c_last = ctx.counters()
+    ms_e2e, hits_e2e, launches_e2e = timed_e2e(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
     # per-shard counts and a hits-per-read histogram, gathered with NCCL (the only collective on this path)
@@ -288,11 +336,15 @@ def main_gpu(args):
         peak, peak_src = peaks()
         reads_total, seeds_total, hits_total, hits_on_total, walks_total = tot
         value = reads_total / (ms_dev * 1e-3)
-        # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches:
-        # algorithmic bytes per launch = seeds x (8 B packed k-mer + 32 B one index bucket) + on-path hits x 8 B record
-        alg_bytes = (acc["n_seeds"] * 40 + acc["n_hits_on"] * 8) / args.steps
+        # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches.  Algorithmic bytes per launch =
+        # seeds x (8 B packed k-mer + 128 B = ONE index bucket line, the DRAM access unit: profiles/r01c_gather_peak.md)
+        # + hits x 8 B compact record.  The 32-B-sector accounting of SURVEY 8d (40 B per seed) is reported beside it.
+        n_probe_hits = acc["n_hits"] if c_last["offpath_mode"] == 2 else acc["n_hits_on"]
+        alg_bytes = (acc["n_seeds"] * 136 + n_probe_hits * 8) / args.steps
+        alg_bytes_sector = (acc["n_seeds"] * 40 + n_probe_hits * 8) / args.steps
         on_ms = acc["ms_on"] / args.steps
         achieved = alg_bytes / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
+        achieved_sector = alg_bytes_sector / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
         per_step = {k_: acc[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_read_index", "ms_off", "ms_resolve")}
         e2e_value = n_reads * args.steps * world / (ms_e2e * 1e-3)
         hp, hb = batches_h[0]
@@ -307,17 +359,28 @@ def main_gpu(args):
                              f"{c0['index_bytes'] / 1e6:.0f} MB index: inputs larger than L2",
                        "sharding": "reads sharded by rank, graph + index replicated, NCCL all-reduce of counts only"},
             "seeds_per_s": hits_total / (ms_dev * 1e-3), "query_seeds_per_s": seeds_total / (ms_dev * 1e-3),
-            "kernel_ms_per_step": per_step,
+            "kernel_ms_per_step": per_step, "probe_slow_seeds_per_step": acc["n_on_probe_sectors"] / args.steps,
             "e2e": {"value": e2e_value, "unit": "reads/s",
                     "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
-                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 32), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 32), "ms_per_step": ms_e2e / args.steps,
+                    "pipelines": n_pipes},
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
+            "offpath_mode": "index (walks from the starting loci materialised into the index)" if c_last["offpath_mode"] == 2
+                            else "walk (graph walked from the starting loci for every chunk)",
             "roofline": {"bound": "hbm", "kernel": "seeds_on_paths_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms},
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms,
+                         "bytes_per_seed": "8 B k-mer + 128 B bucket line + 8 B per hit",
+                         "sector_accounting": {"bytes_per_seed": "8 B k-mer + 32 B sector + 8 B per hit (SURVEY 8d, P=1)",
+                                               "achieved": achieved_sector, "frac": achieved_sector / peak},
+                         "probes_per_s": acc["n_seeds"] / args.steps / (on_ms * 1e-3) if on_ms > 0 else 0.0,
+                         "random_line_ceiling_probes_per_s": 4.0e10,
+                         "traffic_source": TRAFFIC_SOURCE},
             "clocks": clocks,
             "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
-                      "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"]},
+                      "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"],
+                      "offpath_entries": c0["n_offpath_entries"], "offpath_walks": c0["n_offpath_walks"],
+                      "stash_used": c0["index_stash_used"]},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -327,6 +390,8 @@ def main_gpu(args):
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference",
                                         "sample": f"unavailable: {type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
+    for cx in pipes[1:]:
+        cx.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -341,6 +406,8 @@ def main():
     ap.add_argument("--shape", default="chr22", help="bench_support.synth.SHAPES key")
     ap.add_argument("--reads", type=int, default=READS_PER_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
+    ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "psi_b200" else args.warmup
     if args.impl == "reference":

@@ -148,6 +148,11 @@ const char* psi_b200_last_error(const psi_b200_ctx* ctx);
  * non-blocking stream). */
 int  psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream);
 int  psi_b200_sync(psi_b200_ctx* ctx);
+/* Tuning knobs (set before find_loci / set_loci):
+ *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
+ *                       (the reference's scheme), 2 always materialise those walks into the index;
+ *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28). */
+int  psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value);
 
 /* The graph the finder borrows (seed_finder.hpp:1747), flattened: CSR
  * adjacency + concatenated labels (gum layout graph_traits_succinct.hpp:27-57,
@@ -198,13 +203,18 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
 
 /* Finds the seeds of the submitted chunk.  The result is the SET of hits
  * (each (read, offset, node, offset) once), resident in device
- * memory; *n_hits is its size (synchronises the stream). */
+ * memory; *n_hits is its size (synchronises the stream).  Records are ordered by (read, read offset)
+ * up to blocks of 512 seeds; PSI_B200_SORTED gives the exact canonical order. */
 int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
 
 /* Copies the records of the last seeds_all to the host in the reference
  * CLI's byte layout (src/psikt.cpp:172-181, seed.hpp:32-46): per hit 4 x u64
  * {node_id, node_offset, read_id, read_offset}. */
 int  psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits);
+/* Per record of the last (unsorted) seeds_all: 1 = found on an indexed path (seeds_on_paths), 2 = found only by
+ * an off-path walk (seeds_off_paths); lets a caller route hits to the two callbacks of
+ * seeds_all(reads, index, traverser, callback1, callback2) (seed_finder.hpp:1734-1743). */
+int  psi_b200_fetch_kinds(psi_b200_ctx* ctx, uint8_t* kinds, uint64_t cap, uint64_t* n_hits);
 /* Device pointer to the same records (valid until the next seeds_all). */
 int  psi_b200_fetch_device(psi_b200_ctx* ctx, const uint64_t** d_hits, uint64_t* n_hits);
 
@@ -217,17 +227,21 @@ void psi_b200_host_free(void* p);
 typedef struct {
   uint64_t n_nodes, n_edges, n_bases;
   uint64_t n_path_bases;       /* indexed path text length */
-  uint64_t n_index_entries;    /* distinct (k-mer, locus) pairs */
+  uint64_t n_index_entries;    /* distinct (k-mer, locus) pairs in the device index */
   uint64_t n_index_kmers;      /* distinct k-mers */
-  uint64_t index_bytes;        /* device bytes of the path index */
-  uint64_t index_buckets;      /* 32-byte buckets */
+  uint64_t index_bytes;        /* device bytes of the index */
+  uint64_t index_buckets;      /* 128-byte buckets (one DRAM line each) */
   uint32_t index_slot_bytes;   /* 8 or 16 */
+  uint32_t index_stash_used;   /* keys that found MAX_DISP + 1 lines full */
+  uint64_t n_offpath_entries;  /* (k-mer, locus) pairs of the materialised off-path walks (0 in walk mode) */
+  uint64_t n_offpath_walks;    /* k-walks from the starting loci that are not on an indexed path */
+  uint32_t offpath_mode;       /* 1 = walk the graph per chunk, 2 = walks materialised into the index */
   uint32_t reserved0;
   uint64_t n_loci;
   uint64_t n_reads, n_seeds;   /* last chunk */
   uint64_t n_hits_on, n_hits_off, n_hits;
   uint64_t n_walks;            /* k-walks completed by the off-path kernel */
-  uint64_t n_on_probe_sectors; /* 32-byte buckets read by the on-path probe (diagnostic builds) */
+  uint64_t n_on_probe_sectors; /* seeds whose probe needed more than the home line (locus lists, displaced keys) */
   float ms_index_build, ms_find_loci;
   float ms_h2d, ms_pack, ms_read_index, ms_on, ms_off, ms_resolve, ms_sort, ms_d2h;
   uint32_t launches;           /* kernels of this library launched since create / reset */

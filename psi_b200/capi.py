@@ -27,10 +27,10 @@ SYMBOLS = [
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_global_error",
-    "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync",
+    "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
     "psi_b200_submit_chunk", "psi_b200_submit_chunk_device", "psi_b200_seeds_all",
-    "psi_b200_fetch", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
+    "psi_b200_fetch", "psi_b200_fetch_kinds", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
     "psi_b200_counters", "psi_b200_reset_counters", "psi_b200_version",
 ]
 
@@ -63,7 +63,9 @@ class Counters(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("n_bases", C.c_uint64),
                 ("n_path_bases", C.c_uint64), ("n_index_entries", C.c_uint64), ("n_index_kmers", C.c_uint64),
                 ("index_bytes", C.c_uint64), ("index_buckets", C.c_uint64),
-                ("index_slot_bytes", C.c_uint32), ("reserved0", C.c_uint32),
+                ("index_slot_bytes", C.c_uint32), ("index_stash_used", C.c_uint32),
+                ("n_offpath_entries", C.c_uint64), ("n_offpath_walks", C.c_uint64),
+                ("offpath_mode", C.c_uint32), ("reserved0", C.c_uint32),
                 ("n_loci", C.c_uint64), ("n_reads", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("n_hits_on", C.c_uint64), ("n_hits_off", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_walks", C.c_uint64), ("n_on_probe_sectors", C.c_uint64),
@@ -114,6 +116,7 @@ def lib() -> C.CDLL:
     L.psi_b200_destroy.restype = None
     L.psi_b200_set_stream.argtypes = [vp, vp]
     L.psi_b200_sync.argtypes = [vp]
+    L.psi_b200_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
     L.psi_b200_set_graph.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp]
     L.psi_b200_set_paths.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
     L.psi_b200_find_loci.argtypes = [vp, C.c_uint, u64p]
@@ -123,6 +126,7 @@ def lib() -> C.CDLL:
     L.psi_b200_submit_chunk_device.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, C.c_uint]
     L.psi_b200_seeds_all.argtypes = [vp, C.c_uint, u64p]
     L.psi_b200_fetch.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.psi_b200_fetch_kinds.argtypes = [vp, vp, C.c_uint64, u64p]
     L.psi_b200_fetch_device.argtypes = [vp, C.POINTER(vp), u64p]
     L.psi_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.psi_b200_host_free.argtypes = [vp]
@@ -301,6 +305,9 @@ class Context:
     def set_stream(self, cuda_stream: int):
         self._ck(lib().psi_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_option(self, name: str, value: int):
+        self._ck(lib().psi_b200_set_option(self._h, name.encode(), value))
+
     def sync(self):
         self._ck(lib().psi_b200_sync(self._h))
 
@@ -362,6 +369,15 @@ class Context:
         out = np.zeros((n, 4), np.uint64)
         if n:
             self._ck(lib().psi_b200_fetch(self._h, _ptr(out), n, C.byref(cnt)))
+        return out
+
+    def fetch_kinds(self) -> np.ndarray:
+        """Per record: 1 = on an indexed path, 2 = off-path (same order as fetch())."""
+        cnt = C.c_uint64()
+        self._ck(lib().psi_b200_fetch_kinds(self._h, None, 0, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.uint8)
+        if cnt.value:
+            self._ck(lib().psi_b200_fetch_kinds(self._h, _ptr(out), cnt.value, C.byref(cnt)))
         return out
 
     def fetch_into(self, addr: int, cap: int) -> int:

@@ -249,6 +249,11 @@ int psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream)
   })
 }
 
+int psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value)
+{
+  CTX_GUARD(ctx, engine_set_option(*ctx->c, name, value))
+}
+
 int psi_b200_sync(psi_b200_ctx* ctx)
 {
   CTX_GUARD(ctx, {
@@ -317,6 +322,15 @@ int psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_
     if (n_hits) *n_hits = ctx->c->n_hits;
     if (cap && !hits) throw ArgError("fetch: null buffer");
     if (cap) engine_fetch(*ctx->c, hits, cap);
+  })
+}
+
+int psi_b200_fetch_kinds(psi_b200_ctx* ctx, uint8_t* kinds, uint64_t cap, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (n_hits) *n_hits = ctx->c->n_hits;
+    if (cap && !kinds) throw ArgError("fetch_kinds: null buffer");
+    if (cap) engine_fetch_kinds(*ctx->c, kinds, cap);
   })
 }
 

@@ -4,10 +4,7 @@
 //   * KmerTable: the bucketised hash used for BOTH device indexes
 //       - the path index       (k-mer -> locus / locus list; probed by seeds_on_paths)
 //       - the chunk read index (k-mer -> chain of read seeds; probed by seeds_off_paths)
-//     A bucket is one 32-byte DRAM sector; 4 buckets form a 128-byte line and a
-//     key may only live in its home line (home bucket first, then the other
-//     three), so a probe costs one sector in the common case and never leaves
-//     one L2 line.  Keys that find their line full go to a small stash.
+//     A bucket is one 128-byte line = one DRAM access (see the KmerTable section).
 #ifndef PSI_B200_DEVICE_COMMON_CUH
 #define PSI_B200_DEVICE_COMMON_CUH
 
@@ -71,25 +68,50 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 }
 
 // Bijection on kb-bit integers (odd multiplications and right xor-shifts are
-// invertible modulo 2^kb); the TOP bits of the result select the bucket.
+// invertible modulo 2^kb); the TOP bits of the result select the bucket line.
+// Two multiply rounds: every input bit reaches the top bits, and the probe
+// kernel stays far from being issue bound (a third round bought nothing
+// measurable in bucket balance).
 __host__ __device__ __forceinline__ uint64_t mix_kb(uint64_t x, uint32_t kb)
 {
   const uint64_t m = low_mask64(kb);
   const uint32_t s = (kb >> 1) ? (kb >> 1) : 1;
+  x ^= x >> s;
   x = (x * 0x9e3779b97f4a7c15ULL) & m;
   x ^= x >> s;
   x = (x * 0xd6e8feb86659fd93ULL) & m;
   x ^= x >> s;
-  x = (x * 0xca5a826395121157ULL) & m;
   return x;
 }
 
 // ----------------------------------------------------------- KmerTable --
+//
+// Measured on B200 (profiles/r01c_gather_peak.md): a random access costs one
+// 128-byte DRAM line whatever part of it is used, ~48 G lines/s.  So a bucket IS
+// a 128-byte line: 16 slots of 8 bytes (fmt 8) or 8 slots of 16 bytes (fmt 16).
+// A key lives in its home line or, when that line was full at insertion, in one
+// of the next MAX_DISP lines (linear probing over lines), else in a small stash.
+// Lookups read the home line -- four co-operating lanes load one 32-byte sector
+// each in ONE warp instruction (seeds_on_paths), or one thread loads the four
+// sectors back to back (walkers) -- and only continue past a line without a free
+// slot.
+//
+// fmt 8 slot (64 bits), valid while kbits - line_bits <= 27:
+//   [63:37] remainder of the bijectively mixed k-mer (the line index holds the rest)
+//   [36:34] displacement from the home line (0..7)
+//   [33]    entry reaches only via an off-path walk      [32] payload is a locus list
+//   [31:0]  payload: global position, or offset of the list in the multi array,
+//           or (read index) head of the seed chain
+// fmt 16 slot: full k-mer, payload, flags (bit 0 list, bit 1 off-path; NIL32 = empty).
+
+constexpr uint32_t MAX_DISP = 7;
+constexpr uint32_t FLAG_MULTI = 1u;
+constexpr uint32_t FLAG_OFF = 2u;
 
 struct alignas(16) Slot16 {
   uint64_t key;
   uint32_t payload;
-  uint32_t flags;  // 0 = single, 1 = multi, NIL32 = empty
+  uint32_t flags;  // FLAG_* bits; NIL32 = empty
 };
 
 struct KmerTable {
@@ -98,21 +120,32 @@ struct KmerTable {
   uint32_t* stash_used; // device counter of occupied stash slots
   uint32_t line_bits;   // log2(n_lines)
   uint32_t kbits;       // 2k
-  uint32_t rem_bits;    // format 8 only: kbits - 2 - line_bits (<= 29)
-  uint32_t fmt;         // 8: 4 x 8-byte slots per bucket; 16: 2 x 16-byte slots
+  uint32_t rem_bits;    // fmt 8 only: kbits - line_bits (<= 27)
+  uint32_t fmt;         // 8 or 16 (bytes per slot)
   uint32_t stash_mask;
   uint32_t stash_nonempty;  // host-known: 0 lets lookups skip the stash entirely
 };
 
 struct Home {
   uint64_t line;
-  uint32_t sec;
-  uint64_t tag;   // fmt 8: (remainder << 2) | sec ; fmt 16: the k-mer itself
+  uint64_t tag;   // fmt 8: remainder << 3 (displacement 0); fmt 16: the k-mer itself
+};
+
+struct Found {
+  uint32_t payload;
+  uint32_t flags;
 };
 
 __device__ __forceinline__ void ld_sector_nc(const void* p, uint64_t (&v)[4])
 {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
+// coherent variant for tables that are being written by the same kernel
+__device__ __forceinline__ void ld_sector_cg(const void* p, uint64_t (&v)[4])
+{
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
 }
 
@@ -151,29 +184,51 @@ __device__ __forceinline__ Home home_of(const KmerTable& t, uint64_t kmer)
   Home h;
   if (FMT == 8) {
     const uint64_t x = mix_kb(kmer, t.kbits);
-    h.line = t.line_bits ? (x >> (t.kbits - t.line_bits)) : 0;
-    h.sec = (uint32_t)(x >> t.rem_bits) & 3u;
-    h.tag = ((x & low_mask64(t.rem_bits)) << 2) | h.sec;
+    h.line = t.line_bits ? (x >> t.rem_bits) : 0;        // top line_bits of the kbits-bit value
+    h.tag = (x & low_mask64(t.rem_bits)) << 3;
   }
   else {
     const uint64_t x = mix64(kmer);
     h.line = t.line_bits ? (x >> (64 - t.line_bits)) : 0;
-    h.sec = (uint32_t)(x >> 17) & 3u;
     h.tag = kmer;
   }
   return h;
 }
 
+// Compare the slots of one 32-byte sector.  `want` = tag | displacement (fmt 8) or the k-mer (fmt 16).
+// Returns true on a match; `has_empty` reports a free slot in the sector.
+template <int FMT>
+__device__ __forceinline__ bool match_sector(const uint64_t (&v)[4], uint64_t want, Found& f, bool& has_empty)
+{
+  bool hit = false;
+  if (FMT == 8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (v[j] == EMPTY8) has_empty = true;
+      else if ((v[j] >> 34) == want) { f.payload = (uint32_t)v[j]; f.flags = (uint32_t)(v[j] >> 32) & 3u; hit = true; }
+    }
+  }
+  else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t fl = (uint32_t)(v[2 * j + 1] >> 32);
+      if (fl == NIL32) has_empty = true;
+      else if (v[2 * j] == want) { f.payload = (uint32_t)v[2 * j + 1]; f.flags = fl & 3u; hit = true; }
+    }
+  }
+  return hit;
+}
+
 // ---- stash (full keys) ----
 
-__device__ __forceinline__ bool stash_find(const KmerTable& t, uint64_t kmer, uint32_t& payload, bool& multi)
+__device__ __forceinline__ bool stash_find(const KmerTable& t, uint64_t kmer, Found& f)
 {
   if (!t.stash_nonempty) return false;
   uint32_t p = (uint32_t)mix64(kmer ^ 0x5bd1e995u) & t.stash_mask;
   for (uint32_t i = 0; i <= t.stash_mask; ++i) {
     const Slot16 s = ld_slot16_volatile(t.stash + p);
     if (s.flags == NIL32) return false;
-    if (s.key == kmer) { payload = s.payload; multi = s.flags == 1; return true; }
+    if (s.key == kmer) { f.payload = s.payload; f.flags = s.flags & 3u; return true; }
     p = (p + 1) & t.stash_mask;
   }
   return false;
@@ -215,78 +270,73 @@ __device__ __forceinline__ bool stash_insert(const KmerTable& t, uint64_t kmer, 
   return false;
 }
 
-// ---- lookup (read-only tables) ----
+// ---- lookup by one thread (read-only tables): lines home + d, d = from_disp.. ----
 
 template <int FMT>
-__device__ __forceinline__ bool table_find_from(const KmerTable& t, const Home& h, uint64_t kmer,
-                                                uint32_t& payload, bool& multi, uint32_t& sectors)
+__device__ __forceinline__ bool table_find_from(const KmerTable& t, const Home& h, uint64_t kmer, uint32_t from_disp, Found& f)
 {
-  const char* line = (const char*)t.slots + h.line * 128u;
+  const uint64_t line_mask = (1ull << t.line_bits) - 1ull;
 #pragma unroll 1
-  for (uint32_t i = 0; i < 4; ++i) {
-    uint64_t v[4];
-    ld_sector_nc(line + (((h.sec + i) & 3u) << 5), v);
-    ++sectors;
-    bool has_empty = false;
-    if (FMT == 8) {
+  for (uint32_t d = from_disp; d <= MAX_DISP; ++d) {
+    const char* line = (const char*)t.slots + (((h.line + d) & line_mask) << 7);
+    uint64_t v[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (v[j] == EMPTY8) has_empty = true;
-        else if ((v[j] >> 33) == h.tag) { payload = (uint32_t)v[j]; multi = (v[j] >> 32) & 1u; return true; }
-      }
-    }
-    else {
+    for (int i = 0; i < 4; ++i) ld_sector_nc(line + (i << 5), v[i]);
+    const uint64_t want = FMT == 8 ? ((h.tag | d) ) : kmer;
+    bool has_empty = false, hit = false;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t fl = (uint32_t)(v[2 * j + 1] >> 32);
-        if (fl == NIL32) has_empty = true;
-        else if (v[2 * j] == kmer) { payload = (uint32_t)v[2 * j + 1]; multi = fl == 1; return true; }
-      }
-    }
+    for (int i = 0; i < 4; ++i) hit |= match_sector<FMT>(v[i], want, f, has_empty);
+    if (hit) return true;
     if (has_empty) return false;
   }
-  return stash_find(t, kmer, payload, multi);
+  return stash_find(t, kmer, f);
 }
 
 template <int FMT>
-__device__ __forceinline__ bool table_find(const KmerTable& t, uint64_t kmer, uint32_t& payload, bool& multi)
+__device__ __forceinline__ bool table_find(const KmerTable& t, uint64_t kmer, Found& f)
 {
-  uint32_t sectors = 0;
   const Home h = home_of<FMT>(t, kmer);
-  return table_find_from<FMT>(t, h, kmer, payload, multi, sectors);
+  return table_find_from<FMT>(t, h, kmer, 0, f);
+}
+
+__device__ __forceinline__ bool table_find_any(const KmerTable& t, uint64_t kmer, Found& f)
+{
+  return t.fmt == 8 ? table_find<8>(t, kmer, f) : table_find<16>(t, kmer, f);
 }
 
 // ---- insert (table being built) ----
 //
-// Find-or-insert `kmer`.  flags: 0 single / 1 multi.  With chain == true an
-// existing key gets its payload replaced by `payload` and the old payload is
-// returned in `prev` (linked list of read seeds); a fresh key returns NIL32.
-// Returns false when line and stash are full (caller raises the overflow flag).
+// Find-or-insert `kmer`.  With chain == true an existing key gets its payload
+// replaced by `payload` and the old payload is returned in `prev` (linked list
+// of read seeds); a fresh key returns NIL32.  Returns false when MAX_DISP + 1
+// lines and the stash are full (caller raises the overflow flag).
 template <int FMT>
 __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, uint32_t payload, uint32_t flags,
                                              bool chain, uint32_t& prev)
 {
   const Home h = home_of<FMT>(t, kmer);
-  char* line = (char*)t.slots + h.line * 128u;
-  if (FMT == 8) {
-    const uint64_t fresh = (h.tag << 33) | ((uint64_t)(flags & 1u) << 32) | payload;
+  const uint64_t line_mask = (1ull << t.line_bits) - 1ull;
 #pragma unroll 1
-    for (uint32_t i = 0; i < 4; ++i) {
-      unsigned long long* sec = (unsigned long long*)(line + (((h.sec + i) & 3u) << 5));
+  for (uint32_t d = 0; d <= MAX_DISP; ++d) {
+    char* line = (char*)t.slots + (((h.line + d) & line_mask) << 7);
+    if (FMT == 8) {
+      const uint64_t want = h.tag | d;
+      const uint64_t fresh = (want << 34) | ((uint64_t)(flags & 3u) << 32) | payload;
+      unsigned long long* slot = (unsigned long long*)line;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        unsigned long long cur = *(volatile unsigned long long*)(sec + j);
+      for (int j = 0; j < 16; ++j) {
+        unsigned long long cur = *(volatile unsigned long long*)(slot + j);
         while (true) {
           if (cur == EMPTY8) {
-            const unsigned long long old = atomicCAS(sec + j, EMPTY8, fresh);
+            const unsigned long long old = atomicCAS(slot + j, EMPTY8, fresh);
             if (old == EMPTY8) { prev = NIL32; return true; }
             cur = old;
             continue;
           }
-          if ((cur >> 33) == h.tag) {
+          if ((cur >> 34) == want) {
             if (!chain) { prev = (uint32_t)cur; return true; }
             const unsigned long long upd = (cur & 0xffffffff00000000ull) | payload;
-            const unsigned long long old = atomicCAS(sec + j, cur, upd);
+            const unsigned long long old = atomicCAS(slot + j, cur, upd);
             if (old == cur) { prev = (uint32_t)cur; return true; }
             cur = old;
             continue;
@@ -295,26 +345,23 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
         }
       }
     }
-  }
-  else {
-    const Slot16 empty{ ~0ull, NIL32, NIL32 };
+    else {
+      const Slot16 empty{ ~0ull, NIL32, NIL32 };
+      Slot16* slot = (Slot16*)line;
 #pragma unroll 1
-    for (uint32_t i = 0; i < 4; ++i) {
-      Slot16* sec = (Slot16*)(line + (((h.sec + i) & 3u) << 5));
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
-        Slot16 cur = ld_slot16_volatile(sec + j);
+      for (int j = 0; j < 8; ++j) {
+        Slot16 cur = ld_slot16_volatile(slot + j);
         while (true) {
           if (cur.flags == NIL32) {
             Slot16 old;
-            if (cas128(sec + j, empty, Slot16{ kmer, payload, flags & 1u }, old)) { prev = NIL32; return true; }
+            if (cas128(slot + j, empty, Slot16{ kmer, payload, flags & 3u }, old)) { prev = NIL32; return true; }
             cur = old;
             continue;
           }
           if (cur.key == kmer) {
             if (!chain) { prev = cur.payload; return true; }
             Slot16 old;
-            if (cas128(sec + j, cur, Slot16{ kmer, payload, cur.flags }, old)) { prev = cur.payload; return true; }
+            if (cas128(slot + j, cur, Slot16{ kmer, payload, cur.flags }, old)) { prev = cur.payload; return true; }
             cur = old;
             continue;
           }
@@ -326,21 +373,19 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
   return stash_insert(t, kmer, payload, flags, chain, prev);
 }
 
-// membership of (kmer, gpos) in the path index
+// membership of (kmer, gpos) among the ON-PATH entries of the index.
+// multi list layout: [n_on, n_total, on-path loci (sorted)..., off-path loci (sorted)...]
 __device__ __forceinline__ bool index_contains(const KmerTable& t, const uint32_t* __restrict__ multi,
                                                uint64_t kmer, uint32_t gpos)
 {
-  uint32_t payload;
-  bool is_multi;
-  const bool found = t.fmt == 8 ? table_find<8>(t, kmer, payload, is_multi) : table_find<16>(t, kmer, payload, is_multi);
-  if (!found) return false;
-  if (!is_multi) return payload == gpos;
-  const uint32_t cnt = __ldg(multi + payload);
-  // sorted list: binary search
+  Found f;
+  if (!table_find_any(t, kmer, f)) return false;
+  if (!(f.flags & FLAG_MULTI)) return !(f.flags & FLAG_OFF) && f.payload == gpos;
+  const uint32_t cnt = __ldg(multi + f.payload);
   uint32_t lo = 0, hi = cnt;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    const uint32_t v = __ldg(multi + payload + 1 + mid);
+    const uint32_t v = __ldg(multi + f.payload + 2 + mid);
     if (v == gpos) return true;
     if (v < gpos) lo = mid + 1; else hi = mid;
   }

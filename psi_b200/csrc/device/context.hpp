@@ -95,10 +95,16 @@ struct Shared {
   DevBuf<uint64_t> node_id;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
 
-  // ---- path index ----
-  bool has_index = false;
+  // ---- index: (k-mer -> loci) for every k-window of the indexed paths and, when the
+  // off-path walks have been materialised, for every k-walk from a starting locus ----
+  bool has_index = false;        // paths have been indexed
+  bool has_table = false;        // `index` is allocated and probeable
+  bool offpath_indexed = false;  // the k-walks from the starting loci are IN the table (no per-chunk walk needed)
   HostTable index;
-  DevBuf<uint32_t> multi;        // [count, gpos...] runs of k-mers with several loci
+  DevBuf<uint32_t> multi;        // [n_on, n_total, on-path loci..., off-path loci...] per k-mer with several loci
+  DevBuf<uint64_t> on_kmer;      // distinct on-path (k-mer, locus) pairs, sorted: kept to re-merge when the loci change
+  DevBuf<uint32_t> on_gpos;
+  uint64_t n_on_pairs = 0, n_off_pairs = 0;
 
   // ---- starting loci ----
   uint64_t n_loci = 0;
@@ -128,17 +134,26 @@ struct Ctx {
   DevBuf<uint64_t> read_ptr;
   const char* d_bases = nullptr; // points to `bases` or to caller's device memory
   const uint64_t* d_read_ptr = nullptr;
+  DevBuf<uint64_t> reads2;       // the chunk's bases, 2 bits each
+  DevBuf<uint32_t> reads_n;      // 1 bit per base: not A/C/G/T
   DevBuf<uint32_t> seed_first;   // n_reads + 1: first seed of each read (exclusive scan)
   DevBuf<uint32_t> seed_read;    // per seed: local read index
   DevBuf<uint64_t> seed_kmer;
-  DevBuf<uint32_t> seed_valid;   // bitmap
+  DevBuf<uint8_t> seed_valid;    // per seed: 1 = only A/C/G/T inside
   DevBuf<uint32_t> seed_next;    // chain links of the read index
   HostTable read_index;
   DevBuf<char> scan_tmp;
   uint64_t* h_pinned = nullptr;  // small pinned scratch for async counter read-back
 
   // ---- results ----
-  DevBuf<Hit> hits;              // compact, on-path first then off-path
+  DevBuf<uint32_t> seed_hit;     // per seed: locus found by the probe
+  DevBuf<uint8_t> seed_kind;     // per seed: 0 none, 1 on an indexed path, 2 off-path, 3 queued for the slow kernel
+  DevBuf<uint32_t> slow_queue;   // seeds the one-line probe could not settle
+  DevBuf<Hit> hits;              // overflow hit list: locus lists, walker hits
+  DevBuf<uint8_t> hit_kind;
+  DevBuf<Hit> sorted_hits;       // dense compact hits (PSI_B200_SORTED / NO_RESOLVE)
+  DevBuf<uint8_t> rec_kind;      // per record: 1 on-path, 2 off-path
+  bool kinds_valid = false;
   DevBuf<unsigned long long> dedup;  // off-path (chain head, gpos) set
   DevBuf<uint64_t> records;      // 4 x u64 per hit, reference layout
   DevBuf<unsigned long long> dev_counters;  // see DC_* below
@@ -146,19 +161,25 @@ struct Ctx {
   bool records_valid = false;
   uint32_t spill_items = 4096;   // per-warp global spill of the walker
   DevBuf<char> walk_spill;
+
+  // ---- options (psi_b200_set_option) ----
+  int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
+  uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this
 };
 
 // indices into Ctx::dev_counters
 enum {
-  DC_HITS = 0,        // compact hits appended
+  DC_HITS = 0,        // records written by the compaction
   DC_WALKS = 1,       // completed k-walks (off-path kernel)
   DC_ERR = 2,         // bit 0: walker stack overflow, bit 1: table overflow, bit 2: dedup overflow
-  DC_SECTORS = 3,     // sectors read by the on-path probe (diagnostic)
+  DC_HITS_ON = 3,     // records that are on-path hits
   DC_WORK = 4,        // dynamic work counter of the walkers
   DC_SEEDS = 5,       // total seeds of the chunk
   DC_AUX = 6,
   DC_AUX2 = 7,
-  DC_COUNT = 8
+  DC_OVF = 8,         // entries of the overflow hit list
+  DC_SLOW = 9,        // seeds queued for seeds_slow_kernel
+  DC_COUNT = 10
 };
 
 }  // namespace psi_b200

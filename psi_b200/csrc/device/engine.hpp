@@ -20,15 +20,15 @@ void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap);
 void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, const char* bases,
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
 void engine_seeds(Ctx& c, unsigned flags);
+void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap);
+void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);
 
 // ---- helpers shared by the .cu files ----
 
 // Size a KmerTable for n_keys distinct k-mers of 2k = kbits bits; allocates and
-// clears the slots.  max_inflate_bytes bounds how far the table may be grown
-// beyond its natural size to keep the compact 8-byte slot format.
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t max_inflate_bytes,
-                 uint64_t stash_slots);
+// clears the slots.
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots);
 void table_clear(Ctx& c, HostTable& t);
 
 // CUDA-event timer slots (Ctx::ev holds a start/stop pair per slot)

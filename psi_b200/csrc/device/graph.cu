@@ -103,7 +103,11 @@ Ctx* engine_fork(Ctx& parent)
   c->counters.n_index_kmers = pc.n_index_kmers; c->counters.index_bytes = pc.index_bytes;
   c->counters.index_buckets = pc.index_buckets; c->counters.index_slot_bytes = pc.index_slot_bytes;
   c->counters.n_loci = pc.n_loci; c->counters.ms_index_build = pc.ms_index_build; c->counters.ms_find_loci = pc.ms_find_loci;
+  c->counters.n_offpath_entries = pc.n_offpath_entries; c->counters.index_stash_used = pc.index_stash_used;
+  c->counters.offpath_mode = pc.offpath_mode; c->counters.n_offpath_walks = pc.n_offpath_walks;
   c->spill_items = parent.spill_items;
+  c->opt_offpath_mode = parent.opt_offpath_mode;
+  c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
   return c;
 }
 
@@ -178,6 +182,9 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   c.sh->graph_has_n = n_count != 0;
   c.sh->has_graph = true;
   c.sh->has_index = false;
+  c.sh->has_table = false;
+  c.sh->offpath_indexed = false;
+  c.sh->n_on_pairs = c.sh->n_off_pairs = 0;
   c.sh->n_loci = 0;
   c.counters.n_nodes = n_nodes;
   c.counters.n_edges = n_edges;
@@ -193,22 +200,19 @@ static uint32_t ceil_log2(uint64_t x)
   return b;
 }
 
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t max_inflate_bytes,
-                 uint64_t stash_slots)
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots)
 {
-  // natural size: ~6 keys per 128-byte line for 8-byte slots (16 slots, load
-  // 0.39), ~3 per line for 16-byte slots (8 slots).
-  uint32_t lb8 = ceil_log2((n_keys + 5) / 6 + 1);
-  uint32_t lb16 = ceil_log2((n_keys + 2) / 3 + 1);
-  uint32_t fmt = 16, line_bits = lb16, rem_bits = 0;
-  if (kbits >= 2) {
-    uint32_t lb = lb8;
-    if (lb > kbits - 2) lb = kbits - 2;           // tiny k: one possible key per (line, bucket)
-    uint32_t need = kbits - 2 > 29 ? kbits - 2 - 29 : 0;  // remainder must fit 29 bits
-    if (lb < need && (128ull << need) <= max_inflate_bytes) lb = need;
-    if (kbits - 2 - lb <= 29) { fmt = 8; line_bits = lb; rem_bits = kbits - 2 - lb; }
+  // A bucket is a 128-byte line.  Size for at most ~10 keys per 16-slot line
+  // (fmt 8) or ~5 per 8-slot line (fmt 16): with a power-of-two line count the
+  // mean load is 0.31-0.63, about 3 % of the lines overflow into their successor
+  // at the upper end, and a lookup still reads exactly one line in ~97 % of the cases.
+  uint32_t fmt = 16, line_bits = ceil_log2((n_keys + 4) / 5 + 1), rem_bits = 0;
+  {
+    uint32_t lb = ceil_log2((n_keys + 9) / 10 + 1);
+    if (lb > kbits) lb = kbits;               // tiny k: at most one possible key per line
+    if (kbits - lb <= 27) { fmt = 8; line_bits = lb; rem_bits = kbits - lb; }
   }
-  if (fmt == 16 && line_bits > 63) throw ArgError("table too large");
+  if (line_bits > 40) throw ArgError("table too large");
   const uint64_t n_lines = 1ull << line_bits;
   t.n_lines = n_lines;
   t.slots.ensure(n_lines * 128);

@@ -16,6 +16,8 @@
 #include "engine.hpp"
 #include "walker.cuh"
 
+#include <algorithm>
+#include <string>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -133,7 +135,18 @@ compact_pairs_kernel(const uint64_t* __restrict__ kmer, const uint32_t* __restri
   ugpos[scan[i]] = gpos[i];
 }
 
-// head[i] = 1 iff unique pair i starts a new k-mer run.
+// Concatenate the on-path pairs and the off-path pairs: value = gpos | (off << 32).
+__global__ void __launch_bounds__(256)
+concat_pairs_kernel(const uint64_t* __restrict__ on_kmer, const uint32_t* __restrict__ on_gpos, uint64_t n_on,
+                    const uint64_t* __restrict__ off_kmer, const uint32_t* __restrict__ off_gpos, uint64_t n_off,
+                    uint64_t* __restrict__ key, uint64_t* __restrict__ val)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_on) { key[i] = on_kmer[i]; val[i] = on_gpos[i]; }
+  else if (i < n_on + n_off) { key[i] = off_kmer[i - n_on]; val[i] = (uint64_t)off_gpos[i - n_on] | (1ull << 32); }
+}
+
+// head[i] = 1 iff pair i starts a new k-mer run.
 __global__ void __launch_bounds__(256)
 flag_run_heads_kernel(const uint64_t* __restrict__ ukmer, uint64_t n, uint32_t* __restrict__ head)
 {
@@ -153,36 +166,47 @@ scatter_run_starts_kernel(const uint32_t* __restrict__ head, const uint32_t* __r
   run_start[scan[i]] = (uint32_t)i;
 }
 
-// words each run needs in the multi array: 0 for single-locus k-mers, else 1 + count
+// words each run needs in the multi array: 0 for single-locus k-mers, else 2 + count
 __global__ void __launch_bounds__(256)
 run_multi_words_kernel(const uint32_t* __restrict__ run_start, uint32_t n_runs, uint32_t* __restrict__ words)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_runs) return;
   const uint32_t len = run_start[r + 1] - run_start[r];
-  words[r] = len > 1 ? len + 1 : 0;
+  words[r] = len > 1 ? len + 2 : 0;
 }
 
 // One thread per distinct k-mer: write its locus list (if several) and insert
-// it into the table.
+// it into the table.  Within a run the on-path loci come first (stable sort of
+// the concatenation), each group ascending.
 template <int FMT>
 __global__ void __launch_bounds__(256)
-insert_runs_kernel(KmerTable t, const uint64_t* __restrict__ ukmer, const uint32_t* __restrict__ ugpos,
+insert_runs_kernel(KmerTable t, const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                    const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ multi_off,
                    uint32_t n_runs, uint32_t* __restrict__ multi, unsigned long long* __restrict__ err_flag)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_runs) return;
   const uint32_t b = run_start[r], e = run_start[r + 1];
-  const uint64_t kmer = ukmer[b];
+  const uint64_t kmer = key[b];
   uint32_t payload, flags;
-  if (e - b == 1) { payload = ugpos[b]; flags = 0; }
+  if (e - b == 1) {
+    const uint64_t v = val[b];
+    payload = (uint32_t)v;
+    flags = (v >> 32) ? FLAG_OFF : 0u;
+  }
   else {
     const uint32_t m = multi_off[r];
-    multi[m] = e - b;
-    for (uint32_t i = b; i < e; ++i) multi[m + 1 + (i - b)] = ugpos[i];
+    uint32_t n_on = 0;
+    for (uint32_t i = b; i < e; ++i) {
+      const uint64_t v = val[i];
+      multi[m + 2 + (i - b)] = (uint32_t)v;
+      n_on += (v >> 32) ? 0u : 1u;
+    }
+    multi[m] = n_on;
+    multi[m + 1] = e - b;
     payload = m;
-    flags = 1;
+    flags = FLAG_MULTI;
   }
   uint32_t prev;
   if (!table_insert<FMT>(t, kmer, payload, flags, false, prev)) atomicOr(err_flag, 2ull);
@@ -199,14 +223,141 @@ static void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, uint64
   c.counters.launches += 2;
 }
 
+// Sort n (kmer, gpos) pairs by (kmer, gpos) and drop duplicates.  On return the unique pairs are
+// in (kmer_out, gpos_out)[0, result); the inputs are clobbered.
+static uint64_t sort_unique_pairs(Ctx& c, DevBuf<uint64_t>& kmer_a, DevBuf<uint32_t>& gpos_a, uint64_t n,
+                                  DevBuf<uint64_t>& kmer_out, DevBuf<uint32_t>& gpos_out)
+{
+  if (n == 0) return 0;
+  DevBuf<uint64_t> kmer_b;
+  DevBuf<uint32_t> gpos_b;
+  kmer_b.ensure(n); gpos_b.ensure(n);
+  // LSD: stable sort by gpos, then stable sort by kmer
+  size_t tmp1 = 0, tmp2 = 0;
+  PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n, 0, 32, c.stream));
+  PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+  DevBuf<char> tmp;
+  tmp.ensure(std::max(tmp1, tmp2));
+  PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n, 0, 32, c.stream));
+  PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+  c.counters.launches += 12;
+  // sorted pairs are in (kmer_a, gpos_a)
+  DevBuf<uint32_t> flag, scan;
+  flag.ensure(n + 1); scan.ensure(n + 1);
+  flag_unique_pairs_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, n, flag.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, flag.p, scan.p, n + 1);
+  uint32_t n_unique = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_unique, scan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  kmer_out.ensure(n_unique); gpos_out.ensure(n_unique);
+  compact_pairs_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, flag.p, scan.p, n, kmer_out.p, gpos_out.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaGetLastError());
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  return n_unique;
+}
+
+// (Re)build the device index from the resident on-path pairs plus `n_off` off-path pairs
+// (both sorted by (kmer, gpos) and duplicate free).
+static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gpos, uint64_t n_off)
+{
+  Shared& sh = *c.sh;
+  const uint64_t n_on = sh.n_on_pairs;
+  const uint64_t n = n_on + n_off;
+  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
+  sh.has_table = false;
+  sh.n_off_pairs = n_off;
+  if (n >= 0xfffffff0ull) throw ArgError("index: more than 2^32 (k-mer, locus) pairs");
+  if (n == 0) {
+    table_alloc(c, sh.index, 1, 2 * c.k, 1024);
+    sh.index.view.stash_nonempty = 0;
+    sh.multi.ensure(4);
+    sh.has_table = true;
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    c.counters.n_index_entries = c.counters.n_index_kmers = 0;
+    return;
+  }
+  PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+  DevBuf<uint64_t> key_a, val_a, key_b, val_b;
+  key_a.ensure(n); val_a.ensure(n);
+  concat_pairs_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(sh.on_kmer.p, sh.on_gpos.p, n_on, off_kmer, off_gpos, n_off, key_a.p, val_a.p);
+  ++c.counters.launches;
+  const uint64_t* key = key_a.p;
+  const uint64_t* val = val_a.p;
+  if (n_off && n_on) {  // stable sort by k-mer keeps on-path loci ahead of off-path loci, each group ascending
+    key_b.ensure(n); val_b.ensure(n);
+    size_t tmp_bytes = 0;
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_a.p, key_b.p, val_a.p, val_b.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+    DevBuf<char> tmp;
+    tmp.ensure(tmp_bytes);
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_a.p, key_b.p, val_a.p, val_b.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+    c.counters.launches += 6;
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    key = key_b.p;
+    val = val_b.p;
+  }
+
+  // k-mer runs
+  DevBuf<uint32_t> flag, scan;
+  flag.ensure(n + 1); scan.ensure(n + 1);
+  flag_run_heads_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(key, n, flag.p);
+  ++c.counters.launches;
+  PSI_CUDA(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, flag.p, scan.p, n + 1);
+  uint32_t n_runs = 0;
+  PSI_CUDA(cudaMemcpyAsync(&n_runs, scan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  DevBuf<uint32_t> run_start, words, multi_off;
+  run_start.ensure((uint64_t)n_runs + 2); words.ensure((uint64_t)n_runs + 2); multi_off.ensure((uint64_t)n_runs + 2);
+  scatter_run_starts_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(flag.p, scan.p, n, n_runs, run_start.p);
+  run_multi_words_kernel<<<grid_for(n_runs, 256), 256, 0, c.stream>>>(run_start.p, n_runs, words.p);
+  c.counters.launches += 2;
+  PSI_CUDA(cudaMemsetAsync(words.p + n_runs, 0, sizeof(uint32_t), c.stream));
+  exclusive_scan_u32(c, words.p, multi_off.p, (uint64_t)n_runs + 1);
+  uint32_t multi_words = 0;
+  PSI_CUDA(cudaMemcpyAsync(&multi_words, multi_off.p + n_runs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  sh.multi.ensure((uint64_t)multi_words + 4);
+
+  table_alloc(c, sh.index, n_runs, 2 * c.k, (uint64_t)n_runs / 512 + 1024);
+  if (sh.index.view.fmt == 8)
+    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+  else
+    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+  ++c.counters.launches;
+  PSI_CUDA(cudaGetLastError());
+  unsigned long long err = 0;
+  uint32_t stash_used = 0;
+  PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(&stash_used, sh.index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  if (err & 2ull) throw OverflowError("path index: hash stash exhausted");
+  sh.index.view.stash_nonempty = stash_used ? 1u : 0u;
+  sh.has_table = true;
+  c.counters.n_index_entries = n;
+  c.counters.n_index_kmers = n_runs;
+  c.counters.n_offpath_entries = n_off;
+  c.counters.index_buckets = sh.index.n_lines;
+  c.counters.index_bytes = sh.index.n_lines * 128 + ((uint64_t)multi_words + 4) * 4 +
+                           ((uint64_t)sh.index.view.stash_mask + 1) * sizeof(Slot16);
+  c.counters.index_slot_bytes = sh.index.view.fmt;
+  c.counters.index_stash_used = stash_used;
+}
+
 void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
                         const uint32_t* head_off, const uint32_t* tail_trim)
 {
   if (!c.sh->has_graph) throw StateError("set_paths: no graph");
   if (c.sh.use_count() > 1) throw StateError("set_paths: the index is shared with forked contexts");
   PSI_CUDA(cudaSetDevice(c.device));
-  c.sh->has_index = false;
-  c.counters.n_path_bases = c.counters.n_index_entries = c.counters.n_index_kmers = 0;
+  Shared& sh = *c.sh;
+  sh.has_index = false;
+  sh.has_table = false;
+  sh.offpath_indexed = false;
+  sh.n_on_pairs = sh.n_off_pairs = 0;
+  c.counters.n_path_bases = c.counters.n_index_entries = c.counters.n_index_kmers = c.counters.n_offpath_entries = 0;
   c.counters.index_bytes = c.counters.index_buckets = 0;
   c.counters.ms_index_build = 0;
   if (n_paths == 0) return;
@@ -214,7 +365,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   if (n_paths >= 0x7fffffffull) throw ArgError("set_paths: too many paths");
   const uint64_t n_entries = path_ptr[n_paths];
   for (uint64_t e = 0; e < n_entries; ++e)
-    if (path_nodes[e] >= c.sh->n_nodes) throw ArgError("set_paths: node rank out of range");
+    if (path_nodes[e] >= sh.n_nodes) throw ArgError("set_paths: node rank out of range");
 
   PhaseTimer timer(c, T_INDEX);
   DevBuf<uint64_t> d_path_ptr;
@@ -236,9 +387,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   }
   const GraphView g = make_graph_view(c);
   unsigned long long* d_cnt = c.dev_counters.p + DC_AUX;
-  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
   PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-  PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
 
   // pass 1: count valid windows
   const unsigned wgrid = (unsigned)std::min<uint64_t>((n_entries + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
@@ -249,98 +398,23 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   if (n_pairs >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows (index them in several contexts)");
   c.counters.n_path_bases = n_pairs;
-  if (n_pairs == 0) {  // paths shorter than k: empty index
-    table_alloc(c, c.sh->index, 1, 2 * c.k, 1ull << 30, 1024);
-    c.sh->index.view.stash_nonempty = 0;
-    c.sh->multi.ensure(2);
-    c.sh->has_index = true;
-    timer.stop();
-    PSI_CUDA(cudaStreamSynchronize(c.stream));
-    c.counters.ms_index_build = timer.ms();
-    return;
+
+  // pass 2: emit (kmer, gpos), sort, unique -> the resident on-path pairs
+  if (n_pairs) {
+    DevBuf<uint64_t> kmer_a;
+    DevBuf<uint32_t> gpos_a;
+    kmer_a.ensure(n_pairs); gpos_a.ensure(n_pairs);
+    PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+    path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, kmer_a.p, gpos_a.p, d_cnt);
+    ++c.counters.launches;
+    sh.on_kmer.release(); sh.on_gpos.release();
+    sh.n_on_pairs = sort_unique_pairs(c, kmer_a, gpos_a, n_pairs, sh.on_kmer, sh.on_gpos);
   }
-
-  // pass 2: emit (kmer, gpos)
-  DevBuf<uint64_t> kmer_a, kmer_b;
-  DevBuf<uint32_t> gpos_a, gpos_b;
-  kmer_a.ensure(n_pairs); kmer_b.ensure(n_pairs);
-  gpos_a.ensure(n_pairs); gpos_b.ensure(n_pairs);
-  PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-  path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, kmer_a.p, gpos_a.p, d_cnt);
-  ++c.counters.launches;
-
-  // sort by (kmer, gpos): LSD = stable sort by gpos, then stable sort by kmer
-  {
-    size_t tmp1 = 0, tmp2 = 0;
-    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n_pairs, 0, 32, c.stream));
-    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n_pairs, 0, (int)(2 * c.k), c.stream));
-    DevBuf<char> tmp;
-    tmp.ensure(std::max(tmp1, tmp2));
-    PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp1, gpos_a.p, gpos_b.p, kmer_a.p, kmer_b.p, (int64_t)n_pairs, 0, 32, c.stream));
-    PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp2, kmer_b.p, kmer_a.p, gpos_b.p, gpos_a.p, (int64_t)n_pairs, 0, (int)(2 * c.k), c.stream));
-    c.counters.launches += 12;
-    PSI_CUDA(cudaStreamSynchronize(c.stream));
-  }
-  // sorted pairs are now in (kmer_a, gpos_a)
-
-  // unique pairs
-  DevBuf<uint32_t> flag, scan;
-  flag.ensure(n_pairs + 1); scan.ensure(n_pairs + 1);
-  flag_unique_pairs_kernel<<<grid_for(n_pairs, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, n_pairs, flag.p);
-  ++c.counters.launches;
-  PSI_CUDA(cudaMemsetAsync(flag.p + n_pairs, 0, sizeof(uint32_t), c.stream));
-  exclusive_scan_u32(c, flag.p, scan.p, n_pairs + 1);
-  uint32_t n_unique = 0;
-  PSI_CUDA(cudaMemcpyAsync(&n_unique, scan.p + n_pairs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-  compact_pairs_kernel<<<grid_for(n_pairs, 256), 256, 0, c.stream>>>(kmer_a.p, gpos_a.p, flag.p, scan.p, n_pairs, kmer_b.p, gpos_b.p);
-  ++c.counters.launches;
-  PSI_CUDA(cudaStreamSynchronize(c.stream));
-  // unique pairs are in (kmer_b, gpos_b)[0, n_unique)
-
-  // k-mer runs
-  flag_run_heads_kernel<<<grid_for(n_unique, 256), 256, 0, c.stream>>>(kmer_b.p, n_unique, flag.p);
-  ++c.counters.launches;
-  PSI_CUDA(cudaMemsetAsync(flag.p + n_unique, 0, sizeof(uint32_t), c.stream));
-  exclusive_scan_u32(c, flag.p, scan.p, (uint64_t)n_unique + 1);
-  uint32_t n_runs = 0;
-  PSI_CUDA(cudaMemcpyAsync(&n_runs, scan.p + n_unique, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-  PSI_CUDA(cudaStreamSynchronize(c.stream));
-  DevBuf<uint32_t> run_start, words, multi_off;
-  run_start.ensure((uint64_t)n_runs + 2); words.ensure((uint64_t)n_runs + 2); multi_off.ensure((uint64_t)n_runs + 2);
-  scatter_run_starts_kernel<<<grid_for(n_unique, 256), 256, 0, c.stream>>>(flag.p, scan.p, n_unique, n_runs, run_start.p);
-  run_multi_words_kernel<<<grid_for(n_runs, 256), 256, 0, c.stream>>>(run_start.p, n_runs, words.p);
-  c.counters.launches += 2;
-  PSI_CUDA(cudaMemsetAsync(words.p + n_runs, 0, sizeof(uint32_t), c.stream));
-  exclusive_scan_u32(c, words.p, multi_off.p, (uint64_t)n_runs + 1);
-  uint32_t multi_words = 0;
-  PSI_CUDA(cudaMemcpyAsync(&multi_words, multi_off.p + n_runs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
-  PSI_CUDA(cudaStreamSynchronize(c.stream));
-  c.sh->multi.ensure((uint64_t)multi_words + 2);
-
-  // table
-  table_alloc(c, c.sh->index, n_runs, 2 * c.k, 1ull << 30, (uint64_t)n_runs / 512 + 1024);
-  if (c.sh->index.view.fmt == 8)
-    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.sh->index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.sh->multi.p, d_err);
-  else
-    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(c.sh->index.view, kmer_b.p, gpos_b.p, run_start.p, multi_off.p, n_runs, c.sh->multi.p, d_err);
-  ++c.counters.launches;
-  PSI_CUDA(cudaGetLastError());
-  unsigned long long err = 0;
-  uint32_t stash_used = 0;
-  PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
-  PSI_CUDA(cudaMemcpyAsync(&stash_used, c.sh->index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  build_table(c, nullptr, nullptr, 0);
+  sh.has_index = true;
   timer.stop();
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  if (err & 2ull) throw OverflowError("path index: hash stash exhausted");
-  c.sh->index.view.stash_nonempty = stash_used ? 1u : 0u;
-  c.sh->has_index = true;
   c.counters.ms_index_build = timer.ms();
-  c.counters.n_index_entries = n_unique;
-  c.counters.n_index_kmers = n_runs;
-  c.counters.index_buckets = c.sh->index.n_lines * 4;
-  c.counters.index_bytes = c.sh->index.n_lines * 128 + ((uint64_t)multi_words + 2) * 4 +
-                           ((uint64_t)c.sh->index.view.stash_mask + 1) * sizeof(Slot16);
-  c.counters.index_slot_bytes = c.sh->index.view.fmt;
 }
 
 // -------------------------------------------------------- starting loci --
@@ -412,6 +486,107 @@ emit_loci_kernel(GraphView g, const uint32_t* __restrict__ flags, const uint32_t
   }
 }
 
+// ------------------------------------------- off-path walks -> index --
+//
+// seeds_off_paths of the reference re-walks the graph from every starting locus
+// for every read chunk (seed_finder.hpp:1703-1722).  The set of k-mers those
+// walks spell does not depend on the reads, so it is enumerated ONCE here -- same
+// walker, same rules -- and every (k-mer, start locus) pair that the path index
+// does not already hold is merged into the index as an off-path entry.  A chunk
+// is then answered by one probe per seed, on-path and off-path alike.  When the
+// walks are too many to store (hypervariable graphs, large k) the per-chunk walk
+// of seeds.cu is used instead (offpath_mode 1); both give the same seed set.
+
+struct OffPathSink {
+  KmerTable t;
+  const uint32_t* multi;
+  uint32_t has_table;
+  uint64_t* out_kmer;           // null: count only
+  uint32_t* out_gpos;
+  uint64_t cap;
+  unsigned long long* count;
+  __device__ bool skip(uint32_t) const { return false; }
+  __device__ void complete(uint64_t kmer, uint32_t origin)
+  {
+    if (has_table && index_contains(t, multi, kmer, origin)) return;
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    if (out_kmer && slot < cap) { out_kmer[slot] = kmer; out_gpos[slot] = origin; }
+  }
+  __device__ void finish() {}
+};
+
+__global__ void __launch_bounds__(WALK_WARPS * 32)
+collect_offpath_kernel(GraphView g, uint32_t k, uint64_t n_loci, const uint32_t* loci_node, const uint32_t* loci_off,
+                       OffPathSink sink, unsigned long long* work, WalkItem* spill, uint32_t spill_items,
+                       unsigned long long* err)
+{
+  __shared__ WalkItem smem[WALK_WARPS * WALK_SMEM_ITEMS];
+  LociSource src{ g, loci_node, loci_off };
+  walk_all(g, k, n_loci, work, smem, spill, spill_items, err, src, sink);
+}
+
+// Decide the off-path mode for the current loci and, in index mode, merge the walks into the table.
+static void materialise_offpath(Ctx& c)
+{
+  Shared& sh = *c.sh;
+  sh.offpath_indexed = false;
+  c.counters.n_offpath_walks = 0;
+  c.counters.offpath_mode = 1;
+  const bool had_off = sh.n_off_pairs != 0;
+  auto drop_off = [&] { if (had_off || !sh.has_table) build_table(c, nullptr, nullptr, 0); };
+  if (sh.n_loci == 0) { drop_off(); sh.offpath_indexed = true; c.counters.offpath_mode = 2; return; }
+  if (c.opt_offpath_mode == 1) { drop_off(); return; }
+  if (!sh.has_table) build_table(c, nullptr, nullptr, 0);
+
+  const GraphView g = make_graph_view(c);
+  const unsigned grid = (unsigned)c.sm_count * 8;
+  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
+  unsigned long long* d_work = c.dev_counters.p + DC_WORK;
+  unsigned long long* d_cnt = c.dev_counters.p + DC_AUX;
+  DevBuf<uint64_t> kmer_a;
+  DevBuf<uint32_t> gpos_a;
+  uint64_t n_walks = 0;
+  // pass 0 counts the uncovered walks, pass 1 stores them
+  for (int pass = 0; pass < 2; ++pass) {
+    while (true) {
+      PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+      PSI_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), c.stream));
+      PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+      c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
+      OffPathSink sink{ sh.index.view, sh.multi.p, sh.has_table ? 1u : 0u, pass ? kmer_a.p : nullptr, gpos_a.p, n_walks, d_cnt };
+      collect_offpath_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, sh.n_loci, sh.loci_node.p, sh.loci_off.p, sink,
+                                                                    d_work, (WalkItem*)c.walk_spill.p, c.spill_items, d_err);
+      ++c.counters.launches;
+      PSI_CUDA(cudaGetLastError());
+      unsigned long long h[2] = { 0, 0 };
+      PSI_CUDA(cudaMemcpyAsync(&h[0], d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+      PSI_CUDA(cudaMemcpyAsync(&h[1], d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      if (h[0] & 1ull) {
+        if (c.spill_items >= (1u << 20)) throw OverflowError("off-path walks: frontier exceeds 2^20 states per warp");
+        c.spill_items *= 4;
+        continue;
+      }
+      if (pass == 0) n_walks = h[1];
+      else if (h[1] != n_walks) throw StateError("off-path walks: enumeration is not reproducible");
+      break;
+    }
+    if (pass == 0) {
+      c.counters.n_offpath_walks = n_walks;
+      if (n_walks >= 0xfffffff0ull || (c.opt_offpath_mode == 0 && n_walks > c.opt_offpath_max_pairs)) { drop_off(); return; }
+      if (n_walks == 0) break;
+      kmer_a.ensure(n_walks); gpos_a.ensure(n_walks);
+    }
+  }
+  DevBuf<uint64_t> off_kmer;
+  DevBuf<uint32_t> off_gpos;
+  const uint64_t n_off = sort_unique_pairs(c, kmer_a, gpos_a, n_walks, off_kmer, off_gpos);
+  kmer_a.release(); gpos_a.release();
+  if (n_off || had_off) build_table(c, off_kmer.p, off_gpos.p, n_off);
+  sh.offpath_indexed = true;
+  c.counters.offpath_mode = 2;
+}
+
 void engine_find_loci(Ctx& c, unsigned step)
 {
   if (!c.sh->has_graph) throw StateError("find_loci: no graph");
@@ -431,7 +606,7 @@ void engine_find_loci(Ctx& c, unsigned step)
     PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
     PSI_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), c.stream));
     c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
-    find_loci_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, step, c.sh->index.view, c.sh->multi.p, c.sh->has_index ? 1u : 0u,
+    find_loci_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, step, c.sh->index.view, c.sh->multi.p, c.sh->has_table ? 1u : 0u,
                                                             flags.p, d_work, (WalkItem*)c.walk_spill.p, c.spill_items, d_err);
     ++c.counters.launches;
     PSI_CUDA(cudaGetLastError());
@@ -455,11 +630,13 @@ void engine_find_loci(Ctx& c, unsigned step)
     emit_loci_kernel<<<grid_for(n_words, 256), 256, 0, c.stream>>>(g, flags.p, scan.p, n_words, c.sh->loci_node.p, c.sh->loci_off.p);
     ++c.counters.launches;
   }
-  timer.stop();
   PSI_CUDA(cudaGetLastError());
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   c.sh->n_loci = n_loci;
   c.counters.n_loci = n_loci;
+  materialise_offpath(c);
+  timer.stop();
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
   c.counters.ms_find_loci = timer.ms();
 }
 
@@ -478,6 +655,22 @@ void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* o
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   c.sh->n_loci = n;
   c.counters.n_loci = n;
+  materialise_offpath(c);
+}
+
+void engine_set_option(Ctx& c, const char* name, long long value)
+{
+  if (!name) throw ArgError("set_option: null name");
+  const std::string n = name;
+  if (n == "offpath_mode") {
+    if (value < 0 || value > 2) throw ArgError("set_option: offpath_mode is 0 (auto), 1 (walk per chunk) or 2 (materialise)");
+    c.opt_offpath_mode = (int)value;
+  }
+  else if (n == "offpath_max_pairs") {
+    if (value < 0) throw ArgError("set_option: offpath_max_pairs must be >= 0");
+    c.opt_offpath_max_pairs = (uint64_t)value;
+  }
+  else throw ArgError("set_option: unknown option '" + n + "'");
 }
 
 void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap)

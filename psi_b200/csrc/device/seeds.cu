@@ -21,115 +21,130 @@ void engine_index_chunk(Ctx& c);
 // and the chunk's seeds yields |path occurrences| x |seed occurrences| hits.
 // The reference co-traverses an FM-index and a suffix tree in lexicographic
 // order (2 wavelet-tree ranks + one tree descent per character, then <= 32 LF
-// steps per located occurrence); here each seed is ONE probe:
-//   thread = ITEMS seeds; packed k-mer (coalesced 8 B) -> home bucket ->
-//   one 32-byte sector load (LDG.256, all ITEMS loads in flight before the
-//   first compare) -> tag compare -> warp-aggregated reservation of output
-//   slots (one atomic per warp for 32 x ITEMS probes) -> 8-byte compact hits.
+// steps per located occurrence); here each seed is ONE probe of ONE 128-byte
+// bucket line (the DRAM access unit, profiles/r01c_gather_peak.md):
+//   4 lanes per seed; packed k-mer (8 B, broadcast within the quad) -> home line ->
+//   each lane loads one 32-byte sector of the line (one LDG.256 per lane, the
+//   quad's four sectors are one 128-byte request; ITEMS requests in flight per
+//   thread before the first compare) -> 4 tag compares per lane -> the lane that
+//   holds the key stores the seed's result: seed_hit[s] = locus, seed_kind[s] =
+//   1 (on an indexed path) / 2 (only reachable by an off-path walk) / 0 (none).
+// No atomics, no compaction here: the results are per seed, in seed order; the
+// compaction happens in compact_resolve_kernel.  The rare seeds that one line
+// cannot settle (locus lists; home line full and key displaced) are queued for
+// seeds_slow_kernel.  When the off-path walks are materialised in the index
+// (offpath_mode 2) the same probe also answers seeds_off_paths.
 // Because the index holds DISTINCT (k-mer, locus) pairs and a seed index is
-// unique, the hits of this kernel are already a set.
+// unique, the hits are already a set.
 
-template <int FMT>
-__device__ __forceinline__ int eval_sector(const uint64_t (&v)[4], const Home& h, uint64_t kmer,
-                                           uint32_t& payload, bool& multi)
+__device__ __forceinline__ uint8_t kind_of(uint32_t flags, uint32_t mode)
 {
-  // 1 = found, 0 = definitely absent (bucket has a free slot), -1 = bucket full, look further
-  bool has_empty = false;
-  if (FMT == 8) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (v[j] == EMPTY8) has_empty = true;
-      else if ((v[j] >> 33) == h.tag) { payload = (uint32_t)v[j]; multi = (v[j] >> 32) & 1u; return 1; }
-    }
-  }
-  else {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t fl = (uint32_t)(v[2 * j + 1] >> 32);
-      if (fl == NIL32) has_empty = true;
-      else if (v[2 * j] == kmer) { payload = (uint32_t)v[2 * j + 1]; multi = fl == 1; return 1; }
-    }
-  }
-  return has_empty ? 0 : -1;
+  return (flags & FLAG_OFF) ? ((mode & PSI_B200_OFF_PATHS) ? 2 : 0) : ((mode & PSI_B200_ON_PATHS) ? 1 : 0);
 }
 
-template <int FMT, int ITEMS, bool COUNT_SECTORS>
-__global__ void __launch_bounds__(256)
-seeds_on_paths_kernel(KmerTable t, const uint32_t* __restrict__ multi,
-                      const uint64_t* __restrict__ seed_kmer, const uint32_t* __restrict__ seed_valid,
-                      const unsigned long long* __restrict__ n_seeds_p,
-                      Hit* __restrict__ hits, uint64_t hits_cap, unsigned long long* __restrict__ hit_count,
-                      unsigned long long* __restrict__ sector_count)
+template <int FMT, int ITEMS>
+__global__ void __launch_bounds__(256, 4)
+seeds_on_paths_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const uint8_t* __restrict__ seed_valid,
+                      const unsigned long long* __restrict__ n_seeds_p, uint32_t mode,
+                      uint32_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
+                      uint32_t* __restrict__ slow_queue, unsigned long long* __restrict__ slow_count)
 {
   const uint32_t n_seeds = (uint32_t)*n_seeds_p;
-  const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
-  if (blockIdx.x * (256u * ITEMS) >= n_seeds) return;   // whole CTA out of range
+  const uint32_t block_base = blockIdx.x * (64u * ITEMS);
+  if (block_base >= n_seeds) return;   // whole CTA out of range
+  const uint32_t lane = lane_id();
+  const uint32_t sub = lane & 3u;
+  const uint32_t quad_shift = lane & ~3u;
+  const uint32_t quad = threadIdx.x >> 2;
 
   uint64_t km[ITEMS];
-  bool ok[ITEMS];
-  Home hm[ITEMS];
   uint64_t v[ITEMS][4];
+  uint32_t okmask = 0;
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    const uint32_t s = base + i * 256u;
-    ok[i] = s < n_seeds && ((__ldg(seed_valid + (s >> 5)) >> (s & 31u)) & 1u);
-    km[i] = ok[i] ? __ldg(seed_kmer + s) : 0;
+    const uint32_t s = block_base + i * 64u + quad;
+    const bool ok = s < n_seeds && __ldg(seed_valid + s) != 0;
+    km[i] = ok ? __ldg(seed_kmer + s) : 0;
+    okmask |= (ok ? 1u : 0u) << i;
+  }
+  uint32_t want[ITEMS];   // fmt 8: tag | displacement 0 (30 bits)
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const Home h = home_of<FMT>(t, km[i]);
+    want[i] = (uint32_t)h.tag;
+    // every lane loads (the quads of invalid seeds read the line of k-mer 0: harmless, keeps the loop branch free)
+    ld_sector_nc((const char*)t.slots + (h.line << 7) + (sub << 5), v[i]);
   }
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
-    if (ok[i]) {
-      hm[i] = home_of<FMT>(t, km[i]);
-      ld_sector_nc((const char*)t.slots + hm[i].line * 128u + (hm[i].sec << 5), v[i]);
-    }
-  }
-  uint32_t payload[ITEMS];
-  uint32_t count[ITEMS];
-  bool is_multi[ITEMS];
-  uint32_t total = 0, sectors = 0;
+    bool hit = false, empty = false;
+    uint32_t pl = 0, fl = 0;
+    if (FMT == 8) {
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    count[i] = 0;
-    is_multi[i] = false;
-    payload[i] = 0;
-    if (ok[i]) {
-      ++sectors;
-      int st = eval_sector<FMT>(v[i], hm[i], km[i], payload[i], is_multi[i]);
-      if (st < 0) {  // home bucket full: the other three buckets of the line, then the stash
-        bool found = false;
-        const char* line = (const char*)t.slots + hm[i].line * 128u;
-        for (uint32_t j = 1; j < 4 && st < 0; ++j) {
-          uint64_t w[4];
-          ld_sector_nc(line + (((hm[i].sec + j) & 3u) << 5), w);
-          ++sectors;
-          st = eval_sector<FMT>(w, hm[i], km[i], payload[i], is_multi[i]);
-        }
-        if (st < 0) found = stash_find(t, km[i], payload[i], is_multi[i]);
-        else found = st == 1;
-        st = found ? 1 : 0;
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t hi = (uint32_t)(v[i][j] >> 32);
+        empty |= hi == 0xffffffffu;             // no valid entry has all of rem/disp/flags set (flags 3 is never stored)
+        if ((hi >> 2) == want[i]) { hit = true; pl = (uint32_t)v[i][j]; fl = hi & 3u; }
       }
-      if (st == 1) count[i] = is_multi[i] ? __ldg(multi + payload[i]) : 1u;
-    }
-    total += count[i];
-  }
-  // one reservation per warp for all its probes
-  uint64_t slot = warp_reserve(hit_count, total);
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    if (!count[i]) continue;
-    const uint32_t s = base + i * 256u;
-    if (!is_multi[i]) {
-      if (slot < hits_cap) hits[slot] = Hit{ s, payload[i] };
-      ++slot;
     }
     else {
-      for (uint32_t j = 0; j < count[i]; ++j, ++slot)
-        if (slot < hits_cap) hits[slot] = Hit{ s, __ldg(multi + payload[i] + 1 + j) };
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t f2 = (uint32_t)(v[i][2 * j + 1] >> 32);
+        empty |= f2 == NIL32;
+        if (f2 != NIL32 && v[i][2 * j] == km[i]) { hit = true; pl = (uint32_t)v[i][2 * j + 1]; fl = f2 & 3u; }
+      }
+    }
+    const bool ok = (okmask >> i) & 1u;
+    hit &= ok;
+    const uint32_t q_hit = (__ballot_sync(0xffffffffu, hit) >> quad_shift) & 15u;
+    const uint32_t q_empty = (__ballot_sync(0xffffffffu, empty) >> quad_shift) & 15u;
+    const uint32_t s = block_base + i * 64u + quad;
+    if (hit) {
+      uint8_t kind = kind_of(fl, mode);
+      if (fl & FLAG_MULTI) { kind = 3; slow_queue[atomicAdd(slow_count, 1ull)] = s; }
+      seed_hit[s] = pl;
+      seed_kind[s] = kind;
+    }
+    else if (sub == 0 && q_hit == 0 && s < n_seeds) {
+      // nobody holds the key: absent when the line has a free slot, else it may sit in a following line
+      uint8_t kind = 0;
+      if (ok && q_empty == 0) { kind = 3; slow_queue[atomicAdd(slow_count, 1ull)] = s; }
+      seed_kind[s] = kind;
     }
   }
-  if (COUNT_SECTORS) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sectors += __shfl_xor_sync(0xffffffffu, sectors, d);
-    if (lane_id() == 0) atomicAdd(sector_count, (unsigned long long)sectors);
+}
+
+// The seeds the probe kernel could not settle from one line: full search (following lines, stash) and
+// locus lists, whose entries go to the overflow hit list.  One thread per queued seed.
+__global__ void __launch_bounds__(256)
+seeds_slow_kernel(KmerTable t, const uint32_t* __restrict__ multi, const uint64_t* __restrict__ seed_kmer,
+                  const uint32_t* __restrict__ slow_queue, const unsigned long long* __restrict__ slow_count, uint32_t mode,
+                  uint32_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
+                  Hit* __restrict__ ovf, uint8_t* __restrict__ ovf_kind, uint64_t ovf_cap, unsigned long long* __restrict__ ovf_count)
+{
+  const uint64_t n = *slow_count;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = slow_queue[q];
+    Found f;
+    uint8_t kind = 0;
+    if (table_find_any(t, __ldg(seed_kmer + s), f)) {
+      if (!(f.flags & FLAG_MULTI)) {
+        kind = kind_of(f.flags, mode);
+        seed_hit[s] = f.payload;
+      }
+      else {
+        const uint32_t n_on = __ldg(multi + f.payload), n_all = __ldg(multi + f.payload + 1);
+        const uint32_t from = (mode & PSI_B200_ON_PATHS) ? 0u : n_on;
+        const uint32_t to = (mode & PSI_B200_OFF_PATHS) ? n_all : n_on;
+        if (to > from) {
+          uint64_t slot = atomicAdd(ovf_count, (unsigned long long)(to - from));
+          for (uint32_t j = from; j < to; ++j, ++slot)
+            if (slot < ovf_cap) { ovf[slot] = Hit{ s, __ldg(multi + f.payload + 2 + j) }; ovf_kind[slot] = j < n_on ? 1 : 2; }
+        }
+      }
+    }
+    seed_kind[s] = kind;
   }
 }
 
@@ -143,21 +158,6 @@ seeds_on_paths_kernel(KmerTable t, const uint32_t* __restrict__ multi,
 //   - several walks from one locus spelling the same k-mer -> the first one to
 //     claim (chain head, locus) in a device hash set reports, the others skip.
 
-struct LociSource {
-  GraphView g;
-  const uint32_t* node;
-  const uint32_t* off;
-  __device__ bool init(uint64_t idx, WalkItem& it) const
-  {
-    const uint32_t v = __ldg(node + idx), o = __ldg(off + idx);
-    if (v >= g.n_nodes) return false;
-    const NodeRec r = g.rec[v];
-    if (o >= r.seq_len) return false;
-    it.kmer = 0; it.origin = r.seq_start + o; it.node = v; it.off = o; it.depth = 0;
-    return true;
-  }
-};
-
 struct ReadIndexSink {
   KmerTable rt;                 // chunk read index
   const uint32_t* next;         // seed chains
@@ -166,7 +166,8 @@ struct ReadIndexSink {
   uint32_t has_index;
   unsigned long long* dedup;    // hash set of (chain head << 32 | locus)
   uint64_t dedup_mask;
-  Hit* hits;
+  Hit* hits;                    // overflow hit list (shared with seeds_slow_kernel)
+  uint8_t* hit_kind;
   uint64_t hits_cap;
   unsigned long long* hit_count;
   unsigned long long* walk_count;
@@ -191,17 +192,16 @@ struct ReadIndexSink {
   __device__ void complete(uint64_t kmer, uint32_t origin)
   {
     ++walks;
-    uint32_t head;
-    bool m;
-    const bool found = rt.fmt == 8 ? table_find<8>(rt, kmer, head, m) : table_find<16>(rt, kmer, head, m);
-    if (!found) return;
+    Found f;
+    if (!table_find_any(rt, kmer, f)) return;
+    const uint32_t head = f.payload;
     if (has_index && index_contains(pt, multi, kmer, origin)) return;
     if (!claim(((uint64_t)head << 32) | origin)) return;
     uint32_t n = 0;
     for (uint32_t s = head; s != NIL32; s = __ldg(next + s)) ++n;
     uint64_t slot = atomicAdd(hit_count, (unsigned long long)n);
     for (uint32_t s = head; s != NIL32; s = __ldg(next + s), ++slot)
-      if (slot < hits_cap) hits[slot] = Hit{ s, origin };
+      if (slot < hits_cap) { hits[slot] = Hit{ s, origin }; hit_kind[slot] = 2; }
   }
 
   __device__ void finish()
@@ -225,11 +225,110 @@ seeds_off_paths_kernel(GraphView g, uint32_t k, uint64_t n_loci, const uint32_t*
 
 // ============================================================= resolve ==
 //
-// Compact hit (seed, global position) -> the reference's output record
+// Per-seed results + overflow list -> the dense output: the reference's records
 // (seed.hpp:32-46 as written by src/psikt.cpp:172-181): node_id, node_offset,
 // read_id, read_offset, 4 x u64.  read_id / read_offset replace
 // Records::position_to_id/offset (sequence.hpp:1201-1213,1277-1289); the node
 // lookup replaces position_to_id/offset(PathIndex) (pathindex.hpp:378-416).
+// A CTA takes 512 consecutive items (seeds first, then overflow entries), counts
+// its hits with ballots, reserves their output range with ONE atomic and writes
+// them in item order, so the output of a chunk is ordered by (read, offset) up
+// to the CTA granularity and the stores of a warp are contiguous.
+struct Resolved {
+  uint64_t node_id, node_off, read_id, read_off;
+};
+
+__device__ __forceinline__ Resolved resolve_one(const GraphView& g, const uint64_t* __restrict__ node_id, uint32_t seed, uint32_t gpos,
+                                                const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
+                                                uint32_t d, uint64_t first_read_id)
+{
+  Resolved o;
+  const uint32_t r = __ldg(seed_read + seed);
+  o.read_id = first_read_id + r;
+  o.read_off = (uint64_t)(seed - __ldg(seed_first + r)) * d;
+  const uint32_t v = node_of_pos(g, gpos);
+  o.node_off = gpos - __ldg(&g.rec[v].seq_start);
+  o.node_id = __ldg(node_id + v);
+  return o;
+}
+
+template <bool RECORDS>
+__global__ void __launch_bounds__(256)
+compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
+                       const uint32_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
+                       const unsigned long long* __restrict__ n_seeds_p,
+                       const Hit* __restrict__ ovf, const uint8_t* __restrict__ ovf_kind,
+                       const unsigned long long* __restrict__ n_ovf_p, uint64_t ovf_cap,
+                       const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
+                       uint32_t d, uint64_t first_read_id,
+                       uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, Hit* __restrict__ out_hits, uint64_t cap,
+                       unsigned long long* __restrict__ total, unsigned long long* __restrict__ total_on)
+{
+  __shared__ uint32_t s_cnt[16];
+  __shared__ unsigned long long s_base;
+  const uint64_t n_seeds = *n_seeds_p;
+  uint64_t n_ovf = *n_ovf_p;
+  if (n_ovf > ovf_cap) n_ovf = ovf_cap;
+  const uint64_t n_items = n_seeds + n_ovf;
+  const uint64_t base = (uint64_t)blockIdx.x * 512u;
+  if (base >= n_items) return;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+
+  uint32_t seed[2], gpos[2];
+  uint8_t kind[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t i = base + h * 256u + threadIdx.x;
+    kind[h] = 0; seed[h] = 0; gpos[h] = 0;
+    if (i < n_seeds) {
+      kind[h] = __ldg(seed_kind + i);
+      if (kind[h] > 2) kind[h] = 0;
+      seed[h] = (uint32_t)i;
+      if (kind[h]) gpos[h] = __ldg(seed_hit + i);
+    }
+    else if (i < n_items) {
+      const Hit x = ovf[i - n_seeds];
+      kind[h] = ovf_kind[i - n_seeds];
+      seed[h] = x.seed;
+      gpos[h] = x.gpos;
+    }
+  }
+  const uint32_t m0 = __ballot_sync(0xffffffffu, kind[0] != 0), m1 = __ballot_sync(0xffffffffu, kind[1] != 0);
+  const uint32_t on = __popc(__ballot_sync(0xffffffffu, kind[0] == 1)) + __popc(__ballot_sync(0xffffffffu, kind[1] == 1));
+  if (lane == 0) {
+    s_cnt[warp] = __popc(m0);
+    s_cnt[8 + warp] = __popc(m1);
+    if (on) atomicAdd(total_on, (unsigned long long)on);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = run; run += c; }
+    s_base = run ? atomicAdd(total, (unsigned long long)run) : 0ull;
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t out[2] = { s_base + s_cnt[warp] + __popc(m0 & lt), s_base + s_cnt[8 + warp] + __popc(m1 & lt) };
+  // both resolutions are issued before either is stored: two chains of dependent loads in flight per thread
+  Resolved r[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (RECORDS && kind[h] && out[h] < cap) r[h] = resolve_one(g, node_id, seed[h], gpos[h], seed_read, seed_first, d, first_read_id);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!kind[h] || out[h] >= cap) continue;
+    if (RECORDS) {
+      ulonglong2* o = reinterpret_cast<ulonglong2*>(records + 4 * out[h]);
+      o[0] = make_ulonglong2(r[h].node_id, r[h].node_off);
+      o[1] = make_ulonglong2(r[h].read_id, r[h].read_off);
+      rec_kind[out[h]] = kind[h];
+    }
+    else out_hits[out[h]] = Hit{ seed[h], gpos[h] };
+  }
+}
+
+// sorted compact hits -> records (only used with PSI_B200_SORTED)
 __global__ void __launch_bounds__(256)
 resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ node_id, const Hit* __restrict__ hits, uint64_t n_hits,
                     const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
@@ -238,13 +337,10 @@ resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ node_id, const Hit
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_hits) return;
   const Hit h = hits[i];
-  const uint32_t r = __ldg(seed_read + h.seed);
-  const uint64_t read_off = (uint64_t)(h.seed - __ldg(seed_first + r)) * d;
-  const uint32_t v = node_of_pos(g, h.gpos);
-  const uint64_t node_off = h.gpos - __ldg(&g.rec[v].seq_start);
-  ulonglong2* out = reinterpret_cast<ulonglong2*>(records + 4 * i);
-  out[0] = make_ulonglong2(__ldg(node_id + v), node_off);
-  out[1] = make_ulonglong2(first_read_id + r, read_off);
+  const Resolved r = resolve_one(g, node_id, h.seed, h.gpos, seed_read, seed_first, d, first_read_id);
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(records + 4 * i);
+  o[0] = make_ulonglong2(r.node_id, r.node_off);
+  o[1] = make_ulonglong2(r.read_id, r.read_off);
 }
 
 // ================================================================ host ==
@@ -260,82 +356,136 @@ void engine_seeds(Ctx& c, unsigned flags)
 {
   if (!c.has_chunk) throw StateError("seeds_all: no read chunk submitted");
   PSI_CUDA(cudaSetDevice(c.device));
-  const bool do_on = (flags & PSI_B200_ON_PATHS) && c.sh->has_index;
-  const bool do_off = (flags & PSI_B200_OFF_PATHS) && c.sh->n_loci > 0;
+  Shared& sh = *c.sh;
+  // index mode: the off-path walks are entries of the table, one probe answers both questions.
+  const bool index_mode = sh.offpath_indexed;
+  const bool want_on = (flags & PSI_B200_ON_PATHS) && sh.has_index;
+  const bool want_off = (flags & PSI_B200_OFF_PATHS) && sh.n_loci > 0;
+  const bool do_probe = sh.has_table && (want_on || (want_off && index_mode && sh.n_off_pairs > 0));
+  const bool do_walk = want_off && !index_mode;
+  const unsigned probe_mode = (want_on ? PSI_B200_ON_PATHS : 0u) | (want_off && index_mode ? PSI_B200_OFF_PATHS : 0u);
+  const bool sorted = (flags & PSI_B200_SORTED) != 0;
+  const bool resolve = !(flags & PSI_B200_NO_RESOLVE);
   const GraphView g = make_graph_view(c);
   unsigned long long* dc = c.dev_counters.p;
   c.records_valid = false;
+  c.kinds_valid = false;
   c.ev_state[T_ON] = c.ev_state[T_OFF] = c.ev_state[T_RESOLVE] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
 
-  if (c.hits.cap == 0) c.hits.ensure(std::max<uint64_t>(2 * c.n_seeds_cap, 1u << 20));
-  if (c.dedup.cap == 0) c.dedup.ensure(1u << 20);
-  uint64_t n_on = 0, n_total = 0, n_walks = 0, n_sectors = 0, n_seeds = 0;
+  c.seed_hit.ensure(c.n_seeds_cap, 1.25);
+  c.seed_kind.ensure(c.n_seeds_cap + 16, 1.25);
+  if (c.hits.cap == 0) { c.hits.ensure(1u << 20); c.hit_kind.ensure(c.hits.cap); }
+  uint64_t out_cap_want = std::max<uint64_t>(c.n_seeds_cap + c.n_seeds_cap / 4, 1u << 20);
+  uint64_t n_total = 0, n_on = 0, n_walks = 0, n_seeds = 0, n_slow = 0;
+  bool redo_search = true;
 
   for (int attempt = 0;; ++attempt) {
-    if (attempt > 12) throw OverflowError("seeds_all: device buffers keep overflowing");
-    PSI_CUDA(cudaMemsetAsync(dc + DC_HITS, 0, 5 * sizeof(unsigned long long), c.stream));  // HITS..WORK
-    const uint64_t hits_cap = c.hits.cap;
+    if (attempt > 16) throw OverflowError("seeds_all: device buffers keep overflowing");
+    if (redo_search) {
+      PSI_CUDA(cudaMemsetAsync(dc + DC_HITS, 0, 5 * sizeof(unsigned long long), c.stream));  // HITS..WORK
+      PSI_CUDA(cudaMemsetAsync(dc + DC_OVF, 0, 2 * sizeof(unsigned long long), c.stream));   // OVF, SLOW
+      PhaseTimer t_on(c, T_ON);
+      if (do_probe) {
+        constexpr int ITEMS = 4;
+        const unsigned grid = grid_for(c.n_seeds_cap, 64, ITEMS);
+        c.slow_queue.ensure(c.n_seeds_cap, 1.25);
+        if (sh.index.view.fmt == 8)
+          seeds_on_paths_kernel<8, ITEMS><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
+                                                                     probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
+        else
+          seeds_on_paths_kernel<16, ITEMS><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
+                                                                      probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
+        seeds_slow_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, c.seed_kmer.p, c.slow_queue.p,
+                                                                         dc + DC_SLOW, probe_mode, c.seed_hit.p, c.seed_kind.p,
+                                                                         c.hits.p, c.hit_kind.p, c.hits.cap, dc + DC_OVF);
+        c.counters.launches += 2;
+      }
+      else {
+        PSI_CUDA(cudaMemsetAsync(c.seed_kind.p, 0, c.n_seeds_cap, c.stream));
+      }
+      t_on.stop();
 
-    PhaseTimer t_on(c, T_ON);
-    if (do_on) {
-      constexpr int ITEMS = 4;
-      const unsigned grid = grid_for(c.n_seeds_cap, 256, ITEMS);
-      if (c.sh->index.view.fmt == 8)
-        seeds_on_paths_kernel<8, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.sh->index.view, c.sh->multi.p, c.seed_kmer.p, c.seed_valid.p,
-                                                                         dc + DC_SEEDS, c.hits.p, hits_cap, dc + DC_HITS, dc + DC_SECTORS);
-      else
-        seeds_on_paths_kernel<16, ITEMS, false><<<grid, 256, 0, c.stream>>>(c.sh->index.view, c.sh->multi.p, c.seed_kmer.p, c.seed_valid.p,
-                                                                          dc + DC_SEEDS, c.hits.p, hits_cap, dc + DC_HITS, dc + DC_SECTORS);
+      if (do_walk) {
+        engine_index_chunk(c);
+        PhaseTimer t_off(c, T_OFF);
+        if (c.dedup.cap == 0) c.dedup.ensure(1u << 20);
+        const uint64_t dedup_slots = next_pow2(c.dedup.cap) == c.dedup.cap ? c.dedup.cap : next_pow2(c.dedup.cap) / 2;
+        PSI_CUDA(cudaMemsetAsync(c.dedup.p, 0xff, dedup_slots * sizeof(unsigned long long), c.stream));
+        const unsigned grid = (unsigned)c.sm_count * 8;
+        c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
+        ReadIndexSink sink;
+        sink.rt = c.read_index.view;
+        sink.rt.stash_nonempty = 1;  // not known without a sync; probing an empty stash costs one load, and only for full lines
+        sink.next = c.seed_next.p;
+        sink.pt = sh.index.view;
+        sink.multi = sh.multi.p;
+        sink.has_index = sh.has_table ? 1u : 0u;
+        sink.dedup = c.dedup.p;
+        sink.dedup_mask = dedup_slots - 1;
+        sink.hits = c.hits.p;
+        sink.hit_kind = c.hit_kind.p;
+        sink.hits_cap = c.hits.cap;
+        sink.hit_count = dc + DC_OVF;
+        sink.walk_count = dc + DC_WALKS;
+        sink.err = dc + DC_ERR;
+        sink.walks = 0;
+        seeds_off_paths_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, sh.n_loci, sh.loci_node.p, sh.loci_off.p, sink,
+                                                                       dc + DC_WORK, (WalkItem*)c.walk_spill.p, c.spill_items);
+        ++c.counters.launches;
+        t_off.stop();
+      }
+      redo_search = false;
+    }
+    else {
+      PSI_CUDA(cudaMemsetAsync(dc + DC_HITS, 0, sizeof(unsigned long long), c.stream));
+      PSI_CUDA(cudaMemsetAsync(dc + DC_HITS_ON, 0, sizeof(unsigned long long), c.stream));
+    }
+
+    // compaction (+ resolution unless the hits are to be sorted first)
+    PhaseTimer t_res(c, T_RESOLVE);
+    uint64_t out_cap = 0;
+    {
+      const unsigned grid = grid_for(c.n_seeds_cap + c.hits.cap, 256, 2);
+      if (sorted || !resolve) {
+        c.sorted_hits.ensure(out_cap_want);
+        out_cap = c.sorted_hits.cap;
+        compact_resolve_kernel<false><<<grid, 256, 0, c.stream>>>(g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p,
+                                                                 c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, c.seed_first.p,
+                                                                 c.distance, c.first_read_id, nullptr, nullptr, c.sorted_hits.p, out_cap,
+                                                                 dc + DC_HITS, dc + DC_HITS_ON);
+      }
+      else {
+        c.records.ensure(4 * out_cap_want);
+        c.rec_kind.ensure(out_cap_want);
+        out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
+        compact_resolve_kernel<true><<<grid, 256, 0, c.stream>>>(g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p,
+                                                                c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, c.seed_first.p,
+                                                                c.distance, c.first_read_id, c.records.p, c.rec_kind.p, nullptr, out_cap,
+                                                                dc + DC_HITS, dc + DC_HITS_ON);
+      }
       ++c.counters.launches;
     }
-    t_on.stop();
-    PSI_CUDA(cudaMemcpyAsync(c.h_pinned + 0, dc + DC_HITS, sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
-
-    if (do_off) {
-      engine_index_chunk(c);
-      PhaseTimer t_off(c, T_OFF);
-      const uint64_t dedup_slots = next_pow2(c.dedup.cap) == c.dedup.cap ? c.dedup.cap : next_pow2(c.dedup.cap) / 2;
-      PSI_CUDA(cudaMemsetAsync(c.dedup.p, 0xff, dedup_slots * sizeof(unsigned long long), c.stream));
-      const unsigned grid = (unsigned)c.sm_count * 8;
-      c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
-      ReadIndexSink sink;
-      sink.rt = c.read_index.view;
-      sink.rt.stash_nonempty = 1;  // not known without a sync; probing an empty stash costs one load, and only for full lines
-      sink.next = c.seed_next.p;
-      sink.pt = c.sh->index.view;
-      sink.multi = c.sh->multi.p;
-      sink.has_index = c.sh->has_index ? 1u : 0u;
-      sink.dedup = c.dedup.p;
-      sink.dedup_mask = dedup_slots - 1;
-      sink.hits = c.hits.p;
-      sink.hits_cap = hits_cap;
-      sink.hit_count = dc + DC_HITS;
-      sink.walk_count = dc + DC_WALKS;
-      sink.err = dc + DC_ERR;
-      sink.walks = 0;
-      seeds_off_paths_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, c.sh->n_loci, c.sh->loci_node.p, c.sh->loci_off.p, sink,
-                                                                     dc + DC_WORK, (WalkItem*)c.walk_spill.p, c.spill_items);
-      ++c.counters.launches;
-      t_off.stop();
-    }
+    t_res.stop();
     PSI_CUDA(cudaGetLastError());
-    PSI_CUDA(cudaMemcpyAsync(c.h_pinned + 1, dc, DC_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(c.h_pinned, dc, DC_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
     PSI_CUDA(cudaStreamSynchronize(c.stream));
-    n_on = c.h_pinned[0];
-    n_total = c.h_pinned[1 + DC_HITS];
-    n_walks = c.h_pinned[1 + DC_WALKS];
-    n_sectors = c.h_pinned[1 + DC_SECTORS];
-    n_seeds = c.h_pinned[1 + DC_SEEDS];
-    const uint64_t err = c.h_pinned[1 + DC_ERR];
+    n_total = c.h_pinned[DC_HITS];
+    n_on = c.h_pinned[DC_HITS_ON];
+    n_walks = c.h_pinned[DC_WALKS];
+    n_seeds = c.h_pinned[DC_SEEDS];
+    n_slow = c.h_pinned[DC_SLOW];
+    const uint64_t n_ovf = c.h_pinned[DC_OVF];
+    const uint64_t err = c.h_pinned[DC_ERR];
     bool retry = false;
-    if (n_total > hits_cap) { c.hits.ensure(n_total, 1.25); retry = true; }
+    if (n_ovf > c.hits.cap) { c.hits.ensure(n_ovf, 1.25); c.hit_kind.ensure(c.hits.cap); retry = redo_search = true; }
     if (err & 1ull) {
       if (c.spill_items >= (1u << 20)) throw OverflowError("seeds_off_paths: walk frontier exceeds 2^20 states per warp");
       c.spill_items *= 4;
-      retry = true;
+      retry = redo_search = true;
     }
     if (err & 2ull) throw OverflowError("read index: hash stash exhausted");
-    if (err & 4ull) { c.dedup.ensure(c.dedup.cap * 4); retry = true; }
+    if (err & 4ull) { c.dedup.ensure(c.dedup.cap * 4); retry = redo_search = true; }
+    if (!retry && n_total > out_cap) { out_cap_want = n_total + n_total / 8; retry = true; }   // only the compaction is redone
     if (!retry) break;
   }
 
@@ -345,20 +495,21 @@ void engine_seeds(Ctx& c, unsigned flags)
   c.counters.n_hits_off = n_total - n_on;
   c.counters.n_hits = n_total;
   c.counters.n_walks = n_walks;
-  c.counters.n_on_probe_sectors = n_sectors;
+  c.counters.n_on_probe_sectors = n_slow;   // seeds that needed more than their home line
+  c.counters.offpath_mode = index_mode ? 2u : 1u;
 
-  if ((flags & PSI_B200_SORTED) && n_total > 1) {
+  if (sorted && n_total > 1) {
     PhaseTimer t_sort(c, T_SORT);
     // canonical order: (seed index, global position) ascending == (read_id, read_offset, node rank, node_offset)
     DevBuf<unsigned long long> tmp_keys;
     tmp_keys.ensure(n_total);
     size_t tmp = 0;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(c.hits.p);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(c.sorted_hits.p);
     // Hit{seed, gpos} is little-endian (seed low, gpos high): sort by gpos bits first, then seed bits
     cub::DoubleBuffer<unsigned long long> db(keys, tmp_keys.p);
     PSI_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, db, (int64_t)n_total, 0, 64, c.stream));
     c.scan_tmp.ensure(tmp);
-    // 64-bit value = gpos << 32 | seed; canonical order needs seed major: swap halves via two stable passes
+    // 64-bit value = gpos << 32 | seed; canonical order needs seed major: two stable passes
     PSI_CUDA(cub::DeviceRadixSort::SortKeys(c.scan_tmp.p, tmp, db, (int64_t)n_total, 32, 64, c.stream));
     PSI_CUDA(cub::DeviceRadixSort::SortKeys(c.scan_tmp.p, tmp, db, (int64_t)n_total, 0, 32, c.stream));
     if (db.Current() != keys)
@@ -367,19 +518,17 @@ void engine_seeds(Ctx& c, unsigned flags)
     PSI_CUDA(cudaStreamSynchronize(c.stream));
     c.counters.launches += 8;
   }
-
-  if (!(flags & PSI_B200_NO_RESOLVE)) {
-    PhaseTimer t_res(c, T_RESOLVE);
+  if (sorted && resolve) {
     c.records.ensure(4 * std::max<uint64_t>(n_total, 1), 1.25);
     if (n_total) {
-      resolve_hits_kernel<<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, c.sh->node_id.p, c.hits.p, n_total, c.seed_read.p,
+      resolve_hits_kernel<<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
                                                                       c.seed_first.p, c.distance, c.first_read_id, c.records.p);
       ++c.counters.launches;
     }
-    t_res.stop();
     PSI_CUDA(cudaGetLastError());
-    c.records_valid = true;
   }
+  c.records_valid = resolve;
+  c.kinds_valid = resolve && !sorted;
 }
 
 void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap)
@@ -390,6 +539,15 @@ void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap)
   PhaseTimer t(c, T_D2H);
   if (n) PSI_CUDA(cudaMemcpyAsync(hits, c.records.p, n * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
   t.stop();
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap)
+{
+  if (!c.kinds_valid) throw StateError("fetch_kinds: no unsorted resolved records");
+  PSI_CUDA(cudaSetDevice(c.device));
+  const uint64_t n = c.n_hits < cap ? c.n_hits : cap;
+  if (n) PSI_CUDA(cudaMemcpyAsync(kinds, c.rec_kind.p, n, cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
 }
 

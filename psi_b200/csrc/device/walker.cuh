@@ -177,6 +177,22 @@ __device__ void walk_all(const GraphView& g, uint32_t k, uint64_t n_items, unsig
   sink.finish();
 }
 
+// Work source of the walkers: one item per starting locus.
+struct LociSource {
+  GraphView g;
+  const uint32_t* node;
+  const uint32_t* off;
+  __device__ bool init(uint64_t idx, WalkItem& it) const
+  {
+    const uint32_t v = __ldg(node + idx), o = __ldg(off + idx);
+    if (v >= g.n_nodes) return false;
+    const NodeRec r = g.rec[v];
+    if (o >= r.seq_len) return false;
+    it.kmer = 0; it.origin = r.seq_start + o; it.node = v; it.off = o; it.depth = 0;
+    return true;
+  }
+};
+
 }  // namespace dev
 }  // namespace psi_b200
 #endif

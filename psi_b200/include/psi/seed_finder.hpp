@@ -503,7 +503,6 @@ class SeedFinder {
     check(psi_b200_counters(ctx, &c));
     TraverserStats::seeds_off_paths() += c.n_hits_off;
     TraverserStats::nof_godowns() += c.n_walks;
-    last_on = c.n_hits_on;
     stats_ptr->set_timer("seeds-on-paths", (c.ms_on) * 1e-3);
     stats_ptr->set_timer("seeds-off-paths", (c.ms_read_index + c.ms_off) * 1e-3);
     stats_ptr->set_timer("seeds-off-path", (c.ms_read_index + c.ms_off) * 1e-3);
@@ -519,14 +518,20 @@ class SeedFinder {
     check(psi_b200_seeds_all(ctx, flags, &n));
     fetch(n);
     account();
-    // records are on-path hits first, then off-path hits
+    // with two callbacks the per-record kind (1 on an indexed path, 2 off-path) routes the hit
+    std::vector<uint8_t> kinds;
+    if (cb2 && n) {
+      kinds.resize(n);
+      uint64_t got = 0;
+      check(psi_b200_fetch_kinds(ctx, kinds.data(), n, &got));
+    }
     Seed<> hit;
     hit.match_len = seed_len;
     hit.gocc = 0;
     for (uint64_t i = 0; i < n; ++i) {
       const uint64_t* r = host_records + 4 * i;
       hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
-      const callback_type& cb = (cb2 && i >= last_on) ? cb2 : cb1;
+      const callback_type& cb = (!kinds.empty() && kinds[i] == 2) ? cb2 : cb1;
       if (cb) cb(hit);
     }
   }
@@ -546,7 +551,6 @@ class SeedFinder {
   mutable uint64_t serial = 0;
   mutable uint64_t* host_records = nullptr;
   mutable uint64_t host_cap = 0;
-  mutable uint64_t last_on = 0;
 };
 
 }  // namespace psi

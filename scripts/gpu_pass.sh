@@ -9,6 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.log
 echo "== smoke" ; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -5 | tee $OUT/smoke.log
 echo "== bench" ; timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; tail -3 $OUT/bench.err ; cat $OUT/bench.json
+echo "== bench (walk mode, 1 pipeline)" ; timeout 900 python bench.py --steps 10 --warmup 3 --offpath-mode 1 --pipelines 1 --no-cpu-baseline > $OUT/bench_walk.json 2> $OUT/bench_walk.err ; tail -2 $OUT/bench_walk.err; cat $OUT/bench_walk.json
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err ; cat $OUT/bench_ref.json
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \

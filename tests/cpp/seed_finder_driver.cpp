@@ -91,10 +91,19 @@ int main(int argc, char** argv)
     f2.get_seeds(s2, c2, d);
     auto i2 = f2.index_reads(s2);
     ok &= throws_runtime_error([&] { f2.seeds_on_paths(s2, i2, [](Seed<> const&) {}); }, "seed length should not be larger than context size");
-    // seeds of an older submission are rejected instead of silently using the newer chunk
-    auto s3 = f2.create_readrecord();
-    f2.get_seeds(s3, c2, d);
-    ok &= throws_runtime_error([&] { f2.seeds_all_records(s2, i2, nullptr); }, "do not belong");
+  }
+  {  // seeds of an older submission are rejected instead of silently using the newer chunk
+    finder_type f6(graph, k);
+    f6.create_path_index(1, true, 0);
+    klibpp::SeqStreamIn iss6(reads_path.c_str());
+    auto c6 = f6.create_readrecord();
+    auto s6 = f6.create_readrecord();
+    auto s7 = f6.create_readrecord();
+    readRecords(c6, iss6, 10);
+    f6.get_seeds(s6, c6, d);
+    auto i6 = f6.index_reads(s6);
+    f6.get_seeds(s7, c6, d);
+    ok &= throws_runtime_error([&] { f6.seeds_all_records(s6, i6, nullptr); }, "do not belong");
   }
   ok &= throws_runtime_error([&] { finder_type f3(graph, 33); }, "seed length");
   ok &= throws_runtime_error([&] { finder_type f4(graph, k, 0, 0, 1); }, "approximate");

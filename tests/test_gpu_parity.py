@@ -37,8 +37,10 @@ def run_chunks(ctx, rp, bases, d, chunk, flags=capi.ALL):
     return np.concatenate(parts) if parts else np.zeros((0, 4), np.uint64), total
 
 
-def make_ctx(g, k, n_paths, seed=1, ids="coord"):
+def make_ctx(g, k, n_paths, seed=1, ids="coord", mode=0):
+    """mode: 0 auto (off-path walks materialised into the index), 1 walk the graph per chunk."""
     ctx = capi.Context(k, 0)
+    ctx.set_option("offpath_mode", mode)
     ctx.set_graph(g, ids=ids)
     ps = None
     if n_paths:
@@ -48,11 +50,13 @@ def make_ctx(g, k, n_paths, seed=1, ids="coord"):
     return ctx, ps
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_seeds_all_matches_reference_golden(name):
+def test_seeds_all_matches_reference_golden(name, mode):
     c = CASES[name]
     g, rp, bases = load_case(c)
-    ctx, _ = make_ctx(g, c["k"], c["n_paths"])
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"], mode=mode)
+    assert ctx.counters()["offpath_mode"] == (1 if mode == 1 else 2)
     rec, total = run_chunks(ctx, rp, bases, c["d"], c["chunk"])
     got = capi.canonical(rec)
     assert total == len(got), "device output must already be a set (no duplicates)"
@@ -64,12 +68,13 @@ def test_seeds_all_matches_reference_golden(name):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
 @pytest.mark.parametrize("name", ["x_k12", "m_k20", "m_k32", "fuzz_02", "fuzz_03", "fuzz_06", "fuzz_09", "multi_k32"])
-def test_phases_match_oracle(name):
+def test_phases_match_oracle(name, mode):
     """seeds_on_paths, starting loci and seeds_off_paths each against the oracle on the same paths."""
     c = CASES[name]
     g, rp, bases = load_case(c)
-    ctx, ps = make_ctx(g, c["k"], c["n_paths"], seed=5)
+    ctx, ps = make_ctx(g, c["k"], c["n_paths"], seed=5, mode=mode)
     og, orr = orc.OGraph.of(g), orc.OReads(rp, bases)
     op = orc.OPaths(ps.path_ptr, ps.nodes, ps.head_off, ps.tail_trim)
     # loci
@@ -98,12 +103,14 @@ def test_phases_match_oracle(name):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
 @pytest.mark.parametrize("name", ["x_k12", "fuzz_04", "m_k20"])
-def test_no_paths_all_loci_equals_closed_form(name):
+def test_no_paths_all_loci_equals_closed_form(name, mode):
     """`-n 0` + every locus: the pure graph-walk formulation (traverser only)."""
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx = capi.Context(c["k"], 0)
+    ctx.set_option("offpath_mode", mode)
     ctx.set_graph(g, ids="coord")
     node, off = util.all_loci(g)
     ctx.set_loci(node, off)
@@ -287,7 +294,38 @@ def test_counters_report_kernel_launches_and_index_shape():
     ctx.close()
 
 
-def test_random_larger_graph_properties():
+def test_offpath_budget_falls_back_to_walking():
+    """auto mode materialises only when the walks fit the budget; the seed set does not depend on the mode."""
+    c = CASES["m_k20"]
+    g, rp, bases = load_case(c)
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_option("offpath_max_pairs", 100)     # far fewer than the k-walks of this dense graph
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
+    ctx.find_loci()
+    cn = ctx.counters()
+    assert cn["offpath_mode"] == 1 and cn["n_offpath_walks"] > 100 and cn["n_offpath_entries"] == 0
+    rec, total = run_chunks(ctx, rp, bases, c["d"], 0)
+    assert util.md5_tuples(capi.canonical(rec)) == c["md5"]
+    ctx.close()
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
+    ctx.find_loci()
+    cn2 = ctx.counters()
+    assert cn2["offpath_mode"] == 2 and 0 < cn2["n_offpath_entries"] <= cn2["n_offpath_walks"] == cn["n_offpath_walks"]
+    rec, total = run_chunks(ctx, rp, bases, c["d"], 0)
+    assert util.md5_tuples(capi.canonical(rec)) == c["md5"]
+    assert ctx.counters()["n_walks"] == 0        # nothing is walked per chunk in index mode
+    with pytest.raises(capi.PsiError):
+        ctx.set_option("offpath_mode", 7)
+    with pytest.raises(capi.PsiError):
+        ctx.set_option("no_such_option", 1)
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+def test_random_larger_graph_properties(mode):
     """A 200 kbp random bubble graph with 20 000 reads: chunked == unchunked, set == oracle."""
     import tempfile, os
     text = util.random_bubble_gfa(99, backbone=200000, sites=6000)
@@ -297,7 +335,7 @@ def test_random_larger_graph_properties():
         g = capi.Graph.load_gfa(p)
     rp, bases = util.random_walk_reads(g, 20000, 100, seed=5)
     k = 20
-    ctx, _ = make_ctx(g, k, 8)
+    ctx, _ = make_ctx(g, k, 8, mode=mode)
     rec, total = run_chunks(ctx, rp, bases, k, 0)
     rec2, total2 = run_chunks(ctx, rp, bases, k, 3000)
     a, b = capi.canonical(rec), capi.canonical(rec2)
