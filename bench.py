@@ -126,7 +126,7 @@ def reference_run(n_reads_per_core=None, cores=None, shape="chr22_1_51", budget_
     if not orc.have_reference():
         raise RuntimeError("oracle/_ref/psi_ref_driver missing")
     cores = cores or max(1, (os.cpu_count() or 1))
-    cores = min(cores, 64)
+    cores = min(cores, 32)
     g = build_graph(shape)
     # calibrated so that one process takes roughly budget_s: ~6.7e3 reads/s/core measured in the survey on this shape
     n_per = n_reads_per_core or max(2000, int(2500 * budget_s))
@@ -142,16 +142,31 @@ def reference_run(n_reads_per_core=None, cores=None, shape="chr22_1_51", budget_
             f.write(b">r%d\n" % i)
             f.write(b[i].tobytes())
             f.write(b"\n")
-    procs = []
     env = dict(os.environ, TMPDIR=td, OMP_PROC_BIND="false", OMP_NUM_THREADS="1")
-    for c in range(cores):
-        cmd = [os.fspath(orc.REF_DRIVER), "--gfa", gfa, "--fastq", fa, "-k", str(K), "-d", str(K), "-n", str(N_PATHS),
-               "--first-read", str(c * n_per), "--max-reads", str(n_per)]
-        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env))
-    stats = []
-    for p in procs:
-        out, _ = p.communicate()
-        stats.append(json.loads(out.strip().splitlines()[-1]))
+    stats, used, last_err = [], cores, ""
+    while used >= 1:
+        # one single-threaded reference process per core on disjoint read ranges; halve the count if a process dies
+        # (e.g. out of memory on a box with many cores)
+        procs = []
+        for c in range(used):
+            cmd = [os.fspath(orc.REF_DRIVER), "--gfa", gfa, "--fastq", fa, "-k", str(K), "-d", str(K), "-n", str(N_PATHS),
+                   "--first-read", str(c * n_per), "--max-reads", str(n_per)]
+            procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+        stats = []
+        for p in procs:
+            out, err = p.communicate()
+            lines = out.strip().splitlines()
+            if p.returncode == 0 and lines:
+                stats.append(json.loads(lines[-1]))
+            else:
+                last_err = (err or "").strip().splitlines()[-1:] or [f"exit code {p.returncode}"]
+        if len(stats) == used:
+            break
+        log(f"[bench] reference: {used - len(stats)} of {used} processes failed ({last_err}); retrying with {used // 2}")
+        used //= 2
+    if not stats or len(stats) != used:
+        raise RuntimeError(f"reference driver failed: {last_err}")
+    cores = used
     import shutil
     shutil.rmtree(td, ignore_errors=True)
     # timed region = seeding + seeds_on_paths + seeds_off_paths (index build excluded, as for the GPU arm)
@@ -325,12 +340,24 @@ def main_gpu(args):
     ms_e2e, hits_e2e, launches_e2e = timed_e2e(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-shard counts and a hits-per-read histogram, gathered with NCCL (the only collective on this path)
-    tot = torch.tensor([n_reads * args.steps, acc["n_seeds"], hits_dev, acc["n_hits_on"], acc["n_walks"]],
-                       device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(tot)
-    tot = tot.tolist()
+    # per-shard counts and a hits-per-read histogram, reduced with NCCL (the only collective on this path)
+    from psi_b200 import shard
+
+    class _DevArray:   # view the device records of the last step as a torch tensor (no copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<i8", "data": (ptr, True), "version": 2}
+    step_device(0)
+    ptr, n_rec = ctx.fetch_device()
+    if n_rec:
+        rec = torch.as_tensor(_DevArray(ptr, n_rec), device=dev)
+        per_read = torch.bincount(rec[:, 2] - rank * n_reads, minlength=n_reads)[:n_reads]
+        hist = torch.bincount(torch.clamp(per_read, max=shard.HIST_BINS - 1), minlength=shard.HIST_BINS).cpu().numpy()
+    else:
+        hist = np.zeros(shard.HIST_BINS, np.int64)
+        hist[0] = n_reads
+    counts, hist = shard.all_reduce_counts({"reads": n_reads * args.steps, "seeds": acc["n_seeds"], "hits": hits_dev,
+                                            "hits_on": acc["n_hits_on"], "walks": acc["n_walks"]}, hist, device=dev)
+    tot = [counts["reads"], counts["seeds"], counts["hits"], counts["hits_on"], counts["walks"]]
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -377,6 +404,8 @@ def main_gpu(args):
                          "random_line_ceiling_probes_per_s": 4.0e10,
                          "traffic_source": TRAFFIC_SOURCE},
             "clocks": clocks,
+            "hits_per_read_histogram": {"bins": "reads with h hits in one step, h = 0..62, last bin >= 63; summed over ranks",
+                                        "counts": [int(x) for x in hist]},
             "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
                       "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"],
                       "offpath_entries": c0["n_offpath_entries"], "offpath_walks": c0["n_offpath_walks"],
