@@ -228,6 +228,9 @@ def main_gpu(args):
     ps = g.pick_paths(N_PATHS, seed=1)
     ctx = capi.Context(K, local)
     ctx.set_option("offpath_mode", args.offpath_mode)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ctx.set_option(name, int(val))
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_graph(g, ids="internal")
     ctx.set_paths(ps)
@@ -345,7 +348,7 @@ def main_gpu(args):
 
     class _DevArray:   # view the device records of the last step as a torch tensor (no copy)
         def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<i8", "data": (ptr, True), "version": 2}
+            self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<i8", "data": (ptr, False), "version": 2}
     step_device(0)
     ptr, n_rec = ctx.fetch_device()
     if n_rec:
@@ -436,6 +439,7 @@ def main():
     ap.add_argument("--reads", type=int, default=READS_PER_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "psi_b200" else args.warmup

@@ -170,6 +170,100 @@ gather_bulk_kernel(const char* __restrict__ table, uint64_t n_sectors_mask, cons
   if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
 }
 
+
+// TMA bulk copies of a whole 128-byte line per probe into shared memory: ITEMS lines per thread in flight,
+// no registers hold data.  Dynamic shared memory: ITEMS * 256 * 128 bytes.
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+gather_bulk128_kernel(const char* __restrict__ table, uint64_t n_sectors_mask, const uint64_t* __restrict__ keys, uint32_t n,
+                      unsigned long long* __restrict__ sink)
+{
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ alignas(8) uint64_t bar;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_a), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(ITEMS * 256 * 128) : "memory");
+  __syncthreads();
+  const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t s = base + i * 256u;
+    const uint64_t key = s < n ? keys[s] : 0;
+    const uint64_t line = (mix64(key) & n_sectors_mask) >> 2;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dyn + ((size_t)(i * 256 + threadIdx.x) << 7));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+                 :: "r"(dst), "l"(table + (line << 7)), "r"(bar_a) : "memory");
+  }
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar_a) : "memory");
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint4* ln = reinterpret_cast<const uint4*>(dyn + ((size_t)(i * 256 + threadIdx.x) << 7));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const uint4 w = ln[(j + threadIdx.x) & 7]; acc ^= w.x ^ w.y ^ w.z ^ w.w; }
+  }
+  if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
+}
+
+// cp.async (LDGSTS) 16 bytes per lane, 8 lanes per 128-byte line, ITEMS instructions per thread in flight.
+// Dynamic shared memory: ITEMS * 256 * 16 bytes.
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+gather_ldgsts_kernel(const char* __restrict__ table, uint64_t n_sectors_mask, const uint64_t* __restrict__ keys, uint32_t n,
+                     unsigned long long* __restrict__ sink)
+{
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const uint32_t sub = threadIdx.x & 7u;
+  const uint32_t grp = threadIdx.x >> 3;                       // 32 line groups per CTA
+  const uint32_t base = blockIdx.x * (32u * ITEMS) + grp;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t s = base + i * 32u;
+    const uint64_t key = s < n ? keys[s] : 0;
+    const uint64_t line = (mix64(key) & n_sectors_mask) >> 2;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dyn + ((size_t)(i * 32 + grp) << 7) + (sub << 4));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(table + (line << 7) + (sub << 4)) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint4 w = *reinterpret_cast<const uint4*>(dyn + ((size_t)(i * 32 + grp) << 7) + (sub << 4));
+    acc ^= w.x ^ w.y ^ w.z ^ w.w;
+  }
+  if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
+}
+
+// one 32-byte sector per probe, one thread per probe, REGS-light: how far does occupancy carry the line rate?
+template <int ITEMS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+gather_occ_kernel(const char* __restrict__ table, uint64_t n_sectors_mask, const uint64_t* __restrict__ keys, uint32_t n,
+                  unsigned long long* __restrict__ sink)
+{
+  const uint32_t base = blockIdx.x * (256u * ITEMS) + threadIdx.x;
+  uint64_t v[ITEMS][4];
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint32_t s = base + i * 256u;
+    const uint64_t key = s < n ? keys[s] : 0;
+    ld_sector(table + ((mix64(key) & n_sectors_mask) << 5), v[i]);
+  }
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) acc ^= v[i][0] ^ v[i][1] ^ v[i][2] ^ v[i][3];
+  if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
+}
+
 template <class F>
 static float time_launch(F launch, int reps, char* flush, size_t flush_bytes)
 {
@@ -278,5 +372,24 @@ int main(int argc, char** argv)
     const unsigned grid2b = (n + 256 * 2 - 1) / (256 * 2);
     report("tma_bulk_32B_items2", time_launch([&] { gather_bulk_kernel<2><<<grid2b, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
   }
+    {
+      // in-flight capacity experiments
+      CK(cudaFuncSetAttribute(gather_bulk128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 * 256 * 128));
+      CK(cudaFuncSetAttribute(gather_bulk128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 128));
+      CK(cudaFuncSetAttribute(gather_bulk128_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 128));
+      report("tma_bulk_128B_items1", time_launch([&] { gather_bulk128_kernel<1><<<(n + 255) / 256, 256, 1 * 256 * 128>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      report("tma_bulk_128B_items2", time_launch([&] { gather_bulk128_kernel<2><<<(n + 511) / 512, 256, 2 * 256 * 128>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      report("tma_bulk_128B_items4", time_launch([&] { gather_bulk128_kernel<4><<<(n + 1023) / 1024, 256, 4 * 256 * 128>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      CK(cudaFuncSetAttribute(gather_ldgsts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+      CK(cudaFuncSetAttribute(gather_ldgsts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 256 * 16));
+      report("ldgsts_128B_items4", time_launch([&] { gather_ldgsts_kernel<4><<<(n + 127) / 128, 256, 4 * 256 * 16>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      report("ldgsts_128B_items8", time_launch([&] { gather_ldgsts_kernel<8><<<(n + 255) / 256, 256, 8 * 256 * 16>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      report("ldgsts_128B_items16", time_launch([&] { gather_ldgsts_kernel<16><<<(n + 511) / 512, 256, 16 * 256 * 16>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 128, n);
+      report("sector_items1_occ8", time_launch([&] { gather_occ_kernel<1, 8><<<(n + 255) / 256, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
+      report("sector_items2_occ8", time_launch([&] { gather_occ_kernel<2, 8><<<(n + 511) / 512, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
+      report("sector_items4_occ4", time_launch([&] { gather_occ_kernel<4, 4><<<(n + 1023) / 1024, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
+      report("sector_items4_occ2", time_launch([&] { gather_occ_kernel<4, 2><<<(n + 1023) / 1024, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
+      report("sector_items8_occ2", time_launch([&] { gather_occ_kernel<8, 2><<<(n + 2047) / 2048, 256>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes), 32, n);
+    }
   return 0;
 }

@@ -13,25 +13,10 @@
 #include "engine.hpp"
 
 #include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
 
 namespace psi_b200 {
 
 using namespace dev;
-
-// seeds of read r: offsets 0, d, 2d, ... while off + k <= len; reads shorter than k have none
-struct SeedCountOp {
-  const uint64_t* read_ptr;
-  uint64_t n_reads;
-  uint32_t k, d;
-  __host__ __device__ uint32_t operator()(uint64_t r) const
-  {
-    if (r >= n_reads) return 0;
-    const uint64_t len = read_ptr[r + 1] - read_ptr[r];
-    return len >= k ? (uint32_t)((len - k) / d) + 1 : 0;
-  }
-};
 
 // K1a: the chunk's bases, ASCII -> 2 bits per base + a 1-bit "not A/C/G/T" mask, whatever the read
 // boundaries are (positions stay global byte offsets).  One thread per 32 bases: two 16-byte loads,
@@ -85,23 +70,120 @@ pack_reads_kernel(const char* __restrict__ bases, uint64_t n_bases, uint64_t* __
   nmask[w] = mask;
 }
 
-// K1b: one thread per read: its seeds (offsets 0, d, 2d, ...) cut out of the 2-bit array.
+// K1b: seeding.  A CTA owns READS_PER_CTA consecutive reads.
+//   pass 1 (count_seeds_kernel):   seeds per CTA -> cta_count[]
+//   pass 2 (scan_cta_counts_kernel, one CTA): exclusive scan -> cta_first[], total -> n_seeds
+//   pass 3 (extract_seeds_kernel): recomputes the per-read counts, scans them inside the CTA
+//          (-> seed_first[], the replacement of SeedMap's rank/select, sequence.hpp:1148-1220) and then
+//          walks the CTA's seeds IN SEED ORDER -- thread t takes seeds t, t + 256, ... and finds the read by a
+//          binary search of the CTA-local prefix sums in shared memory -- so that the stores of seed_kmer /
+//          seed_valid / seed_read are contiguous; the k-mers are cut out of the 2-bit array.
+constexpr int READS_PER_CTA = 1024;   // 256 threads x 4 reads
+
+__device__ __forceinline__ uint32_t seed_count(const uint64_t* __restrict__ read_ptr, uint64_t r, uint64_t n_reads, uint32_t k, uint32_t d)
+{
+  if (r >= n_reads) return 0;
+  const uint64_t len = read_ptr[r + 1] - read_ptr[r];
+  return len >= k ? (uint32_t)((len - k) / d) + 1 : 0;     // reads shorter than k have no seeds
+}
+
+// sum over the CTA; result valid in every thread
+__device__ __forceinline__ uint32_t cta_sum(uint32_t x, uint32_t* s_warp)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = x;
+  __syncthreads();
+  uint32_t t = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += s_warp[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+count_seeds_kernel(const uint64_t* __restrict__ read_ptr, uint64_t n_reads, uint32_t k, uint32_t d, uint32_t* __restrict__ cta_count)
+{
+  __shared__ uint32_t s_warp[8];
+  const uint64_t r0 = (uint64_t)blockIdx.x * READS_PER_CTA + threadIdx.x * 4u;
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c += seed_count(read_ptr, r0 + i, n_reads, k, d);
+  c = cta_sum(c, s_warp);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_cta_counts_kernel(const uint32_t* __restrict__ cta_count, uint32_t n_ctas, uint32_t* __restrict__ cta_first,
+                       unsigned long long* __restrict__ n_seeds_out)
+{
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_ctas; base += 1024u) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t x = i < n_ctas ? cta_count[i] : 0;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31u) >= (uint32_t)o) incl += y; }
+    if ((threadIdx.x & 31u) == 31u) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t before = s_carry;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) before += s_warp[w];
+    if (i < n_ctas) cta_first[i] = before + incl - x;
+    __syncthreads();
+    if (threadIdx.x == 1023u) s_carry = before + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { cta_first[n_ctas] = s_carry; *n_seeds_out = s_carry; }
+}
+
 __global__ void __launch_bounds__(256)
 extract_seeds_kernel(const uint64_t* __restrict__ seq2, const uint32_t* __restrict__ nmask, const uint64_t* __restrict__ read_ptr,
-                     const uint32_t* __restrict__ seed_first, uint64_t n_reads, uint32_t k, uint32_t d,
-                     uint64_t* __restrict__ seed_kmer, uint8_t* __restrict__ seed_valid, uint32_t* __restrict__ seed_read,
-                     unsigned long long* __restrict__ n_seeds_out)
+                     const uint32_t* __restrict__ cta_first, uint64_t n_reads, uint32_t k, uint32_t d,
+                     uint32_t* __restrict__ seed_first, uint64_t* __restrict__ seed_kmer, uint8_t* __restrict__ seed_valid,
+                     uint32_t* __restrict__ seed_read)
 {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0) *n_seeds_out = seed_first[n_reads];
-  if (r >= n_reads) return;
-  const uint32_t first = seed_first[r];
-  const uint32_t cnt = seed_first[r + 1] - first;
-  uint64_t pos = read_ptr[r];
-  for (uint32_t j = 0; j < cnt; ++j, pos += d) {
-    seed_kmer[first + j] = extract_bases(seq2, pos, k);
-    seed_valid[first + j] = extract_nmask(nmask, pos, k) ? 0 : 1;
-    seed_read[first + j] = (uint32_t)r;
+  __shared__ uint32_t s_first[READS_PER_CTA + 1];   // CTA-local exclusive prefix sums of the seed counts
+  __shared__ uint32_t s_warp[8];
+  const uint64_t r_base = (uint64_t)blockIdx.x * READS_PER_CTA;
+  const uint64_t r0 = r_base + threadIdx.x * 4u;
+  uint32_t c[4];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { c[i] = seed_count(read_ptr, r0 + i, n_reads, k, d); mine += c[i]; }
+  // exclusive scan of `mine` over the CTA
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += y; }
+  if (lane == 31u) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+  uint32_t run = before + incl - mine;
+  const uint32_t first0 = cta_first[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s_first[threadIdx.x * 4u + i] = run;
+    if (r0 + i <= n_reads) seed_first[r0 + i] = first0 + run;   // r == n_reads gets the total
+    run += c[i];
+  }
+  if (threadIdx.x == 255u) s_first[READS_PER_CTA] = run;
+  __syncthreads();
+  const uint32_t n_cta_seeds = s_first[READS_PER_CTA];
+  for (uint32_t ls = threadIdx.x; ls < n_cta_seeds; ls += 256u) {
+    // read = last index with s_first[index] <= ls
+    uint32_t lo = 0, hi = READS_PER_CTA;
+#pragma unroll 1
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+    const uint64_t r = r_base + lo;
+    const uint64_t pos = __ldg(read_ptr + r) + (uint64_t)(ls - s_first[lo]) * d;
+    const uint32_t s = first0 + ls;
+    seed_kmer[s] = extract_bases(seq2, pos, k);
+    seed_valid[s] = extract_nmask(nmask, pos, k) ? 0 : 1;
+    seed_read[s] = (uint32_t)r;
   }
 }
 
@@ -165,14 +247,6 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
   c.distance = distance;
   c.n_seeds_cap = seeds_cap;
 
-  {
-    SeedCountOp op{ c.d_read_ptr, n_reads, c.k, distance };
-    auto counts = thrust::make_transform_iterator(thrust::counting_iterator<uint64_t>(0), op);
-    size_t tmp = 0;
-    PSI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, c.seed_first.p, (int64_t)(n_reads + 1), c.stream));
-    c.scan_tmp.ensure(tmp);
-    PSI_CUDA(cub::DeviceScan::ExclusiveSum(c.scan_tmp.p, tmp, counts, c.seed_first.p, (int64_t)(n_reads + 1), c.stream));
-  }
   const uint64_t n_words = (n_bases + 31) >> 5;
   c.reads2.ensure(n_words + 2, 1.25);
   c.reads_n.ensure(n_words + 2, 1.25);
@@ -185,9 +259,15 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
     else
       pack_reads_kernel<false><<<grid_for(n_words, 256), 256, 0, c.stream>>>(c.d_bases, n_bases, c.reads2.p, c.reads_n.p);
   }
-  extract_seeds_kernel<<<grid_for(n_reads + 1, 256), 256, 0, c.stream>>>(c.reads2.p, c.reads_n.p, c.d_read_ptr, c.seed_first.p, n_reads,
-                                                                         c.k, distance, c.seed_kmer.p, c.seed_valid.p,
-                                                                         c.seed_read.p, c.dev_counters.p + DC_SEEDS);
+  {
+    const unsigned n_ctas = (unsigned)((n_reads + 1 + READS_PER_CTA - 1) / READS_PER_CTA);   // + 1: seed_first[n_reads] = total
+    c.cta_first.ensure(2 * (size_t)n_ctas + 2, 1.25);
+    uint32_t* cta_count = c.cta_first.p + n_ctas + 1;
+    count_seeds_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_read_ptr, n_reads, c.k, distance, cta_count);
+    scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, c.cta_first.p, c.dev_counters.p + DC_SEEDS);
+    extract_seeds_kernel<<<n_ctas, 256, 0, c.stream>>>(c.reads2.p, c.reads_n.p, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
+                                                        c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
+  }
   c.counters.launches += 4;
   t_pack.stop();
   PSI_CUDA(cudaGetLastError());

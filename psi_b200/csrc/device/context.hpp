@@ -65,6 +65,19 @@ struct alignas(16) NodeRec {
   uint32_t outdeg;
 };
 
+// Position -> node in two 16-byte gathers: rank16[pos >> 6] holds the node-start bits of 64 positions and the
+// number of node starts before them; node_res[rank] holds what a record needs from the node.
+struct alignas(16) Rank16 {
+  uint64_t bits;     // bit i: a node starts at position 64 * w + i
+  uint32_t prefix;   // node starts before position 64 * w
+  uint32_t pad;
+};
+struct alignas(16) NodeRes {
+  uint32_t seq_start;
+  uint32_t pad;
+  uint64_t node_id;
+};
+
 // A compact hit: (seed index within the chunk, global graph position).
 struct alignas(8) Hit {
   uint32_t seed;
@@ -94,6 +107,9 @@ struct Shared {
   DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
   DevBuf<uint64_t> node_id;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
+  DevBuf<Rank16> rank16;         // empty when the graph has zero-length nodes (then pos2node is used)
+  DevBuf<NodeRes> node_res;
+  bool has_rank16 = false;
 
   // ---- index: (k-mer -> loci) for every k-window of the indexed paths and, when the
   // off-path walks have been materialised, for every k-walk from a starting locus ----
@@ -136,6 +152,7 @@ struct Ctx {
   const uint64_t* d_read_ptr = nullptr;
   DevBuf<uint64_t> reads2;       // the chunk's bases, 2 bits each
   DevBuf<uint32_t> reads_n;      // 1 bit per base: not A/C/G/T
+  DevBuf<uint32_t> cta_first;    // per CTA of the seeding kernels: first seed, then the raw counts
   DevBuf<uint32_t> seed_first;   // n_reads + 1: first seed of each read (exclusive scan)
   DevBuf<uint32_t> seed_read;    // per seed: local read index
   DevBuf<uint64_t> seed_kmer;
@@ -163,6 +180,7 @@ struct Ctx {
   DevBuf<char> walk_spill;
 
   // ---- options (psi_b200_set_option) ----
+  unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
   int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
   uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this
 };

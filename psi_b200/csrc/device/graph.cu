@@ -107,6 +107,7 @@ Ctx* engine_fork(Ctx& parent)
   c->counters.offpath_mode = pc.offpath_mode; c->counters.n_offpath_walks = pc.n_offpath_walks;
   c->spill_items = parent.spill_items;
   c->opt_offpath_mode = parent.opt_offpath_mode;
+  c->opt_probe_ctas_per_sm = parent.opt_probe_ctas_per_sm;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
   return c;
 }
@@ -144,6 +145,20 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
     rec[v].outdeg = (uint32_t)(row_ptr[v + 1] - row_ptr[v]);
   }
   rec[n_nodes] = NodeRec{ (uint32_t)n_bases, 0, (uint32_t)n_edges, 0 };
+  // rank structure for position -> node (zero-length nodes would share a start bit: fall back to pos2node then)
+  bool zero_len = false;
+  std::vector<Rank16> rank16((n_bases >> 6) + 2, Rank16{ 0, 0, 0 });
+  std::vector<NodeRes> node_res(n_nodes + 1);
+  for (uint64_t v = 0; v < n_nodes; ++v) {
+    node_res[v] = NodeRes{ rec[v].seq_start, 0, node_id[v] };
+    if (rec[v].seq_len == 0) { zero_len = true; continue; }
+    rank16[rec[v].seq_start >> 6].bits |= 1ull << (rec[v].seq_start & 63u);
+  }
+  node_res[n_nodes] = NodeRes{ (uint32_t)n_bases, 0, 0 };
+  {
+    uint32_t run = 0;
+    for (auto& r : rank16) { r.prefix = run; run += (uint32_t)__builtin_popcountll(r.bits); }
+  }
   for (uint64_t e = 0; e < n_edges; ++e)
     if (col[e] >= n_nodes) throw ArgError("set_graph: successor rank out of range");
 
@@ -157,6 +172,11 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   c.sh->seq2.ensure(n_words + 2);
   c.sh->nmask.ensure(n_words + 2);
   c.sh->pos2node.ensure((n_bases >> Ctx::POS2NODE_SHIFT) + 2);
+  c.sh->rank16.ensure(rank16.size());
+  c.sh->node_res.ensure(node_res.size());
+  c.sh->has_rank16 = !zero_len;
+  PSI_CUDA(cudaMemcpyAsync(c.sh->rank16.p, rank16.data(), rank16.size() * sizeof(Rank16), cudaMemcpyHostToDevice, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(c.sh->node_res.p, node_res.data(), node_res.size() * sizeof(NodeRes), cudaMemcpyHostToDevice, c.stream));
 
   DevBuf<char> ascii;
   ascii.ensure(n_bases + 1);
@@ -212,7 +232,7 @@ void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t
     if (lb > kbits) lb = kbits;               // tiny k: at most one possible key per line
     if (kbits - lb <= 27) { fmt = 8; line_bits = lb; rem_bits = kbits - lb; }
   }
-  if (line_bits > 40) throw ArgError("table too large");
+  if (line_bits > 32) throw ArgError("table too large");   // line indices travel as 32-bit values
   const uint64_t n_lines = 1ull << line_bits;
   t.n_lines = n_lines;
   t.slots.ensure(n_lines * 128);

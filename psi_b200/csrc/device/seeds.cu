@@ -23,12 +23,10 @@ void engine_index_chunk(Ctx& c);
 // order (2 wavelet-tree ranks + one tree descent per character, then <= 32 LF
 // steps per located occurrence); here each seed is ONE probe of ONE 128-byte
 // bucket line (the DRAM access unit, profiles/r01c_gather_peak.md):
-//   4 lanes per seed; packed k-mer (8 B, broadcast within the quad) -> home line ->
-//   each lane loads one 32-byte sector of the line (one LDG.256 per lane, the
-//   quad's four sectors are one 128-byte request; ITEMS requests in flight per
-//   thread before the first compare) -> 4 tag compares per lane -> the lane that
-//   holds the key stores the seed's result: seed_hit[s] = locus, seed_kind[s] =
-//   1 (on an indexed path) / 2 (only reachable by an off-path walk) / 0 (none).
+//   packed k-mer (coalesced 8 B) -> home line -> the whole line is copied into shared
+//   memory asynchronously (cp.async, 8 lanes x 16 B) -> 16 tag compares -> the seed's
+//   result: seed_hit[s] = locus, seed_kind[s] = 1 (on an indexed path) / 2 (only
+//   reachable by an off-path walk) / 0 (none).
 // No atomics, no compaction here: the results are per seed, in seed order; the
 // compaction happens in compact_resolve_kernel.  The rare seeds that one line
 // cannot settle (locus lists; home line full and key displaced) are queued for
@@ -42,77 +40,84 @@ __device__ __forceinline__ uint8_t kind_of(uint32_t flags, uint32_t mode)
   return (flags & FLAG_OFF) ? ((mode & PSI_B200_OFF_PATHS) ? 2 : 0) : ((mode & PSI_B200_ON_PATHS) ? 1 : 0);
 }
 
-template <int FMT, int ITEMS>
-__global__ void __launch_bounds__(256, 4)
+// One thread per seed; a CTA handles 256 consecutive seeds:
+//   1. coalesced loads of k-mer + validity, hash -> home line and tag (registers);
+//   2. the warp copies its 32 home lines into shared memory with cp.async (LDGSTS): 8 lanes x 16 bytes
+//      per line, 8 instructions per lane, the line index of each seed comes by shuffle from its owner.
+//      No data registers are tied up while the lines are in flight, so ~6 CTAs x 256 lines = 1500
+//      lines per SM are outstanding -- what the random-line rate needs (profiles/r01j_gather_peak.md);
+//   3. every thread scans ITS seed's line in shared memory (8 x LDS.128, chunk order rotated by the lane
+//      so that a warp's loads do not collide on banks), compares the 16 tags and stores the seed's result:
+//      seed_hit[s], seed_kind[s] -- fully coalesced stores, no atomics, no ballots.
+template <int FMT>
+__global__ void __launch_bounds__(256)
 seeds_on_paths_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const uint8_t* __restrict__ seed_valid,
                       const unsigned long long* __restrict__ n_seeds_p, uint32_t mode,
                       uint32_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
                       uint32_t* __restrict__ slow_queue, unsigned long long* __restrict__ slow_count)
 {
+  __shared__ __align__(128) unsigned char s_lines[256 * 128];
   const uint32_t n_seeds = (uint32_t)*n_seeds_p;
-  const uint32_t block_base = blockIdx.x * (64u * ITEMS);
+  const uint32_t block_base = blockIdx.x * 256u;
   if (block_base >= n_seeds) return;   // whole CTA out of range
   const uint32_t lane = lane_id();
-  const uint32_t sub = lane & 3u;
-  const uint32_t quad_shift = lane & ~3u;
-  const uint32_t quad = threadIdx.x >> 2;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t s = block_base + threadIdx.x;
+  const bool ok = s < n_seeds && __ldg(seed_valid + s) != 0;
+  const uint64_t kmer = ok ? __ldg(seed_kmer + s) : 0;
+  const Home h = home_of<FMT>(t, kmer);
+  const uint32_t my_line = (uint32_t)h.line;           // line_bits <= 32 (checked when the table is allocated)
 
-  uint64_t km[ITEMS];
-  uint64_t v[ITEMS][4];
-  uint32_t okmask = 0;
+  unsigned char* warp_lines = s_lines + ((size_t)warp << 12);   // 32 lines of 128 bytes
+  const uint32_t sub = lane & 7u;
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const uint32_t s = block_base + i * 64u + quad;
-    const bool ok = s < n_seeds && __ldg(seed_valid + s) != 0;
-    km[i] = ok ? __ldg(seed_kmer + s) : 0;
-    okmask |= (ok ? 1u : 0u) << i;
+  for (int it = 0; it < 8; ++it) {
+    const uint32_t owner = it * 4u + (lane >> 3);
+    const uint32_t line = __shfl_sync(0xffffffffu, my_line, owner);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(warp_lines + (owner << 7) + (sub << 4));
+    const char* src = (const char*)t.slots + ((uint64_t)line << 7) + (sub << 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
   }
-  uint32_t want[ITEMS];   // fmt 8: tag | displacement 0 (30 bits)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + (lane << 7));
+  bool hit = false, empty = false;
+  uint32_t pl = 0, fl = 0;
+  if (FMT == 8) {
+    const uint32_t want = (uint32_t)h.tag;             // tag | displacement 0 (30 bits)
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const Home h = home_of<FMT>(t, km[i]);
-    want[i] = (uint32_t)h.tag;
-    // every lane loads (the quads of invalid seeds read the line of k-mer 0: harmless, keeps the loop branch free)
-    ld_sector_nc((const char*)t.slots + (h.line << 7) + (sub << 5), v[i]);
+    for (int j = 0; j < 8; ++j) {
+      const uint4 w = ln[(j + lane) & 7u];             // two slots: (w.x, w.y) and (w.z, w.w), high word second
+      empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has all of rem/disp/flags set
+      if ((w.y >> 2) == want) { hit = true; pl = w.x; fl = w.y & 3u; }
+      if ((w.w >> 2) == want) { hit = true; pl = w.z; fl = w.w & 3u; }
+    }
   }
+  else {
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    bool hit = false, empty = false;
-    uint32_t pl = 0, fl = 0;
-    if (FMT == 8) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t hi = (uint32_t)(v[i][j] >> 32);
-        empty |= hi == 0xffffffffu;             // no valid entry has all of rem/disp/flags set (flags 3 is never stored)
-        if ((hi >> 2) == want[i]) { hit = true; pl = (uint32_t)v[i][j]; fl = hi & 3u; }
-      }
+    for (int j = 0; j < 8; ++j) {
+      const uint4 w = ln[(j + lane) & 7u];             // one slot: key (w.x, w.y), payload w.z, flags w.w
+      empty |= w.w == NIL32;
+      if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer) { hit = true; pl = w.z; fl = w.w & 3u; }
     }
-    else {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t f2 = (uint32_t)(v[i][2 * j + 1] >> 32);
-        empty |= f2 == NIL32;
-        if (f2 != NIL32 && v[i][2 * j] == km[i]) { hit = true; pl = (uint32_t)v[i][2 * j + 1]; fl = f2 & 3u; }
-      }
-    }
-    const bool ok = (okmask >> i) & 1u;
-    hit &= ok;
-    const uint32_t q_hit = (__ballot_sync(0xffffffffu, hit) >> quad_shift) & 15u;
-    const uint32_t q_empty = (__ballot_sync(0xffffffffu, empty) >> quad_shift) & 15u;
-    const uint32_t s = block_base + i * 64u + quad;
+  }
+  if (s >= n_seeds) return;
+  uint8_t kind = 0;
+  if (ok) {
     if (hit) {
-      uint8_t kind = kind_of(fl, mode);
+      kind = kind_of(fl, mode);
       if (fl & FLAG_MULTI) { kind = 3; slow_queue[atomicAdd(slow_count, 1ull)] = s; }
       seed_hit[s] = pl;
-      seed_kind[s] = kind;
     }
-    else if (sub == 0 && q_hit == 0 && s < n_seeds) {
-      // nobody holds the key: absent when the line has a free slot, else it may sit in a following line
-      uint8_t kind = 0;
-      if (ok && q_empty == 0) { kind = 3; slow_queue[atomicAdd(slow_count, 1ull)] = s; }
-      seed_kind[s] = kind;
+    else if (!empty) {
+      // the line is full and does not hold the key: it may sit in a following line (~1 % of the lines are full)
+      kind = 3;
+      slow_queue[atomicAdd(slow_count, 1ull)] = s;
     }
   }
+  seed_kind[s] = kind;
 }
 
 // The seeds the probe kernel could not settle from one line: full search (following lines, stash) and
@@ -246,9 +251,20 @@ __device__ __forceinline__ Resolved resolve_one(const GraphView& g, const uint64
   const uint32_t r = __ldg(seed_read + seed);
   o.read_id = first_read_id + r;
   o.read_off = (uint64_t)(seed - __ldg(seed_first + r)) * d;
-  const uint32_t v = node_of_pos(g, gpos);
-  o.node_off = gpos - __ldg(&g.rec[v].seq_start);
-  o.node_id = __ldg(node_id + v);
+  if (g.rank16) {
+    // two dependent 16-byte gathers: start bits + prefix count of the 64 positions, then the node's record
+    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(g.rank16 + (gpos >> 6)));
+    const uint64_t bits = ((uint64_t)rw.y << 32) | rw.x;
+    const uint32_t v = rw.z + (uint32_t)__popcll(bits & (~0ull >> (63u - (gpos & 63u)))) - 1u;
+    const uint4 nr = __ldg(reinterpret_cast<const uint4*>(g.node_res + v));
+    o.node_off = gpos - nr.x;
+    o.node_id = ((uint64_t)nr.w << 32) | nr.z;
+  }
+  else {
+    const uint32_t v = node_of_pos(g, gpos);
+    o.node_off = gpos - __ldg(&g.rec[v].seq_start);
+    o.node_id = __ldg(node_id + v);
+  }
   return o;
 }
 
@@ -386,15 +402,20 @@ void engine_seeds(Ctx& c, unsigned flags)
       PSI_CUDA(cudaMemsetAsync(dc + DC_OVF, 0, 2 * sizeof(unsigned long long), c.stream));   // OVF, SLOW
       PhaseTimer t_on(c, T_ON);
       if (do_probe) {
-        constexpr int ITEMS = 4;
-        const unsigned grid = grid_for(c.n_seeds_cap, 64, ITEMS);
+        const unsigned grid = grid_for(c.n_seeds_cap, 256);
         c.slow_queue.ensure(c.n_seeds_cap, 1.25);
+        static bool carveout_set = false;   // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split
+        if (!carveout_set) {
+          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          carveout_set = true;
+        }
         if (sh.index.view.fmt == 8)
-          seeds_on_paths_kernel<8, ITEMS><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
-                                                                     probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
+          seeds_on_paths_kernel<8><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
+                                                              probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
         else
-          seeds_on_paths_kernel<16, ITEMS><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
-                                                                      probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
+          seeds_on_paths_kernel<16><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
+                                                               probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
         seeds_slow_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, c.seed_kmer.p, c.slow_queue.p,
                                                                          dc + DC_SLOW, probe_mode, c.seed_hit.p, c.seed_kind.p,
                                                                          c.hits.p, c.hit_kind.p, c.hits.cap, dc + DC_OVF);
