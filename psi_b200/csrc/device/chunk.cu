@@ -173,11 +173,17 @@ extract_seeds_kernel(const uint64_t* __restrict__ seq2, const uint32_t* __restri
   if (threadIdx.x == 255u) s_first[READS_PER_CTA] = run;
   __syncthreads();
   const uint32_t n_cta_seeds = s_first[READS_PER_CTA];
+  // reads of one length (the usual case) have the same number of seeds: the read of a seed is then a division
+  const uint32_t per_read = s_first[1];
+  const bool uniform = __syncthreads_and(c[0] == per_read && c[1] == per_read && c[2] == per_read && c[3] == per_read) && per_read != 0;
   for (uint32_t ls = threadIdx.x; ls < n_cta_seeds; ls += 256u) {
     // read = last index with s_first[index] <= ls
     uint32_t lo = 0, hi = READS_PER_CTA;
+    if (uniform) lo = ls / per_read;
+    else {
 #pragma unroll 1
-    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+      while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+    }
     const uint64_t r = r_base + lo;
     const uint64_t pos = __ldg(read_ptr + r) + (uint64_t)(ls - s_first[lo]) * d;
     const uint32_t s = first0 + ls;

@@ -107,8 +107,12 @@ struct Shared {
   DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
   DevBuf<uint64_t> node_id;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
-  DevBuf<Rank16> rank16;         // empty when the graph has zero-length nodes (then pos2node is used)
-  DevBuf<NodeRes> node_res;
+  // rank16 and node_res live back to back in one allocation so that ONE L2 access-policy window can pin them
+  // (they are gathered at random by every hit; together ~1.1 bytes per graph base)
+  DevBuf<char> gather_pool;
+  Rank16* rank16 = nullptr;      // unused when the graph has zero-length nodes (then pos2node is used)
+  NodeRes* node_res = nullptr;
+  size_t gather_pool_bytes = 0;
   bool has_rank16 = false;
 
   // ---- index: (k-mer -> loci) for every k-window of the indexed paths and, when the
@@ -180,6 +184,8 @@ struct Ctx {
   DevBuf<char> walk_spill;
 
   // ---- options (psi_b200_set_option) ----
+  int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
+  size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
   int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
   uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this

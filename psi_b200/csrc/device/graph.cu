@@ -7,6 +7,7 @@
 // labels, an N bitmap and a sampled position->node table.
 #include "engine.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -108,6 +109,9 @@ Ctx* engine_fork(Ctx& parent)
   c->spill_items = parent.spill_items;
   c->opt_offpath_mode = parent.opt_offpath_mode;
   c->opt_probe_ctas_per_sm = parent.opt_probe_ctas_per_sm;
+  c->opt_l2_persist = parent.opt_l2_persist;
+  c->l2_window_bytes = parent.l2_window_bytes;
+  c->l2_persist_bytes = parent.l2_persist_bytes;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
   return c;
 }
@@ -172,11 +176,27 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   c.sh->seq2.ensure(n_words + 2);
   c.sh->nmask.ensure(n_words + 2);
   c.sh->pos2node.ensure((n_bases >> Ctx::POS2NODE_SHIFT) + 2);
-  c.sh->rank16.ensure(rank16.size());
-  c.sh->node_res.ensure(node_res.size());
-  c.sh->has_rank16 = !zero_len;
-  PSI_CUDA(cudaMemcpyAsync(c.sh->rank16.p, rank16.data(), rank16.size() * sizeof(Rank16), cudaMemcpyHostToDevice, c.stream));
-  PSI_CUDA(cudaMemcpyAsync(c.sh->node_res.p, node_res.data(), node_res.size() * sizeof(NodeRes), cudaMemcpyHostToDevice, c.stream));
+  {
+    const size_t rank_bytes = rank16.size() * sizeof(Rank16), res_bytes = node_res.size() * sizeof(NodeRes);
+    c.sh->gather_pool.ensure(rank_bytes + res_bytes + 256);
+    c.sh->rank16 = reinterpret_cast<Rank16*>(c.sh->gather_pool.p);
+    c.sh->node_res = reinterpret_cast<NodeRes*>(c.sh->gather_pool.p + rank_bytes);
+    c.sh->gather_pool_bytes = rank_bytes + res_bytes;
+    c.sh->has_rank16 = !zero_len;
+    PSI_CUDA(cudaMemcpyAsync(c.sh->rank16, rank16.data(), rank_bytes, cudaMemcpyHostToDevice, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(c.sh->node_res, node_res.data(), res_bytes, cudaMemcpyHostToDevice, c.stream));
+    // Let the gathered arrays persist in L2 across the streaming kernels of a chunk (set-aside capped by the device).
+    cudaDeviceProp prop;
+    PSI_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    c.l2_window_bytes = 0;
+    if (c.opt_l2_persist && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      const size_t want = std::min<size_t>(c.sh->gather_pool_bytes, (size_t)prop.persistingL2CacheMaxSize);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+        c.l2_window_bytes = std::min<size_t>(c.sh->gather_pool_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      else (void)cudaGetLastError();
+      c.l2_persist_bytes = want;
+    }
+  }
 
   DevBuf<char> ascii;
   ascii.ensure(n_bases + 1);

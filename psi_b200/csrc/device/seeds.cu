@@ -290,6 +290,7 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
   if (base >= n_items) return;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
+  // all independent loads first: kind and locus of both items (the locus is loaded whether or not it is a hit)
   uint32_t seed[2], gpos[2];
   uint8_t kind[2];
 #pragma unroll
@@ -298,9 +299,8 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
     kind[h] = 0; seed[h] = 0; gpos[h] = 0;
     if (i < n_seeds) {
       kind[h] = __ldg(seed_kind + i);
-      if (kind[h] > 2) kind[h] = 0;
+      gpos[h] = __ldg(seed_hit + i);
       seed[h] = (uint32_t)i;
-      if (kind[h]) gpos[h] = __ldg(seed_hit + i);
     }
     else if (i < n_items) {
       const Hit x = ovf[i - n_seeds];
@@ -309,6 +309,10 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
       gpos[h] = x.gpos;
     }
   }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) if (kind[h] > 2) kind[h] = 0;
+
+  // count, and let one thread reserve the CTA's output range; the atomic's round trip overlaps the gathers below
   const uint32_t m0 = __ballot_sync(0xffffffffu, kind[0] != 0), m1 = __ballot_sync(0xffffffffu, kind[1] != 0);
   const uint32_t on = __popc(__ballot_sync(0xffffffffu, kind[0] == 1)) + __popc(__ballot_sync(0xffffffffu, kind[1] == 1));
   if (lane == 0) {
@@ -320,17 +324,24 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
   if (threadIdx.x == 0) {
     uint32_t run = 0;
 #pragma unroll
-    for (int w = 0; w < 16; ++w) { const uint32_t c = s_cnt[w]; s_cnt[w] = run; run += c; }
+    for (int w = 0; w < 16; ++w) run += s_cnt[w];
     s_base = run ? atomicAdd(total, (unsigned long long)run) : 0ull;
   }
-  __syncthreads();
-  const uint32_t lt = (1u << lane) - 1u;
-  const uint64_t out[2] = { s_base + s_cnt[warp] + __popc(m0 & lt), s_base + s_cnt[8 + warp] + __popc(m1 & lt) };
-  // both resolutions are issued before either is stored: two chains of dependent loads in flight per thread
+  // resolution of both items: two independent chains of gathers per thread
   Resolved r[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h)
-    if (RECORDS && kind[h] && out[h] < cap) r[h] = resolve_one(g, node_id, seed[h], gpos[h], seed_read, seed_first, d, first_read_id);
+    if (RECORDS && kind[h]) r[h] = resolve_one(g, node_id, seed[h], gpos[h], seed_read, seed_first, d, first_read_id);
+  __syncthreads();
+  uint32_t pre0 = 0, pre1 = 0;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    const uint32_t c = s_cnt[w];
+    if (w < (int)warp) pre0 += c;
+    if (w < 8 + (int)warp) pre1 += c;
+  }
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t out[2] = { s_base + pre0 + __popc(m0 & lt), s_base + pre1 + __popc(m1 & lt) };
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if (!kind[h] || out[h] >= cap) continue;
@@ -464,6 +475,16 @@ void engine_seeds(Ctx& c, unsigned flags)
 
     // compaction (+ resolution unless the hits are to be sorted first)
     PhaseTimer t_res(c, T_RESOLVE);
+    const bool pin = c.l2_window_bytes != 0 && sh.has_rank16;
+    if (pin) {   // gathers of this kernel into rank16/node_res persist in the L2 set-aside, everything else streams
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = sh.gather_pool.p;
+      attr.accessPolicyWindow.num_bytes = c.l2_window_bytes;
+      attr.accessPolicyWindow.hitRatio = c.l2_persist_bytes >= c.l2_window_bytes ? 1.0f : (float)c.l2_persist_bytes / (float)c.l2_window_bytes;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     uint64_t out_cap = 0;
     {
       const unsigned grid = grid_for(c.n_seeds_cap + c.hits.cap, 256, 2);
@@ -485,6 +506,11 @@ void engine_seeds(Ctx& c, unsigned flags)
                                                                 dc + DC_HITS, dc + DC_HITS_ON);
       }
       ++c.counters.launches;
+    }
+    if (pin) {
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.num_bytes = 0;
+      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     t_res.stop();
     PSI_CUDA(cudaGetLastError());

@@ -55,8 +55,8 @@ inline GraphView make_graph_view(const Ctx& c)
   g.seq2 = c.sh->seq2.p;
   g.nmask = c.sh->nmask.p;
   g.pos2node = c.sh->pos2node.p;
-  g.rank16 = c.sh->has_rank16 ? c.sh->rank16.p : nullptr;
-  g.node_res = c.sh->node_res.p;
+  g.rank16 = c.sh->has_rank16 ? c.sh->rank16 : nullptr;
+  g.node_res = c.sh->node_res;
   g.n_nodes = c.sh->n_nodes;
   g.pos2node_shift = Ctx::POS2NODE_SHIFT;
   g.n_bases = c.sh->n_bases;
