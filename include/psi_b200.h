@@ -245,7 +245,7 @@ typedef struct {
   float ms_index_build, ms_find_loci;
   float ms_h2d, ms_pack, ms_read_index, ms_on, ms_off, ms_resolve, ms_sort, ms_d2h;
   uint32_t launches;           /* kernels of this library launched since create / reset */
-  uint32_t reserved1;
+  float ms_probe;              /* the seeds_on_paths probe kernel alone (ms_on also covers the slow-queue kernel) */
 } psi_b200_counters_t;
 int  psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out);
 int  psi_b200_reset_counters(psi_b200_ctx* ctx);

@@ -72,7 +72,7 @@ class Counters(C.Structure):
                 ("ms_index_build", C.c_float), ("ms_find_loci", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_read_index", C.c_float), ("ms_on", C.c_float),
                 ("ms_off", C.c_float), ("ms_resolve", C.c_float), ("ms_sort", C.c_float), ("ms_d2h", C.c_float),
-                ("launches", C.c_uint32), ("reserved1", C.c_uint32)]
+                ("launches", C.c_uint32), ("ms_probe", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}

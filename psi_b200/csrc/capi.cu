@@ -364,6 +364,7 @@ int psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out)
     c.counters.ms_pack = PhaseTimer::timer_ms(c, T_PACK);
     c.counters.ms_read_index = PhaseTimer::timer_ms(c, T_READ_INDEX);
     c.counters.ms_on = PhaseTimer::timer_ms(c, T_ON);
+    c.counters.ms_probe = PhaseTimer::timer_ms(c, T_PROBE);
     c.counters.ms_off = PhaseTimer::timer_ms(c, T_OFF);
     c.counters.ms_resolve = PhaseTimer::timer_ms(c, T_RESOLVE);
     c.counters.ms_sort = PhaseTimer::timer_ms(c, T_SORT);

@@ -33,7 +33,7 @@ void table_clear(Ctx& c, HostTable& t);
 
 // CUDA-event timer slots (Ctx::ev holds a start/stop pair per slot)
 enum { T_INDEX = 0, T_LOCI = 1, T_H2D = 2, T_PACK = 3, T_READ_INDEX = 4, T_ON = 5, T_OFF = 6, T_RESOLVE = 7,
-       T_SORT = 8, T_D2H = 9, T_USER = 10, T_COUNT = 12 };
+       T_SORT = 8, T_D2H = 9, T_USER = 10, T_PROBE = 11, T_COUNT = 12 };
 
 struct PhaseTimer {
   Ctx& c;

@@ -397,7 +397,7 @@ void engine_seeds(Ctx& c, unsigned flags)
   unsigned long long* dc = c.dev_counters.p;
   c.records_valid = false;
   c.kinds_valid = false;
-  c.ev_state[T_ON] = c.ev_state[T_OFF] = c.ev_state[T_RESOLVE] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
+  c.ev_state[T_ON] = c.ev_state[T_PROBE] = c.ev_state[T_OFF] = c.ev_state[T_RESOLVE] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
 
   c.seed_hit.ensure(c.n_seeds_cap, 1.25);
   c.seed_kind.ensure(c.n_seeds_cap + 16, 1.25);
@@ -421,12 +421,14 @@ void engine_seeds(Ctx& c, unsigned flags)
           PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           carveout_set = true;
         }
+        PhaseTimer t_probe(c, T_PROBE);
         if (sh.index.view.fmt == 8)
           seeds_on_paths_kernel<8><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
                                                               probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
         else
           seeds_on_paths_kernel<16><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
                                                                probe_mode, c.seed_hit.p, c.seed_kind.p, c.slow_queue.p, dc + DC_SLOW);
+        t_probe.stop();
         seeds_slow_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, c.seed_kmer.p, c.slow_queue.p,
                                                                          dc + DC_SLOW, probe_mode, c.seed_hit.p, c.seed_kind.p,
                                                                          c.hits.p, c.hit_kind.p, c.hits.cap, dc + DC_OVF);

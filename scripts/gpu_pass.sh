@@ -13,10 +13,10 @@ echo "== bench (walk mode, 1 pipeline)" ; timeout 900 python bench.py --steps 10
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err ; cat $OUT/bench_ref.json
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.json 2> $OUT/ncu_launches.err
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipelines 1 > $OUT/bench_under_ncu.json 2> $OUT/ncu_launches.err
 tail -2 $OUT/ncu_launches.err
-echo "== ncu full (seeds_on_paths)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:seeds_on_paths -s 3 -c 2 -o $OUT/prof_on \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> $OUT/ncu_full.err
+echo "== ncu full (seeds_on_paths, compact_resolve)"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:seeds_on_paths|compact_resolve" -s 6 -c 4 -o $OUT/prof_on \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipelines 1 > /dev/null 2> $OUT/ncu_full.err
 tail -2 $OUT/ncu_full.err
 ls -la $OUT
