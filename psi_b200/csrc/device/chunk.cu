@@ -35,6 +35,46 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w4, uint32_t& bad)
   return (p | (p >> 4)) & 0xffu;                            // four codes, first base in the low bits
 }
 
+// K1 (direct): the k bases at byte address p (any alignment) -> packed k-mer, straight from the ASCII chunk.
+// The k bytes lie in at most 9 aligned 32-bit words (k <= 32); a funnel shift re-aligns them into groups of
+// four characters which pack4 converts.  `valid` is false when a character is not A/C/G/T.  Neighbouring
+// seeds read neighbouring words, so the loads of a warp coalesce in L1 and every byte comes from DRAM once.
+// The two halves are separate so that a thread can issue the loads of several seeds before packing the first.
+struct AsciiWords {
+  uint32_t x[10];
+  uint32_t sh;
+};
+
+__device__ __forceinline__ void load_ascii_words(const char* p, uint32_t k, AsciiWords& a)
+{
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
+  a.sh = (uint32_t)(addr & 3u) * 8u;
+  const uint32_t n_words = (uint32_t)(((addr + k - 1) >> 2) - (addr >> 2)) + 1u;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a.x[i] = (uint32_t)i < n_words ? __ldg(w + i) : 0u;
+  a.x[9] = 0u;
+}
+
+__device__ __forceinline__ uint64_t pack_ascii_words(const AsciiWords& a, uint32_t k, bool& valid)
+{
+  uint64_t bits = 0;
+  uint32_t any_bad = 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (4u * g < k) {
+      uint32_t bad;
+      uint32_t code = pack4(__funnelshift_r(a.x[g], a.x[g + 1], a.sh), bad);
+      const uint32_t cnt = k - 4u * g;                 // characters of this group inside the k-mer
+      if (cnt < 4u) { bad &= (1u << (8u * cnt)) - 1u; code &= (1u << (2u * cnt)) - 1u; }
+      any_bad |= bad;
+      bits |= (uint64_t)code << (8 * g);
+    }
+  }
+  valid = any_bad == 0;
+  return bits;
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 pack_reads_kernel(const char* __restrict__ bases, uint64_t n_bases, uint64_t* __restrict__ seq2, uint32_t* __restrict__ nmask)
@@ -193,6 +233,94 @@ extract_seeds_kernel(const uint64_t* __restrict__ seq2, const uint32_t* __restri
   }
 }
 
+// K1 direct: seeding straight from the ASCII chunk (no 2-bit staging of the reads).  A CTA owns DIRECT_READS
+// consecutive reads, one per thread: their start offsets and the CTA-local prefix sums of their seed counts go to
+// shared memory, then the CTA walks its seeds IN SEED ORDER, DIRECT_UNROLL seeds per thread and round, so that
+// every thread has DIRECT_UNROLL independent groups of loads in flight and all stores are contiguous.
+// Per seed: k bytes in (each chunk byte is read from DRAM once when d >= k), 8 + 1 + 4 bytes out.
+constexpr int DIRECT_READS = 256;
+constexpr int DIRECT_UNROLL = 4;
+
+__global__ void __launch_bounds__(256)
+count_seeds_direct_kernel(const uint64_t* __restrict__ read_ptr, uint64_t n_reads, uint32_t k, uint32_t d, uint32_t* __restrict__ cta_count)
+{
+  __shared__ uint32_t s_warp[8];
+  const uint32_t c = cta_sum(seed_count(read_ptr, (uint64_t)blockIdx.x * DIRECT_READS + threadIdx.x, n_reads, k, d), s_warp);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(256)
+seed_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, const uint32_t* __restrict__ cta_first,
+                  uint64_t n_reads, uint32_t k, uint32_t d, uint32_t* __restrict__ seed_first, uint64_t* __restrict__ seed_kmer,
+                  uint8_t* __restrict__ seed_valid, uint32_t* __restrict__ seed_read)
+{
+  __shared__ uint32_t s_first[DIRECT_READS + 1];
+  __shared__ uint64_t s_ptr[DIRECT_READS];
+  __shared__ uint32_t s_warp[8];
+  const uint64_t r_base = (uint64_t)blockIdx.x * DIRECT_READS;
+  const uint64_t r = r_base + threadIdx.x;
+  uint64_t p0 = 0;
+  uint32_t mine = 0;
+  if (r < n_reads) {
+    p0 = read_ptr[r];
+    const uint64_t len = read_ptr[r + 1] - p0;
+    mine = len >= k ? (uint32_t)((len - k) / d) + 1 : 0;      // reads shorter than k have no seeds
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += y; }
+  if (lane == 31u) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+  const uint32_t excl = before + incl - mine;
+  const uint32_t first0 = cta_first[blockIdx.x];
+  s_first[threadIdx.x] = excl;
+  s_ptr[threadIdx.x] = p0;
+  if (r <= n_reads) seed_first[r] = first0 + excl;              // r == n_reads gets the total
+  if (threadIdx.x == DIRECT_READS - 1) s_first[DIRECT_READS] = excl + mine;
+  __syncthreads();
+  const uint32_t n_cta_seeds = s_first[DIRECT_READS];
+  // reads of one length (the usual case) have the same number of seeds: the read of a seed is then a division
+  const uint32_t per_read = s_first[1];
+  const bool uniform = __syncthreads_and(mine == per_read) && per_read != 0;
+  for (uint32_t base = 0; base < n_cta_seeds; base += 256u * DIRECT_UNROLL) {
+    const char* p[DIRECT_UNROLL];
+    uint32_t rd[DIRECT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DIRECT_UNROLL; ++u) {
+      const uint32_t ls_raw = base + u * 256u + threadIdx.x;
+      const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;   // inactive slots re-read seed 0 (valid memory), store nothing
+      uint32_t lo = 0, hi = DIRECT_READS;
+      if (uniform) lo = ls / per_read;
+      else {
+#pragma unroll 1
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+      }
+      rd[u] = lo;
+      p[u] = bases + s_ptr[lo] + (uint64_t)(ls - s_first[lo]) * d;
+    }
+    AsciiWords aw[DIRECT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DIRECT_UNROLL; ++u) load_ascii_words(p[u], k, aw[u]);
+    uint64_t kmer[DIRECT_UNROLL];
+    bool valid[DIRECT_UNROLL];
+#pragma unroll
+    for (int u = 0; u < DIRECT_UNROLL; ++u) kmer[u] = pack_ascii_words(aw[u], k, valid[u]);
+#pragma unroll
+    for (int u = 0; u < DIRECT_UNROLL; ++u) {
+      const uint32_t ls = base + u * 256u + threadIdx.x;
+      if (ls < n_cta_seeds) {
+        const uint32_t s = first0 + ls;
+        seed_kmer[s] = kmer[u];
+        seed_valid[s] = valid[u] ? 1 : 0;
+        seed_read[s] = (uint32_t)(r_base + rd[u]);
+      }
+    }
+  }
+}
+
 // K4: one thread per valid seed; k-mer -> chain of seeds.
 template <int FMT>
 __global__ void __launch_bounds__(256)
@@ -253,19 +381,31 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
   c.distance = distance;
   c.n_seeds_cap = seeds_cap;
 
-  const uint64_t n_words = (n_bases + 31) >> 5;
-  c.reads2.ensure(n_words + 2, 1.25);
-  c.reads_n.ensure(n_words + 2, 1.25);
-  if (n_words) {
-    // the word after the last one is read by extract_bases of the final seed
-    PSI_CUDA(cudaMemsetAsync(c.reads2.p + n_words, 0, 2 * sizeof(uint64_t), c.stream));
-    PSI_CUDA(cudaMemsetAsync(c.reads_n.p + n_words, 0, 2 * sizeof(uint32_t), c.stream));
-    if ((reinterpret_cast<uintptr_t>(c.d_bases) & 15u) == 0)
-      pack_reads_kernel<true><<<grid_for(n_words, 256), 256, 0, c.stream>>>(c.d_bases, n_bases, c.reads2.p, c.reads_n.p);
-    else
-      pack_reads_kernel<false><<<grid_for(n_words, 256), 256, 0, c.stream>>>(c.d_bases, n_bases, c.reads2.p, c.reads_n.p);
+  if (c.opt_seeding_mode == 0) {
+    // direct: ASCII -> seeds (3 launches)
+    const unsigned n_ctas = (unsigned)((n_reads + 1 + DIRECT_READS - 1) / DIRECT_READS);   // + 1: seed_first[n_reads] = total
+    c.cta_first.ensure(2 * (size_t)n_ctas + 2, 1.25);
+    uint32_t* cta_count = c.cta_first.p + n_ctas + 1;
+    count_seeds_direct_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_read_ptr, n_reads, c.k, distance, cta_count);
+    scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, c.cta_first.p, c.dev_counters.p + DC_SEEDS);
+    seed_reads_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_bases, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
+                                                     c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
+    c.counters.launches += 3;
   }
-  {
+  else {
+    // staged: ASCII -> 2-bit reads -> seeds (4 launches); kept for A/B measurements
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    c.reads2.ensure(n_words + 2, 1.25);
+    c.reads_n.ensure(n_words + 2, 1.25);
+    if (n_words) {
+      // the word after the last one is read by extract_bases of the final seed
+      PSI_CUDA(cudaMemsetAsync(c.reads2.p + n_words, 0, 2 * sizeof(uint64_t), c.stream));
+      PSI_CUDA(cudaMemsetAsync(c.reads_n.p + n_words, 0, 2 * sizeof(uint32_t), c.stream));
+      if ((reinterpret_cast<uintptr_t>(c.d_bases) & 15u) == 0)
+        pack_reads_kernel<true><<<grid_for(n_words, 256), 256, 0, c.stream>>>(c.d_bases, n_bases, c.reads2.p, c.reads_n.p);
+      else
+        pack_reads_kernel<false><<<grid_for(n_words, 256), 256, 0, c.stream>>>(c.d_bases, n_bases, c.reads2.p, c.reads_n.p);
+    }
     const unsigned n_ctas = (unsigned)((n_reads + 1 + READS_PER_CTA - 1) / READS_PER_CTA);   // + 1: seed_first[n_reads] = total
     c.cta_first.ensure(2 * (size_t)n_ctas + 2, 1.25);
     uint32_t* cta_count = c.cta_first.p + n_ctas + 1;
@@ -273,8 +413,8 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
     scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, c.cta_first.p, c.dev_counters.p + DC_SEEDS);
     extract_seeds_kernel<<<n_ctas, 256, 0, c.stream>>>(c.reads2.p, c.reads_n.p, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
                                                         c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
+    c.counters.launches += 4;
   }
-  c.counters.launches += 4;
   t_pack.stop();
   PSI_CUDA(cudaGetLastError());
   c.has_chunk = true;

@@ -187,6 +187,8 @@ struct Ctx {
   int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
+  int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
+  int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
   int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
   uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this
 };

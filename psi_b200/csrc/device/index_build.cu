@@ -677,6 +677,14 @@ void engine_set_option(Ctx& c, const char* name, long long value)
     if (value < 1 || value > 32) throw ArgError("set_option: probe_ctas_per_sm must be in [1, 32]");
     c.opt_probe_ctas_per_sm = (unsigned)value;
   }
+  else if (n == "seeding_mode") {
+    if (value < 0 || value > 1) throw ArgError("set_option: seeding_mode is 0 (direct from ASCII) or 1 (2-bit staging)");
+    c.opt_seeding_mode = (int)value;
+  }
+  else if (n == "resolve_items") {
+    if (value != 2 && value != 4) throw ArgError("set_option: resolve_items is 2 or 4");
+    c.opt_resolve_items = (int)value;
+  }
   else throw ArgError("set_option: unknown option '" + n + "'");
 }
 

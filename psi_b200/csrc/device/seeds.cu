@@ -268,7 +268,13 @@ __device__ __forceinline__ Resolved resolve_one(const GraphView& g, const uint64
   return o;
 }
 
-template <bool RECORDS>
+// one 32-byte record per store instruction (STG.256): every 32-byte sector of the output is written exactly once
+__device__ __forceinline__ void st_record(uint64_t* dst, const Resolved& r)
+{
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "l"(r.node_id), "l"(r.node_off), "l"(r.read_id), "l"(r.read_off) : "memory");
+}
+
+template <bool RECORDS, int ITEMS>
 __global__ void __launch_bounds__(256)
 compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
                        const uint32_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
@@ -280,21 +286,22 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
                        uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, Hit* __restrict__ out_hits, uint64_t cap,
                        unsigned long long* __restrict__ total, unsigned long long* __restrict__ total_on)
 {
-  __shared__ uint32_t s_cnt[16];
+  __shared__ uint32_t s_cnt[8 * ITEMS];
+  __shared__ uint32_t s_on[8];
   __shared__ unsigned long long s_base;
   const uint64_t n_seeds = *n_seeds_p;
   uint64_t n_ovf = *n_ovf_p;
   if (n_ovf > ovf_cap) n_ovf = ovf_cap;
   const uint64_t n_items = n_seeds + n_ovf;
-  const uint64_t base = (uint64_t)blockIdx.x * 512u;
+  const uint64_t base = (uint64_t)blockIdx.x * (256u * ITEMS);
   if (base >= n_items) return;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
-  // all independent loads first: kind and locus of both items (the locus is loaded whether or not it is a hit)
-  uint32_t seed[2], gpos[2];
-  uint8_t kind[2];
+  // all independent loads first: kind and locus of every item (the locus is loaded whether or not it is a hit)
+  uint32_t seed[ITEMS], gpos[ITEMS];
+  uint8_t kind[ITEMS];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < ITEMS; ++h) {
     const uint64_t i = base + h * 256u + threadIdx.x;
     kind[h] = 0; seed[h] = 0; gpos[h] = 0;
     if (i < n_seeds) {
@@ -310,48 +317,56 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
     }
   }
 #pragma unroll
-  for (int h = 0; h < 2; ++h) if (kind[h] > 2) kind[h] = 0;
+  for (int h = 0; h < ITEMS; ++h) if (kind[h] > 2) kind[h] = 0;
 
-  // count, and let one thread reserve the CTA's output range; the atomic's round trip overlaps the gathers below
-  const uint32_t m0 = __ballot_sync(0xffffffffu, kind[0] != 0), m1 = __ballot_sync(0xffffffffu, kind[1] != 0);
-  const uint32_t on = __popc(__ballot_sync(0xffffffffu, kind[0] == 1)) + __popc(__ballot_sync(0xffffffffu, kind[1] == 1));
+  // count, and let one thread reserve the CTA's output range (two atomics per CTA: same-address atomics serialise
+  // in L2, so their number, not their latency, is what matters); the round trip overlaps the gathers below
+  uint32_t m[ITEMS];
+  uint32_t on = 0;
+#pragma unroll
+  for (int h = 0; h < ITEMS; ++h) {
+    m[h] = __ballot_sync(0xffffffffu, kind[h] != 0);
+    on += __popc(__ballot_sync(0xffffffffu, kind[h] == 1));
+  }
   if (lane == 0) {
-    s_cnt[warp] = __popc(m0);
-    s_cnt[8 + warp] = __popc(m1);
-    if (on) atomicAdd(total_on, (unsigned long long)on);
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) s_cnt[8 * h + warp] = __popc(m[h]);
+    s_on[warp] = on;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t run = 0;
+    uint32_t run = 0, run_on = 0;
 #pragma unroll
-    for (int w = 0; w < 16; ++w) run += s_cnt[w];
+    for (int w = 0; w < 8 * ITEMS; ++w) run += s_cnt[w];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) run_on += s_on[w];
     s_base = run ? atomicAdd(total, (unsigned long long)run) : 0ull;
+    if (run_on) atomicAdd(total_on, (unsigned long long)run_on);
   }
-  // resolution of both items: two independent chains of gathers per thread
-  Resolved r[2];
+  // resolution of all items: ITEMS independent chains of gathers per thread
+  Resolved r[ITEMS];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int h = 0; h < ITEMS; ++h)
     if (RECORDS && kind[h]) r[h] = resolve_one(g, node_id, seed[h], gpos[h], seed_read, seed_first, d, first_read_id);
   __syncthreads();
-  uint32_t pre0 = 0, pre1 = 0;
-#pragma unroll
-  for (int w = 0; w < 16; ++w) {
-    const uint32_t c = s_cnt[w];
-    if (w < (int)warp) pre0 += c;
-    if (w < 8 + (int)warp) pre1 += c;
-  }
   const uint32_t lt = (1u << lane) - 1u;
-  const uint64_t out[2] = { s_base + pre0 + __popc(m0 & lt), s_base + pre1 + __popc(m1 & lt) };
+  uint32_t run = 0;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (!kind[h] || out[h] >= cap) continue;
-    if (RECORDS) {
-      ulonglong2* o = reinterpret_cast<ulonglong2*>(records + 4 * out[h]);
-      o[0] = make_ulonglong2(r[h].node_id, r[h].node_off);
-      o[1] = make_ulonglong2(r[h].read_id, r[h].read_off);
-      rec_kind[out[h]] = kind[h];
+  for (int h = 0; h < ITEMS; ++h) {
+    uint32_t pre = run;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t c = s_cnt[8 * h + w];
+      if (w < (int)warp) pre += c;
+      run += c;
     }
-    else out_hits[out[h]] = Hit{ seed[h], gpos[h] };
+    const uint64_t out = s_base + pre + __popc(m[h] & lt);
+    if (!kind[h] || out >= cap) continue;
+    if (RECORDS) {
+      st_record(records + 4 * out, r[h]);
+      rec_kind[out] = kind[h];
+    }
+    else out_hits[out] = Hit{ seed[h], gpos[h] };
   }
 }
 
@@ -489,24 +504,25 @@ void engine_seeds(Ctx& c, unsigned flags)
     }
     uint64_t out_cap = 0;
     {
-      const unsigned grid = grid_for(c.n_seeds_cap + c.hits.cap, 256, 2);
+      const unsigned items = (unsigned)c.opt_resolve_items;
+      const unsigned grid = grid_for(c.n_seeds_cap + c.hits.cap, 256, items);
+#define PSI_RESOLVE_ARGS(REC, KINDS, HITS) \
+  g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p, c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, \
+  c.seed_first.p, c.distance, c.first_read_id, REC, KINDS, HITS, out_cap, dc + DC_HITS, dc + DC_HITS_ON
       if (sorted || !resolve) {
         c.sorted_hits.ensure(out_cap_want);
         out_cap = c.sorted_hits.cap;
-        compact_resolve_kernel<false><<<grid, 256, 0, c.stream>>>(g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p,
-                                                                 c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, c.seed_first.p,
-                                                                 c.distance, c.first_read_id, nullptr, nullptr, c.sorted_hits.p, out_cap,
-                                                                 dc + DC_HITS, dc + DC_HITS_ON);
+        if (items == 4) compact_resolve_kernel<false, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        else compact_resolve_kernel<false, 2><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
       }
       else {
         c.records.ensure(4 * out_cap_want);
         c.rec_kind.ensure(out_cap_want);
         out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
-        compact_resolve_kernel<true><<<grid, 256, 0, c.stream>>>(g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p,
-                                                                c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, c.seed_first.p,
-                                                                c.distance, c.first_read_id, c.records.p, c.rec_kind.p, nullptr, out_cap,
-                                                                dc + DC_HITS, dc + DC_HITS_ON);
+        if (items == 4) compact_resolve_kernel<true, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else compact_resolve_kernel<true, 2><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
       }
+#undef PSI_RESOLVE_ARGS
       ++c.counters.launches;
     }
     if (pin) {

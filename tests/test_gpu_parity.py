@@ -122,6 +122,59 @@ def test_no_paths_all_loci_equals_closed_form(name, mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("seeding,items", [(1, 2), (0, 4), (1, 4)], ids=["staged-2", "direct-4", "staged-4"])
+@pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "fuzz_07", "fuzz_10", "fuzz_11"])
+def test_kernel_variants_give_the_same_set(name, seeding, items):
+    """The alternative kernels behind the tuning options (2-bit staged seeding, 4 items per thread in the resolve
+    kernel) must give the reference's set too; the defaults are covered by every other test."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_option("seeding_mode", seeding)
+    ctx.set_option("resolve_items", items)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
+    ctx.find_loci()
+    rec, total = run_chunks(ctx, rp, bases, c["d"], c["chunk"])
+    got = capi.canonical(rec)
+    assert total == len(got) == c["count"]
+    assert util.md5_tuples(got) == c["md5"]
+    ctx.close()
+
+
+def test_ragged_reads_every_alignment_and_k():
+    """Seeding straight from the ASCII chunk: reads of every length 0..70 (so seeds start at every byte alignment),
+    N / lower case sprinkled in, k from 3 to 32 and d from 1 to k + 3, against the oracle."""
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    og = orc.OGraph.of(g)
+    _, full = util.read_fasta(util.GOLDEN / "inputs/reads_n10000l100e0i0.fa.gz")
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([np.arange(0, 71), rng.integers(0, 71, 400)])
+    rng.shuffle(lens)
+    rp = np.zeros(len(lens) + 1, np.uint64)
+    rp[1:] = np.cumsum(lens)
+    # slices of real reads so that most seeds hit the graph
+    starts = rng.integers(0, len(full) // 100 - 1, len(lens)) * 100 + rng.integers(0, 30, len(lens))
+    bases = np.concatenate([full[s:s + n] for s, n in zip(starts, lens)]).copy()
+    for i in rng.integers(0, len(bases), 60):
+        bases[i] = ord("N") if i % 2 else bases[i] | 0x20
+    for k in (3, 4, 5, 12, 19, 20, 27, 28, 31, 32):
+        ctx = capi.Context(k, 0)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(g.pick_paths(2, seed=3))
+        ctx.find_loci()
+        for d in sorted({1, 2, k, k + 3}):
+            if k < 8 and d < k:
+                continue        # tiny k with overlapping seeds: millions of hits, nothing new to learn
+            ctx.submit_chunk(rp, bases, 11, d)
+            n = ctx.seeds_all()
+            got = capi.canonical(ctx.fetch())
+            want, _ = orc.seeds_closed_form(og, orc.OReads(rp, bases, 11), k, d)
+            assert n == len(got), (k, d)
+            assert np.array_equal(got, want), (k, d)
+        ctx.close()
+
+
 def test_traverser_known_answers_on_gpu():
     """reference test/src/test_traverser.cpp:81-96 through the CUDA walker."""
     g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
