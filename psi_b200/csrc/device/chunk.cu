@@ -36,43 +36,53 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w4, uint32_t& bad)
 }
 
 // K1 (direct): the k bases at byte address p (any alignment) -> packed k-mer, straight from the ASCII chunk.
-// The k bytes lie in at most 9 aligned 32-bit words (k <= 32); a funnel shift re-aligns them into groups of
-// four characters which pack4 converts.  `valid` is false when a character is not A/C/G/T.  Neighbouring
-// seeds read neighbouring words, so the loads of a warp coalesce in L1 and every byte comes from DRAM once.
-// The two halves are separate so that a thread can issue the loads of several seeds before packing the first.
+// K4 = ceil(k / 4) groups of four characters.  The k bytes lie in K4 or K4 + 1 aligned 32-bit words; a funnel
+// shift re-aligns them, then per group (all byte-parallel, ~15 instructions per 4 bases):
+//   x = (c >> 1) & 3 ; x ^= x >> 1            A,C,G,T (either case) -> 0,1,2,3 in every byte
+//   code = (x * 0x01041040) >> 24             gathers the four 2-bit codes into one byte (the partial
+//                                             products occupy disjoint bit fields, so nothing carries)
+//   PRMT("ACGT", nibbles(code)) == upper(c)   validates the four characters with one byte permute
+// Neighbouring seeds read neighbouring words, so the loads of a warp coalesce in L1 and every chunk byte comes
+// from DRAM once.  Loading and packing are separate so that a thread can have the words of several seeds in flight.
+template <int K4>
 struct AsciiWords {
-  uint32_t x[10];
+  uint32_t x[K4 + 1];
   uint32_t sh;
 };
 
-__device__ __forceinline__ void load_ascii_words(const char* p, uint32_t k, AsciiWords& a)
+template <int K4>
+__device__ __forceinline__ void load_ascii_words(const char* p, uint32_t k, AsciiWords<K4>& a)
 {
   const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
-  a.sh = (uint32_t)(addr & 3u) * 8u;
-  const uint32_t n_words = (uint32_t)(((addr + k - 1) >> 2) - (addr >> 2)) + 1u;
+  const uint32_t off = (uint32_t)(addr & 3u);
+  a.sh = off * 8u;
+  // words 0 .. K4-1 always hold bytes of the k-mer (k > 4 (K4 - 1)); word K4 only when the k-mer spills into it
 #pragma unroll
-  for (int i = 0; i < 9; ++i) a.x[i] = (uint32_t)i < n_words ? __ldg(w + i) : 0u;
-  a.x[9] = 0u;
+  for (int i = 0; i < K4; ++i) a.x[i] = __ldg(w + i);
+  a.x[K4] = off + k > 4u * K4 ? __ldg(w + K4) : 0u;
 }
 
-__device__ __forceinline__ uint64_t pack_ascii_words(const AsciiWords& a, uint32_t k, bool& valid)
+// tail_mask: byte mask of the characters of the LAST group that belong to the k-mer (all ones when k % 4 == 0)
+template <int K4>
+__device__ __forceinline__ uint64_t pack_ascii_words(const AsciiWords<K4>& a, uint32_t tail_mask, bool& valid)
 {
-  uint64_t bits = 0;
-  uint32_t any_bad = 0;
+  uint32_t lo = 0, hi = 0, any_bad = 0;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    if (4u * g < k) {
-      uint32_t bad;
-      uint32_t code = pack4(__funnelshift_r(a.x[g], a.x[g + 1], a.sh), bad);
-      const uint32_t cnt = k - 4u * g;                 // characters of this group inside the k-mer
-      if (cnt < 4u) { bad &= (1u << (8u * cnt)) - 1u; code &= (1u << (2u * cnt)) - 1u; }
-      any_bad |= bad;
-      bits |= (uint64_t)code << (8 * g);
-    }
+  for (int g = 0; g < K4; ++g) {
+    uint32_t c = __funnelshift_r(a.x[g], a.x[g + 1], a.sh);
+    if (g == K4 - 1) c = (c & tail_mask) | (0x41414141u & ~tail_mask);    // beyond the k-mer: 'A' = code 0, valid
+    uint32_t x = (c >> 1) & 0x03030303u;
+    x ^= (x >> 1) & 0x01010101u;
+    const uint32_t code = (x * 0x01041040u) >> 24;
+    const uint32_t t = (code | (code << 4)) & 0x0f0fu;
+    const uint32_t sel = (t | (t << 2)) & 0x3333u;                        // one code per nibble
+    any_bad |= (c & 0xdfdfdfdfu) ^ __byte_perm(0x54474341u, 0u, sel);     // non-zero bytes are not A/C/G/T
+    if (g < 4) lo |= code << (8 * g);
+    else hi |= code << (8 * (g - 4));
   }
   valid = any_bad == 0;
-  return bits;
+  return ((uint64_t)hi << 32) | lo;
 }
 
 template <bool VEC>
@@ -249,6 +259,7 @@ count_seeds_direct_kernel(const uint64_t* __restrict__ read_ptr, uint64_t n_read
   if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
 }
 
+template <int K4>
 __global__ void __launch_bounds__(256)
 seed_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, const uint32_t* __restrict__ cta_first,
                   uint64_t n_reads, uint32_t k, uint32_t d, uint32_t* __restrict__ seed_first, uint64_t* __restrict__ seed_kmer,
@@ -282,43 +293,55 @@ seed_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ r
   if (threadIdx.x == DIRECT_READS - 1) s_first[DIRECT_READS] = excl + mine;
   __syncthreads();
   const uint32_t n_cta_seeds = s_first[DIRECT_READS];
-  // reads of one length (the usual case) have the same number of seeds: the read of a seed is then a division
+  // reads of one length (the usual case) have the same number of seeds: the read of a seed is then a division,
+  // done as a multiplication by floor(2^32 / per_read) plus one correction step
   const uint32_t per_read = s_first[1];
-  const bool uniform = __syncthreads_and(mine == per_read) && per_read != 0;
+  const bool uniform = __syncthreads_and(mine == per_read) && per_read > 1u;
+  const bool one_each = !uniform && __syncthreads_and(mine == 1u);   // per_read == 1: the seed index is the read index
+  const uint32_t magic = uniform ? (uint32_t)(0x100000000ull / per_read) : 0u;
+  const uint32_t tail = k - 4u * (K4 - 1);                           // characters in the last group, 1..4
+  const uint32_t tail_mask = tail >= 4u ? 0xffffffffu : (1u << (8u * tail)) - 1u;
   for (uint32_t base = 0; base < n_cta_seeds; base += 256u * DIRECT_UNROLL) {
-    const char* p[DIRECT_UNROLL];
+    AsciiWords<K4> aw[DIRECT_UNROLL];
     uint32_t rd[DIRECT_UNROLL];
 #pragma unroll
     for (int u = 0; u < DIRECT_UNROLL; ++u) {
       const uint32_t ls_raw = base + u * 256u + threadIdx.x;
       const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;   // inactive slots re-read seed 0 (valid memory), store nothing
-      uint32_t lo = 0, hi = DIRECT_READS;
-      if (uniform) lo = ls / per_read;
+      uint32_t lo = 0;
+      if (uniform) {
+        lo = __umulhi(ls, magic);
+        if ((lo + 1u) * per_read <= ls) ++lo;
+      }
+      else if (one_each) lo = ls;
       else {
+        uint32_t hi = DIRECT_READS;
 #pragma unroll 1
         while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
       }
       rd[u] = lo;
-      p[u] = bases + s_ptr[lo] + (uint64_t)(ls - s_first[lo]) * d;
+      load_ascii_words<K4>(bases + s_ptr[lo] + (uint64_t)(ls - s_first[lo]) * d, k, aw[u]);
     }
-    AsciiWords aw[DIRECT_UNROLL];
-#pragma unroll
-    for (int u = 0; u < DIRECT_UNROLL; ++u) load_ascii_words(p[u], k, aw[u]);
-    uint64_t kmer[DIRECT_UNROLL];
-    bool valid[DIRECT_UNROLL];
-#pragma unroll
-    for (int u = 0; u < DIRECT_UNROLL; ++u) kmer[u] = pack_ascii_words(aw[u], k, valid[u]);
 #pragma unroll
     for (int u = 0; u < DIRECT_UNROLL; ++u) {
+      bool valid;
+      const uint64_t kmer = pack_ascii_words<K4>(aw[u], tail_mask, valid);
       const uint32_t ls = base + u * 256u + threadIdx.x;
       if (ls < n_cta_seeds) {
         const uint32_t s = first0 + ls;
-        seed_kmer[s] = kmer[u];
-        seed_valid[s] = valid[u] ? 1 : 0;
+        seed_kmer[s] = kmer;
+        seed_valid[s] = valid ? 1 : 0;
         seed_read[s] = (uint32_t)(r_base + rd[u]);
       }
     }
   }
+}
+
+template <int K4>
+static void launch_seed_reads(Ctx& c, unsigned n_ctas, uint64_t n_reads, unsigned distance)
+{
+  seed_reads_kernel<K4><<<n_ctas, 256, 0, c.stream>>>(c.d_bases, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
+                                                       c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
 }
 
 // K4: one thread per valid seed; k-mer -> chain of seeds.
@@ -388,8 +411,16 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
     uint32_t* cta_count = c.cta_first.p + n_ctas + 1;
     count_seeds_direct_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_read_ptr, n_reads, c.k, distance, cta_count);
     scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, c.cta_first.p, c.dev_counters.p + DC_SEEDS);
-    seed_reads_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_bases, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
-                                                     c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
+    switch ((c.k + 3) / 4) {
+      case 1: launch_seed_reads<1>(c, n_ctas, n_reads, distance); break;
+      case 2: launch_seed_reads<2>(c, n_ctas, n_reads, distance); break;
+      case 3: launch_seed_reads<3>(c, n_ctas, n_reads, distance); break;
+      case 4: launch_seed_reads<4>(c, n_ctas, n_reads, distance); break;
+      case 5: launch_seed_reads<5>(c, n_ctas, n_reads, distance); break;
+      case 6: launch_seed_reads<6>(c, n_ctas, n_reads, distance); break;
+      case 7: launch_seed_reads<7>(c, n_ctas, n_reads, distance); break;
+      default: launch_seed_reads<8>(c, n_ctas, n_reads, distance); break;
+    }
     c.counters.launches += 3;
   }
   else {

@@ -189,6 +189,7 @@ struct Ctx {
   unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
   int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
+  int opt_resolve_ctas = 6;                    // resident CTAs per SM the resolve kernel is compiled for (5 or 6)
   int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
   uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this
 };

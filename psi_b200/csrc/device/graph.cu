@@ -112,6 +112,7 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
   c->opt_resolve_items = parent.opt_resolve_items;
+  c->opt_resolve_ctas = parent.opt_resolve_ctas;
   c->l2_window_bytes = parent.l2_window_bytes;
   c->l2_persist_bytes = parent.l2_persist_bytes;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;

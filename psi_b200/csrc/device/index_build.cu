@@ -681,6 +681,10 @@ void engine_set_option(Ctx& c, const char* name, long long value)
     if (value < 0 || value > 1) throw ArgError("set_option: seeding_mode is 0 (direct from ASCII) or 1 (2-bit staging)");
     c.opt_seeding_mode = (int)value;
   }
+  else if (n == "resolve_ctas") {
+    if (value != 5 && value != 6) throw ArgError("set_option: resolve_ctas is 5 or 6");
+    c.opt_resolve_ctas = (int)value;
+  }
   else if (n == "resolve_items") {
     if (value != 2 && value != 4) throw ArgError("set_option: resolve_items is 2 or 4");
     c.opt_resolve_items = (int)value;

@@ -274,8 +274,8 @@ __device__ __forceinline__ void st_record(uint64_t* dst, const Resolved& r)
   asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "l"(r.node_id), "l"(r.node_off), "l"(r.read_id), "l"(r.read_off) : "memory");
 }
 
-template <bool RECORDS, int ITEMS>
-__global__ void __launch_bounds__(256)
+template <bool RECORDS, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
                        const uint32_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
                        const unsigned long long* __restrict__ n_seeds_p,
@@ -512,15 +512,16 @@ void engine_seeds(Ctx& c, unsigned flags)
       if (sorted || !resolve) {
         c.sorted_hits.ensure(out_cap_want);
         out_cap = c.sorted_hits.cap;
-        if (items == 4) compact_resolve_kernel<false, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
-        else compact_resolve_kernel<false, 2><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        if (items == 4) compact_resolve_kernel<false, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        else compact_resolve_kernel<false, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
       }
       else {
         c.records.ensure(4 * out_cap_want);
         c.rec_kind.ensure(out_cap_want);
         out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
-        if (items == 4) compact_resolve_kernel<true, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else compact_resolve_kernel<true, 2><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        if (items == 4) compact_resolve_kernel<true, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else if (c.opt_resolve_ctas >= 6) compact_resolve_kernel<true, 2, 6><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else compact_resolve_kernel<true, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
       }
 #undef PSI_RESOLVE_ARGS
       ++c.counters.launches;

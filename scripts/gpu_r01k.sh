@@ -16,7 +16,7 @@ except Exception as e:
 PY
 }
 echo "== bench (defaults)" ; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; tail -3 $OUT/bench.err ; show $OUT/bench.json
-for v in "seeding_mode=1" "resolve_items=4" "l2_persist=0" "seeding_mode=1 resolve_items=4"; do
+for v in "seeding_mode=1" "resolve_items=4" "resolve_ctas=5"; do
   tagv=$(echo "$v" | tr ' =' '__')
   opts=""; for o in $v; do opts="$opts --opt $o"; done
   echo "== bench $v"
