@@ -267,17 +267,25 @@ def main_gpu(args):
         ctx.submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
         return ctx.seeds_all(capi.ALL)
 
-    def step_e2e(i, p=0):
+    def step_e2e(i, p=0, compact=True):
         hp, hb = batches_h[i % N_BATCHES]
         cx, rec_host = pipes[p], rec_hosts[p]
         cx.submit_chunk_ptr(n_reads, hp.data_ptr(), hb.data_ptr(), rank * n_reads, K)
+        if compact:      # 4 x u32 records: the same fields, half the bytes over PCIe
+            cx.seeds_all(capi.ALL | capi.COMPACT)
+            return cx.fetch32_into(rec_host.data_ptr(), rec_host.shape[0])
         cx.seeds_all(capi.ALL)
         return cx.fetch_into(rec_host.data_ptr(), rec_host.shape[0])
 
-    def timed_e2e(steps, warmup):
-        """K steps through the C-ABI with host buffers, round-robin over the pipelines, one host thread each."""
+    def step_resident(i, p=0):
+        dp, db = batches_d[i % N_BATCHES]
+        pipes[p].submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
+        return pipes[p].seeds_all(capi.ALL)
+
+    def timed_e2e(steps, warmup, step_fn=step_e2e):
+        """K steps through the C-ABI, round-robin over the pipelines, one host thread each."""
         for i in range(warmup):
-            step_e2e(i, i % n_pipes)
+            step_fn(i, i % n_pipes)
         barrier()
         for cx in pipes:
             cx.reset_counters()
@@ -287,7 +295,7 @@ def main_gpu(args):
         def work(p):
             try:
                 for i in range(p, steps, n_pipes):
-                    hits[p] += step_e2e(warmup + i, p)
+                    hits[p] += step_fn(warmup + i, p)
             except Exception as e:   # surfaced after join
                 errors.append(e)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -345,6 +353,11 @@ def main_gpu(args):
     ms_dev, hits_dev, acc, launches = timed(step_device, args.steps, args.warmup)
     c_last = ctx.counters()
     ms_e2e, hits_e2e, launches_e2e = timed_e2e(args.steps, args.warmup)
+    ms_e2e_wide, hits_e2e_wide, _ = timed_e2e(args.steps, args.warmup, lambda i, p=0: step_e2e(i, p, compact=False))
+    # the resident-input step again with the pipelines running concurrently (kernels of one chunk fill the launch and
+    # latency gaps of the other); `value` stays the single-pipeline figure the per-kernel timers belong to
+    ms_pipe, hits_pipe, _ = timed_e2e(args.steps, args.warmup, step_resident)
+    assert hits_e2e == hits_e2e_wide == hits_pipe == hits_dev, (hits_e2e, hits_e2e_wide, hits_pipe, hits_dev)
     clocks = sampler.stop() if rank == 0 else None
 
     # per-shard counts and a hits-per-read histogram, reduced with NCCL (the only collective on this path)
@@ -396,8 +409,17 @@ def main_gpu(args):
             "kernel_ms_per_step": per_step, "probe_slow_seeds_per_step": acc["n_on_probe_sectors"] / args.steps,
             "e2e": {"value": e2e_value, "unit": "reads/s",
                     "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
-                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 32), "ms_per_step": ms_e2e / args.steps,
-                    "pipelines": n_pipes},
+                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 16), "ms_per_step": ms_e2e / args.steps,
+                    "pipelines": n_pipes,
+                    "records": "4 x u32 {node_id, node_offset, read_id, read_offset} per hit (PSI_B200_COMPACT + psi_b200_fetch32)"},
+            "e2e_wide_records": {"value": n_reads * args.steps * world / (ms_e2e_wide * 1e-3), "unit": "reads/s",
+                                 "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
+                                 "d2h_bytes_per_step": int(hits_e2e_wide / args.steps * 32),
+                                 "ms_per_step": ms_e2e_wide / args.steps, "pipelines": n_pipes,
+                                 "records": "4 x u64 per hit, the byte layout psikt writes (psi_b200_fetch)"},
+            "value_pipelined": {"value": n_reads * args.steps * world / (ms_pipe * 1e-3), "unit": "reads/s",
+                                "ms_per_step": ms_pipe / args.steps, "pipelines": n_pipes,
+                                "note": "inputs resident in HBM, the pipelines' kernels overlap on the GPU"},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "offpath_mode": "index (walks from the starting loci materialised into the index)" if c_last["offpath_mode"] == 2
                             else "walk (graph walked from the starting loci for every chunk)",

@@ -200,6 +200,8 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
 #define PSI_B200_ALL        3u   /* seeds_all       (seed_finder.hpp:1724-1732) */
 #define PSI_B200_SORTED     4u   /* additionally sort records canonically on the device */
 #define PSI_B200_NO_RESOLVE 8u   /* keep compact device records only (benchmark of the probe alone) */
+#define PSI_B200_COMPACT   16u   /* resolve into 4 x u32 records (psi_b200_fetch32): same fields, half the bytes over PCIe;
+                                    PSI_B200_ERR_ARG when a node id or a read id of the chunk does not fit 32 bits */
 
 /* Finds the seeds of the submitted chunk.  The result is the SET of hits
  * (each (read, offset, node, offset) once), resident in device
@@ -211,6 +213,11 @@ int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
  * CLI's byte layout (src/psikt.cpp:172-181, seed.hpp:32-46): per hit 4 x u64
  * {node_id, node_offset, read_id, read_offset}. */
 int  psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits);
+/* The same records after a seeds_all with PSI_B200_COMPACT: per hit 4 x u32 {node_id, node_offset, read_id,
+ * read_offset} -- the fields of Seed<> (seed.hpp:32-46) a caller widens when it builds the callback argument or
+ * writes the CLI's 4 x size_t (src/psikt.cpp:172-181).  PSI_B200_ERR_STATE when the last seeds_all was not compact
+ * (and psi_b200_fetch fails likewise after a compact one). */
+int  psi_b200_fetch32(psi_b200_ctx* ctx, uint32_t* hits, uint64_t cap, uint64_t* n_hits);
 /* Per record of the last (unsorted) seeds_all: 1 = found on an indexed path (seeds_on_paths), 2 = found only by
  * an off-path walk (seeds_off_paths); lets a caller route hits to the two callbacks of
  * seeds_all(reads, index, traverser, callback1, callback2) (seed_finder.hpp:1734-1743). */

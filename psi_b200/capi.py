@@ -18,7 +18,7 @@ LIB_PATH = _HERE / "libpsi_b200.so"
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5, -6
-ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE = 1, 2, 3, 4, 8
+ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE, COMPACT = 1, 2, 3, 4, 8, 16
 
 # every symbol include/psi_b200.h declares
 SYMBOLS = [
@@ -30,7 +30,7 @@ SYMBOLS = [
     "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
     "psi_b200_submit_chunk", "psi_b200_submit_chunk_device", "psi_b200_seeds_all",
-    "psi_b200_fetch", "psi_b200_fetch_kinds", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
+    "psi_b200_fetch", "psi_b200_fetch32", "psi_b200_fetch_kinds", "psi_b200_fetch_device", "psi_b200_host_alloc", "psi_b200_host_free",
     "psi_b200_counters", "psi_b200_reset_counters", "psi_b200_version",
 ]
 
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.psi_b200_submit_chunk_device.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, C.c_uint64, C.c_uint]
     L.psi_b200_seeds_all.argtypes = [vp, C.c_uint, u64p]
     L.psi_b200_fetch.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.psi_b200_fetch32.argtypes = [vp, vp, C.c_uint64, u64p]
     L.psi_b200_fetch_kinds.argtypes = [vp, vp, C.c_uint64, u64p]
     L.psi_b200_fetch_device.argtypes = [vp, C.POINTER(vp), u64p]
     L.psi_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -370,6 +371,21 @@ class Context:
         if n:
             self._ck(lib().psi_b200_fetch(self._h, _ptr(out), n, C.byref(cnt)))
         return out
+
+    def fetch32(self, n=None) -> np.ndarray:
+        """(n, 4) u32 records, same fields, after seeds_all(flags | COMPACT)."""
+        cnt = C.c_uint64()
+        self._ck(lib().psi_b200_fetch32(self._h, None, 0, C.byref(cnt)))
+        n = cnt.value if n is None else min(n, cnt.value)
+        out = np.zeros((n, 4), np.uint32)
+        if n:
+            self._ck(lib().psi_b200_fetch32(self._h, _ptr(out), n, C.byref(cnt)))
+        return out
+
+    def fetch32_into(self, addr: int, cap: int) -> int:
+        cnt = C.c_uint64()
+        self._ck(lib().psi_b200_fetch32(self._h, C.c_void_p(addr), cap, C.byref(cnt)))
+        return cnt.value
 
     def fetch_kinds(self) -> np.ndarray:
         """Per record: 1 = on an indexed path, 2 = off-path (same order as fetch())."""

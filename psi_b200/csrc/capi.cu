@@ -321,7 +321,16 @@ int psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_
   CTX_GUARD(ctx, {
     if (n_hits) *n_hits = ctx->c->n_hits;
     if (cap && !hits) throw ArgError("fetch: null buffer");
-    if (cap) engine_fetch(*ctx->c, hits, cap);
+    if (cap) engine_fetch(*ctx->c, hits, cap, false);
+  })
+}
+
+int psi_b200_fetch32(psi_b200_ctx* ctx, uint32_t* hits, uint64_t cap, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (n_hits) *n_hits = ctx->c->n_hits;
+    if (cap && !hits) throw ArgError("fetch32: null buffer");
+    if (cap) engine_fetch(*ctx->c, hits, cap, true);
   })
 }
 

@@ -106,6 +106,7 @@ struct Shared {
   DevBuf<uint64_t> seq2;         // 2-bit labels
   DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
   DevBuf<uint64_t> node_id;
+  uint64_t max_node_id = 0;      // PSI_B200_COMPACT records need it below 2^32
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
   // rank16 and node_res live back to back in one allocation so that ONE L2 access-policy window can pin them
   // (they are gathered at random by every hit; together ~1.1 bytes per graph base)
@@ -180,6 +181,7 @@ struct Ctx {
   DevBuf<unsigned long long> dev_counters;  // see DC_* below
   uint64_t n_hits = 0;
   bool records_valid = false;
+  bool records_compact = false;  // records hold 4 x u32 per hit (PSI_B200_COMPACT)
   uint32_t spill_items = 4096;   // per-warp global spill of the walker
   DevBuf<char> walk_spill;
 

@@ -21,7 +21,7 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
 void engine_seeds(Ctx& c, unsigned flags);
 void engine_set_option(Ctx& c, const char* name, long long value);
-void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap);
+void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);
 void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);
 
 // ---- helpers shared by the .cu files ----

@@ -154,14 +154,17 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   rec[n_nodes] = NodeRec{ (uint32_t)n_bases, 0, (uint32_t)n_edges, 0 };
   // rank structure for position -> node (zero-length nodes would share a start bit: fall back to pos2node then)
   bool zero_len = false;
+  uint64_t max_id = 0;
   std::vector<Rank16> rank16((n_bases >> 6) + 2, Rank16{ 0, 0, 0 });
   std::vector<NodeRes> node_res(n_nodes + 1);
   for (uint64_t v = 0; v < n_nodes; ++v) {
     node_res[v] = NodeRes{ rec[v].seq_start, 0, node_id[v] };
+    if (node_id[v] > max_id) max_id = node_id[v];
     if (rec[v].seq_len == 0) { zero_len = true; continue; }
     rank16[rec[v].seq_start >> 6].bits |= 1ull << (rec[v].seq_start & 63u);
   }
   node_res[n_nodes] = NodeRes{ (uint32_t)n_bases, 0, 0 };
+  c.sh->max_node_id = max_id;
   {
     uint32_t run = 0;
     for (auto& r : rank16) { r.prefix = run; run += (uint32_t)__builtin_popcountll(r.bits); }

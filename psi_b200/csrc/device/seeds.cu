@@ -274,7 +274,16 @@ __device__ __forceinline__ void st_record(uint64_t* dst, const Resolved& r)
   asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "l"(r.node_id), "l"(r.node_off), "l"(r.read_id), "l"(r.read_off) : "memory");
 }
 
-template <bool RECORDS, int ITEMS, int MIN_CTAS>
+// compact form of the same record: 4 x u32 in the same field order (PSI_B200_COMPACT; the host checked that every node id
+// and read id of the chunk fits 32 bits) -- half the bytes to write here and to move over PCIe
+__device__ __forceinline__ void st_record32(uint64_t* dst, const Resolved& r)
+{
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((uint32_t)r.node_id), "r"((uint32_t)r.node_off),
+               "r"((uint32_t)r.read_id), "r"((uint32_t)r.read_off) : "memory");
+}
+
+// RECORDS: 0 = dense compact hits only, 1 = 4 x u64 records, 2 = 4 x u32 records
+template <int RECORDS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
                        const uint32_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
@@ -363,7 +372,8 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
     const uint64_t out = s_base + pre + __popc(m[h] & lt);
     if (!kind[h] || out >= cap) continue;
     if (RECORDS) {
-      st_record(records + 4 * out, r[h]);
+      if (RECORDS == 2) st_record32(records + 2 * out, r[h]);
+      else st_record(records + 4 * out, r[h]);
       rec_kind[out] = kind[h];
     }
     else out_hits[out] = Hit{ seed[h], gpos[h] };
@@ -371,6 +381,7 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
 }
 
 // sorted compact hits -> records (only used with PSI_B200_SORTED)
+template <bool COMPACT>
 __global__ void __launch_bounds__(256)
 resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ node_id, const Hit* __restrict__ hits, uint64_t n_hits,
                     const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
@@ -380,6 +391,7 @@ resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ node_id, const Hit
   if (i >= n_hits) return;
   const Hit h = hits[i];
   const Resolved r = resolve_one(g, node_id, h.seed, h.gpos, seed_read, seed_first, d, first_read_id);
+  if (COMPACT) { st_record32(records + 2 * i, r); return; }
   ulonglong2* o = reinterpret_cast<ulonglong2*>(records + 4 * i);
   o[0] = make_ulonglong2(r.node_id, r.node_off);
   o[1] = make_ulonglong2(r.read_id, r.read_off);
@@ -408,6 +420,11 @@ void engine_seeds(Ctx& c, unsigned flags)
   const unsigned probe_mode = (want_on ? PSI_B200_ON_PATHS : 0u) | (want_off && index_mode ? PSI_B200_OFF_PATHS : 0u);
   const bool sorted = (flags & PSI_B200_SORTED) != 0;
   const bool resolve = !(flags & PSI_B200_NO_RESOLVE);
+  const bool compact = (flags & PSI_B200_COMPACT) != 0;
+  if (compact && resolve) {
+    if (sh.max_node_id > 0xffffffffull) throw ArgError("seeds_all: PSI_B200_COMPACT needs node ids below 2^32");
+    if (c.first_read_id + c.n_reads > 0x100000000ull) throw ArgError("seeds_all: PSI_B200_COMPACT needs read ids below 2^32");
+  }
   const GraphView g = make_graph_view(c);
   unsigned long long* dc = c.dev_counters.p;
   c.records_valid = false;
@@ -512,16 +529,17 @@ void engine_seeds(Ctx& c, unsigned flags)
       if (sorted || !resolve) {
         c.sorted_hits.ensure(out_cap_want);
         out_cap = c.sorted_hits.cap;
-        if (items == 4) compact_resolve_kernel<false, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
-        else compact_resolve_kernel<false, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        if (items == 4) compact_resolve_kernel<0, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        else compact_resolve_kernel<0, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
       }
       else {
         c.records.ensure(4 * out_cap_want);
         c.rec_kind.ensure(out_cap_want);
         out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
-        if (items == 4) compact_resolve_kernel<true, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else if (c.opt_resolve_ctas >= 6) compact_resolve_kernel<true, 2, 6><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else compact_resolve_kernel<true, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        if (compact) compact_resolve_kernel<2, 2, 6><<<grid_for(c.n_seeds_cap + c.hits.cap, 256, 2), 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else if (items == 4) compact_resolve_kernel<1, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else if (c.opt_resolve_ctas >= 6) compact_resolve_kernel<1, 2, 6><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        else compact_resolve_kernel<1, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
       }
 #undef PSI_RESOLVE_ARGS
       ++c.counters.launches;
@@ -587,23 +605,31 @@ void engine_seeds(Ctx& c, unsigned flags)
   if (sorted && resolve) {
     c.records.ensure(4 * std::max<uint64_t>(n_total, 1), 1.25);
     if (n_total) {
-      resolve_hits_kernel<<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
-                                                                      c.seed_first.p, c.distance, c.first_read_id, c.records.p);
+      if (compact)
+        resolve_hits_kernel<true><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
+                                                                                c.seed_first.p, c.distance, c.first_read_id, c.records.p);
+      else
+        resolve_hits_kernel<false><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
+                                                                                 c.seed_first.p, c.distance, c.first_read_id, c.records.p);
       ++c.counters.launches;
     }
     PSI_CUDA(cudaGetLastError());
   }
   c.records_valid = resolve;
+  c.records_compact = resolve && compact;
   c.kinds_valid = resolve && !sorted;
 }
 
-void engine_fetch(Ctx& c, uint64_t* hits, uint64_t cap)
+void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact)
 {
   if (!c.records_valid) throw StateError("fetch: no resolved seed records (call seeds_all without NO_RESOLVE first)");
+  if (compact != c.records_compact)
+    throw StateError(compact ? "fetch32: the last seeds_all was not run with PSI_B200_COMPACT"
+                             : "fetch: the last seeds_all was run with PSI_B200_COMPACT (use psi_b200_fetch32)");
   PSI_CUDA(cudaSetDevice(c.device));
   const uint64_t n = c.n_hits < cap ? c.n_hits : cap;
   PhaseTimer t(c, T_D2H);
-  if (n) PSI_CUDA(cudaMemcpyAsync(hits, c.records.p, n * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+  if (n) PSI_CUDA(cudaMemcpyAsync(hits, c.records.p, n * (compact ? 16u : 32u), cudaMemcpyDeviceToHost, c.stream));
   t.stop();
   PSI_CUDA(cudaStreamSynchronize(c.stream));
 }

@@ -434,6 +434,8 @@ class SeedFinder {
     const psi_b200_graph_view& v = graph_ptr->view();
     if (graph_ptr->get_node_count() == 0) throw std::runtime_error("empty graph");
     check(psi_b200_set_graph(ctx, v.n_nodes, v.seq_start, v.seq, v.row_ptr, v.col, v.internal_id));
+    max_node_id = 0;
+    for (uint64_t i = 0; i < v.n_nodes; ++i) if (v.internal_id[i] > max_node_id) max_node_id = v.internal_id[i];
   }
 
   unsigned int set_context(unsigned int context, bool patched, std::function<void(std::string const&)> = nullptr,
@@ -484,7 +486,7 @@ class SeedFinder {
       throw std::runtime_error("seeds do not belong to the chunk last given to get_seeds()");
   }
 
-  void fetch(uint64_t n) const
+  void fetch(uint64_t n, bool compact = false) const
   {
     if (n > host_cap) {
       if (host_records) psi_b200_host_free(host_records);
@@ -494,7 +496,8 @@ class SeedFinder {
       host_records = static_cast<uint64_t*>(p);
     }
     uint64_t got = 0;
-    if (n) check(psi_b200_fetch(ctx, host_records, n, &got));
+    if (n && compact) check(psi_b200_fetch32(ctx, reinterpret_cast<uint32_t*>(host_records), n, &got));
+    else if (n) check(psi_b200_fetch(ctx, host_records, n, &got));
   }
 
   void account() const
@@ -514,9 +517,12 @@ class SeedFinder {
   {
     check_serial(seeds, idx);
     auto timer = timer_name ? std::make_unique<Timer>(stats_ptr->timeit_ts(timer_name)) : nullptr;
+    // 4 x u32 records (half the device-to-host bytes) whenever every id of this chunk fits 32 bits; the fields are
+    // widened into Seed<> below either way
+    const bool compact = max_node_id <= 0xffffffffull && seeds.rec_offset + seeds.n_reads <= 0x100000000ull;
     uint64_t n = 0;
-    check(psi_b200_seeds_all(ctx, flags, &n));
-    fetch(n);
+    check(psi_b200_seeds_all(ctx, compact ? flags | PSI_B200_COMPACT : flags, &n));
+    fetch(n, compact);
     account();
     // with two callbacks the per-record kind (1 on an indexed path, 2 off-path) routes the hit
     std::vector<uint8_t> kinds;
@@ -528,9 +534,16 @@ class SeedFinder {
     Seed<> hit;
     hit.match_len = seed_len;
     hit.gocc = 0;
+    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(host_records);
     for (uint64_t i = 0; i < n; ++i) {
-      const uint64_t* r = host_records + 4 * i;
-      hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
+      if (compact) {
+        const uint32_t* r = r32 + 4 * i;
+        hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
+      }
+      else {
+        const uint64_t* r = host_records + 4 * i;
+        hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
+      }
       const callback_type& cb = (!kinds.empty() && kinds[i] == 2) ? cb2 : cb1;
       if (cb) cb(hit);
     }
@@ -551,6 +564,7 @@ class SeedFinder {
   mutable uint64_t serial = 0;
   mutable uint64_t* host_records = nullptr;
   mutable uint64_t host_cap = 0;
+  uint64_t max_node_id = 0;
 };
 
 }  // namespace psi

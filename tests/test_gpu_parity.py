@@ -211,6 +211,49 @@ def test_internal_ids_and_sorted_output():
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "m_k20", "fuzz_05"])
+def test_compact_records_equal_wide_records(name, mode):
+    """PSI_B200_COMPACT: 4 x u32 records carry the same fields in the same order as the CLI's 4 x u64."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"], mode=mode)
+    ctx.submit_chunk(rp, bases, 7, c["d"])
+    n = ctx.seeds_all(capi.ALL)
+    wide, kinds = ctx.fetch(), ctx.fetch_kinds()
+    n32 = ctx.seeds_all(capi.ALL | capi.COMPACT)
+    narrow, kinds32 = ctx.fetch32(), ctx.fetch_kinds()
+    assert n == n32 == c["count"] and narrow.dtype == np.uint32 and narrow.shape == wide.shape
+    assert np.array_equal(capi.canonical(narrow.astype(np.uint64)), capi.canonical(wide))
+    with_kind = lambda r, kd: np.unique(np.column_stack([r.astype(np.uint64), kd.astype(np.uint64)]), axis=0)
+    assert np.array_equal(with_kind(narrow, kinds32), with_kind(wide, kinds))   # fetch_kinds lines up with either form
+    with pytest.raises(capi.PsiError) as e:
+        ctx.fetch()              # the resident records are compact
+    assert e.value.code == capi.ERR_STATE
+    ns = ctx.seeds_all(capi.ALL | capi.COMPACT | capi.SORTED)
+    srt = ctx.fetch32().astype(np.uint64)
+    assert ns == n and np.array_equal(capi.canonical(srt), capi.canonical(wide))
+    key = srt[:, 2] * np.uint64(1 << 20) + srt[:, 3]
+    assert np.all(key[1:] >= key[:-1]), "SORTED output is not ordered by (read, read offset)"
+    ctx.seeds_all(capi.ALL)
+    with pytest.raises(capi.PsiError) as e:
+        ctx.fetch32()            # and the other way round
+    assert e.value.code == capi.ERR_STATE
+    ctx.close()
+
+
+def test_compact_records_refuse_ids_beyond_32_bits():
+    c = CASES["fuzz_00"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], 2)
+    ctx.submit_chunk(rp, bases, 2 ** 32 - 5, c["d"])     # the chunk's last read ids do not fit u32
+    with pytest.raises(capi.PsiError) as e:
+        ctx.seeds_all(capi.ALL | capi.COMPACT)
+    assert e.value.code == capi.ERR_ARG
+    assert ctx.seeds_all(capi.ALL) == c["count"]          # the wide form is unaffected
+    ctx.close()
+
+
 def test_first_read_id_offsets_read_ids():
     c = CASES["fuzz_00"]
     g, rp, bases = load_case(c)
