@@ -5,12 +5,13 @@ synthetic chr22-shape graph (BASELINE.json configs[1]), one process per GPU.
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]    # the reference's own CPU path (oracle/_ref)
 
-A step = one pass of the hot path (pack -> seeds_on_paths -> read index ->
-seeds_off_paths -> resolve) over one batch of 1 M synthetic 100 bp reads.
+A step = one pass of the hot path (seeding -> seeds_on_paths / seeds_off_paths ->
+seed records; one fused kernel in index mode) over one batch of 1 M synthetic 100 bp reads.
   value : whole-job reads/s with the batch already resident in HBM
   e2e   : same through the C-ABI with pinned HOST buffers, H2D of the reads and D2H of
           the seed records inside the timed region
-  roofline : seeds_on_paths probe kernel, algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline : the dominant kernel (fused one-pass kernel, else the seeds_on_paths probe), algorithmic bytes /
+             CUDA-event time vs measured HBM peak; the probe kernel alone is reported beside it
   cpu_baseline : the unmodified reference (oracle/_ref/psi_ref_driver) on the host cores, bounded sample
 Prints ONE JSON line on rank 0.
 """
@@ -31,10 +32,13 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, os.fspath(ROOT))
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one seeds_on_paths launch on this workload from the
-# last `ncu --set full` capture (see profiles/); None until a capture of the current kernel exists.
-TRAFFIC_BYTES_PER_LAUNCH = 662.9e6
-TRAFFIC_SOURCE = "profiles/r01i_kernels_ncu_raw.csv: seeds_on_paths_kernel<8>, dram__bytes_read.sum 635.3 MB + dram__bytes_write.sum 27.6 MB (mean of 2 launches)"
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of the dominant kernel on this workload from
+# the last `ncu --set full` capture (see profiles/); None until a capture of the current kernel exists.
+TRAFFIC = {
+    "seeds_on_paths_kernel": (662.9e6, "profiles/r01i_kernels_ncu_raw.csv: seeds_on_paths_kernel<8>, dram__bytes_read.sum 635.3 MB + "
+                                       "dram__bytes_write.sum 27.6 MB (mean of 2 launches)"),
+    "seeds_fused_kernel": (None, "no ncu capture of this kernel yet"),
+}
 
 K = 20
 READ_LEN = 100
@@ -358,6 +362,16 @@ def main_gpu(args):
     # latency gaps of the other); `value` stays the single-pipeline figure the per-kernel timers belong to
     ms_pipe, hits_pipe, _ = timed_e2e(args.steps, args.warmup, step_resident)
     assert hits_e2e == hits_e2e_wide == hits_pipe == hits_dev, (hits_e2e, hits_e2e_wide, hits_pipe, hits_dev)
+    # the same resident step through the separate seeding / probe / resolve kernels: per-kernel times, and the
+    # seeds_on_paths probe alone for its own roofline
+    fused_run = bool(c_last["fused"])
+    if fused_run:
+        ctx.set_option("fused", 0)
+        ms_sep, hits_sep, acc_sep, _ = timed(step_device, args.steps, args.warmup)
+        ctx.set_option("fused", 1)
+        assert hits_sep == hits_dev, (hits_sep, hits_dev)
+    else:
+        ms_sep, acc_sep = ms_dev, acc
     clocks = sampler.stop() if rank == 0 else None
 
     # per-shard counts and a hits-per-read histogram, reduced with NCCL (the only collective on this path)
@@ -386,13 +400,42 @@ def main_gpu(args):
         # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches.  Algorithmic bytes per launch =
         # seeds x (8 B packed k-mer + 128 B = ONE index bucket line, the DRAM access unit: profiles/r01c_gather_peak.md)
         # + hits x 8 B compact record.  The 32-B-sector accounting of SURVEY 8d (40 B per seed) is reported beside it.
-        n_probe_hits = acc["n_hits"] if c_last["offpath_mode"] == 2 else acc["n_hits_on"]
-        alg_bytes = (acc["n_seeds"] * 136 + n_probe_hits * 8) / args.steps
-        alg_bytes_sector = (acc["n_seeds"] * 40 + n_probe_hits * 8) / args.steps
-        on_ms = acc["ms_probe"] / args.steps      # the probe kernel alone; ms_on = probe + slow-queue kernel
+        n_probe_hits = acc_sep["n_hits"] if c_last["offpath_mode"] == 2 else acc_sep["n_hits_on"]
+        alg_bytes = (acc_sep["n_seeds"] * 136 + n_probe_hits * 8) / args.steps
+        alg_bytes_sector = (acc_sep["n_seeds"] * 40 + n_probe_hits * 8) / args.steps
+        on_ms = acc_sep["ms_probe"] / args.steps  # the probe kernel alone; ms_on = probe + slow-queue kernel
         achieved = alg_bytes / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
         achieved_sector = alg_bytes_sector / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
         per_step = {k_: acc[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_probe", "ms_read_index", "ms_off", "ms_resolve")}
+        probe_roof = {"bound": "hbm", "kernel": "seeds_on_paths_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                      "frac": achieved / peak, "traffic": TRAFFIC["seeds_on_paths_kernel"][0], "peak_source": peak_src,
+                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms,
+                      "bytes_per_seed": "8 B k-mer + 128 B bucket line + 8 B per hit",
+                      "sector_accounting": {"bytes_per_seed": "8 B k-mer + 32 B sector + 8 B per hit (SURVEY 8d, P=1)",
+                                            "achieved": achieved_sector, "frac": achieved_sector / peak},
+                      "probes_per_s": acc_sep["n_seeds"] / args.steps / (on_ms * 1e-3) if on_ms > 0 else 0.0,
+                      "random_line_ceiling_probes_per_s": 4.0e10,
+                      "traffic_source": TRAFFIC["seeds_on_paths_kernel"][1]}
+        if fused_run:
+            # the fused kernel is the step: chunk bytes + read offsets in, one bucket line per seed, one 32-byte record
+            # + 1 kind byte per hit out (the position -> node gathers hit L2-resident arrays and are not counted)
+            hb0 = batches_h[0][1]
+            f_bytes = hb0.numel() + 8 * (n_reads + 1) + (acc["n_seeds"] * 128 + acc["n_hits"] * 33) / args.steps
+            f_sector = hb0.numel() + 8 * (n_reads + 1) + (acc["n_seeds"] * 32 + acc["n_hits"] * 33) / args.steps
+            f_ms = acc["ms_probe"] / args.steps
+            f_ach = f_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0
+            roof = {"bound": "hbm", "kernel": "seeds_fused_kernel", "achieved": f_ach, "peak": peak, "unit": "GB/s",
+                    "frac": f_ach / peak, "traffic": TRAFFIC["seeds_fused_kernel"][0], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": f_bytes, "launch_ms": f_ms,
+                    "bytes_per_read": "read bytes + 8 B offset + per seed one 128 B bucket line + per hit a 32 B record and 1 kind byte",
+                    "sector_accounting": {"bytes": "the same with 32 B per seed instead of the 128 B line (SURVEY 8d, P=1)",
+                                          "achieved": f_sector / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0,
+                                          "frac": f_sector / (f_ms * 1e-3) / 1e9 / peak if f_ms > 0 else 0.0},
+                    "probes_per_s": acc["n_seeds"] / args.steps / (f_ms * 1e-3) if f_ms > 0 else 0.0,
+                    "random_line_ceiling_probes_per_s": 4.0e10,
+                    "traffic_source": TRAFFIC["seeds_fused_kernel"][1]}
+        else:
+            roof = probe_roof
         e2e_value = n_reads * args.steps * world / (ms_e2e * 1e-3)
         hp, hb = batches_h[0]
         line = {
@@ -423,15 +466,13 @@ def main_gpu(args):
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "offpath_mode": "index (walks from the starting loci materialised into the index)" if c_last["offpath_mode"] == 2
                             else "walk (graph walked from the starting loci for every chunk)",
-            "roofline": {"bound": "hbm", "kernel": "seeds_on_paths_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms,
-                         "bytes_per_seed": "8 B k-mer + 128 B bucket line + 8 B per hit",
-                         "sector_accounting": {"bytes_per_seed": "8 B k-mer + 32 B sector + 8 B per hit (SURVEY 8d, P=1)",
-                                               "achieved": achieved_sector, "frac": achieved_sector / peak},
-                         "probes_per_s": acc["n_seeds"] / args.steps / (on_ms * 1e-3) if on_ms > 0 else 0.0,
-                         "random_line_ceiling_probes_per_s": 4.0e10,
-                         "traffic_source": TRAFFIC_SOURCE},
+            "roofline": roof,
+            "route": "fused one-pass kernel (seeding + probe + records)" if fused_run else "separate seeding / probe / resolve kernels",
+            "separate_kernels": {"note": "the same resident step with set_option('fused', 0): per-kernel CUDA-event times and the "
+                                         "seeds_on_paths probe kernel's own roofline",
+                                 "ms_per_step": ms_sep / args.steps,
+                                 "kernel_ms_per_step": {k_: acc_sep[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_probe", "ms_resolve")},
+                                 "roofline_probe": probe_roof},
             "clocks": clocks,
             "hits_per_read_histogram": {"bins": "reads with h hits in one step, h = 0..62, last bin >= 63; summed over ranks",
                                         "counts": [int(x) for x in hist]},

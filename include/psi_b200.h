@@ -243,7 +243,7 @@ typedef struct {
   uint64_t n_offpath_entries;  /* (k-mer, locus) pairs of the materialised off-path walks (0 in walk mode) */
   uint64_t n_offpath_walks;    /* k-walks from the starting loci that are not on an indexed path */
   uint32_t offpath_mode;       /* 1 = walk the graph per chunk, 2 = walks materialised into the index */
-  uint32_t reserved0;
+  uint32_t fused;              /* 1 = the last seeds_all ran the fused one-pass kernel (seeding + probe + records) */
   uint64_t n_loci;
   uint64_t n_reads, n_seeds;   /* last chunk */
   uint64_t n_hits_on, n_hits_off, n_hits;

@@ -65,7 +65,7 @@ class Counters(C.Structure):
                 ("index_bytes", C.c_uint64), ("index_buckets", C.c_uint64),
                 ("index_slot_bytes", C.c_uint32), ("index_stash_used", C.c_uint32),
                 ("n_offpath_entries", C.c_uint64), ("n_offpath_walks", C.c_uint64),
-                ("offpath_mode", C.c_uint32), ("reserved0", C.c_uint32),
+                ("offpath_mode", C.c_uint32), ("fused", C.c_uint32),
                 ("n_loci", C.c_uint64), ("n_reads", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("n_hits_on", C.c_uint64), ("n_hits_off", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_walks", C.c_uint64), ("n_on_probe_sectors", C.c_uint64),

@@ -11,6 +11,7 @@
 //   seed -> (read id, offset): SeedMap (sequence.hpp:1148-1220) is replaced by
 //   seed_read[] plus the exclusive scan seed_first[] (offset = (s - first) * d).
 #include "engine.hpp"
+#include "seeding.cuh"
 
 #include <cub/device/device_scan.cuh>
 
@@ -33,56 +34,6 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w4, uint32_t& bad)
   bad = expected ^ (w4 & 0xdfdfdfdfu);                      // non-zero bytes are not A/C/G/T
   const uint32_t p = (sel | (sel >> 2)) & 0x0f0fu;
   return (p | (p >> 4)) & 0xffu;                            // four codes, first base in the low bits
-}
-
-// K1 (direct): the k bases at byte address p (any alignment) -> packed k-mer, straight from the ASCII chunk.
-// K4 = ceil(k / 4) groups of four characters.  The k bytes lie in K4 or K4 + 1 aligned 32-bit words; a funnel
-// shift re-aligns them, then per group (all byte-parallel, ~15 instructions per 4 bases):
-//   x = (c >> 1) & 3 ; x ^= x >> 1            A,C,G,T (either case) -> 0,1,2,3 in every byte
-//   code = (x * 0x01041040) >> 24             gathers the four 2-bit codes into one byte (the partial
-//                                             products occupy disjoint bit fields, so nothing carries)
-//   PRMT("ACGT", nibbles(code)) == upper(c)   validates the four characters with one byte permute
-// Neighbouring seeds read neighbouring words, so the loads of a warp coalesce in L1 and every chunk byte comes
-// from DRAM once.  Loading and packing are separate so that a thread can have the words of several seeds in flight.
-template <int K4>
-struct AsciiWords {
-  uint32_t x[K4 + 1];
-  uint32_t sh;
-};
-
-template <int K4>
-__device__ __forceinline__ void load_ascii_words(const char* p, uint32_t k, AsciiWords<K4>& a)
-{
-  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~uintptr_t(3));
-  const uint32_t off = (uint32_t)(addr & 3u);
-  a.sh = off * 8u;
-  // words 0 .. K4-1 always hold bytes of the k-mer (k > 4 (K4 - 1)); word K4 only when the k-mer spills into it
-#pragma unroll
-  for (int i = 0; i < K4; ++i) a.x[i] = __ldg(w + i);
-  a.x[K4] = off + k > 4u * K4 ? __ldg(w + K4) : 0u;
-}
-
-// tail_mask: byte mask of the characters of the LAST group that belong to the k-mer (all ones when k % 4 == 0)
-template <int K4>
-__device__ __forceinline__ uint64_t pack_ascii_words(const AsciiWords<K4>& a, uint32_t tail_mask, bool& valid)
-{
-  uint32_t lo = 0, hi = 0, any_bad = 0;
-#pragma unroll
-  for (int g = 0; g < K4; ++g) {
-    uint32_t c = __funnelshift_r(a.x[g], a.x[g + 1], a.sh);
-    if (g == K4 - 1) c = (c & tail_mask) | (0x41414141u & ~tail_mask);    // beyond the k-mer: 'A' = code 0, valid
-    uint32_t x = (c >> 1) & 0x03030303u;
-    x ^= (x >> 1) & 0x01010101u;
-    const uint32_t code = (x * 0x01041040u) >> 24;
-    const uint32_t t = (code | (code << 4)) & 0x0f0fu;
-    const uint32_t sel = (t | (t << 2)) & 0x3333u;                        // one code per nibble
-    any_bad |= (c & 0xdfdfdfdfu) ^ __byte_perm(0x54474341u, 0u, sel);     // non-zero bytes are not A/C/G/T
-    if (g < 4) lo |= code << (8 * g);
-    else hi |= code << (8 * (g - 4));
-  }
-  valid = any_bad == 0;
-  return ((uint64_t)hi << 32) | lo;
 }
 
 template <bool VEC>
@@ -393,16 +344,28 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
   }
   t_h2d.stop();
 
-  PhaseTimer t_pack(c, T_PACK);
-  c.seed_first.ensure(n_reads + 2, 1.25);
-  c.seed_read.ensure(seeds_cap, 1.25);
-  c.seed_kmer.ensure(seeds_cap, 1.25);
-  c.seed_valid.ensure(seeds_cap + 16, 1.25);
   c.n_reads = n_reads;
   c.n_read_bases = n_bases;
   c.first_read_id = first_read_id;
   c.distance = distance;
   c.n_seeds_cap = seeds_cap;
+  c.ev_state[T_PACK] = 0;
+  c.chunk_seeded = false;    // seeding is deferred: the fused route (fused.cu) seeds inside its own kernel
+  c.has_chunk = true;
+  c.counters.n_reads = n_reads;
+}
+
+// K1 of the separate-kernel route: seed_first / seed_kmer / seed_valid / seed_read of the submitted chunk.
+void engine_seed_chunk(Ctx& c)
+{
+  if (c.chunk_seeded) return;
+  const uint64_t n_reads = c.n_reads, n_bases = c.n_read_bases, seeds_cap = c.n_seeds_cap;
+  const unsigned distance = c.distance;
+  PhaseTimer t_pack(c, T_PACK);
+  c.seed_first.ensure(n_reads + 2, 1.25);
+  c.seed_read.ensure(seeds_cap, 1.25);
+  c.seed_kmer.ensure(seeds_cap, 1.25);
+  c.seed_valid.ensure(seeds_cap + 16, 1.25);
 
   if (c.opt_seeding_mode == 0) {
     // direct: ASCII -> seeds (3 launches)
@@ -448,8 +411,7 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
   }
   t_pack.stop();
   PSI_CUDA(cudaGetLastError());
-  c.has_chunk = true;
-  c.counters.n_reads = n_reads;
+  c.chunk_seeded = true;
 }
 
 // Build the read index of the current chunk (lazily, only when seeds_off_paths

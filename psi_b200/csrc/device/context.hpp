@@ -84,6 +84,13 @@ struct alignas(8) Hit {
   uint32_t gpos;
 };
 
+// A seed the fused kernel's one-line probe could not settle (fused.cu): everything the slow kernel needs.
+struct alignas(16) SlowItem {
+  uint64_t kmer;
+  uint32_t read;   // read index within the chunk
+  uint32_t off;    // offset of the seed in the read
+};
+
 struct HostTable {
   dev::KmerTable view{};
   DevBuf<char> slots;
@@ -148,6 +155,7 @@ struct Ctx {
 
   // ---- current chunk ----
   bool has_chunk = false;
+  bool chunk_seeded = false;     // seed_kmer / seed_valid / seed_read / seed_first hold the chunk's seeds (engine_seed_chunk)
   bool chunk_indexed = false;
   uint64_t n_reads = 0, n_read_bases = 0, first_read_id = 0, n_seeds_cap = 0;
   unsigned distance = 0;
@@ -171,6 +179,7 @@ struct Ctx {
   DevBuf<uint32_t> seed_hit;     // per seed: locus found by the probe
   DevBuf<uint8_t> seed_kind;     // per seed: 0 none, 1 on an indexed path, 2 off-path, 3 queued for the slow kernel
   DevBuf<uint32_t> slow_queue;   // seeds the one-line probe could not settle
+  DevBuf<SlowItem> slow_items;   // the same for the fused kernel
   DevBuf<Hit> hits;              // overflow hit list: locus lists, walker hits
   DevBuf<uint8_t> hit_kind;
   DevBuf<Hit> sorted_hits;       // dense compact hits (PSI_B200_SORTED / NO_RESOLVE)
@@ -189,6 +198,8 @@ struct Ctx {
   int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
+  int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
+  int opt_fused_items = 2;                     // seeds per thread and batch of the fused kernel (1 or 2)
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
   int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
   int opt_resolve_ctas = 6;                    // resident CTAs per SM the resolve kernel is compiled for (5 or 6)

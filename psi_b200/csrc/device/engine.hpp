@@ -19,7 +19,9 @@ void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* o
 void engine_get_loci(Ctx& c, uint32_t* node, uint32_t* off, uint64_t cap);
 void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, const char* bases,
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
+void engine_seed_chunk(Ctx& c);   // the seeding kernels of the separate-kernel route (idempotent per chunk)
 void engine_seeds(Ctx& c, unsigned flags);
+void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact);
 void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);
 void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);

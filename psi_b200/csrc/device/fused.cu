@@ -1,0 +1,397 @@
+// fused.cu -- the whole per-chunk hot path in ONE kernel (index mode):
+//   ASCII reads -> seeds (K1) -> one bucket-line probe per seed (K3) -> seed records (resolve).
+//
+// Stands behind the loop body of find_seeds() (reference src/psikt.cpp:190-208):
+//   get_seeds (seed_finder.hpp:1099-1109, sequence.hpp:1688-1745)
+//   -> seeds_all = seeds_on_paths + seeds_off_paths (seed_finder.hpp:1426-1457,1703-1743)
+//   -> write_callback (src/psikt.cpp:172-181),
+// when the k-walks from the starting loci are materialised in the index (offpath_mode 2), so that one probe
+// answers both phases.  The separate kernels (chunk.cu, seeds.cu) stay for walk mode, PSI_B200_SORTED and
+// PSI_B200_NO_RESOLVE; both routes produce the same set and the parity suite runs every case through both.
+//
+// Why fuse: per step of 1 M x 100 bp reads the three-kernel route writes and re-reads 13 B (k-mer, validity,
+// read index) + 5 B (locus, kind) per seed between its kernels and pays three launch tails; the fused kernel
+// touches only what the problem requires: the chunk's bytes once, one 128-byte index line per seed, one record
+// per hit.  The packing arithmetic and the record resolution run in the issue slots the line waits leave idle.
+//
+// Shape: a CTA owns FUSED_READS consecutive reads (their start offsets and the prefix sums of their seed counts
+// live in shared memory) and walks its seeds in seed order in batches of 256 x ITEMS:
+//   1. the ASCII words of the batch were loaded during the previous batch (software prefetch, registers);
+//      pack -> k-mer + validity, hash -> home line + tag;
+//   2. each warp copies the 32 x ITEMS home lines of its seeds into shared memory with cp.async (8 lanes x
+//      16 B per line; invalid / inactive seeds issue a zero-fill copy that reads nothing);
+//   3. the ASCII words of the NEXT batch are requested;
+//   4. wait, every thread scans its own lines (16 tag compares each);
+//   5. hits are counted with ballots, ONE atomic per batch reserves the CTA's output range while the threads
+//      already run the two gathers position -> node; records are stored in seed order.
+// The ~0.3 % of the seeds one line cannot settle (locus lists, displaced keys) are queued with their k-mer and
+// (read, offset); seeds_slow_fused_kernel resolves them and appends their records.
+#include "engine.hpp"
+#include "records.cuh"
+#include "seeding.cuh"
+
+#include <algorithm>
+
+namespace psi_b200 {
+
+using namespace dev;
+
+constexpr int FUSED_READS = 256;
+
+template <int FMT, int K4, int ITEMS>
+__global__ void __launch_bounds__(256, ITEMS == 1 ? 5 : 3)
+seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_id,
+                   const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, uint64_t n_reads,
+                   uint32_t k, uint32_t d, uint32_t mode, uint64_t first_read_id, uint32_t compact,
+                   uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, uint64_t cap,
+                   SlowItem* __restrict__ slow_queue, uint64_t slow_cap, unsigned long long* __restrict__ dc)
+{
+  extern __shared__ __align__(128) unsigned char s_lines[];     // 256 x ITEMS lines of 128 bytes
+  __shared__ uint32_t s_first[FUSED_READS + 1];
+  __shared__ uint64_t s_ptr[FUSED_READS];
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_cnt[8 * ITEMS];
+  __shared__ unsigned long long s_base;
+
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint64_t r_base = (uint64_t)blockIdx.x * FUSED_READS;
+
+  // ---- the CTA's reads: start offsets and CTA-local prefix sums of the seed counts (sequence.hpp:1712) ----
+  {
+    const uint64_t r = r_base + threadIdx.x;
+    uint64_t p0 = 0;
+    uint32_t mine = 0;
+    if (r < n_reads) {
+      p0 = read_ptr[r];
+      const uint64_t len = read_ptr[r + 1] - p0;
+      mine = len >= k ? (uint32_t)((len - k) / d) + 1 : 0;      // reads shorter than k have no seeds
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += y; }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+    s_first[threadIdx.x] = before + incl - mine;
+    s_ptr[threadIdx.x] = p0;
+    if (threadIdx.x == FUSED_READS - 1) s_first[FUSED_READS] = before + incl;
+    __syncthreads();
+  }
+  const uint32_t n_cta_seeds = s_first[FUSED_READS];
+  if (n_cta_seeds == 0) return;
+  // reads of one length (the usual case) have the same number of seeds: the read of a seed is then a division,
+  // done as a multiplication by floor(2^32 / per_read) plus one correction step
+  const uint32_t per_read = s_first[1];
+  bool uniform, one_each;
+  {
+    const uint32_t r_in_cta = (uint32_t)min((uint64_t)FUSED_READS, n_reads - r_base);
+    const uint32_t mine = threadIdx.x < r_in_cta ? s_first[threadIdx.x + 1] - s_first[threadIdx.x] : per_read;
+    uniform = __syncthreads_and(mine == per_read) && per_read > 1u;
+    one_each = !uniform && __syncthreads_and(mine == 1u) && per_read == 1u;
+  }
+  const uint32_t magic = uniform ? (uint32_t)(0x100000000ull / per_read) : 0u;
+  const uint32_t tail = k - 4u * (K4 - 1);                           // characters in the last group, 1..4
+  const uint32_t tail_mask = tail >= 4u ? 0xffffffffu : (1u << (8u * tail)) - 1u;
+
+  unsigned char* warp_lines = s_lines + (size_t)warp * (ITEMS * 32 * 128);
+  const uint32_t sub = lane & 7u;
+
+  // locate the seeds of a batch and request their characters
+  AsciiWords<K4> aw[ITEMS];
+  uint32_t rd[ITEMS], roff[ITEMS];
+  auto fetch_batch = [&](uint32_t base) {
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      const uint32_t ls_raw = base + h * 256u + threadIdx.x;
+      const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;   // inactive slots re-read seed 0 (valid memory), emit nothing
+      uint32_t lo = 0;
+      if (uniform) {
+        lo = __umulhi(ls, magic);
+        if ((lo + 1u) * per_read <= ls) ++lo;
+      }
+      else if (one_each) lo = ls;
+      else {
+        uint32_t hi = FUSED_READS;
+#pragma unroll 1
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+      }
+      rd[h] = lo;
+      roff[h] = (ls - s_first[lo]) * d;
+      load_ascii_words<K4>(bases + s_ptr[lo] + roff[h], k, aw[h]);
+    }
+  };
+  fetch_batch(0);
+
+  uint32_t on_total = 0;    // thread 0 only
+  for (uint32_t base = 0; base < n_cta_seeds; base += 256u * ITEMS) {
+    // ---- 1. pack + hash ----
+    uint64_t kmer[ITEMS];
+    uint32_t my_line[ITEMS], want[ITEMS], cur_rd[ITEMS], cur_off[ITEMS];
+    bool ok[ITEMS];
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      bool valid;
+      kmer[h] = pack_ascii_words<K4>(aw[h], tail_mask, valid);
+      ok[h] = valid && base + h * 256u + threadIdx.x < n_cta_seeds;
+      const Home hm = home_of<FMT>(t, kmer[h]);
+      my_line[h] = (uint32_t)hm.line;                      // line_bits <= 32 (checked when the table is allocated)
+      want[h] = (uint32_t)hm.tag;                          // fmt 8: tag | displacement 0 (30 bits)
+      cur_rd[h] = rd[h];
+      cur_off[h] = roff[h];
+    }
+    // ---- 2. the warp copies its home lines into shared memory ----
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok[h]);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t owner = it * 4u + (lane >> 3);
+        const uint32_t line = __shfl_sync(0xffffffffu, my_line[h], owner);
+        const uint32_t bytes = (okmask >> owner) & 1u ? 16u : 0u;      // 0: zero fill, nothing is read
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(warp_lines + ((h * 32u + owner) << 7) + (sub << 4));
+        const char* src = (const char*)t.slots + (bytes ? ((uint64_t)line << 7) + (sub << 4) : 0ull);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- 3. characters of the next batch ----
+    if (base + 256u * ITEMS < n_cta_seeds) fetch_batch(base + 256u * ITEMS);
+    // ---- 4. scan ----
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    uint32_t gpos[ITEMS];
+    uint8_t kind[ITEMS];
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + ((h * 32u + lane) << 7));
+      bool hit = false, empty = false;
+      uint32_t pl = 0, fl = 0;
+      if (FMT == 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 w = ln[(j + lane) & 7u];             // two slots: (w.x, w.y) and (w.z, w.w), high word second
+          empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has all of rem/disp/flags set
+          if ((w.y >> 2) == want[h]) { hit = true; pl = w.x; fl = w.y & 3u; }
+          if ((w.w >> 2) == want[h]) { hit = true; pl = w.z; fl = w.w & 3u; }
+        }
+      }
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 w = ln[(j + lane) & 7u];             // one slot: key (w.x, w.y), payload w.z, flags w.w
+          empty |= w.w == NIL32;
+          if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer[h]) { hit = true; pl = w.z; fl = w.w & 3u; }
+        }
+      }
+      kind[h] = 0;
+      gpos[h] = pl;
+      if (ok[h]) {
+        bool slow = false;
+        if (hit) {
+          if (fl & FLAG_MULTI) slow = true;
+          else kind[h] = kind_of(fl, mode);
+        }
+        else slow = !empty;    // the line is full and does not hold the key: it may sit in a following line
+        if (slow) {
+          const unsigned long long q = atomicAdd(dc + DC_SLOW, 1ull);
+          if (q < slow_cap) slow_queue[q] = SlowItem{ kmer[h], (uint32_t)(r_base + cur_rd[h]), cur_off[h] };
+        }
+      }
+    }
+    // ---- 5. count, reserve, resolve, store ----
+    uint32_t m[ITEMS];
+    uint32_t on = 0;
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      m[h] = __ballot_sync(0xffffffffu, kind[h] != 0);
+      on += __popc(__ballot_sync(0xffffffffu, kind[h] == 1));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < ITEMS; ++h) s_cnt[8 * h + warp] = __popc(m[h]);
+      s_warp[warp] = on;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < 8 * ITEMS; ++w) run += s_cnt[w];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) on_total += s_warp[w];
+      s_base = run ? atomicAdd(dc + DC_HITS, (unsigned long long)run) : 0ull;
+    }
+    Resolved r[ITEMS];
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h)
+      if (kind[h]) {
+        r[h].read_id = first_read_id + r_base + cur_rd[h];
+        r[h].read_off = cur_off[h];
+        resolve_node(g, node_id, gpos[h], r[h].node_id, r[h].node_off);
+      }
+    __syncthreads();
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t run = 0;
+#pragma unroll
+    for (int h = 0; h < ITEMS; ++h) {
+      uint32_t pre = run;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t c = s_cnt[8 * h + w];
+        if (w < (int)warp) pre += c;
+        run += c;
+      }
+      const uint64_t out = s_base + pre + __popc(m[h] & lt);
+      if (!kind[h] || out >= cap) continue;
+      if (compact) st_record32(records + 2 * out, r[h]);
+      else st_record(records + 4 * out, r[h]);
+      rec_kind[out] = kind[h];
+    }
+    __syncthreads();     // s_cnt / s_base / line buffers are reused by the next batch
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(dc + DC_SEEDS, (unsigned long long)n_cta_seeds);
+    if (on_total) atomicAdd(dc + DC_HITS_ON, (unsigned long long)on_total);
+  }
+}
+
+// The queued seeds: full search (following lines, stash) and locus lists; their records are appended to the
+// CTAs' output.  One thread per queued seed.
+__global__ void __launch_bounds__(256)
+seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphView g, const uint64_t* __restrict__ node_id,
+                        const SlowItem* __restrict__ slow_queue, uint64_t slow_cap, uint32_t mode, uint64_t first_read_id,
+                        uint32_t compact, uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, uint64_t cap,
+                        unsigned long long* __restrict__ dc)
+{
+  uint64_t n = dc[DC_SLOW];
+  if (n > slow_cap) n = slow_cap;     // the host grows the queue and repeats the step
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const SlowItem it = slow_queue[q];
+    Found f;
+    if (!table_find_any(t, it.kmer, f)) continue;
+    Resolved r;
+    r.read_id = first_read_id + it.read;
+    r.read_off = it.off;
+    if (!(f.flags & FLAG_MULTI)) {
+      const uint8_t kind = kind_of(f.flags, mode);
+      if (!kind) continue;
+      const uint64_t out = atomicAdd(dc + DC_HITS, 1ull);
+      if (kind == 1) atomicAdd(dc + DC_HITS_ON, 1ull);
+      if (out >= cap) continue;
+      resolve_node(g, node_id, f.payload, r.node_id, r.node_off);
+      if (compact) st_record32(records + 2 * out, r);
+      else st_record(records + 4 * out, r);
+      rec_kind[out] = kind;
+    }
+    else {
+      const uint32_t n_on = __ldg(multi + f.payload), n_all = __ldg(multi + f.payload + 1);
+      const uint32_t from = (mode & PSI_B200_ON_PATHS) ? 0u : n_on;
+      const uint32_t to = (mode & PSI_B200_OFF_PATHS) ? n_all : n_on;
+      if (to <= from) continue;
+      uint64_t out = atomicAdd(dc + DC_HITS, (unsigned long long)(to - from));
+      if (n_on > from) atomicAdd(dc + DC_HITS_ON, (unsigned long long)(n_on - from));
+      for (uint32_t j = from; j < to; ++j, ++out) {
+        if (out >= cap) break;
+        resolve_node(g, node_id, __ldg(multi + f.payload + 2 + j), r.node_id, r.node_off);
+        if (compact) st_record32(records + 2 * out, r);
+        else st_record(records + 4 * out, r);
+        rec_kind[out] = j < n_on ? 1 : 2;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host --
+
+template <int FMT, int K4, int ITEMS>
+static void launch_fused(Ctx& c, const GraphView& g, unsigned probe_mode, bool compact, uint64_t out_cap)
+{
+  Shared& sh = *c.sh;
+  auto kern = seeds_fused_kernel<FMT, K4, ITEMS>;
+  const size_t smem = (size_t)256 * ITEMS * 128;
+  static bool attr_set = false;     // per instantiation
+  if (!attr_set) {
+    PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, (c.n_reads + FUSED_READS - 1) / FUSED_READS);
+  kern<<<grid, 256, smem, c.stream>>>(sh.index.view, g, sh.node_id.p, c.d_bases, c.d_read_ptr, c.n_reads, c.k, c.distance,
+                                      probe_mode, c.first_read_id, compact ? 1u : 0u, c.records.p, c.rec_kind.p, out_cap,
+                                      c.slow_items.p, c.slow_items.cap, c.dev_counters.p);
+}
+
+template <int FMT, int ITEMS>
+static void launch_fused_k(Ctx& c, const GraphView& g, unsigned probe_mode, bool compact, uint64_t out_cap)
+{
+  switch ((c.k + 3) / 4) {
+    case 1: launch_fused<FMT, 1, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 2: launch_fused<FMT, 2, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 3: launch_fused<FMT, 3, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 4: launch_fused<FMT, 4, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 5: launch_fused<FMT, 5, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 6: launch_fused<FMT, 6, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 7: launch_fused<FMT, 7, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    default: launch_fused<FMT, 8, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+  }
+}
+
+// seeds_all of the submitted chunk through the fused kernel.  Preconditions (checked by engine_seeds): the index
+// answers every requested phase by itself (probe_mode != 0, no per-chunk walk), records are wanted, unsorted.
+void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact)
+{
+  Shared& sh = *c.sh;
+  const GraphView g = make_graph_view(c);
+  unsigned long long* dc = c.dev_counters.p;
+  uint64_t out_cap_want = std::max<uint64_t>(c.n_seeds_cap + c.n_seeds_cap / 4, 1u << 20);
+  if (c.slow_items.cap == 0) c.slow_items.ensure(std::max<uint64_t>(c.n_seeds_cap / 16, 1u << 16));
+  c.ev_state[T_PACK] = c.ev_state[T_READ_INDEX] = c.ev_state[T_RESOLVE] = 0;   // no such phases on this route
+  c.ev_state[T_OFF] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
+
+  for (int attempt = 0;; ++attempt) {
+    if (attempt > 16) throw OverflowError("seeds_all: device buffers keep overflowing");
+    c.records.ensure(4 * out_cap_want);
+    c.rec_kind.ensure(out_cap_want);
+    const uint64_t out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
+    PSI_CUDA(cudaMemsetAsync(dc, 0, DC_COUNT * sizeof(unsigned long long), c.stream));
+    PhaseTimer t_on(c, T_ON);
+    PhaseTimer t_probe(c, T_PROBE);
+    if (sh.index.view.fmt == 8) {
+      if (c.opt_fused_items == 1) launch_fused_k<8, 1>(c, g, probe_mode, compact, out_cap);
+      else launch_fused_k<8, 2>(c, g, probe_mode, compact, out_cap);
+    }
+    else {
+      if (c.opt_fused_items == 1) launch_fused_k<16, 1>(c, g, probe_mode, compact, out_cap);
+      else launch_fused_k<16, 2>(c, g, probe_mode, compact, out_cap);
+    }
+    t_probe.stop();
+    seeds_slow_fused_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, g, sh.node_id.p, c.slow_items.p,
+                                                                           c.slow_items.cap, probe_mode, c.first_read_id,
+                                                                           compact ? 1u : 0u, c.records.p, c.rec_kind.p, out_cap, dc);
+    t_on.stop();
+    c.counters.launches += 2;
+    PSI_CUDA(cudaGetLastError());
+    PSI_CUDA(cudaMemcpyAsync(c.h_pinned, dc, DC_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    const uint64_t n_total = c.h_pinned[DC_HITS], n_slow = c.h_pinned[DC_SLOW];
+    bool retry = false;
+    if (n_slow > c.slow_items.cap) { c.slow_items.ensure(n_slow, 1.25); retry = true; }
+    if (n_total > out_cap) { out_cap_want = n_total + n_total / 8; retry = true; }
+    if (retry) continue;
+    c.n_hits = n_total;
+    c.counters.n_seeds = c.h_pinned[DC_SEEDS];
+    c.counters.n_hits_on = c.h_pinned[DC_HITS_ON];
+    c.counters.n_hits_off = n_total - c.h_pinned[DC_HITS_ON];
+    c.counters.n_hits = n_total;
+    c.counters.n_walks = 0;
+    c.counters.n_on_probe_sectors = n_slow;
+    c.counters.offpath_mode = 2u;
+    c.counters.fused = 1u;
+    break;
+  }
+  c.records_valid = true;
+  c.records_compact = compact;
+  c.kinds_valid = true;
+}
+
+}  // namespace psi_b200

@@ -677,6 +677,13 @@ void engine_set_option(Ctx& c, const char* name, long long value)
     if (value < 1 || value > 32) throw ArgError("set_option: probe_ctas_per_sm must be in [1, 32]");
     c.opt_probe_ctas_per_sm = (unsigned)value;
   }
+  else if (n == "fused") {
+    c.opt_fused = value != 0;
+  }
+  else if (n == "fused_items") {
+    if (value != 1 && value != 2) throw ArgError("set_option: fused_items is 1 or 2");
+    c.opt_fused_items = (int)value;
+  }
   else if (n == "seeding_mode") {
     if (value < 0 || value > 1) throw ArgError("set_option: seeding_mode is 0 (direct from ASCII) or 1 (2-bit staging)");
     c.opt_seeding_mode = (int)value;

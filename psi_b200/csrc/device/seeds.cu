@@ -2,6 +2,7 @@
 // the resolve step that turns compact hits into the reference's seed records.
 #include "engine.hpp"
 #include "walker.cuh"
+#include "records.cuh"
 
 #include <algorithm>
 
@@ -34,11 +35,6 @@ void engine_index_chunk(Ctx& c);
 // (offpath_mode 2) the same probe also answers seeds_off_paths.
 // Because the index holds DISTINCT (k-mer, locus) pairs and a seed index is
 // unique, the hits are already a set.
-
-__device__ __forceinline__ uint8_t kind_of(uint32_t flags, uint32_t mode)
-{
-  return (flags & FLAG_OFF) ? ((mode & PSI_B200_OFF_PATHS) ? 2 : 0) : ((mode & PSI_B200_ON_PATHS) ? 1 : 0);
-}
 
 // One thread per seed; a CTA handles 256 consecutive seeds:
 //   1. coalesced loads of k-mer + validity, hash -> home line and tag (registers);
@@ -239,49 +235,6 @@ seeds_off_paths_kernel(GraphView g, uint32_t k, uint64_t n_loci, const uint32_t*
 // its hits with ballots, reserves their output range with ONE atomic and writes
 // them in item order, so the output of a chunk is ordered by (read, offset) up
 // to the CTA granularity and the stores of a warp are contiguous.
-struct Resolved {
-  uint64_t node_id, node_off, read_id, read_off;
-};
-
-__device__ __forceinline__ Resolved resolve_one(const GraphView& g, const uint64_t* __restrict__ node_id, uint32_t seed, uint32_t gpos,
-                                                const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
-                                                uint32_t d, uint64_t first_read_id)
-{
-  Resolved o;
-  const uint32_t r = __ldg(seed_read + seed);
-  o.read_id = first_read_id + r;
-  o.read_off = (uint64_t)(seed - __ldg(seed_first + r)) * d;
-  if (g.rank16) {
-    // two dependent 16-byte gathers: start bits + prefix count of the 64 positions, then the node's record
-    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(g.rank16 + (gpos >> 6)));
-    const uint64_t bits = ((uint64_t)rw.y << 32) | rw.x;
-    const uint32_t v = rw.z + (uint32_t)__popcll(bits & (~0ull >> (63u - (gpos & 63u)))) - 1u;
-    const uint4 nr = __ldg(reinterpret_cast<const uint4*>(g.node_res + v));
-    o.node_off = gpos - nr.x;
-    o.node_id = ((uint64_t)nr.w << 32) | nr.z;
-  }
-  else {
-    const uint32_t v = node_of_pos(g, gpos);
-    o.node_off = gpos - __ldg(&g.rec[v].seq_start);
-    o.node_id = __ldg(node_id + v);
-  }
-  return o;
-}
-
-// one 32-byte record per store instruction (STG.256): every 32-byte sector of the output is written exactly once
-__device__ __forceinline__ void st_record(uint64_t* dst, const Resolved& r)
-{
-  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "l"(r.node_id), "l"(r.node_off), "l"(r.read_id), "l"(r.read_off) : "memory");
-}
-
-// compact form of the same record: 4 x u32 in the same field order (PSI_B200_COMPACT; the host checked that every node id
-// and read id of the chunk fits 32 bits) -- half the bytes to write here and to move over PCIe
-__device__ __forceinline__ void st_record32(uint64_t* dst, const Resolved& r)
-{
-  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(dst), "r"((uint32_t)r.node_id), "r"((uint32_t)r.node_off),
-               "r"((uint32_t)r.read_id), "r"((uint32_t)r.read_off) : "memory");
-}
-
 // RECORDS: 0 = dense compact hits only, 1 = 4 x u64 records, 2 = 4 x u32 records
 template <int RECORDS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
@@ -425,10 +378,17 @@ void engine_seeds(Ctx& c, unsigned flags)
     if (sh.max_node_id > 0xffffffffull) throw ArgError("seeds_all: PSI_B200_COMPACT needs node ids below 2^32");
     if (c.first_read_id + c.n_reads > 0x100000000ull) throw ArgError("seeds_all: PSI_B200_COMPACT needs read ids below 2^32");
   }
-  const GraphView g = make_graph_view(c);
-  unsigned long long* dc = c.dev_counters.p;
   c.records_valid = false;
   c.kinds_valid = false;
+  c.counters.fused = 0;
+  // the usual case -- the index answers every requested phase, records wanted in emission order -- is ONE kernel
+  if (c.opt_fused && do_probe && !do_walk && !sorted && resolve) {
+    engine_seeds_fused(c, probe_mode, compact);
+    return;
+  }
+  engine_seed_chunk(c);
+  const GraphView g = make_graph_view(c);
+  unsigned long long* dc = c.dev_counters.p;
   c.ev_state[T_ON] = c.ev_state[T_PROBE] = c.ev_state[T_OFF] = c.ev_state[T_RESOLVE] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
 
   c.seed_hit.ensure(c.n_seeds_cap, 1.25);

@@ -26,9 +26,10 @@ def build(shape):
                                   a["path_nodes"], sort=True)
 
 
-def make_ctx(g, k, n_paths, mode=0):
+def make_ctx(g, k, n_paths, mode=0, fused=1):
     ctx = capi.Context(k, 0)
     ctx.set_option("offpath_mode", mode)
+    ctx.set_option("fused", fused)     # 0: index-mode steps through the separate seeding / probe / resolve kernels
     ctx.set_graph(g, ids="coord")
     ctx.set_paths(g.pick_paths(n_paths, seed=1))
     ctx.find_loci()
@@ -119,12 +120,12 @@ def test_chr22_shape_sample_equals_oracle(chr22):
     g, k = chr22, 20
     rp, bases = synth.reads(g, 100_000, 100, 77)
     want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), k, k)
-    for mode in (0, 1):
-        ctx = make_ctx(g, k, 16, mode)
+    for mode, fused in ((0, 1), (0, 0), (1, 1)):
+        ctx = make_ctx(g, k, 16, mode, fused)
         assert ctx.counters()["offpath_mode"] == (2 if mode == 0 else 1)
         got = sort_rows(run(ctx, rp, bases, k))
         ctx.close()
-        assert got.shape == want.shape and np.array_equal(got, want), f"mode {mode}"
+        assert got.shape == want.shape and np.array_equal(got, want), f"mode {mode} fused {fused}"
 
 
 def test_chr22_shape_full_read_set_properties(chr22):
@@ -148,8 +149,15 @@ def test_chr22_shape_full_read_set_properties(chr22):
     assert n_on + n_off == len(rows)
     assert (cs_on[0] + cs_off[0]) % (1 << 64) == checksum(whole)[0]
     # chunking (ragged last chunk) does not change the set
+    assert ctx.counters()["fused"] == 1
     assert checksum(run(ctx, rp, bases, k, 300_001)) == checksum(whole)
     ctx.close()
+    # the separate-kernel route gives the same set as the fused kernel
+    ctx = make_ctx(g, k, 16, 0, fused=0)
+    unfused = run(ctx, rp, bases, k)
+    assert ctx.counters()["fused"] == 0
+    ctx.close()
+    assert checksum(unfused) == checksum(whole)
     # walking the graph per chunk (the reference's own scheme) gives the same set
     ctx = make_ctx(g, k, 16, 1)
     walked = run(ctx, rp, bases, k, 500_000)

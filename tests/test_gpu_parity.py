@@ -37,10 +37,20 @@ def run_chunks(ctx, rp, bases, d, chunk, flags=capi.ALL):
     return np.concatenate(parts) if parts else np.zeros((0, 4), np.uint64), total
 
 
-def make_ctx(g, k, n_paths, seed=1, ids="coord", mode=0):
-    """mode: 0 auto (off-path walks materialised into the index), 1 walk the graph per chunk."""
+# the three routes through the device code: index mode through the fused one-pass kernel (the default), index mode
+# through the separate seeding / probe / resolve kernels, and walk mode (graph walked per chunk)
+ROUTES = [(0, 1), (0, 0), (1, 1)]
+ROUTE_IDS = ["index", "index-unfused", "walk"]
+
+
+def make_ctx(g, k, n_paths, seed=1, ids="coord", mode=0, fused=1):
+    """mode: 0 auto (off-path walks materialised into the index), 1 walk the graph per chunk;
+    fused: 0 keeps index-mode steps on the separate kernels."""
+    if isinstance(mode, tuple):
+        mode, fused = mode
     ctx = capi.Context(k, 0)
     ctx.set_option("offpath_mode", mode)
+    ctx.set_option("fused", fused)
     ctx.set_graph(g, ids=ids)
     ps = None
     if n_paths:
@@ -50,14 +60,15 @@ def make_ctx(g, k, n_paths, seed=1, ids="coord", mode=0):
     return ctx, ps
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_seeds_all_matches_reference_golden(name, mode):
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx, _ = make_ctx(g, c["k"], c["n_paths"], mode=mode)
-    assert ctx.counters()["offpath_mode"] == (1 if mode == 1 else 2)
+    assert ctx.counters()["offpath_mode"] == (1 if mode[0] == 1 else 2)
     rec, total = run_chunks(ctx, rp, bases, c["d"], c["chunk"])
+    assert ctx.counters()["fused"] == (1 if mode == (0, 1) else 0), "the route under test did not run"
     got = capi.canonical(rec)
     assert total == len(got), "device output must already be a set (no duplicates)"
     assert len(got) == c["count"]
@@ -68,7 +79,7 @@ def test_seeds_all_matches_reference_golden(name, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
 @pytest.mark.parametrize("name", ["x_k12", "m_k20", "m_k32", "fuzz_02", "fuzz_03", "fuzz_06", "fuzz_09", "multi_k32"])
 def test_phases_match_oracle(name, mode):
     """seeds_on_paths, starting loci and seeds_off_paths each against the oracle on the same paths."""
@@ -103,14 +114,15 @@ def test_phases_match_oracle(name, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
 @pytest.mark.parametrize("name", ["x_k12", "fuzz_04", "m_k20"])
 def test_no_paths_all_loci_equals_closed_form(name, mode):
     """`-n 0` + every locus: the pure graph-walk formulation (traverser only)."""
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx = capi.Context(c["k"], 0)
-    ctx.set_option("offpath_mode", mode)
+    ctx.set_option("offpath_mode", mode[0])
+    ctx.set_option("fused", mode[1])
     ctx.set_graph(g, ids="coord")
     node, off = util.all_loci(g)
     ctx.set_loci(node, off)
@@ -122,16 +134,22 @@ def test_no_paths_all_loci_equals_closed_form(name, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("seeding,items", [(1, 2), (0, 4), (1, 4)], ids=["staged-2", "direct-4", "staged-4"])
+@pytest.mark.parametrize("seeding,items,fused", [(1, 2, 0), (0, 4, 0), (1, 4, 0), (0, 1, 1)],
+                         ids=["staged-2", "direct-4", "staged-4", "fused-1"])
 @pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "fuzz_07", "fuzz_10", "fuzz_11"])
-def test_kernel_variants_give_the_same_set(name, seeding, items):
+def test_kernel_variants_give_the_same_set(name, seeding, items, fused):
     """The alternative kernels behind the tuning options (2-bit staged seeding, 4 items per thread in the resolve
-    kernel) must give the reference's set too; the defaults are covered by every other test."""
+    kernel, one seed per thread and batch in the fused kernel) must give the reference's set too; the defaults are
+    covered by every other test."""
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx = capi.Context(c["k"], 0)
-    ctx.set_option("seeding_mode", seeding)
-    ctx.set_option("resolve_items", items)
+    ctx.set_option("fused", fused)
+    if fused:
+        ctx.set_option("fused_items", items)
+    else:
+        ctx.set_option("seeding_mode", seeding)
+        ctx.set_option("resolve_items", items)
     ctx.set_graph(g, ids="coord")
     ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
     ctx.find_loci()
@@ -142,7 +160,8 @@ def test_kernel_variants_give_the_same_set(name, seeding, items):
     ctx.close()
 
 
-def test_ragged_reads_every_alignment_and_k():
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+def test_ragged_reads_every_alignment_and_k(fused):
     """Seeding straight from the ASCII chunk: reads of every length 0..70 (so seeds start at every byte alignment),
     N / lower case sprinkled in, k from 3 to 32 and d from 1 to k + 3, against the oracle."""
     g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
@@ -160,6 +179,7 @@ def test_ragged_reads_every_alignment_and_k():
         bases[i] = ord("N") if i % 2 else bases[i] | 0x20
     for k in (3, 4, 5, 12, 19, 20, 27, 28, 31, 32):
         ctx = capi.Context(k, 0)
+        ctx.set_option("fused", fused)
         ctx.set_graph(g, ids="coord")
         ctx.set_paths(g.pick_paths(2, seed=3))
         ctx.find_loci()
@@ -211,7 +231,7 @@ def test_internal_ids_and_sorted_output():
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
 @pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "m_k20", "fuzz_05"])
 def test_compact_records_equal_wide_records(name, mode):
     """PSI_B200_COMPACT: 4 x u32 records carry the same fields in the same order as the CLI's 4 x u64."""
@@ -269,10 +289,11 @@ def test_first_read_id_offsets_read_ids():
     ctx.close()
 
 
-def test_edge_cases_short_reads_n_bases_empty_chunk():
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
+def test_edge_cases_short_reads_n_bases_empty_chunk(mode):
     g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
     k = 12
-    ctx, _ = make_ctx(g, k, 4)
+    ctx, _ = make_ctx(g, k, 4, mode=mode)
     og = orc.OGraph.of(g)
     full_ptr, full_bases = util.read_fasta(util.GOLDEN / "inputs/reads_n10000l100e0i0.fa.gz")
     r0 = full_bases[:100].copy()
@@ -345,8 +366,8 @@ def test_repeats_multi_locus_kmers():
     rp = np.zeros(len(reads) + 1, np.uint64)
     rp[1:] = np.cumsum([len(r) for r in reads])
     bases = np.frombuffer("".join(reads).encode(), np.uint8)
-    for k in (8, 12):
-        ctx, _ = make_ctx(g, k, 2)
+    for k, fused in ((8, 1), (12, 1), (8, 0), (12, 0)):
+        ctx, _ = make_ctx(g, k, 2, fused=fused)
         ctx.submit_chunk(rp, bases, 0, 1)
         n = ctx.seeds_all()
         got = capi.canonical(ctx.fetch())
@@ -354,6 +375,7 @@ def test_repeats_multi_locus_kmers():
         assert n == len(got)
         assert np.array_equal(got, want)
         assert len(want) > 50
+        assert ctx.counters()["fused"] == fused and ctx.counters()["n_on_probe_sectors"] > 0   # locus lists -> slow queue
         ctx.close()
 
 
@@ -420,7 +442,7 @@ def test_offpath_budget_falls_back_to_walking():
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", [0, 1], ids=["index", "walk"])
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
 def test_random_larger_graph_properties(mode):
     """A 200 kbp random bubble graph with 20 000 reads: chunked == unchunked, set == oracle."""
     import tempfile, os
