@@ -199,7 +199,7 @@ struct Ctx {
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
-  int opt_fused_items = 2;                     // seeds per thread and batch of the fused kernel (1 or 2)
+  int opt_fused_ctas = 4;                      // resident CTAs per SM the fused kernel is compiled for (3, 4 or 5)
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
   int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
   int opt_resolve_ctas = 6;                    // resident CTAs per SM the resolve kernel is compiled for (5 or 6)

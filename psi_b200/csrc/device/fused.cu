@@ -15,13 +15,13 @@
 // per hit.  The packing arithmetic and the record resolution run in the issue slots the line waits leave idle.
 //
 // Shape: a CTA owns FUSED_READS consecutive reads (their start offsets and the prefix sums of their seed counts
-// live in shared memory) and walks its seeds in seed order in batches of 256 x ITEMS:
-//   1. the ASCII words of the batch were loaded during the previous batch (software prefetch, registers);
-//      pack -> k-mer + validity, hash -> home line + tag;
-//   2. each warp copies the 32 x ITEMS home lines of its seeds into shared memory with cp.async (8 lanes x
-//      16 B per line; invalid / inactive seeds issue a zero-fill copy that reads nothing);
-//   3. the ASCII words of the NEXT batch are requested;
-//   4. wait, every thread scans its own lines (16 tag compares each);
+// live in shared memory) and walks its seeds in seed order in batches of 256, one seed per thread:
+//   1. the characters of the batch were requested during the previous batch (cp.async into a per-thread staging
+//      slot: no register waits for them); pack -> k-mer + validity, hash -> home line + tag;
+//   2. each warp copies the 32 home lines of its seeds into shared memory with cp.async (8 lanes x 16 B per
+//      line; invalid / inactive seeds issue a zero-fill copy that reads nothing);
+//   3. the characters of the NEXT batch are requested;
+//   4. wait for the lines only, every thread scans its own line (16 tag compares);
 //   5. hits are counted with ballots, ONE atomic per batch reserves the CTA's output range while the threads
 //      already run the two gathers position -> node; records are stored in seed order.
 // The ~0.3 % of the seeds one line cannot settle (locus lists, displaced keys) are queued with their k-mer and
@@ -37,21 +37,34 @@ namespace psi_b200 {
 using namespace dev;
 
 constexpr int FUSED_READS = 256;
+// Bucket lines sit in shared memory at a stride of 144 bytes: lane l then reads 16-byte chunk j of its own line at
+// bank 4 (l + j) mod 32 -- conflict-free within every quarter warp, no per-chunk address arithmetic.
+constexpr uint32_t FUSED_LINE_STRIDE = 144;
+// The characters of a seed are staged in shared memory as K4 + 1 aligned 32-bit words at an odd word stride per thread.
+template <int K4> struct FusedCfg {
+  static constexpr uint32_t WORDS = (K4 + 1) | 1;
+  static constexpr size_t SMEM = (size_t)256 * FUSED_LINE_STRIDE + (size_t)256 * WORDS * 4;
+};
 
-template <int FMT, int K4, int ITEMS>
-__global__ void __launch_bounds__(256, ITEMS == 1 ? 5 : 3)
+template <int FMT, int K4, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_id,
                    const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, uint64_t n_reads,
                    uint32_t k, uint32_t d, uint32_t mode, uint64_t first_read_id, uint32_t compact,
                    uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, uint64_t cap,
                    SlowItem* __restrict__ slow_queue, uint64_t slow_cap, unsigned long long* __restrict__ dc)
 {
-  extern __shared__ __align__(128) unsigned char s_lines[];     // 256 x ITEMS lines of 128 bytes
+  constexpr uint32_t STRIDE = FUSED_LINE_STRIDE;
+  constexpr uint32_t WORDS = FusedCfg<K4>::WORDS;
+  extern __shared__ __align__(128) unsigned char s_dyn[];       // 256 bucket lines, then 256 x WORDS staged characters
+  unsigned char* s_lines = s_dyn;
+  uint32_t* s_ascii = reinterpret_cast<uint32_t*>(s_dyn + 256 * STRIDE);
   __shared__ uint32_t s_first[FUSED_READS + 1];
   __shared__ uint64_t s_ptr[FUSED_READS];
   __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_cnt[8 * ITEMS];
-  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_cnt[2][8];          // hits per warp, double-buffered by batch parity
+  __shared__ uint32_t s_on[2][8];
+  __shared__ unsigned long long s_base[2];
 
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t r_base = (uint64_t)blockIdx.x * FUSED_READS;
@@ -94,160 +107,159 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   const uint32_t tail = k - 4u * (K4 - 1);                           // characters in the last group, 1..4
   const uint32_t tail_mask = tail >= 4u ? 0xffffffffu : (1u << (8u * tail)) - 1u;
 
-  unsigned char* warp_lines = s_lines + (size_t)warp * (ITEMS * 32 * 128);
+  unsigned char* warp_lines = s_lines + (size_t)warp * (32 * STRIDE);
+  uint32_t* my_words = s_ascii + threadIdx.x * WORDS;
+  const uint32_t my_words_sa = (uint32_t)__cvta_generic_to_shared(my_words);
   const uint32_t sub = lane & 7u;
 
-  // locate the seeds of a batch and request their characters
-  AsciiWords<K4> aw[ITEMS];
-  uint32_t rd[ITEMS], roff[ITEMS];
+  // Locate this thread's seed of the batch starting at `base` and request its characters: K4 + 1 aligned words go to
+  // the thread's staging slot with cp.async, so no register waits for them while the previous batch is processed.
+  uint32_t rd = 0, roff = 0, sh = 0;
   auto fetch_batch = [&](uint32_t base) {
-#pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      const uint32_t ls_raw = base + h * 256u + threadIdx.x;
-      const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;   // inactive slots re-read seed 0 (valid memory), emit nothing
-      uint32_t lo = 0;
-      if (uniform) {
-        lo = __umulhi(ls, magic);
-        if ((lo + 1u) * per_read <= ls) ++lo;
-      }
-      else if (one_each) lo = ls;
-      else {
-        uint32_t hi = FUSED_READS;
-#pragma unroll 1
-        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
-      }
-      rd[h] = lo;
-      roff[h] = (ls - s_first[lo]) * d;
-      load_ascii_words<K4>(bases + s_ptr[lo] + roff[h], k, aw[h]);
+    const uint32_t ls_raw = base + threadIdx.x;
+    const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;     // inactive slots re-read seed 0 (valid memory), emit nothing
+    uint32_t lo = 0;
+    if (uniform) {
+      lo = __umulhi(ls, magic);
+      if ((lo + 1u) * per_read <= ls) ++lo;
     }
+    else if (one_each) lo = ls;
+    else {
+      uint32_t hi = FUSED_READS;
+#pragma unroll 1
+      while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
+    }
+    rd = lo;
+    roff = (ls - s_first[lo]) * d;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(bases + s_ptr[lo] + roff);
+    const char* w = reinterpret_cast<const char*>(addr & ~uintptr_t(3));
+    const uint32_t off = (uint32_t)(addr & 3u);
+    sh = off * 8u;
+    // words 0 .. K4-1 always hold bytes of the k-mer (k > 4 (K4 - 1)); word K4 only when the k-mer spills into it
+#pragma unroll
+    for (int i = 0; i < K4; ++i)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(my_words_sa + 4u * i), "l"(w + 4 * i) : "memory");
+    const uint32_t last = off + k > 4u * K4 ? 4u : 0u;          // 0: zero fill, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(my_words_sa + 4u * K4), "l"(last ? w + 4 * K4 : w), "r"(last) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   fetch_batch(0);
 
   uint32_t on_total = 0;    // thread 0 only
-  for (uint32_t base = 0; base < n_cta_seeds; base += 256u * ITEMS) {
+  uint32_t par = 0;
+  for (uint32_t base = 0; base < n_cta_seeds; base += 256u, par ^= 1u) {
     // ---- 1. pack + hash ----
-    uint64_t kmer[ITEMS];
-    uint32_t my_line[ITEMS], want[ITEMS], cur_rd[ITEMS], cur_off[ITEMS];
-    bool ok[ITEMS];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's characters have arrived
+    AsciiWords<K4> aw;
 #pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      bool valid;
-      kmer[h] = pack_ascii_words<K4>(aw[h], tail_mask, valid);
-      ok[h] = valid && base + h * 256u + threadIdx.x < n_cta_seeds;
-      const Home hm = home_of<FMT>(t, kmer[h]);
-      my_line[h] = (uint32_t)hm.line;                      // line_bits <= 32 (checked when the table is allocated)
-      want[h] = (uint32_t)hm.tag;                          // fmt 8: tag | displacement 0 (30 bits)
-      cur_rd[h] = rd[h];
-      cur_off[h] = roff[h];
-    }
+    for (int i = 0; i <= K4; ++i) aw.x[i] = my_words[i];
+    aw.sh = sh;
+    bool valid;
+    const uint64_t kmer = pack_ascii_words<K4>(aw, tail_mask, valid);
+    const bool ok = valid && base + threadIdx.x < n_cta_seeds;
+    const Home hm = home_of<FMT>(t, kmer);
+    const uint32_t my_line = (uint32_t)hm.line;              // line_bits <= 32 (checked when the table is allocated)
+    const uint32_t want = (uint32_t)hm.tag;                  // fmt 8: tag | displacement 0 (30 bits)
+    const uint32_t cur_rd = rd, cur_off = roff;
     // ---- 2. the warp copies its home lines into shared memory ----
-#pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      const uint32_t okmask = __ballot_sync(0xffffffffu, ok[h]);
+    {
+      const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(warp_lines + (lane >> 3) * STRIDE + (sub << 4));
+      const char* src0 = (const char*)t.slots + (sub << 4);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const uint32_t owner = it * 4u + (lane >> 3);
-        const uint32_t line = __shfl_sync(0xffffffffu, my_line[h], owner);
+        const uint32_t line = __shfl_sync(0xffffffffu, my_line, owner);
         const uint32_t bytes = (okmask >> owner) & 1u ? 16u : 0u;      // 0: zero fill, nothing is read
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(warp_lines + ((h * 32u + owner) << 7) + (sub << 4));
-        const char* src = (const char*)t.slots + (bytes ? ((uint64_t)line << 7) + (sub << 4) : 0ull);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(bytes) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     :: "r"(dst0 + it * 4u * STRIDE), "l"(src0 + (bytes ? (uint64_t)line << 7 : 0ull)), "r"(bytes) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- 3. characters of the next batch ----
-    if (base + 256u * ITEMS < n_cta_seeds) fetch_batch(base + 256u * ITEMS);
-    // ---- 4. scan ----
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const bool more = base + 256u < n_cta_seeds;
+    if (more) {
+      fetch_batch(base + 256u);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // the lines have arrived, the characters may still fly
+    }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    uint32_t gpos[ITEMS];
-    uint8_t kind[ITEMS];
-#pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + ((h * 32u + lane) << 7));
-      bool hit = false, empty = false;
-      uint32_t pl = 0, fl = 0;
+    // ---- 4. scan ----
+    uint32_t gpos = 0;
+    uint8_t kind = 0;
+    {
+      const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + lane * STRIDE);
+      bool hit = false;
+      uint32_t fl = 0;
       if (FMT == 8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint4 w = ln[(j + lane) & 7u];             // two slots: (w.x, w.y) and (w.z, w.w), high word second
-          empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has all of rem/disp/flags set
-          if ((w.y >> 2) == want[h]) { hit = true; pl = w.x; fl = w.y & 3u; }
-          if ((w.w >> 2) == want[h]) { hit = true; pl = w.z; fl = w.w & 3u; }
+          const uint4 w = ln[j];                             // two slots: (w.x, w.y) and (w.z, w.w), high word second
+          if ((w.y >> 2) == want) { hit = true; gpos = w.x; fl = w.y & 3u; }
+          if ((w.w >> 2) == want) { hit = true; gpos = w.z; fl = w.w & 3u; }
         }
       }
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint4 w = ln[(j + lane) & 7u];             // one slot: key (w.x, w.y), payload w.z, flags w.w
-          empty |= w.w == NIL32;
-          if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer[h]) { hit = true; pl = w.z; fl = w.w & 3u; }
+          const uint4 w = ln[j];                             // one slot: key (w.x, w.y), payload w.z, flags w.w
+          if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer) { hit = true; gpos = w.z; fl = w.w & 3u; }
         }
       }
-      kind[h] = 0;
-      gpos[h] = pl;
-      if (ok[h]) {
+      if (ok) {
         bool slow = false;
         if (hit) {
           if (fl & FLAG_MULTI) slow = true;
-          else kind[h] = kind_of(fl, mode);
+          else kind = kind_of(fl, mode);
         }
-        else slow = !empty;    // the line is full and does not hold the key: it may sit in a following line
+        else {
+          // a miss is final only when the line has a free slot (else the key may sit in a following line): second
+          // look, taken by the seeds that missed only
+          bool empty = false;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 w = ln[j];
+            if (FMT == 8) empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has all of rem/disp/flags set
+            else empty |= w.w == NIL32;
+          }
+          slow = !empty;
+        }
         if (slow) {
           const unsigned long long q = atomicAdd(dc + DC_SLOW, 1ull);
-          if (q < slow_cap) slow_queue[q] = SlowItem{ kmer[h], (uint32_t)(r_base + cur_rd[h]), cur_off[h] };
+          if (q < slow_cap) slow_queue[q] = SlowItem{ kmer, (uint32_t)(r_base + cur_rd), cur_off };
         }
       }
     }
+    __syncwarp();            // every lane has read its line: the warp's buffers may be overwritten by the next batch
     // ---- 5. count, reserve, resolve, store ----
-    uint32_t m[ITEMS];
-    uint32_t on = 0;
-#pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      m[h] = __ballot_sync(0xffffffffu, kind[h] != 0);
-      on += __popc(__ballot_sync(0xffffffffu, kind[h] == 1));
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int h = 0; h < ITEMS; ++h) s_cnt[8 * h + warp] = __popc(m[h]);
-      s_warp[warp] = on;
-    }
+    const uint32_t m = __ballot_sync(0xffffffffu, kind != 0);
+    const uint32_t m_on = __ballot_sync(0xffffffffu, kind == 1);
+    if (lane == 0) { s_cnt[par][warp] = __popc(m); s_on[par][warp] = __popc(m_on); }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t run = 0;
 #pragma unroll
-      for (int w = 0; w < 8 * ITEMS; ++w) run += s_cnt[w];
-#pragma unroll
-      for (int w = 0; w < 8; ++w) on_total += s_warp[w];
-      s_base = run ? atomicAdd(dc + DC_HITS, (unsigned long long)run) : 0ull;
+      for (int w = 0; w < 8; ++w) { run += s_cnt[par][w]; on_total += s_on[par][w]; }
+      s_base[par] = run ? atomicAdd(dc + DC_HITS, (unsigned long long)run) : 0ull;
     }
-    Resolved r[ITEMS];
+    Resolved r;
+    if (kind) {
+      r.read_id = first_read_id + r_base + cur_rd;
+      r.read_off = cur_off;
+      resolve_node(g, node_id, gpos, r.node_id, r.node_off);
+    }
+    uint32_t pre = 0;
 #pragma unroll
-    for (int h = 0; h < ITEMS; ++h)
-      if (kind[h]) {
-        r[h].read_id = first_read_id + r_base + cur_rd[h];
-        r[h].read_off = cur_off[h];
-        resolve_node(g, node_id, gpos[h], r[h].node_id, r[h].node_off);
-      }
+    for (int w = 0; w < 8; ++w) if (w < (int)warp) pre += s_cnt[par][w];
     __syncthreads();
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t run = 0;
-#pragma unroll
-    for (int h = 0; h < ITEMS; ++h) {
-      uint32_t pre = run;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const uint32_t c = s_cnt[8 * h + w];
-        if (w < (int)warp) pre += c;
-        run += c;
-      }
-      const uint64_t out = s_base + pre + __popc(m[h] & lt);
-      if (!kind[h] || out >= cap) continue;
-      if (compact) st_record32(records + 2 * out, r[h]);
-      else st_record(records + 4 * out, r[h]);
-      rec_kind[out] = kind[h];
+    const uint64_t out = s_base[par] + pre + __popc(m & ((1u << lane) - 1u));
+    if (kind && out < cap) {
+      if (compact) st_record32(records + 2 * out, r);
+      else st_record(records + 4 * out, r);
+      rec_kind[out] = kind;
     }
-    __syncthreads();     // s_cnt / s_base / line buffers are reused by the next batch
+    // no barrier here: the next batch writes the other halves of s_cnt / s_on / s_base, and a warp can only be two
+    // batches ahead of another after a barrier that the slower one has passed
   }
   if (threadIdx.x == 0) {
     atomicAdd(dc + DC_SEEDS, (unsigned long long)n_cta_seeds);
@@ -303,12 +315,12 @@ seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphVi
 
 // ---------------------------------------------------------------- host --
 
-template <int FMT, int K4, int ITEMS>
+template <int FMT, int K4, int MIN_CTAS>
 static void launch_fused(Ctx& c, const GraphView& g, unsigned probe_mode, bool compact, uint64_t out_cap)
 {
   Shared& sh = *c.sh;
-  auto kern = seeds_fused_kernel<FMT, K4, ITEMS>;
-  const size_t smem = (size_t)256 * ITEMS * 128;
+  auto kern = seeds_fused_kernel<FMT, K4, MIN_CTAS>;
+  const size_t smem = FusedCfg<K4>::SMEM;
   static bool attr_set = false;     // per instantiation
   if (!attr_set) {
     PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -321,18 +333,18 @@ static void launch_fused(Ctx& c, const GraphView& g, unsigned probe_mode, bool c
                                       c.slow_items.p, c.slow_items.cap, c.dev_counters.p);
 }
 
-template <int FMT, int ITEMS>
+template <int FMT, int MIN_CTAS>
 static void launch_fused_k(Ctx& c, const GraphView& g, unsigned probe_mode, bool compact, uint64_t out_cap)
 {
   switch ((c.k + 3) / 4) {
-    case 1: launch_fused<FMT, 1, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 2: launch_fused<FMT, 2, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 3: launch_fused<FMT, 3, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 4: launch_fused<FMT, 4, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 5: launch_fused<FMT, 5, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 6: launch_fused<FMT, 6, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    case 7: launch_fused<FMT, 7, ITEMS>(c, g, probe_mode, compact, out_cap); break;
-    default: launch_fused<FMT, 8, ITEMS>(c, g, probe_mode, compact, out_cap); break;
+    case 1: launch_fused<FMT, 1, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 2: launch_fused<FMT, 2, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 3: launch_fused<FMT, 3, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 4: launch_fused<FMT, 4, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 5: launch_fused<FMT, 5, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 6: launch_fused<FMT, 6, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    case 7: launch_fused<FMT, 7, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
+    default: launch_fused<FMT, 8, MIN_CTAS>(c, g, probe_mode, compact, out_cap); break;
   }
 }
 
@@ -356,13 +368,30 @@ void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact)
     PSI_CUDA(cudaMemsetAsync(dc, 0, DC_COUNT * sizeof(unsigned long long), c.stream));
     PhaseTimer t_on(c, T_ON);
     PhaseTimer t_probe(c, T_PROBE);
+    const bool pin = c.l2_window_bytes != 0 && sh.has_rank16;
+    if (pin) {   // the position -> node gathers persist in the L2 set-aside, the index lines and the chunk stream through
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = sh.gather_pool.p;
+      attr.accessPolicyWindow.num_bytes = c.l2_window_bytes;
+      attr.accessPolicyWindow.hitRatio = c.l2_persist_bytes >= c.l2_window_bytes ? 1.0f : (float)c.l2_persist_bytes / (float)c.l2_window_bytes;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     if (sh.index.view.fmt == 8) {
-      if (c.opt_fused_items == 1) launch_fused_k<8, 1>(c, g, probe_mode, compact, out_cap);
-      else launch_fused_k<8, 2>(c, g, probe_mode, compact, out_cap);
+      if (c.opt_fused_ctas == 5) launch_fused_k<8, 5>(c, g, probe_mode, compact, out_cap);
+      else if (c.opt_fused_ctas == 3) launch_fused_k<8, 3>(c, g, probe_mode, compact, out_cap);
+      else launch_fused_k<8, 4>(c, g, probe_mode, compact, out_cap);
     }
     else {
-      if (c.opt_fused_items == 1) launch_fused_k<16, 1>(c, g, probe_mode, compact, out_cap);
-      else launch_fused_k<16, 2>(c, g, probe_mode, compact, out_cap);
+      if (c.opt_fused_ctas == 5) launch_fused_k<16, 5>(c, g, probe_mode, compact, out_cap);
+      else if (c.opt_fused_ctas == 3) launch_fused_k<16, 3>(c, g, probe_mode, compact, out_cap);
+      else launch_fused_k<16, 4>(c, g, probe_mode, compact, out_cap);
+    }
+    if (pin) {
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.num_bytes = 0;
+      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     t_probe.stop();
     seeds_slow_fused_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, g, sh.node_id.p, c.slow_items.p,

@@ -680,9 +680,9 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   else if (n == "fused") {
     c.opt_fused = value != 0;
   }
-  else if (n == "fused_items") {
-    if (value != 1 && value != 2) throw ArgError("set_option: fused_items is 1 or 2");
-    c.opt_fused_items = (int)value;
+  else if (n == "fused_ctas") {
+    if (value < 3 || value > 5) throw ArgError("set_option: fused_ctas is 3, 4 or 5");
+    c.opt_fused_ctas = (int)value;
   }
   else if (n == "seeding_mode") {
     if (value < 0 || value > 1) throw ArgError("set_option: seeding_mode is 0 (direct from ASCII) or 1 (2-bit staging)");

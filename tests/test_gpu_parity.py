@@ -134,19 +134,19 @@ def test_no_paths_all_loci_equals_closed_form(name, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("seeding,items,fused", [(1, 2, 0), (0, 4, 0), (1, 4, 0), (0, 1, 1)],
-                         ids=["staged-2", "direct-4", "staged-4", "fused-1"])
+@pytest.mark.parametrize("seeding,items,fused", [(1, 2, 0), (0, 4, 0), (1, 4, 0), (0, 3, 1), (0, 5, 1)],
+                         ids=["staged-2", "direct-4", "staged-4", "fused-3ctas", "fused-5ctas"])
 @pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "fuzz_07", "fuzz_10", "fuzz_11"])
 def test_kernel_variants_give_the_same_set(name, seeding, items, fused):
     """The alternative kernels behind the tuning options (2-bit staged seeding, 4 items per thread in the resolve
-    kernel, one seed per thread and batch in the fused kernel) must give the reference's set too; the defaults are
+    kernel, the fused kernel compiled for 3 or 5 resident CTAs) must give the reference's set too; the defaults are
     covered by every other test."""
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx = capi.Context(c["k"], 0)
     ctx.set_option("fused", fused)
     if fused:
-        ctx.set_option("fused_items", items)
+        ctx.set_option("fused_ctas", items)
     else:
         ctx.set_option("seeding_mode", seeding)
         ctx.set_option("resolve_items", items)
