@@ -22,8 +22,9 @@
 //      line; invalid / inactive seeds issue a zero-fill copy that reads nothing);
 //   3. the characters of the NEXT batch are requested;
 //   4. wait for the lines only, every thread scans its own line (16 tag compares);
-//   5. hits are counted with ballots, ONE atomic per batch reserves the CTA's output range while the threads
-//      already run the two gathers position -> node; records are stored in seed order.
+//   5. the warp appends its hits (locus, seed index) to a CTA-local list -- no CTA-wide barrier inside a batch;
+//   6. every FUSED_FLUSH batches and after the last one the list becomes records: ONE atomic reserves the CTA's
+//      output range, every thread has the position -> node gathers of up to FUSED_FLUSH hits in flight together.
 // The ~0.3 % of the seeds one line cannot settle (locus lists, displaced keys) are queued with their k-mer and
 // (read, offset); seeds_slow_fused_kernel resolves them and appends their records.
 #include "engine.hpp"
@@ -40,6 +41,12 @@ constexpr int FUSED_READS = 256;
 // Bucket lines sit in shared memory at a stride of 144 bytes: lane l then reads 16-byte chunk j of its own line at
 // bank 4 (l + j) mod 32 -- conflict-free within every quarter warp, no per-chunk address arithmetic.
 constexpr uint32_t FUSED_LINE_STRIDE = 144;
+// Hits are collected in a CTA-local list and turned into records every FUSED_FLUSH batches (and after the last one):
+// one output reservation and one burst of position -> node gathers per flush instead of per batch, and no CTA-wide
+// barrier inside a batch.  A seed settled by the one-line probe has at most one hit, so the list cannot overflow.
+constexpr int FUSED_FLUSH = 5;
+constexpr int FUSED_LIST = FUSED_FLUSH * 256;
+constexpr int FUSED_WIDTH = 3;      // hits per thread whose gathers are in flight together during a flush
 // The characters of a seed are staged in shared memory as K4 + 1 aligned 32-bit words at an odd word stride per thread.
 template <int K4> struct FusedCfg {
   static constexpr uint32_t WORDS = (K4 + 1) | 1;
@@ -62,9 +69,11 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   __shared__ uint32_t s_first[FUSED_READS + 1];
   __shared__ uint64_t s_ptr[FUSED_READS];
   __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_cnt[2][8];          // hits per warp, double-buffered by batch parity
-  __shared__ uint32_t s_on[2][8];
-  __shared__ unsigned long long s_base[2];
+  // the CTA's hits since the last flush: locus, and seed index relative to the window start (bit 15: off-path entry)
+  __shared__ uint32_t s_hit_gpos[FUSED_LIST];
+  __shared__ uint16_t s_hit_idx[FUSED_LIST];
+  __shared__ uint32_t s_count, s_on;
+  __shared__ unsigned long long s_base;
 
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint64_t r_base = (uint64_t)blockIdx.x * FUSED_READS;
@@ -88,7 +97,7 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
     for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
     s_first[threadIdx.x] = before + incl - mine;
     s_ptr[threadIdx.x] = p0;
-    if (threadIdx.x == FUSED_READS - 1) s_first[FUSED_READS] = before + incl;
+    if (threadIdx.x == FUSED_READS - 1) { s_first[FUSED_READS] = before + incl; s_count = 0; s_on = 0; }
     __syncthreads();
   }
   const uint32_t n_cta_seeds = s_first[FUSED_READS];
@@ -112,12 +121,8 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   const uint32_t my_words_sa = (uint32_t)__cvta_generic_to_shared(my_words);
   const uint32_t sub = lane & 7u;
 
-  // Locate this thread's seed of the batch starting at `base` and request its characters: K4 + 1 aligned words go to
-  // the thread's staging slot with cp.async, so no register waits for them while the previous batch is processed.
-  uint32_t rd = 0, roff = 0, sh = 0;
-  auto fetch_batch = [&](uint32_t base) {
-    const uint32_t ls_raw = base + threadIdx.x;
-    const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;     // inactive slots re-read seed 0 (valid memory), emit nothing
+  // CTA-local seed index -> the read (CTA-local) it belongs to
+  auto read_of = [&](uint32_t ls) -> uint32_t {
     uint32_t lo = 0;
     if (uniform) {
       lo = __umulhi(ls, magic);
@@ -129,6 +134,16 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
 #pragma unroll 1
       while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_first[mid] <= ls) lo = mid; else hi = mid; }
     }
+    return lo;
+  };
+
+  // Locate this thread's seed of the batch starting at `base` and request its characters: K4 + 1 aligned words go to
+  // the thread's staging slot with cp.async, so no register waits for them while the previous batch is processed.
+  uint32_t rd = 0, roff = 0, sh = 0;
+  auto fetch_batch = [&](uint32_t base) {
+    const uint32_t ls_raw = base + threadIdx.x;
+    const uint32_t ls = ls_raw < n_cta_seeds ? ls_raw : 0u;     // inactive slots re-read seed 0 (valid memory), emit nothing
+    const uint32_t lo = read_of(ls);
     rd = lo;
     roff = (ls - s_first[lo]) * d;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(bases + s_ptr[lo] + roff);
@@ -145,9 +160,71 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   };
   fetch_batch(0);
 
-  uint32_t on_total = 0;    // thread 0 only
-  uint32_t par = 0;
-  for (uint32_t base = 0; base < n_cta_seeds; base += 256u, par ^= 1u) {
+  // Hits of the window -> records: ONE reservation of the CTA's output range, all gathers of a thread in flight together.
+  uint32_t window = 0;       // CTA-local index of the first seed of the current window
+  auto flush = [&]() {
+    __syncthreads();                                   // every warp has appended its hits
+    const uint32_t n = s_count;
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(dc + DC_HITS, (unsigned long long)n) : 0ull;
+    const bool fast = g.rank16 != nullptr;
+    uint32_t on = 0;
+    bool base_ready = false;
+    unsigned long long out0 = 0;
+    // FUSED_WIDTH hits per thread and pass: their gathers are in flight together
+#pragma unroll
+    for (int p0 = 0; p0 < FUSED_FLUSH; p0 += FUSED_WIDTH) {
+      if (p0 * 256u >= n) break;                       // CTA-uniform
+      uint32_t gp[FUSED_WIDTH], ix[FUSED_WIDTH];
+      uint4 rw[FUSED_WIDTH];
+#pragma unroll
+      for (int i = 0; i < FUSED_WIDTH; ++i) {
+        const uint32_t e = (p0 + i) * 256u + threadIdx.x;
+        gp[i] = e < n ? s_hit_gpos[e] : 0u;
+        ix[i] = e < n ? (uint32_t)s_hit_idx[e] : 0u;
+        if (fast && e < n) rw[i] = __ldg(reinterpret_cast<const uint4*>(g.rank16 + (gp[i] >> 6)));
+      }
+#pragma unroll
+      for (int i = 0; i < FUSED_WIDTH; ++i) {
+        const uint32_t e = (p0 + i) * 256u + threadIdx.x;
+        if (fast && e < n) {
+          const uint64_t bits = ((uint64_t)rw[i].y << 32) | rw[i].x;
+          const uint32_t v = rw[i].z + (uint32_t)__popcll(bits & (~0ull >> (63u - (gp[i] & 63u)))) - 1u;
+          rw[i] = __ldg(reinterpret_cast<const uint4*>(g.node_res + v));
+        }
+        on += (e < n && !(ix[i] & 0x8000u)) ? 1u : 0u;
+      }
+      if (!base_ready) {
+        __syncthreads();                               // s_base is visible
+        out0 = s_base;
+        base_ready = true;
+      }
+#pragma unroll
+      for (int i = 0; i < FUSED_WIDTH; ++i) {
+        const uint32_t e = (p0 + i) * 256u + threadIdx.x;
+        const uint64_t out = out0 + e;
+        if (e < n && out < cap) {
+          Resolved r;
+          const uint32_t ls = window + (ix[i] & 0x7fffu);
+          const uint32_t lo = read_of(ls);
+          r.read_id = first_read_id + r_base + lo;
+          r.read_off = (ls - s_first[lo]) * d;
+          if (fast) { r.node_off = gp[i] - rw[i].x; r.node_id = ((uint64_t)rw[i].w << 32) | rw[i].z; }
+          else resolve_node(g, node_id, gp[i], r.node_id, r.node_off);
+          if (compact) st_record32(records + 2 * out, r);
+          else st_record(records + 4 * out, r);
+          rec_kind[out] = (ix[i] & 0x8000u) ? 2 : 1;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) on += __shfl_xor_sync(0xffffffffu, on, o);
+    if (lane == 0 && on) atomicAdd(&s_on, on);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();                                   // the list is free again
+  };
+
+  uint32_t batch = 0;
+  for (uint32_t base = 0; base < n_cta_seeds; base += 256u, ++batch) {
     // ---- 1. pack + hash ----
     asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's characters have arrived
     AsciiWords<K4> aw;
@@ -186,7 +263,7 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
     __syncwarp();
     // ---- 4. scan ----
     uint32_t gpos = 0;
-    uint8_t kind = 0;
+    uint32_t kind = 0;
     {
       const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + lane * STRIDE);
       bool hit = false;
@@ -231,44 +308,32 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
       }
     }
     __syncwarp();            // every lane has read its line: the warp's buffers may be overwritten by the next batch
-    // ---- 5. count, reserve, resolve, store ----
+    // ---- 5. the warp appends its hits to the CTA's list ----
     const uint32_t m = __ballot_sync(0xffffffffu, kind != 0);
-    const uint32_t m_on = __ballot_sync(0xffffffffu, kind == 1);
-    if (lane == 0) { s_cnt[par][warp] = __popc(m); s_on[par][warp] = __popc(m_on); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) { run += s_cnt[par][w]; on_total += s_on[par][w]; }
-      s_base[par] = run ? atomicAdd(dc + DC_HITS, (unsigned long long)run) : 0ull;
+    if (m) {
+      uint32_t wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&s_count, (uint32_t)__popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (kind) {
+        const uint32_t e = wbase + __popc(m & ((1u << lane) - 1u));
+        s_hit_gpos[e] = gpos;
+        s_hit_idx[e] = (uint16_t)((base + threadIdx.x - window) | (kind == 2 ? 0x8000u : 0u));
+      }
     }
-    Resolved r;
-    if (kind) {
-      r.read_id = first_read_id + r_base + cur_rd;
-      r.read_off = cur_off;
-      resolve_node(g, node_id, gpos, r.node_id, r.node_off);
+    if (batch % FUSED_FLUSH == FUSED_FLUSH - 1 || !more) {
+      flush();
+      window = base + 256u;
     }
-    uint32_t pre = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) if (w < (int)warp) pre += s_cnt[par][w];
-    __syncthreads();
-    const uint64_t out = s_base[par] + pre + __popc(m & ((1u << lane) - 1u));
-    if (kind && out < cap) {
-      if (compact) st_record32(records + 2 * out, r);
-      else st_record(records + 4 * out, r);
-      rec_kind[out] = kind;
-    }
-    // no barrier here: the next batch writes the other halves of s_cnt / s_on / s_base, and a warp can only be two
-    // batches ahead of another after a barrier that the slower one has passed
   }
   if (threadIdx.x == 0) {
     atomicAdd(dc + DC_SEEDS, (unsigned long long)n_cta_seeds);
-    if (on_total) atomicAdd(dc + DC_HITS_ON, (unsigned long long)on_total);
+    if (s_on) atomicAdd(dc + DC_HITS_ON, (unsigned long long)s_on);
   }
 }
 
 // The queued seeds: full search (following lines, stash) and locus lists; their records are appended to the
-// CTAs' output.  One thread per queued seed.
+// CTAs' output.  One thread per queued seed; a warp reserves the output range of its 32 seeds with ONE atomic
+// (same-address atomics serialise in L2: ~15 000 queued seeds per 1 M reads would otherwise queue up there).
 __global__ void __launch_bounds__(256)
 seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphView g, const uint64_t* __restrict__ node_id,
                         const SlowItem* __restrict__ slow_queue, uint64_t slow_cap, uint32_t mode, uint64_t first_read_id,
@@ -277,38 +342,48 @@ seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphVi
 {
   uint64_t n = dc[DC_SLOW];
   if (n > slow_cap) n = slow_cap;     // the host grows the queue and repeats the step
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
-    const SlowItem it = slow_queue[q];
-    Found f;
-    if (!table_find_any(t, it.kmer, f)) continue;
+  const uint32_t lane = lane_id();
+  // warp-uniform trip count: every lane of a warp takes part in the reservation
+  for (uint64_t q0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; q0 < n; q0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t q = q0 + lane;
+    SlowItem it{};
+    Found f{};
+    uint32_t from = 0, to = 0, n_on = 0;      // this seed's hits: loci from..to of its list (or the single payload), the first n_on on paths
+    bool single = false;
+    if (q < n) {
+      it = slow_queue[q];
+      if (table_find_any(t, it.kmer, f)) {
+        if (!(f.flags & FLAG_MULTI)) {
+          const uint8_t kind = kind_of(f.flags, mode);
+          single = true;
+          to = kind ? 1u : 0u;
+          n_on = kind == 1 ? 1u : 0u;
+        }
+        else {
+          const uint32_t l_on = __ldg(multi + f.payload), l_all = __ldg(multi + f.payload + 1);
+          from = (mode & PSI_B200_ON_PATHS) ? 0u : l_on;
+          to = (mode & PSI_B200_OFF_PATHS) ? l_all : l_on;
+          if (to < from) to = from;
+          n_on = l_on > from ? l_on - from : 0u;
+        }
+      }
+    }
+    const uint32_t cnt = to - from;
+    uint64_t out = warp_reserve(dc + DC_HITS, cnt);
+    uint32_t on_sum = n_on;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) on_sum += __shfl_xor_sync(0xffffffffu, on_sum, o);
+    if (lane == 0 && on_sum) atomicAdd(dc + DC_HITS_ON, (unsigned long long)on_sum);
     Resolved r;
     r.read_id = first_read_id + it.read;
     r.read_off = it.off;
-    if (!(f.flags & FLAG_MULTI)) {
-      const uint8_t kind = kind_of(f.flags, mode);
-      if (!kind) continue;
-      const uint64_t out = atomicAdd(dc + DC_HITS, 1ull);
-      if (kind == 1) atomicAdd(dc + DC_HITS_ON, 1ull);
-      if (out >= cap) continue;
-      resolve_node(g, node_id, f.payload, r.node_id, r.node_off);
+    for (uint32_t j = from; j < to; ++j, ++out) {
+      if (out >= cap) break;
+      const uint32_t gpos = single ? f.payload : __ldg(multi + f.payload + 2 + j);
+      resolve_node(g, node_id, gpos, r.node_id, r.node_off);
       if (compact) st_record32(records + 2 * out, r);
       else st_record(records + 4 * out, r);
-      rec_kind[out] = kind;
-    }
-    else {
-      const uint32_t n_on = __ldg(multi + f.payload), n_all = __ldg(multi + f.payload + 1);
-      const uint32_t from = (mode & PSI_B200_ON_PATHS) ? 0u : n_on;
-      const uint32_t to = (mode & PSI_B200_OFF_PATHS) ? n_all : n_on;
-      if (to <= from) continue;
-      uint64_t out = atomicAdd(dc + DC_HITS, (unsigned long long)(to - from));
-      if (n_on > from) atomicAdd(dc + DC_HITS_ON, (unsigned long long)(n_on - from));
-      for (uint32_t j = from; j < to; ++j, ++out) {
-        if (out >= cap) break;
-        resolve_node(g, node_id, __ldg(multi + f.payload + 2 + j), r.node_id, r.node_off);
-        if (compact) st_record32(records + 2 * out, r);
-        else st_record(records + 4 * out, r);
-        rec_kind[out] = j < n_on ? 1 : 2;
-      }
+      rec_kind[out] = single ? (n_on ? 1 : 2) : (j - from < n_on ? 1 : 2);
     }
   }
 }
@@ -394,7 +469,7 @@ void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact)
       PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     t_probe.stop();
-    seeds_slow_fused_kernel<<<(unsigned)c.sm_count * 2, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, g, sh.node_id.p, c.slow_items.p,
+    seeds_slow_fused_kernel<<<(unsigned)c.sm_count, 256, 0, c.stream>>>(sh.index.view, sh.multi.p, g, sh.node_id.p, c.slow_items.p,
                                                                            c.slow_items.cap, probe_mode, c.first_read_id,
                                                                            compact ? 1u : 0u, c.records.p, c.rec_kind.p, out_cap, dc);
     t_on.stop();

@@ -8,7 +8,7 @@ try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     sep = d.get("separate_kernels", {})
     print(round(d["value"] / 1e6, 1), "M reads/s", round(d["ms_per_step"], 4), "ms", {k: round(v, 4) for k, v in d["kernel_ms_per_step"].items() if v},
-          "| pipelined", round(d.get("value_pipelined", {}).get("value", 0) / 1e6, 1),
+          "| one pipeline", round(d.get("value_one_pipeline", {}).get("value", 0) / 1e6, 1), round(d.get("value_one_pipeline", {}).get("ms_per_step", 0), 4),
           "| e2e", round(d["e2e"]["value"] / 1e6, 1), "| roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3),
           "probes/s", round(d["roofline"]["probes_per_s"] / 1e9, 2), "G | separate", round(sep.get("ms_per_step", 0), 4))
 except Exception as e:

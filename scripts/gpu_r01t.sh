@@ -13,7 +13,7 @@ try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     sep = d.get("separate_kernels", {})
     print(d.get("route"), "|", round(d["value"] / 1e6, 1), "M reads/s", round(d["ms_per_step"], 4), "ms", {k: round(v, 4) for k, v in d["kernel_ms_per_step"].items()},
-          "| pipelined", round(d.get("value_pipelined", {}).get("value", 0) / 1e6, 1),
+          "| one pipeline", round(d.get("value_one_pipeline", {}).get("value", 0) / 1e6, 1), round(d.get("value_one_pipeline", {}).get("ms_per_step", 0), 4),
           "| e2e", round(d["e2e"]["value"] / 1e6, 1), round(d["e2e"]["ms_per_step"], 3), "ms",
           "| e2e wide", round(d.get("e2e_wide_records", {}).get("value", 0) / 1e6, 1),
           "| roofline", d["roofline"]["kernel"], round(d["roofline"]["frac"], 3), "probes/s", round(d["roofline"]["probes_per_s"] / 1e9, 2), "G",
@@ -24,7 +24,6 @@ except Exception as e:
 PY
 }
 echo "== bench (defaults)" ; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; tail -3 $OUT/bench.err ; show $OUT/bench.json
-echo "== bench fused_items=1" ; timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --opt fused_items=1 > $OUT/bench_items1.json 2> $OUT/bench_items1.err ; tail -1 $OUT/bench_items1.err ; show $OUT/bench_items1.json
 if [ -z "${3:-}" ]; then
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv \
