@@ -148,10 +148,15 @@ const char* psi_b200_last_error(const psi_b200_ctx* ctx);
  * non-blocking stream). */
 int  psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream);
 int  psi_b200_sync(psi_b200_ctx* ctx);
-/* Tuning knobs (set before find_loci / set_loci):
+/* Tuning knobs.  Set before find_loci / set_loci:
  *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
  *                       (the reference's scheme), 2 always materialise those walks into the index;
- *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28). */
+ *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28).
+ * Any time (they select among kernels that produce the same records):
+ *   "fused"             1 (default): when the index answers the requested phases by itself, a chunk is ONE kernel
+ *                       (seeding + probe + records); 0: separate seeding / probe / resolve kernels;
+ *   "fused_ctas"        resident CTAs per SM the fused kernel is compiled for: 3, 4 (default) or 5;
+ *   "seeding_mode", "resolve_items", "resolve_ctas", "l2_persist": variants of the separate kernels. */
 int  psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value);
 
 /* The graph the finder borrows (seed_finder.hpp:1747), flattened: CSR
@@ -205,8 +210,11 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
 
 /* Finds the seeds of the submitted chunk.  The result is the SET of hits
  * (each (read, offset, node, offset) once), resident in device
- * memory; *n_hits is its size (synchronises the stream).  Records are ordered by (read, read offset)
- * up to blocks of 512 seeds; PSI_B200_SORTED gives the exact canonical order. */
+ * memory; *n_hits is its size (synchronises the stream).  Record order: grouped by blocks of 256
+ * consecutive reads (fused route) or 512 consecutive seeds (separate kernels), blocks in completion
+ * order, the records of seeds with several loci appended at the end; PSI_B200_SORTED gives the exact
+ * canonical order.  The seeding kernels run here, not in submit_chunk: device buffers handed to
+ * psi_b200_submit_chunk_device must stay valid until the last seeds_all of the chunk has returned. */
 int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
 
 /* Copies the records of the last seeds_all to the host in the reference
