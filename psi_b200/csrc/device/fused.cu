@@ -396,11 +396,12 @@ static void launch_fused(Ctx& c, const GraphView& g, unsigned probe_mode, bool c
   Shared& sh = *c.sh;
   auto kern = seeds_fused_kernel<FMT, K4, MIN_CTAS>;
   const size_t smem = FusedCfg<K4>::SMEM;
-  static bool attr_set = false;     // per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {};    // per instantiation and device (function attributes are per device)
+  const int dv = c.device & 63;
+  if (!attr_set[dv]) {
     PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+    attr_set[dv] = true;
   }
   const unsigned grid = (unsigned)std::max<uint64_t>(1, (c.n_reads + FUSED_READS - 1) / FUSED_READS);
   kern<<<grid, 256, smem, c.stream>>>(sh.index.view, g, sh.node_id.p, c.d_bases, c.d_read_ptr, c.n_reads, c.k, c.distance,

@@ -407,7 +407,8 @@ void engine_seeds(Ctx& c, unsigned flags)
       if (do_probe) {
         const unsigned grid = grid_for(c.n_seeds_cap, 256);
         c.slow_queue.ensure(c.n_seeds_cap, 1.25);
-        static bool carveout_set = false;   // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split
+        static bool carveout_done[64] = {};   // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split
+        bool& carveout_set = carveout_done[c.device & 63];
         if (!carveout_set) {
           PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -466,6 +466,38 @@ def test_random_larger_graph_properties(mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
+def test_reads_with_errors_and_foreign_reads(mode):
+    """Seeds that are NOT in the graph -- substitution errors in random-walk reads and reads of random sequence --
+    take the miss path of the probe: a miss is final on a line with a free slot, otherwise the following lines are
+    searched (slow queue).  Overlapping seeds (d = 4) of a 150 kbp bubble graph, k = 16, against the oracle."""
+    import tempfile, os
+    text = util.random_bubble_gfa(7, backbone=150000, sites=4000)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "err.gfa")
+        open(p, "w").write(text)
+        g = capi.Graph.load_gfa(p)
+    rp, bases = util.random_walk_reads(g, 8000, 100, seed=11)
+    bases = bases.copy()
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    flip = rng.random(len(bases)) < 0.03                       # 3 % substitutions
+    bases[flip] = acgt[rng.integers(0, 4, int(flip.sum()))]
+    foreign = acgt[rng.integers(0, 4, 3000 * 100)]             # reads that come from nowhere
+    rp = np.concatenate([rp, rp[-1] + np.arange(1, 3001, dtype=np.uint64) * np.uint64(100)])
+    bases = np.concatenate([bases, foreign])
+    k, d = 16, 4
+    ctx, _ = make_ctx(g, k, 6, mode=mode)
+    rec, total = run_chunks(ctx, rp, bases, d, 4000)
+    got = capi.canonical(rec)
+    want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), k, d)
+    assert total == len(got)
+    assert np.array_equal(got, want)
+    n_seeds = (len(rp) - 1) * ((100 - k) // d + 1)
+    assert 0.2 * n_seeds < len(np.unique(got[:, :2], axis=0)) < 0.8 * n_seeds, "the case must mix hits and misses"
+    ctx.close()
+
+
 def test_forked_contexts_share_the_index_and_run_concurrently():
     """psi_b200_fork: two pipelines on one GPU over one resident index, driven from two host threads."""
     import threading
