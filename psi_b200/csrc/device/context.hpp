@@ -197,7 +197,6 @@ struct Ctx {
   // ---- options (psi_b200_set_option) ----
   int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
-  unsigned opt_probe_ctas_per_sm = 3;          // persistent CTAs of the probe kernel per SM
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
   int opt_fused_ctas = 4;                      // resident CTAs per SM the fused kernel is compiled for (3, 4 or 5)
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads

@@ -108,9 +108,10 @@ Ctx* engine_fork(Ctx& parent)
   c->counters.offpath_mode = pc.offpath_mode; c->counters.n_offpath_walks = pc.n_offpath_walks;
   c->spill_items = parent.spill_items;
   c->opt_offpath_mode = parent.opt_offpath_mode;
-  c->opt_probe_ctas_per_sm = parent.opt_probe_ctas_per_sm;
   c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
+  c->opt_fused = parent.opt_fused;
+  c->opt_fused_ctas = parent.opt_fused_ctas;
   c->opt_resolve_items = parent.opt_resolve_items;
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
   c->l2_window_bytes = parent.l2_window_bytes;

@@ -673,10 +673,6 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   else if (n == "l2_persist") {
     c.opt_l2_persist = value != 0;     // takes effect at the next set_graph
   }
-  else if (n == "probe_ctas_per_sm") {
-    if (value < 1 || value > 32) throw ArgError("set_option: probe_ctas_per_sm must be in [1, 32]");
-    c.opt_probe_ctas_per_sm = (unsigned)value;
-  }
   else if (n == "fused") {
     c.opt_fused = value != 0;
   }
