@@ -445,7 +445,7 @@ def main_gpu(args):
         e2e_value = n_reads * args.steps * world / (ms_e2e * 1e-3)
         hp, hb = batches_h[0]
         line = {
-            "metric": "reads/s (fully-sensitive seed finding, chr22-shape graph, k=20)",
+            "metric": f"reads/s (fully-sensitive seed finding, {args.shape}-shape graph, k={K})",
             "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u64", "data": "synthetic",
@@ -511,12 +511,15 @@ def main():
     ap.add_argument("--impl", default="psi_b200", choices=["psi_b200", "reference"])
     ap.add_argument("--shape", default="chr22", help="bench_support.synth.SHAPES key")
     ap.add_argument("--reads", type=int, default=READS_PER_BATCH)
+    ap.add_argument("--k", type=int, default=K, help="seed length (other BASELINE configs: 32 with --shape mhc)")
+    ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "psi_b200" else args.warmup
+    globals().update(K=args.k, READ_LEN=args.read_len)
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -151,7 +151,9 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
 /* Tuning knobs.  Set before find_loci / set_loci:
  *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
  *                       (the reference's scheme), 2 always materialise those walks into the index;
- *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28).
+ *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28);
+ *   "index_slack"       extra doublings of the index's bucket count: fewer full buckets (slow-path probes) for twice
+ *                       the memory each; -1 (default) = 1 for 16-byte slots (k > ~27) while the index stays small, else 0.
  * Any time (they select among kernels that produce the same records):
  *   "fused"             1 (default): when the index answers the requested phases by itself, a chunk is ONE kernel
  *                       (seeding + probe + records); 0: separate seeding / probe / resolve kernels;

@@ -29,8 +29,8 @@ void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);
 // ---- helpers shared by the .cu files ----
 
 // Size a KmerTable for n_keys distinct k-mers of 2k = kbits bits; allocates and
-// clears the slots.
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots);
+// clears the slots.  slack_bits: extra doublings of the line count (-1: auto).
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits = 0);
 void table_clear(Ctx& c, HostTable& t);
 
 // CUDA-event timer slots (Ctx::ev holds a start/stop pair per slot)

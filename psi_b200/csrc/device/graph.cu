@@ -111,6 +111,7 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
   c->opt_fused = parent.opt_fused;
+  c->opt_index_slack = parent.opt_index_slack;
   c->opt_fused_ctas = parent.opt_fused_ctas;
   c->opt_resolve_items = parent.opt_resolve_items;
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
@@ -247,7 +248,7 @@ static uint32_t ceil_log2(uint64_t x)
   return b;
 }
 
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots)
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits)
 {
   // A bucket is a 128-byte line.  Size for at most ~10 keys per 16-slot line
   // (fmt 8) or ~5 per 8-slot line (fmt 16): with a power-of-two line count the
@@ -258,6 +259,23 @@ void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t
     uint32_t lb = ceil_log2((n_keys + 9) / 10 + 1);
     if (lb > kbits) lb = kbits;               // tiny k: at most one possible key per line
     if (kbits - lb <= 27) { fmt = 8; line_bits = lb; rem_bits = kbits - lb; }
+  }
+  // slack: 2^slack_bits times the lines.  Halving the load makes a full home line (and with it the slow path of the
+  // probe) a rarity -- 1 % -> 0.001 % of the lines at 16 slots, 6 % -> 0.1 % at 8 slots -- for twice the memory.
+  // Measured (r02c): 16-slot lines (chr22 shape, k = 20) gain 1.3 % per step, not worth 1 GB; 8-slot lines (MHC shape,
+  // k = 32) gain 13 % and the probe kernel alone halves its time.  Hence auto (-1): one extra bit for 16-byte slots
+  // while the table stays below 1/16 of the device memory (11 GB on a 180 GB B200), none for 8-byte slots.
+  if (slack_bits < 0) {
+    size_t free_b = 0, total_b = 0;
+    slack_bits = 0;
+    if (fmt == 16 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (256ull << line_bits) <= total_b / 16 &&
+        (256ull << line_bits) <= free_b / 4)
+      slack_bits = 1;
+  }
+  for (int i = 0; i < slack_bits; ++i) {
+    if (fmt == 8 && (rem_bits == 0 || line_bits + 1 > kbits)) break;
+    ++line_bits;
+    if (fmt == 8) --rem_bits;
   }
   if (line_bits > 32) throw ArgError("table too large");   // line indices travel as 32-bit values
   const uint64_t n_lines = 1ull << line_bits;

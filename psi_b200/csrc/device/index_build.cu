@@ -321,7 +321,7 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   sh.multi.ensure((uint64_t)multi_words + 4);
 
-  table_alloc(c, sh.index, n_runs, 2 * c.k, (uint64_t)n_runs / 512 + 1024);
+  table_alloc(c, sh.index, n_runs, 2 * c.k, (uint64_t)n_runs / 512 + 1024, c.opt_index_slack);
   if (sh.index.view.fmt == 8)
     insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
   else
@@ -672,6 +672,10 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   }
   else if (n == "l2_persist") {
     c.opt_l2_persist = value != 0;     // takes effect at the next set_graph
+  }
+  else if (n == "index_slack") {
+    if (value < -1 || value > 3) throw ArgError("set_option: index_slack is -1 (auto), 0, 1, 2 or 3 extra doublings of the bucket count");
+    c.opt_index_slack = (int)value;     // takes effect at the next set_paths / find_loci / set_loci
   }
   else if (n == "fused") {
     c.opt_fused = value != 0;
