@@ -152,6 +152,8 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
  *                       (the reference's scheme), 2 always materialise those walks into the index;
  *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28);
+ *   "build_group_windows" set_paths indexes the paths in groups of at most this many k-windows (32 B of scratch each;
+ *                       default 0 = what the free device memory allows, at most 2^30) and merges the groups' distinct pairs;
  *   "index_slack"       extra doublings of the index's bucket count: fewer full buckets (slow-path probes) for twice
  *                       the memory each; -1 (default) = 1 for 16-byte slots (k > ~27) while the index stays small, else 0.
  * Any time (they select among kernels that produce the same records):

@@ -197,6 +197,7 @@ struct Ctx {
   // ---- options (psi_b200_set_option) ----
   int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
+  uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
   int opt_fused_ctas = 4;                      // resident CTAs per SM the fused kernel is compiled for (3, 4 or 5)

@@ -52,7 +52,7 @@ __device__ __forceinline__ uint32_t path_of_entry(const PathsView& p, uint64_t e
 // the PATH's successors.  count_only: just count valid windows.
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(256)
-path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t n_entries,
+path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint64_t e_end,
                     uint64_t* __restrict__ out_kmer, uint32_t* __restrict__ out_gpos,
                     unsigned long long* __restrict__ out_count)
 {
@@ -60,7 +60,7 @@ path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t n_entries,
   const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long local_count = 0;
-  for (uint64_t e = warp0; e < n_entries; e += n_warps) {
+  for (uint64_t e = e_begin + warp0; e < e_end; e += n_warps) {
     const uint32_t pi = path_of_entry(p, e);
     const uint64_t pbeg = __ldg(p.path_ptr + pi), pend = __ldg(p.path_ptr + pi + 1);
     const uint32_t head = p.head_off ? __ldg(p.head_off + pi) : 0;
@@ -389,27 +389,61 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   unsigned long long* d_cnt = c.dev_counters.p + DC_AUX;
   PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
 
-  // pass 1: count valid windows
-  const unsigned wgrid = (unsigned)std::min<uint64_t>((n_entries + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
-  path_windows_kernel<true><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, nullptr, nullptr, d_cnt);
-  ++c.counters.launches;
-  unsigned long long n_pairs = 0;
-  PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
+  // The paths are indexed in groups: a group's windows are materialised, sorted and made unique (32 B of scratch per
+  // window), then merged into the resident set of distinct pairs.  A group holds as many consecutive paths as fit the
+  // window budget, so the usual case -- everything fits -- is one group and no merge.
+  std::vector<NodeRec> h_rec(sh.n_nodes);
+  PSI_CUDA(cudaMemcpyAsync(h_rec.data(), sh.node_rec.p, (size_t)sh.n_nodes * sizeof(NodeRec), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  if (n_pairs >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows (index them in several contexts)");
-  c.counters.n_path_bases = n_pairs;
-
-  // pass 2: emit (kmer, gpos), sort, unique -> the resident on-path pairs
-  if (n_pairs) {
+  uint64_t budget = c.opt_build_group_windows;
+  if (budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    budget = 1ull << 30;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min<uint64_t>(budget, std::max<uint64_t>(free_b / 48, 1u << 20));
+  }
+  sh.on_kmer.release(); sh.on_gpos.release();
+  sh.n_on_pairs = 0;
+  uint64_t n_windows_total = 0;
+  for (uint64_t g0 = 0; g0 < n_paths;) {
+    uint64_t g1 = g0, bases = 0;
+    while (g1 < n_paths) {
+      uint64_t b = 0;
+      for (uint64_t e = path_ptr[g1]; e < path_ptr[g1 + 1]; ++e) b += h_rec[path_nodes[e]].seq_len;
+      if (g1 > g0 && bases + b > budget) break;
+      bases += b;
+      ++g1;
+    }
+    const uint64_t e0 = path_ptr[g0], e1 = path_ptr[g1];
+    g0 = g1;
+    if (e1 == e0) continue;
+    // pass 1: count valid windows
+    const unsigned wgrid = (unsigned)std::min<uint64_t>((e1 - e0 + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
+    PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+    path_windows_kernel<true><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, nullptr, nullptr, d_cnt);
+    ++c.counters.launches;
+    unsigned long long n_pairs = 0;
+    PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    if (n_pairs + sh.n_on_pairs >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows in one group of paths plus the resident pairs");
+    n_windows_total += n_pairs;
+    if (n_pairs == 0) continue;
+    // pass 2: emit (kmer, gpos), sort, unique; merge with what the earlier groups left
+    const uint64_t n_acc = sh.n_on_pairs;
     DevBuf<uint64_t> kmer_a;
     DevBuf<uint32_t> gpos_a;
-    kmer_a.ensure(n_pairs); gpos_a.ensure(n_pairs);
+    kmer_a.ensure(n_pairs + n_acc); gpos_a.ensure(n_pairs + n_acc);
     PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-    path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, n_entries, kmer_a.p, gpos_a.p, d_cnt);
+    path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt);
     ++c.counters.launches;
-    sh.on_kmer.release(); sh.on_gpos.release();
-    sh.n_on_pairs = sort_unique_pairs(c, kmer_a, gpos_a, n_pairs, sh.on_kmer, sh.on_gpos);
+    if (n_acc) {
+      PSI_CUDA(cudaMemcpyAsync(kmer_a.p + n_pairs, sh.on_kmer.p, n_acc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c.stream));
+      PSI_CUDA(cudaMemcpyAsync(gpos_a.p + n_pairs, sh.on_gpos.p, n_acc * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      sh.on_kmer.release(); sh.on_gpos.release();
+    }
+    sh.n_on_pairs = sort_unique_pairs(c, kmer_a, gpos_a, n_pairs + n_acc, sh.on_kmer, sh.on_gpos);
   }
+  c.counters.n_path_bases = n_windows_total;
   build_table(c, nullptr, nullptr, 0);
   sh.has_index = true;
   timer.stop();
@@ -672,6 +706,10 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   }
   else if (n == "l2_persist") {
     c.opt_l2_persist = value != 0;     // takes effect at the next set_graph
+  }
+  else if (n == "build_group_windows") {
+    if (value < 0) throw ArgError("set_option: build_group_windows must be >= 0 (0 = from the free device memory)");
+    c.opt_build_group_windows = (uint64_t)value;     // takes effect at the next set_paths
   }
   else if (n == "index_slack") {
     if (value < -1 || value > 3) throw ArgError("set_option: index_slack is -1 (auto), 0, 1, 2 or 3 extra doublings of the bucket count");

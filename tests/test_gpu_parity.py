@@ -412,6 +412,31 @@ def test_counters_report_kernel_launches_and_index_shape():
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["x_k12", "m_k20", "multi_k32", "fuzz_08"])
+def test_index_built_in_groups_of_paths_is_the_same_index(name):
+    """set_paths materialises the paths' k-windows in groups that fit a window budget and merges the groups' distinct
+    (k-mer, locus) pairs; a budget of a few thousand windows (one or two paths per group here) must give the very
+    same index -- entries, k-mers, starting loci -- and seed set as one group."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ps = g.pick_paths(max(c["n_paths"], 6), seed=2)
+    out = []
+    for budget in (0, 3000):
+        ctx = capi.Context(c["k"], 0)
+        ctx.set_option("build_group_windows", budget)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(ps)
+        n_loci = ctx.find_loci()
+        cn = ctx.counters()
+        rec, total = run_chunks(ctx, rp, bases, c["d"], 0)
+        on, _ = run_chunks(ctx, rp, bases, c["d"], 0, capi.ON_PATHS)
+        out.append((cn["n_path_bases"], cn["n_index_entries"], cn["n_index_kmers"], n_loci, util.md5_tuples(capi.canonical(rec)),
+                    util.md5_tuples(capi.canonical(on))))
+        assert out[-1][4] == c["md5"]
+        ctx.close()
+    assert out[0] == out[1]
+
+
 def test_offpath_budget_falls_back_to_walking():
     """auto mode materialises only when the walks fit the budget; the seed set does not depend on the mode."""
     c = CASES["m_k20"]
@@ -464,6 +489,44 @@ def test_random_larger_graph_properties(mode):
     # error-free reads: every seed of every read is found at least once
     assert len(np.unique(a[:, :2], axis=0)) == 20000 * 5
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_fresh_graphs_all_routes_vs_oracle(seed):
+    """Fuzz loop of SURVEY 8c on graphs that are NOT among the committed goldens: a fresh random bubble graph per
+    seed (N bases and multi-allelic sites in some), random-walk reads with a few errors, k / d / number of paths
+    drawn per seed; every device route against the oracle's closed form, on-path and off-path phases partition it."""
+    import tempfile, os
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.choice([8, 11, 12, 16, 19, 20, 24, 27, 28, 31, 32]))
+    d = int(rng.choice([1, max(1, k // 2), k, k + 5]))
+    n_paths = int(rng.choice([1, 2, 3, 4, 8]))
+    text = util.random_bubble_gfa(500 + seed, backbone=int(rng.integers(2500, 9000)), sites=int(rng.integers(60, 700)),
+                                  p_snp=float(rng.choice([0.6, 0.8, 1.0])), p_ins=0.1, n_frac=float(rng.choice([0.0, 0.0, 0.002])),
+                                  multi_allele=float(rng.choice([0.0, 0.1, 0.4])))
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "f.gfa")
+        open(p, "w").write(text)
+        g = capi.Graph.load_gfa(p)
+    rp, bases = util.random_walk_reads(g, 600, int(rng.integers(max(k, 40), 130)), seed=seed)
+    bases = bases.copy()
+    flip = rng.random(len(bases)) < 0.01
+    bases[flip] = np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, int(flip.sum()))]
+    og, orr = orc.OGraph.of(g), orc.OReads(rp, bases, 5)
+    want, _ = orc.seeds_closed_form(og, orr, k, d)
+    for mode in ROUTES:
+        ctx, _ = make_ctx(g, k, n_paths, seed=seed, mode=mode)
+        ctx.submit_chunk(rp, bases, 5, d)
+        n = ctx.seeds_all()
+        got = capi.canonical(ctx.fetch())
+        assert n == len(got), (k, d, n_paths, mode)
+        assert np.array_equal(got, want), (k, d, n_paths, mode)
+        n_on = ctx.seeds_all(capi.ON_PATHS)
+        on = capi.canonical(ctx.fetch())
+        n_off = ctx.seeds_all(capi.OFF_PATHS)
+        off = capi.canonical(ctx.fetch())
+        assert n_on + n_off == n and np.array_equal(np.unique(np.concatenate([on, off]), axis=0), want), (k, d, n_paths, mode)
+        ctx.close()
 
 
 @pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
