@@ -44,6 +44,9 @@ SHAPES = {
     # backbone, sites, p_snp, p_ins, tri_frac, seeds
     "chr22": dict(backbone=51_000_000, sites=1_000_000, p_snp=0.90, p_ins=0.05, tri_frac=0.0, seeds=(22, 23)),
     "chr22_1_51": dict(backbone=1_000_000, sites=19_608, p_snp=0.90, p_ins=0.05, tri_frac=0.0, seeds=(22, 23)),
+    # a chromosome-1-sized instance of the chr22 recipe (5x): exercises the grouped index build (16 paths x 255 Mbp = 4 G
+    # path windows) and a 5.4 GB index
+    "chr1": dict(backbone=250_000_000, sites=4_900_000, p_snp=0.90, p_ins=0.05, tri_frac=0.0, seeds=(1, 2)),
     "mhc": dict(backbone=5_000_000, sites=416_667, p_snp=1.0, p_ins=0.0, tri_frac=0.10, seeds=(6, 7)),
 }
 
