@@ -300,12 +300,17 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 build_read_index_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const uint8_t* __restrict__ seed_valid,
                         const unsigned long long* __restrict__ n_seeds_p, uint32_t* __restrict__ seed_next,
-                        unsigned long long* __restrict__ err_flag)
+                        unsigned long long* __restrict__ err_flag, uint32_t* __restrict__ pfx_bits, uint32_t pfx)
 {
   const uint32_t n_seeds = (uint32_t)*n_seeds_p;
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_seeds) return;
   if (!seed_valid[s]) { seed_next[s] = NIL32; return; }
+  {
+    // the prefix filter the walker prunes with (seeds.cu, ReadIndexSink::prune)
+    const uint32_t i = (uint32_t)(seed_kmer[s] & low_mask64(2u * pfx));
+    atomicOr(pfx_bits + (i >> 5), 1u << (i & 31u));
+  }
   uint32_t prev = NIL32;
   if (!table_insert<FMT>(t, seed_kmer[s], s, 0, true, prev)) { atomicOr(err_flag, 2ull); prev = NIL32; }
   seed_next[s] = prev;
@@ -423,12 +428,18 @@ void engine_index_chunk(Ctx& c)
   c.seed_next.ensure(c.n_seeds_cap, 1.25);
   unsigned long long* d_err = c.dev_counters.p + DC_ERR;
   table_alloc(c, c.read_index, c.n_seeds_cap, 2 * c.k, c.n_seeds_cap / 256 + 1024);
+  c.filter_pfx = c.k < FILTER_PFX ? c.k : FILTER_PFX;
+  const size_t filter_words = ((size_t)1 << (2 * c.filter_pfx)) / 32 + 1;
+  c.filter_bits.ensure(filter_words);
+  PSI_CUDA(cudaMemsetAsync(c.filter_bits.p, 0, filter_words * sizeof(uint32_t), c.stream));
   if (c.read_index.view.fmt == 8)
     build_read_index_kernel<8><<<grid_for(c.n_seeds_cap, 256), 256, 0, c.stream>>>(
-        c.read_index.view, c.seed_kmer.p, c.seed_valid.p, c.dev_counters.p + DC_SEEDS, c.seed_next.p, d_err);
+        c.read_index.view, c.seed_kmer.p, c.seed_valid.p, c.dev_counters.p + DC_SEEDS, c.seed_next.p, d_err,
+        c.filter_bits.p, c.filter_pfx);
   else
     build_read_index_kernel<16><<<grid_for(c.n_seeds_cap, 256), 256, 0, c.stream>>>(
-        c.read_index.view, c.seed_kmer.p, c.seed_valid.p, c.dev_counters.p + DC_SEEDS, c.seed_next.p, d_err);
+        c.read_index.view, c.seed_kmer.p, c.seed_valid.p, c.dev_counters.p + DC_SEEDS, c.seed_next.p, d_err,
+        c.filter_bits.p, c.filter_pfx);
   ++c.counters.launches;
   t.stop();
   PSI_CUDA(cudaGetLastError());

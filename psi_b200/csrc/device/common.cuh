@@ -105,6 +105,10 @@ __host__ __device__ __forceinline__ uint64_t mix_kb(uint64_t x, uint32_t kb)
 // fmt 16 slot: full k-mer, payload, flags (bit 0 list, bit 1 off-path; NIL32 = empty).
 
 constexpr uint32_t MAX_DISP = 7;
+// walk mode: the per-chunk bitmap of seed prefixes has 2 * min(k, FILTER_PFX) bits of index -- 8 MB at most, resident
+// in L2 while the graph is walked.  (A second filter on the whole k-mer at depth k was measured too: after the prefix
+// pruning too few walks complete for it to pay for the atomics that build it.)
+constexpr uint32_t FILTER_PFX = 13;
 constexpr uint32_t FLAG_MULTI = 1u;
 constexpr uint32_t FLAG_OFF = 2u;
 

@@ -172,6 +172,8 @@ struct Ctx {
   DevBuf<uint8_t> seed_valid;    // per seed: 1 = only A/C/G/T inside
   DevBuf<uint32_t> seed_next;    // chain links of the read index
   HostTable read_index;
+  DevBuf<uint32_t> filter_bits;  // walk mode: bitmap of the seeds' prefixes (see ReadIndexSink)
+  uint32_t filter_pfx = 0;       // bases of a prefix (min(k, FILTER_PFX))
   DevBuf<char> scan_tmp;
   uint64_t* h_pinned = nullptr;  // small pinned scratch for async counter read-back
 

@@ -476,6 +476,7 @@ struct UncoveredSink {
   {
     return (((volatile const uint32_t*)flags)[origin >> 5] >> (origin & 31u)) & 1u;
   }
+  __device__ bool prune(uint64_t, uint32_t, uint32_t) const { return false; }
   __device__ void complete(uint64_t kmer, uint32_t origin)
   {
     if (!has_index || !index_contains(t, multi, kmer, origin)) atomicOr(flags + (origin >> 5), 1u << (origin & 31u));
@@ -540,6 +541,7 @@ struct OffPathSink {
   uint64_t cap;
   unsigned long long* count;
   __device__ bool skip(uint32_t) const { return false; }
+  __device__ bool prune(uint64_t, uint32_t, uint32_t) const { return false; }
   __device__ void complete(uint64_t kmer, uint32_t origin)
   {
     if (has_table && index_contains(t, multi, kmer, origin)) return;

@@ -160,6 +160,8 @@ seeds_slow_kernel(KmerTable t, const uint32_t* __restrict__ multi, const uint64_
 //     claim (chain head, locus) in a device hash set reports, the others skip.
 
 struct ReadIndexSink {
+  const uint32_t* pfx_bits;     // bitmap of the first `pfx` bases of every read seed (2 pfx bits of index)
+  uint32_t pfx;                 // 0: no prefix filter
   KmerTable rt;                 // chunk read index
   const uint32_t* next;         // seed chains
   KmerTable pt;                 // path index
@@ -176,6 +178,16 @@ struct ReadIndexSink {
   uint32_t walks;
 
   __device__ bool skip(uint32_t) const { return false; }
+
+  // The reference's traverser stops a walk as soon as its prefix is no prefix of a read seed (it descends the seeds'
+  // suffix tree base by base, traverser_bfs.hpp:124-131).  Same pruning, one bit test: when a walk's depth crosses
+  // `pfx`, its first pfx bases must be the prefix of some seed of the chunk.
+  __device__ bool prune(uint64_t kmer, uint32_t d0, uint32_t d1) const
+  {
+    if (d0 >= pfx || d1 < pfx) return false;
+    const uint32_t i = (uint32_t)(kmer & low_mask64(2u * pfx));
+    return !((__ldg(pfx_bits + (i >> 5)) >> (i & 31u)) & 1u);
+  }
 
   __device__ bool claim(uint64_t key)
   {
@@ -441,6 +453,8 @@ void engine_seeds(Ctx& c, unsigned flags)
         const unsigned grid = (unsigned)c.sm_count * 8;
         c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
         ReadIndexSink sink;
+        sink.pfx_bits = c.filter_bits.p;
+        sink.pfx = c.filter_pfx;
         sink.rt = c.read_index.view;
         sink.rt.stash_nonempty = 1;  // not known without a sync; probing an empty stash costs one load, and only for full lines
         sink.next = c.seed_next.p;

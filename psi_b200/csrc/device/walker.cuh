@@ -86,7 +86,9 @@ struct WalkStack {
 };
 
 // Source: yields the initial state of work item `idx` (false = nothing to do).
-// Sink:   skip(origin) -> drop a state early; complete(kmer, origin) at depth k.
+// Sink:   skip(origin) -> drop a state early; prune(kmer, d0, d1) -> drop a state whose depth just went from d0 to d1 < k
+//         (the reference prunes a walk as soon as its prefix is no prefix of a read seed, traverser_bfs.hpp:124-131);
+//         complete(kmer, origin) at depth k.
 template <class Source, class Sink>
 __device__ void walk_all(const GraphView& g, uint32_t k, uint64_t n_items, unsigned long long* work_counter,
                          WalkItem* smem_all, WalkItem* spill_all, uint32_t spill_items,
@@ -143,6 +145,7 @@ __device__ void walk_all(const GraphView& g, uint32_t k, uint64_t n_items, unsig
         else {
           it.kmer |= extract_bases(g.seq2, p, take) << (2u * it.depth);
           it.depth += take;
+          if (it.depth < k && sink.prune(it.kmer, it.depth - take, it.depth)) alive = false;
         }
       }
       if (alive) {
