@@ -198,7 +198,8 @@ int  psi_b200_set_loci(psi_b200_ctx* ctx, uint64_t n_loci,
 int  psi_b200_submit_chunk(psi_b200_ctx* ctx, uint64_t n_reads,
                            const uint64_t* read_ptr, const char* bases,
                            uint64_t first_read_id, unsigned distance);
-/* Same with read_ptr/bases already resident in device memory. */
+/* Same with read_ptr/bases already resident in device memory.  The kernels read the chunk in aligned 32-bit words:
+ * d_bases must be readable up to the next multiple of 4 bytes past n_bases (true of any cudaMalloc'ed buffer). */
 int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
                                   const uint64_t* d_read_ptr, const char* d_bases,
                                   uint64_t n_bases, uint64_t first_read_id,
