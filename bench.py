@@ -262,8 +262,9 @@ def main_gpu(args):
         batches_d.append((hp.to(dev), hb.to(dev)))
     # e2e runs two pipelines (the context and a fork sharing its resident index) from two host threads, so that
     # the upload of one batch overlaps the kernels and the download of the previous one (PCIe is full duplex)
-    n_pipes = max(1, args.pipelines)
-    pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
+    n_pipes = max(1, args.pipelines)                 # e2e: two pipelines keep both PCIe directions busy; more only contend
+    n_vpipes = max(1, args.value_pipelines)          # resident inputs: four pipelines let one kernel's tail overlap the next
+    pipes = [ctx] + [ctx.fork() for _ in range(max(n_pipes, n_vpipes) - 1)]
     rec_hosts = [torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory() for _ in range(n_pipes)]   # room for the seed records
     torch.cuda.synchronize()
 
@@ -287,9 +288,9 @@ def main_gpu(args):
         pipes[p].submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
         return pipes[p].seeds_all(capi.ALL)
 
-    def timed_e2e(steps, warmup, step_fn=step_e2e):
-        """K steps through the C-ABI, round-robin over the pipelines, one host thread each."""
-        for i in range(warmup):
+    def timed_e2e(steps, warmup, step_fn=step_e2e, n_pipes=n_pipes):
+        """K steps through the C-ABI, round-robin over the first n_pipes pipelines, one host thread each."""
+        for i in range(max(warmup, n_pipes)):
             step_fn(i, i % n_pipes)
         barrier()
         for cx in pipes:
@@ -361,7 +362,7 @@ def main_gpu(args):
     ms_e2e_wide, hits_e2e_wide, _ = timed_e2e(args.steps, args.warmup, lambda i, p=0: step_e2e(i, p, compact=False))
     # the resident-input step again with the pipelines running concurrently (kernels of one chunk fill the launch and
     # latency gaps of the other); `value` stays the single-pipeline figure the per-kernel timers belong to
-    ms_pipe, hits_pipe, launches_pipe = timed_e2e(args.steps, args.warmup, step_resident)
+    ms_pipe, hits_pipe, launches_pipe = timed_e2e(args.steps, args.warmup, step_resident, n_vpipes)
     assert hits_e2e == hits_e2e_wide == hits_pipe == hits_dev, (hits_e2e, hits_e2e_wide, hits_pipe, hits_dev)
     # the same resident step through the separate seeding / probe / resolve kernels: per-kernel times, and the
     # seeds_on_paths probe alone for its own roofline
@@ -397,11 +398,11 @@ def main_gpu(args):
     if rank == 0:
         peak, peak_src = peaks()
         reads_total, seeds_total, hits_total, hits_on_total, walks_total = tot
-        # value: K steps issued round-robin over the pipelines (the context and its forks share one resident index; a
+        # value: K steps issued round-robin over --value-pipelines contexts (the context and its forks share one resident index; a
         # pipeline's host-side launch and read-back gaps are filled by the other's kernels) -- the way the library is
         # meant to be driven, and the way e2e is measured.  The one-pipeline loop, whose per-kernel CUDA-event times
         # feed `kernel_ms_per_step` and `roofline`, is reported beside it.
-        ms_value = ms_pipe if n_pipes > 1 else ms_dev
+        ms_value = ms_pipe if n_vpipes > 1 else ms_dev
         value = reads_total / (ms_value * 1e-3)
         # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches.  Algorithmic bytes per launch =
         # seeds x (8 B packed k-mer + 128 B = ONE index bucket line, the DRAM access unit: profiles/r01c_gather_peak.md)
@@ -454,7 +455,8 @@ def main_gpu(args):
                        "l2": f"{N_BATCHES} distinct read batches cycled ({N_BATCHES * n_reads * READ_LEN / 1e6:.0f} MB) and a "
                              f"{c0['index_bytes'] / 1e6:.0f} MB index: inputs larger than L2",
                        "sharding": "reads sharded by rank, graph + index replicated, NCCL all-reduce of counts only",
-                       "pipelines": f"{n_pipes} contexts per GPU sharing one resident index, steps issued round-robin (value and e2e)"},
+                       "pipelines": f"contexts per GPU sharing one resident index, steps issued round-robin: {n_vpipes} for value "
+                                    f"(inputs resident), {n_pipes} for e2e (more only contend for PCIe)"},
             "seeds_per_s": hits_total / (ms_value * 1e-3), "query_seeds_per_s": seeds_total / (ms_value * 1e-3),
             "kernel_ms_per_step": per_step, "probe_slow_seeds_per_step": acc["n_on_probe_sectors"] / args.steps,
             "e2e": {"value": e2e_value, "unit": "reads/s",
@@ -470,7 +472,7 @@ def main_gpu(args):
             "value_one_pipeline": {"value": reads_total / (ms_dev * 1e-3), "unit": "reads/s", "ms_per_step": ms_dev / args.steps,
                                    "note": "the same K steps on ONE context, each step synchronised before the next is issued; "
                                            "kernel_ms_per_step and roofline are this loop's CUDA-event times"},
-            "gpu_launches": int(launches_pipe if n_pipes > 1 else launches), "gpu_launches_e2e": int(launches_e2e),
+            "gpu_launches": int(launches_pipe if n_vpipes > 1 else launches), "gpu_launches_e2e": int(launches_e2e),
             "offpath_mode": "index (walks from the starting loci materialised into the index)" if c_last["offpath_mode"] == 2
                             else "walk (graph walked from the starting loci for every chunk)",
             "roofline": roof,
@@ -515,6 +517,7 @@ def main():
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
+    ap.add_argument("--value-pipelines", type=int, default=4, help="value (inputs resident in HBM): contexts driven concurrently")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()
