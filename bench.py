@@ -263,7 +263,10 @@ def main_gpu(args):
     # e2e runs two pipelines (the context and a fork sharing its resident index) from two host threads, so that
     # the upload of one batch overlaps the kernels and the download of the previous one (PCIe is full duplex)
     n_pipes = max(1, args.pipelines)                 # e2e: two pipelines keep both PCIe directions busy; more only contend
-    n_vpipes = max(1, args.value_pipelines)          # resident inputs: four pipelines let one kernel's tail overlap the next
+    # resident inputs: four pipelines let one chunk's kernel tail overlap the next one's head (5.4 vs 4.7 G reads/s on one
+    # GPU), but every pipeline is a host thread that spins in its stream synchronisation: with fewer than 8 host cores
+    # per rank (8 ranks on this 32-core box) four of them get in each other's way (35.2 vs 37.1 G reads/s at 8 GPUs)
+    n_vpipes = args.value_pipelines if args.value_pipelines > 0 else (4 if (os.cpu_count() or 1) // world >= 8 else 2)
     pipes = [ctx] + [ctx.fork() for _ in range(max(n_pipes, n_vpipes) - 1)]
     rec_hosts = [torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory() for _ in range(n_pipes)]   # room for the seed records
     torch.cuda.synchronize()
@@ -517,7 +520,8 @@ def main():
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
-    ap.add_argument("--value-pipelines", type=int, default=4, help="value (inputs resident in HBM): contexts driven concurrently")
+    ap.add_argument("--value-pipelines", type=int, default=0,
+                    help="value (inputs resident in HBM): contexts driven concurrently; 0 = 4 with >= 8 host cores per rank, else 2")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()
