@@ -240,6 +240,8 @@ def main_gpu(args):
     for kv in args.opt:
         name, val = kv.split("=")
         ctx.set_option(name, int(val))
+    if args.blocking_sync:
+        ctx.set_option("blocking_sync", 1)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_graph(g, ids="internal")
     ctx.set_paths(ps)
@@ -522,6 +524,7 @@ def main():
     ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
     ap.add_argument("--value-pipelines", type=int, default=0,
                     help="value (inputs resident in HBM): contexts driven concurrently; 0 = 4 with >= 8 host cores per rank, else 2")
+    ap.add_argument("--blocking-sync", type=int, default=0, help="1: pipelines sleep on a blocking event instead of spinning")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()

@@ -159,6 +159,8 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  * Any time (they select among kernels that produce the same records):
  *   "fused"             1 (default): when the index answers the requested phases by itself, a chunk is ONE kernel
  *                       (seeding + probe + records); 0: separate seeding / probe / resolve kernels;
+ *   "blocking_sync"     1: seeds_all / fetch wait on a blocking event (the host thread sleeps) instead of spinning in
+ *                       cudaStreamSynchronize -- for more pipelines than host cores per GPU; default 0;
  *   "fused_ctas"        resident CTAs per SM the fused kernel is compiled for: 3, 4 (default) or 5;
  *   "seeding_mode", "resolve_items", "resolve_ctas", "l2_persist": variants of the separate kernels. */
 int  psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value);

@@ -148,6 +148,7 @@ struct Ctx {
   std::string error;
   psi_b200_counters_t counters{};
   cudaEvent_t ev[24]{};
+  cudaEvent_t ev_sync = nullptr;   // cudaEventBlockingSync: lets a host thread sleep while it waits for its chunk
   int ev_state[12]{};   // 0 never recorded, 1 started, 2 start+stop recorded
 
   std::shared_ptr<Shared> sh = std::make_shared<Shared>();
@@ -201,6 +202,7 @@ struct Ctx {
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
+  int opt_blocking_sync = 0;                   // 1: wait for a chunk on a blocking event (thread sleeps) instead of spinning
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
   int opt_fused_ctas = 4;                      // resident CTAs per SM the fused kernel is compiled for (3, 4 or 5)
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads

@@ -61,6 +61,17 @@ struct PhaseTimer {
   }
 };
 
+// Wait until everything queued on the context's stream is done.  Spinning (cudaStreamSynchronize) reacts fastest; with
+// more pipelines than host cores per GPU the spinners starve each other, so "blocking_sync" lets the thread sleep.
+inline void ctx_wait(Ctx& c)
+{
+  if (c.opt_blocking_sync && c.ev_sync) {
+    PSI_CUDA(cudaEventRecord(c.ev_sync, c.stream));
+    PSI_CUDA(cudaEventSynchronize(c.ev_sync));
+  }
+  else PSI_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 inline unsigned grid_for(uint64_t items, unsigned block, unsigned items_per_thread = 1)
 {
   uint64_t per_block = (uint64_t)block * items_per_thread;

@@ -477,7 +477,7 @@ void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact)
     c.counters.launches += 2;
     PSI_CUDA(cudaGetLastError());
     PSI_CUDA(cudaMemcpyAsync(c.h_pinned, dc, DC_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
-    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    ctx_wait(c);
     const uint64_t n_total = c.h_pinned[DC_HITS], n_slow = c.h_pinned[DC_SLOW];
     bool retry = false;
     if (n_slow > c.slow_items.cap) { c.slow_items.ensure(n_slow, 1.25); retry = true; }

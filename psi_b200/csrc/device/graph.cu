@@ -81,6 +81,7 @@ Ctx* engine_create(int device, unsigned seed_len)
     }
   }
   for (auto& ev : c->ev) PSI_CUDA(cudaEventCreate(&ev));
+  PSI_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
   c->dev_counters.ensure(DC_COUNT);
   PSI_CUDA(cudaMemsetAsync(c->dev_counters.p, 0, DC_COUNT * sizeof(unsigned long long), c->stream));
   PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, (2 * DC_COUNT + 8) * sizeof(uint64_t), cudaHostAllocDefault));
@@ -111,6 +112,7 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
   c->opt_fused = parent.opt_fused;
+  c->opt_blocking_sync = parent.opt_blocking_sync;
   c->opt_index_slack = parent.opt_index_slack;
   c->opt_fused_ctas = parent.opt_fused_ctas;
   c->opt_resolve_items = parent.opt_resolve_items;
@@ -127,6 +129,7 @@ void engine_destroy(Ctx* c)
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->ev_sync) cudaEventDestroy(c->ev_sync);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

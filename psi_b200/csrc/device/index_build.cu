@@ -717,6 +717,9 @@ void engine_set_option(Ctx& c, const char* name, long long value)
     if (value < -1 || value > 3) throw ArgError("set_option: index_slack is -1 (auto), 0, 1, 2 or 3 extra doublings of the bucket count");
     c.opt_index_slack = (int)value;     // takes effect at the next set_paths / find_loci / set_loci
   }
+  else if (n == "blocking_sync") {
+    c.opt_blocking_sync = value != 0;
+  }
   else if (n == "fused") {
     c.opt_fused = value != 0;
   }

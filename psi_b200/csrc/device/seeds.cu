@@ -606,7 +606,7 @@ void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact)
   PhaseTimer t(c, T_D2H);
   if (n) PSI_CUDA(cudaMemcpyAsync(hits, c.records.p, n * (compact ? 16u : 32u), cudaMemcpyDeviceToHost, c.stream));
   t.stop();
-  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  ctx_wait(c);
 }
 
 void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap)
