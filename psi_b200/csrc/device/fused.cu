@@ -56,7 +56,7 @@ template <int K4> struct FusedCfg {
 template <int FMT, int K4, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_id,
-                   const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, uint64_t n_reads,
+                   const char* __restrict__ bases, const uint64_t* __restrict__ read_ptr, uint64_t n_reads, uint32_t R,
                    uint32_t k, uint32_t d, uint32_t mode, uint64_t first_read_id, uint32_t compact,
                    uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, uint64_t cap,
                    SlowItem* __restrict__ slow_queue, uint64_t slow_cap, unsigned long long* __restrict__ dc)
@@ -76,14 +76,14 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   __shared__ unsigned long long s_base;
 
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint64_t r_base = (uint64_t)blockIdx.x * FUSED_READS;
+  const uint64_t r_base = (uint64_t)blockIdx.x * R;     // R <= FUSED_READS reads per CTA (host: enough CTAs to fill the GPU)
 
   // ---- the CTA's reads: start offsets and CTA-local prefix sums of the seed counts (sequence.hpp:1712) ----
   {
     const uint64_t r = r_base + threadIdx.x;
     uint64_t p0 = 0;
     uint32_t mine = 0;
-    if (r < n_reads) {
+    if (threadIdx.x < R && r < n_reads) {
       p0 = read_ptr[r];
       const uint64_t len = read_ptr[r + 1] - p0;
       mine = len >= k ? (uint32_t)((len - k) / d) + 1 : 0;      // reads shorter than k have no seeds
@@ -97,7 +97,7 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
     for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
     s_first[threadIdx.x] = before + incl - mine;
     s_ptr[threadIdx.x] = p0;
-    if (threadIdx.x == FUSED_READS - 1) { s_first[FUSED_READS] = before + incl; s_count = 0; s_on = 0; }
+    if (threadIdx.x == FUSED_READS - 1) { s_first[FUSED_READS] = before + incl; s_count = 0; s_on = 0; }   // threads >= R hold the total
     __syncthreads();
   }
   const uint32_t n_cta_seeds = s_first[FUSED_READS];
@@ -107,7 +107,7 @@ seeds_fused_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ node_i
   const uint32_t per_read = s_first[1];
   bool uniform, one_each;
   {
-    const uint32_t r_in_cta = (uint32_t)min((uint64_t)FUSED_READS, n_reads - r_base);
+    const uint32_t r_in_cta = (uint32_t)min((uint64_t)R, n_reads - r_base);
     const uint32_t mine = threadIdx.x < r_in_cta ? s_first[threadIdx.x + 1] - s_first[threadIdx.x] : per_read;
     uniform = __syncthreads_and(mine == per_read) && per_read > 1u;
     one_each = !uniform && __syncthreads_and(mine == 1u) && per_read == 1u;
@@ -403,8 +403,18 @@ static void launch_fused(Ctx& c, const GraphView& g, unsigned probe_mode, bool c
     PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dv] = true;
   }
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, (c.n_reads + FUSED_READS - 1) / FUSED_READS);
-  kern<<<grid, 256, smem, c.stream>>>(sh.index.view, g, sh.node_id.p, c.d_bases, c.d_read_ptr, c.n_reads, c.k, c.distance,
+  // Reads per CTA: 256 when that gives at least 4 CTAs per resident slot; fewer when the reads are few or long (d = 1,
+  // long reads), but never so few that a CTA has less than 5 batches of seeds (n_seeds_cap is an upper bound).
+  const uint64_t slots = (uint64_t)c.sm_count * MIN_CTAS;
+  uint32_t R = FUSED_READS;
+  if (c.n_reads / FUSED_READS < 4 * slots) {
+    const uint64_t seeds_per_read = std::max<uint64_t>(1, c.n_seeds_cap / std::max<uint64_t>(1, c.n_reads));
+    const uint64_t r_min = (5 * 256 + seeds_per_read - 1) / seeds_per_read;
+    const uint64_t r_fill = (c.n_reads + 4 * slots - 1) / (4 * slots);
+    R = (uint32_t)std::min<uint64_t>(FUSED_READS, std::max<uint64_t>(std::max(r_min, r_fill), 1));
+  }
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, (c.n_reads + R - 1) / R);
+  kern<<<grid, 256, smem, c.stream>>>(sh.index.view, g, sh.node_id.p, c.d_bases, c.d_read_ptr, c.n_reads, R, c.k, c.distance,
                                       probe_mode, c.first_read_id, compact ? 1u : 0u, c.records.p, c.rec_kind.p, out_cap,
                                       c.slow_items.p, c.slow_items.cap, c.dev_counters.p);
 }
