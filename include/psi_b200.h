@@ -119,9 +119,38 @@ typedef struct {
 } psi_b200_chunk_view;
 int  psi_b200_reader_open(const char* path, psi_b200_reader** out);
 /* Loads up to max_reads records (0 = all) into the reader's (pinned when a GPU
- * is present) chunk buffer.  view->n_reads == 0 at end of input. */
+ * is present) chunk buffer.  view->n_reads == 0 at end of input.  The view stays valid until the call after the
+ * NEXT one on this reader (two chunk buffers alternate, so that chunk i+1 can be parsed while chunk i is in flight). */
 int  psi_b200_reader_next(psi_b200_reader* r, uint64_t max_reads, psi_b200_chunk_view* view);
 void psi_b200_reader_close(psi_b200_reader* r);
+
+/* A read chunk as 2-bit words: what Records<Dna5QStringSet> holds after readRecords (sequence.hpp:1608-1624), packed
+ * the way the device consumes it -- 4x fewer bytes over PCIe than the characters.
+ *   words   32 bases per 64-bit word, base i of the chunk at bits [2 (i % 32), +2) of word i / 32 (A, C, G, T = 0..3,
+ *           either case; anything else is stored as 0 and listed in exc), reads back to back in read order;
+ *           n_words = n_bases / 32 + 2 (the kernels read one word past the last base);
+ *   exc     ascending base positions (within the chunk) of the characters outside A/C/G/T: a seed covering one
+ *           never matches;
+ *   read_len  != 0: every read has exactly this many bases and read_ptr may be NULL. */
+typedef struct {
+  uint64_t        n_reads;
+  uint64_t        first_read_id;
+  uint64_t        n_bases;
+  uint32_t        read_len;
+  uint32_t        reserved;
+  const uint64_t* read_ptr;      /* n_reads+1 base offsets, or NULL when read_len != 0 */
+  const uint64_t* words;
+  const uint64_t* exc;
+  uint64_t        n_exc;
+  const uint64_t* name_ptr;      /* reader only; may be NULL */
+  const char*     names;
+} psi_b200_packed_chunk;
+/* readRecords straight into 2-bit words (same record semantics as psi_b200_reader_next; same buffer lifetime). */
+int  psi_b200_reader_next_packed(psi_b200_reader* r, uint64_t max_reads, psi_b200_packed_chunk* chunk);
+/* Packs n_bases characters into words[n_bases / 32 + 2]; positions of characters outside A/C/G/T go to exc (at most
+ * exc_cap of them are stored; *n_exc is their true number).  Host code, any thread. */
+int  psi_b200_pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, uint64_t* exc, uint64_t exc_cap,
+                         uint64_t* n_exc);
 
 const char* psi_b200_global_error(void);
 
@@ -148,7 +177,8 @@ const char* psi_b200_last_error(const psi_b200_ctx* ctx);
  * non-blocking stream). */
 int  psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream);
 int  psi_b200_sync(psi_b200_ctx* ctx);
-/* Tuning knobs.  Set before find_loci / set_loci:
+/* Tuning knobs.  Set before set_paths / find_loci / set_loci:
+ *   "code_by_rank"      1: index entries carry (node rank, offset) even when (node id, offset) would fit (test hook);
  *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
  *                       (the reference's scheme), 2 always materialise those walks into the index;
  *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28);
@@ -161,7 +191,7 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  *                       (seeding + probe + records); 0: separate seeding / probe / resolve kernels;
  *   "blocking_sync"     1: seeds_all / fetch wait on a blocking event (the host thread sleeps) instead of spinning in
  *                       cudaStreamSynchronize -- for more pipelines than host cores per GPU; default 0;
- *   "fused_ctas"        resident CTAs per SM the fused kernel is compiled for: 3, 4 (default) or 5;
+ *   "timers"            0: no CUDA-event records around the kernels of a step (default 1);
  *   "seeding_mode", "resolve_items", "resolve_ctas", "l2_persist": variants of the separate kernels. */
 int  psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value);
 
@@ -207,6 +237,13 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
                                   uint64_t n_bases, uint64_t first_read_id,
                                   unsigned distance);
 
+/* The same for a chunk of 2-bit words (psi_b200_packed_chunk): host memory (on_device == 0; copied asynchronously, see
+ * "buffer lifetime" below) or device memory (on_device != 0; words must be readable for n_bases / 32 + 2 words). */
+int  psi_b200_submit_chunk_packed(psi_b200_ctx* ctx, const psi_b200_packed_chunk* chunk, unsigned distance, int on_device);
+/* Buffer lifetime: submit_chunk / submit_chunk_packed queue asynchronous copies FROM the caller's host buffers on the
+ * context's stream and return; the buffers must stay valid and unchanged until the chunk's seeds_all / wait has
+ * returned (or psi_b200_sync).  psi_b200_reader_next* alternates two buffers for exactly this reason. */
+
 #define PSI_B200_ON_PATHS   1u   /* seeds_on_paths  (seed_finder.hpp:1426-1457) */
 #define PSI_B200_OFF_PATHS  2u   /* seeds_off_paths (seed_finder.hpp:1703-1722) */
 #define PSI_B200_ALL        3u   /* seeds_all       (seed_finder.hpp:1724-1732) */
@@ -214,6 +251,11 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
 #define PSI_B200_NO_RESOLVE 8u   /* keep compact device records only (benchmark of the probe alone) */
 #define PSI_B200_COMPACT   16u   /* resolve into 4 x u32 records (psi_b200_fetch32): same fields, half the bytes over PCIe;
                                     PSI_B200_ERR_ARG when a node id or a read id of the chunk does not fit 32 bits */
+
+#define PSI_B200_DENSE     32u   /* per-seed results instead of per-hit records (psi_b200_fetch_dense): one pair of u32
+                                    {node_id, node_off | off-path << 31} per seed, in seed order; 8 bytes per seed over
+                                    PCIe, read id / offset implied.  Needs the off-path walks in the index (offpath_mode
+                                    0 or 2) and ids below 2^32 - 1; excludes SORTED, NO_RESOLVE, COMPACT */
 
 /* Finds the seeds of the submitted chunk.  The result is the SET of hits
  * (each (read, offset, node, offset) once), resident in device
@@ -223,6 +265,28 @@ int  psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads,
  * canonical order.  The seeding kernels run here, not in submit_chunk: device buffers handed to
  * psi_b200_submit_chunk_device must stay valid until the last seeds_all of the chunk has returned. */
 int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
+
+/* The same, split in two so that one host thread can keep several contexts (psi_b200_fork) busy: seeds_all_async
+ * queues the step on the context's stream and returns; psi_b200_wait blocks until it is done, repeats it with larger
+ * device buffers if one overflowed, and reports the counts.  Between the two only psi_b200_fetch_dense_async may be
+ * called on the context.  Steps the fused kernel cannot serve (walk mode, SORTED, NO_RESOLVE) run to completion inside
+ * seeds_all_async; wait then only reports. */
+int  psi_b200_seeds_all_async(psi_b200_ctx* ctx, unsigned flags);
+int  psi_b200_wait(psi_b200_ctx* ctx, uint64_t* n_hits);
+
+/* Results of a PSI_B200_DENSE step.  Seed s of the chunk (seeds in read order; read r of a chunk of equal-length
+ * reads owns seeds r * per_read .. with per_read = (len - k) / d + 1, offset (s % per_read) * d; sequence.hpp:1712)
+ * has dense[2 s] = node id (0xffffffff: no hit) and dense[2 s + 1] = node offset, bit 31 set when the hit was found
+ * off the indexed paths (seeds_off_paths).  Seeds whose k-mer occurs at several loci have their further hits in
+ * `extra`: 4 x u32 {node_id, node_off, read_id, read_off | off-path << 31} each.  n_hits of the step = dense hits +
+ * n_extra.  fetch_dense copies after a completed step; fetch_dense_async queues the copies behind a step in flight
+ * (the buffers -- pinned, for the copy to be asynchronous -- are valid after psi_b200_wait).  When more than
+ * cap_extra extra records exist the first cap_extra are delivered and *n_extra tells (fetch again with more room). */
+int  psi_b200_fetch_dense(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
+                          uint64_t* n_seeds, uint64_t* n_extra);
+int  psi_b200_fetch_dense_async(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+/* Counts of the last completed dense step. */
+int  psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra);
 
 /* Copies the records of the last seeds_all to the host in the reference
  * CLI's byte layout (src/psikt.cpp:172-181, seed.hpp:32-46): per hit 4 x u64
@@ -268,6 +332,11 @@ typedef struct {
   float ms_h2d, ms_pack, ms_read_index, ms_on, ms_off, ms_resolve, ms_sort, ms_d2h;
   uint32_t launches;           /* kernels of this library launched since create / reset */
   float ms_probe;              /* the seeds_on_paths probe kernel alone (ms_on also covers the slow-queue kernel) */
+  /* sums over the fused steps completed since create / reset (CUDA events on the context's stream; "timers" option) */
+  double ms_probe_sum, ms_on_sum;
+  uint64_t timed_steps;
+  uint32_t code_by_rank;       /* 1: index entries carry (node rank, offset), 0: (node id, offset) -- no gather per hit */
+  uint32_t code_off_bits;
 } psi_b200_counters_t;
 int  psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out);
 int  psi_b200_reset_counters(psi_b200_ctx* ctx);

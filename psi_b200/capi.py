@@ -18,7 +18,8 @@ LIB_PATH = _HERE / "libpsi_b200.so"
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5, -6
-ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE, COMPACT = 1, 2, 3, 4, 8, 16
+ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE, COMPACT, DENSE = 1, 2, 3, 4, 8, 16, 32
+NIL32 = 0xFFFFFFFF
 
 # every symbol include/psi_b200.h declares
 SYMBOLS = [
@@ -26,6 +27,8 @@ SYMBOLS = [
     "psi_b200_graph_get_view", "psi_b200_graph_path", "psi_b200_graph_write_gfa",
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
+    "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
+    "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts",
     "psi_b200_global_error",
     "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
@@ -59,6 +62,13 @@ class ChunkView(C.Structure):
                 ("name_ptr", C.POINTER(C.c_uint64)), ("names", C.POINTER(C.c_char))]
 
 
+class PackedChunk(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("first_read_id", C.c_uint64), ("n_bases", C.c_uint64),
+                ("read_len", C.c_uint32), ("reserved", C.c_uint32),
+                ("read_ptr", C.c_void_p), ("words", C.c_void_p), ("exc", C.c_void_p), ("n_exc", C.c_uint64),
+                ("name_ptr", C.c_void_p), ("names", C.c_void_p)]
+
+
 class Counters(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_edges", C.c_uint64), ("n_bases", C.c_uint64),
                 ("n_path_bases", C.c_uint64), ("n_index_entries", C.c_uint64), ("n_index_kmers", C.c_uint64),
@@ -72,7 +82,9 @@ class Counters(C.Structure):
                 ("ms_index_build", C.c_float), ("ms_find_loci", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_pack", C.c_float), ("ms_read_index", C.c_float), ("ms_on", C.c_float),
                 ("ms_off", C.c_float), ("ms_resolve", C.c_float), ("ms_sort", C.c_float), ("ms_d2h", C.c_float),
-                ("launches", C.c_uint32), ("ms_probe", C.c_float)]
+                ("launches", C.c_uint32), ("ms_probe", C.c_float),
+                ("ms_probe_sum", C.c_double), ("ms_on_sum", C.c_double), ("timed_steps", C.c_uint64),
+                ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
@@ -110,6 +122,14 @@ def lib() -> C.CDLL:
     L.psi_b200_reader_next.argtypes = [vp, C.c_uint64, C.POINTER(ChunkView)]
     L.psi_b200_reader_close.argtypes = [vp]
     L.psi_b200_reader_close.restype = None
+    L.psi_b200_reader_next_packed.argtypes = [vp, C.c_uint64, C.POINTER(PackedChunk)]
+    L.psi_b200_pack_bases.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, u64p]
+    L.psi_b200_submit_chunk_packed.argtypes = [vp, C.POINTER(PackedChunk), C.c_uint, C.c_int]
+    L.psi_b200_seeds_all_async.argtypes = [vp, C.c_uint]
+    L.psi_b200_wait.argtypes = [vp, u64p]
+    L.psi_b200_fetch_dense.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]
+    L.psi_b200_fetch_dense_async.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
+    L.psi_b200_dense_counts.argtypes = [vp, u64p, u64p]
     L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
     L.psi_b200_fork.argtypes = [vp, C.POINTER(vp)]
     L.psi_b200_destroy.argtypes = [vp]
@@ -266,6 +286,18 @@ class Reader:
         names = [names_raw[name_ptr[i]:name_ptr[i + 1]].decode() for i in range(n)]
         return v.first_read_id, read_ptr, bases, names
 
+    def next_packed(self, max_reads=0):
+        """Returns a Packed chunk (2-bit words, numpy copies) or None at end of input."""
+        v = PackedChunk()
+        _check(lib().psi_b200_reader_next_packed(self._h, max_reads, C.byref(v)))
+        if v.n_reads == 0:
+            return None
+        n = v.n_reads
+        read_ptr = np.ctypeslib.as_array(C.cast(v.read_ptr, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        words = np.ctypeslib.as_array(C.cast(v.words, C.POINTER(C.c_uint64)), shape=(v.n_bases // 32 + 2,)).copy()
+        exc = np.ctypeslib.as_array(C.cast(v.exc, C.POINTER(C.c_uint64)), shape=(v.n_exc,)).copy() if v.n_exc else np.zeros(0, np.uint64)
+        return Packed(read_ptr, words, exc, v.read_len, v.first_read_id)
+
     def close(self):
         if self._h:
             lib().psi_b200_reader_close(self._h)
@@ -273,6 +305,53 @@ class Reader:
 
     def __del__(self):
         self.close()
+
+
+class Packed:
+    """A read chunk as 2-bit words (psi_b200_packed_chunk), host side."""
+
+    def __init__(self, read_ptr, words, exc, read_len=0, first_read_id=0):
+        self.read_ptr = np.ascontiguousarray(read_ptr, np.uint64)
+        self.words = np.ascontiguousarray(words, np.uint64)
+        self.exc = np.ascontiguousarray(exc, np.uint64)
+        self.read_len = int(read_len)
+        self.first_read_id = int(first_read_id)
+
+    @property
+    def n_reads(self):
+        return len(self.read_ptr) - 1
+
+    @property
+    def n_bases(self):
+        return int(self.read_ptr[-1])
+
+    @classmethod
+    def pack(cls, read_ptr, bases, first_read_id=0) -> "Packed":
+        """psi_b200_pack_bases over an ASCII chunk."""
+        read_ptr = np.ascontiguousarray(read_ptr, np.uint64)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        n = int(read_ptr[-1])
+        words = np.zeros(n // 32 + 2, np.uint64)
+        n_exc = C.c_uint64()
+        _check(lib().psi_b200_pack_bases(_ptr(bases), n, _ptr(words), None, 0, C.byref(n_exc)))
+        exc = np.zeros(n_exc.value, np.uint64)
+        if n_exc.value:
+            _check(lib().psi_b200_pack_bases(_ptr(bases), n, _ptr(words), _ptr(exc), n_exc.value, C.byref(n_exc)))
+        lens = np.diff(read_ptr.astype(np.int64))
+        uniform = int(lens[0]) if len(lens) and (lens == lens[0]).all() and lens[0] > 0 else 0
+        return cls(read_ptr, words, exc, uniform, first_read_id)
+
+    def struct(self, with_read_ptr=None) -> PackedChunk:
+        """with_read_ptr: None = omit the offsets when all reads have one length."""
+        v = PackedChunk()
+        v.n_reads, v.first_read_id, v.n_bases = self.n_reads, self.first_read_id, self.n_bases
+        use_ptr = (self.read_len == 0) if with_read_ptr is None else with_read_ptr
+        v.read_len = self.read_len
+        v.read_ptr = self.read_ptr.ctypes.data if use_ptr else None
+        v.words = self.words.ctypes.data
+        v.exc = self.exc.ctypes.data if len(self.exc) else None
+        v.n_exc = len(self.exc)
+        return v
 
 
 class Context:
@@ -357,6 +436,43 @@ class Context:
         self._ck(lib().psi_b200_submit_chunk_device(self._h, n_reads, C.c_void_p(d_read_ptr), C.c_void_p(d_bases),
                                                     n_bases, first_read_id, distance))
 
+    def submit_chunk_packed(self, p: Packed, distance=0, with_read_ptr=None):
+        self._chunk_keep = p
+        v = p.struct(with_read_ptr)
+        self._ck(lib().psi_b200_submit_chunk_packed(self._h, C.byref(v), distance, 0))
+
+    def submit_chunk_packed_raw(self, n_reads, n_bases, read_len, words_addr, first_read_id=0, distance=0, on_device=False,
+                                read_ptr_addr=None, exc_addr=None, n_exc=0):
+        """Pointers given as integers (pinned torch tensors / device tensors)."""
+        v = PackedChunk()
+        v.n_reads, v.first_read_id, v.n_bases, v.read_len = n_reads, first_read_id, n_bases, read_len
+        v.read_ptr, v.words, v.exc, v.n_exc = read_ptr_addr, words_addr, exc_addr, n_exc
+        self._ck(lib().psi_b200_submit_chunk_packed(self._h, C.byref(v), distance, int(on_device)))
+
+    def seeds_all_async(self, flags=ALL):
+        self._ck(lib().psi_b200_seeds_all_async(self._h, flags))
+
+    def wait(self) -> int:
+        n = C.c_uint64()
+        self._ck(lib().psi_b200_wait(self._h, C.byref(n)))
+        return n.value
+
+    def dense_counts(self):
+        ns, ne = C.c_uint64(), C.c_uint64()
+        self._ck(lib().psi_b200_dense_counts(self._h, C.byref(ns), C.byref(ne)))
+        return ns.value, ne.value
+
+    def fetch_dense(self):
+        """After seeds_all(flags | DENSE): (dense (n_seeds, 2) u32, extra (n_extra, 4) u32)."""
+        ns, ne = self.dense_counts()
+        dense = np.zeros((ns, 2), np.uint32)
+        extra = np.zeros((ne, 4), np.uint32)
+        self._ck(lib().psi_b200_fetch_dense(self._h, _ptr(dense), ns, _ptr(extra), ne, C.byref(C.c_uint64()), C.byref(C.c_uint64())))
+        return dense, extra
+
+    def fetch_dense_async(self, dense_addr: int, cap_seeds: int, extra_addr: int, cap_extra: int):
+        self._ck(lib().psi_b200_fetch_dense_async(self._h, C.c_void_p(dense_addr), cap_seeds, C.c_void_p(extra_addr), cap_extra))
+
     def seeds_all(self, flags=ALL) -> int:
         n = C.c_uint64()
         self._ck(lib().psi_b200_seeds_all(self._h, flags, C.byref(n)))
@@ -413,6 +529,34 @@ class Context:
 
     def reset_counters(self):
         self._ck(lib().psi_b200_reset_counters(self._h))
+
+
+def seed_layout(read_ptr, k: int, d: int):
+    """(read index, read offset) of every seed of a chunk in seed order (sequence.hpp:1712): what the position in
+    the dense result array stands for."""
+    lens = np.diff(np.asarray(read_ptr, np.int64))
+    d = d or k
+    cnt = np.where(lens >= k, (lens - k) // d + 1, 0)
+    read = np.repeat(np.arange(len(lens), dtype=np.int64), cnt)
+    first = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    off = (np.arange(int(cnt.sum()), dtype=np.int64) - np.repeat(first, cnt)) * d
+    return read, off
+
+
+def dense_to_records(dense: np.ndarray, extra: np.ndarray, read_ptr, k: int, d: int, first_read_id=0):
+    """Dense per-seed results + extra list -> ((n, 4) u64 records {node_id, node_off, read_id, read_off}, kinds)."""
+    read, off = seed_layout(read_ptr, k, d)
+    assert len(read) == len(dense), (len(read), len(dense))
+    hit = dense[:, 0] != NIL32
+    rec = np.column_stack([dense[hit, 0].astype(np.uint64), (dense[hit, 1] & 0x7FFFFFFF).astype(np.uint64),
+                           (read[hit] + first_read_id).astype(np.uint64), off[hit].astype(np.uint64)])
+    kinds = np.where(dense[hit, 1] >> 31, 2, 1).astype(np.uint8)
+    if len(extra):
+        ex = np.column_stack([extra[:, 0].astype(np.uint64), extra[:, 1].astype(np.uint64), extra[:, 2].astype(np.uint64),
+                              (extra[:, 3] & 0x7FFFFFFF).astype(np.uint64)])
+        rec = np.concatenate([rec, ex])
+        kinds = np.concatenate([kinds, np.where(extra[:, 3] >> 31, 2, 1).astype(np.uint8)])
+    return rec.reshape(-1, 4), kinds
 
 
 def canonical(records: np.ndarray) -> np.ndarray:

@@ -194,6 +194,35 @@ int psi_b200_reader_next(psi_b200_reader* r, uint64_t max_reads, psi_b200_chunk_
   })
 }
 
+int psi_b200_reader_next_packed(psi_b200_reader* r, uint64_t max_reads, psi_b200_packed_chunk* v)
+{
+  if (!r || !r->r || !v) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  HOST_GUARD({
+    ChunkReader& cr = *r->r;
+    cr.next(max_reads, true);
+    v->n_reads = cr.n_reads();
+    v->first_read_id = cr.first_read_id();
+    v->n_bases = cr.n_bases();
+    v->read_len = cr.uniform_len();
+    v->reserved = 0;
+    v->read_ptr = cr.read_ptr();
+    v->words = cr.words();
+    v->exc = cr.exc();
+    v->n_exc = cr.n_exc();
+    v->name_ptr = cr.name_ptr();
+    v->names = cr.names();
+  })
+}
+
+int psi_b200_pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, uint64_t* exc, uint64_t exc_cap, uint64_t* n_exc)
+{
+  if ((n_bases && !bases) || !words) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  HOST_GUARD({
+    const uint64_t n = pack_bases(bases, n_bases, words, exc, exc_cap);
+    if (n_exc) *n_exc = n;
+  })
+}
+
 void psi_b200_reader_close(psi_b200_reader* r)
 {
   if (!r) return;
@@ -307,6 +336,55 @@ int psi_b200_submit_chunk_device(psi_b200_ctx* ctx, uint64_t n_reads, const uint
   CTX_GUARD(ctx, engine_submit_chunk(*ctx->c, n_reads, d_read_ptr, d_bases, n_bases, first_read_id, distance, true))
 }
 
+int psi_b200_submit_chunk_packed(psi_b200_ctx* ctx, const psi_b200_packed_chunk* chunk, unsigned distance, int on_device)
+{
+  CTX_GUARD(ctx, {
+    if (!chunk) throw ArgError("submit_chunk_packed: null chunk");
+    engine_submit_chunk_packed(*ctx->c, *chunk, distance, on_device != 0);
+  })
+}
+
+int psi_b200_seeds_all_async(psi_b200_ctx* ctx, unsigned flags)
+{
+  CTX_GUARD(ctx, {
+    if (!(flags & PSI_B200_ALL)) throw ArgError("seeds_all: neither ON_PATHS nor OFF_PATHS requested");
+    engine_seeds_async(*ctx->c, flags);
+  })
+}
+
+int psi_b200_wait(psi_b200_ctx* ctx, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    engine_wait(*ctx->c);
+    if (n_hits) *n_hits = ctx->c->n_hits;
+  })
+}
+
+int psi_b200_fetch_dense(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
+                         uint64_t* n_seeds, uint64_t* n_extra)
+{
+  CTX_GUARD(ctx, {
+    engine_fetch_dense(*ctx->c, dense, cap_seeds, extra, cap_extra);
+    if (n_seeds) *n_seeds = ctx->c->n_dense_seeds;
+    if (n_extra) *n_extra = ctx->c->n_extra;
+  })
+}
+
+int psi_b200_fetch_dense_async(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
+{
+  CTX_GUARD(ctx, engine_fetch_dense_async(*ctx->c, dense, cap_seeds, extra, cap_extra))
+}
+
+int psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra)
+{
+  CTX_GUARD(ctx, {
+    if (ctx->c->pending) throw StateError("dense_counts: a step is in flight on this context (call psi_b200_wait first)");
+    if (!ctx->c->records_valid || !ctx->c->records_dense) throw StateError("dense_counts: the last seeds_all was not run with PSI_B200_DENSE");
+    if (n_seeds) *n_seeds = ctx->c->n_dense_seeds;
+    if (n_extra) *n_extra = ctx->c->n_extra;
+  })
+}
+
 int psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {
@@ -346,6 +424,7 @@ int psi_b200_fetch_kinds(psi_b200_ctx* ctx, uint8_t* kinds, uint64_t cap, uint64
 int psi_b200_fetch_device(psi_b200_ctx* ctx, const uint64_t** d_hits, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {
+    if (ctx->c->pending) throw StateError("fetch_device: a step is in flight on this context (call psi_b200_wait first)");
     if (!ctx->c->records_valid) throw StateError("fetch_device: no resolved seed records");
     if (d_hits) *d_hits = ctx->c->records.p;
     if (n_hits) *n_hits = ctx->c->n_hits;
@@ -378,13 +457,19 @@ int psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out)
     c.counters.ms_resolve = PhaseTimer::timer_ms(c, T_RESOLVE);
     c.counters.ms_sort = PhaseTimer::timer_ms(c, T_SORT);
     c.counters.ms_d2h = PhaseTimer::timer_ms(c, T_D2H);
+    c.counters.code_by_rank = c.sh->code_by_rank ? 1u : 0u;
+    c.counters.code_off_bits = c.sh->code_off_bits;
     *out = c.counters;
   })
 }
 
 int psi_b200_reset_counters(psi_b200_ctx* ctx)
 {
-  CTX_GUARD(ctx, { ctx->c->counters.launches = 0; })
+  CTX_GUARD(ctx, {
+    ctx->c->counters.launches = 0;
+    ctx->c->counters.ms_probe_sum = ctx->c->counters.ms_on_sum = 0.0;
+    ctx->c->counters.timed_steps = 0;
+  })
 }
 
 }  // extern "C"

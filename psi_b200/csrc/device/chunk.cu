@@ -288,6 +288,29 @@ seed_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ r
   }
 }
 
+// 2-bit chunks on the separate-kernel route: the exception list becomes the 1-bit "not A/C/G/T" mask the seed
+// extraction kernel reads, and equal-length chunks without offsets get them written out.
+__global__ void __launch_bounds__(256)
+mark_exceptions_kernel(const uint64_t* __restrict__ exc, uint64_t n_exc, uint32_t* __restrict__ nmask)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_exc) return;
+  const uint64_t p = exc[i];
+  atomicOr(nmask + (p >> 5), 1u << (p & 31u));
+}
+
+__global__ void __launch_bounds__(256)
+uniform_read_ptr_kernel(uint64_t n_reads, uint32_t read_len, uint64_t* __restrict__ read_ptr)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= n_reads) read_ptr[r] = r * read_len;
+}
+
+void launch_scan_cta_counts(Ctx& c, const uint32_t* cta_count, uint32_t n_ctas, uint32_t* cta_first, unsigned long long* n_seeds_out)
+{
+  scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, cta_first, n_seeds_out);
+}
+
 template <int K4>
 static void launch_seed_reads(Ctx& c, unsigned n_ctas, uint64_t n_reads, unsigned distance)
 {
@@ -320,9 +343,13 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device)
 {
   if (!c.sh->has_graph) throw StateError("submit_chunk: no graph");
+  if (c.pending) throw StateError("submit_chunk: a step is in flight on this context (call psi_b200_wait first)");
   if (n_reads && (!read_ptr || !bases)) throw ArgError("submit_chunk: null arrays");
   if (n_reads >= 0x7fffffffull) throw ArgError("submit_chunk: more than 2^31 reads in one chunk");
   PSI_CUDA(cudaSetDevice(c.device));
+  c.chunk_packed = false;
+  c.read_len = 0;
+  c.n_exc = 0;
   if (distance == 0) distance = c.k;  // src/psikt.cpp:469
   c.has_chunk = false;
   c.chunk_indexed = false;
@@ -360,6 +387,69 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
   c.counters.n_reads = n_reads;
 }
 
+// get_seeds for a chunk that arrives as 2-bit words (psi_b200_packed_chunk).
+void engine_submit_chunk_packed(Ctx& c, const psi_b200_packed_chunk& ch, unsigned distance, bool on_device)
+{
+  if (!c.sh->has_graph) throw StateError("submit_chunk: no graph");
+  if (c.pending) throw StateError("submit_chunk: a step is in flight on this context (call psi_b200_wait first)");
+  const uint64_t n_reads = ch.n_reads, n_bases = ch.n_bases;
+  if (n_reads && !ch.words) throw ArgError("submit_chunk_packed: null words");
+  if (n_reads && !ch.read_ptr && ch.read_len == 0) throw ArgError("submit_chunk_packed: neither read offsets nor a read length");
+  if (ch.n_exc && !ch.exc) throw ArgError("submit_chunk_packed: null exception list");
+  if (n_reads >= 0x7fffffffull) throw ArgError("submit_chunk: more than 2^31 reads in one chunk");
+  if (!ch.read_ptr && ch.read_len && n_bases != n_reads * ch.read_len) throw ArgError("submit_chunk_packed: n_bases != n_reads * read_len");
+  if (!on_device && ch.read_ptr && n_reads && ch.read_ptr[n_reads] != n_bases) throw ArgError("submit_chunk_packed: read_ptr[n_reads] != n_bases");
+  PSI_CUDA(cudaSetDevice(c.device));
+  if (distance == 0) distance = c.k;  // src/psikt.cpp:469
+  c.has_chunk = false;
+  c.chunk_indexed = false;
+  c.records_valid = false;
+  c.n_hits = 0;
+  const uint64_t seeds_cap = n_bases / distance + n_reads + 1;
+  if (seeds_cap >= 0xfffffff0ull) throw ArgError("submit_chunk: too many seeds in one chunk (use smaller chunks)");
+  const uint64_t n_words = n_bases / 32 + 2;
+
+  c.ev_state[T_READ_INDEX] = 0;
+  PhaseTimer t_h2d(c, T_H2D);
+  if (on_device) {
+    c.d_words = ch.words;
+    c.d_read_ptr = ch.read_ptr;
+    c.d_exc = ch.exc;
+  }
+  else {
+    c.words.ensure(n_words + 2, 1.25);
+    if (n_reads) PSI_CUDA(cudaMemcpyAsync(c.words.p, ch.words, n_words * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+    c.d_words = c.words.p;
+    c.d_read_ptr = nullptr;
+    if (ch.read_ptr) {
+      c.read_ptr.ensure(n_reads + 1, 1.25);
+      PSI_CUDA(cudaMemcpyAsync(c.read_ptr.p, ch.read_ptr, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+      c.d_read_ptr = c.read_ptr.p;
+    }
+    c.d_exc = nullptr;
+    if (ch.n_exc) {
+      c.exc.ensure(ch.n_exc, 1.25);
+      PSI_CUDA(cudaMemcpyAsync(c.exc.p, ch.exc, ch.n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+      c.d_exc = c.exc.p;
+    }
+  }
+  t_h2d.stop();
+
+  c.chunk_packed = true;
+  c.read_len = ch.read_ptr ? 0u : ch.read_len;   // offsets given: the kernels use them (equal lengths are then detected per CTA)
+  c.n_exc = ch.n_exc;
+  c.d_bases = nullptr;
+  c.n_reads = n_reads;
+  c.n_read_bases = n_bases;
+  c.first_read_id = ch.first_read_id;
+  c.distance = distance;
+  c.n_seeds_cap = seeds_cap;
+  c.ev_state[T_PACK] = 0;
+  c.chunk_seeded = false;
+  c.has_chunk = true;
+  c.counters.n_reads = n_reads;
+}
+
 // K1 of the separate-kernel route: seed_first / seed_kmer / seed_valid / seed_read of the submitted chunk.
 void engine_seed_chunk(Ctx& c)
 {
@@ -372,7 +462,32 @@ void engine_seed_chunk(Ctx& c)
   c.seed_kmer.ensure(seeds_cap, 1.25);
   c.seed_valid.ensure(seeds_cap + 16, 1.25);
 
-  if (c.opt_seeding_mode == 0) {
+  if (c.chunk_packed) {
+    // the chunk IS the 2-bit array the staged seeding reads; only the N mask and (equal-length chunks) the offsets are made
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    c.reads_n.ensure(n_words + 2, 1.25);
+    PSI_CUDA(cudaMemsetAsync(c.reads_n.p, 0, (n_words + 2) * sizeof(uint32_t), c.stream));
+    if (c.n_exc) {
+      mark_exceptions_kernel<<<grid_for(c.n_exc, 256), 256, 0, c.stream>>>(c.d_exc, c.n_exc, c.reads_n.p);
+      ++c.counters.launches;
+    }
+    if (!c.d_read_ptr) {
+      c.read_ptr.ensure(n_reads + 1, 1.25);
+      uniform_read_ptr_kernel<<<grid_for(n_reads + 1, 256), 256, 0, c.stream>>>(n_reads, c.read_len, c.read_ptr.p);
+      ++c.counters.launches;
+      c.d_read_ptr = c.read_ptr.p;
+      c.read_len = 0;
+    }
+    const unsigned n_ctas = (unsigned)((n_reads + 1 + READS_PER_CTA - 1) / READS_PER_CTA);   // + 1: seed_first[n_reads] = total
+    c.cta_first.ensure(2 * (size_t)n_ctas + 2, 1.25);
+    uint32_t* cta_count = c.cta_first.p + n_ctas + 1;
+    count_seeds_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_read_ptr, n_reads, c.k, distance, cta_count);
+    scan_cta_counts_kernel<<<1, 1024, 0, c.stream>>>(cta_count, n_ctas, c.cta_first.p, c.dev_counters.p + DC_SEEDS);
+    extract_seeds_kernel<<<n_ctas, 256, 0, c.stream>>>(c.d_words, c.reads_n.p, c.d_read_ptr, c.cta_first.p, n_reads, c.k, distance,
+                                                        c.seed_first.p, c.seed_kmer.p, c.seed_valid.p, c.seed_read.p);
+    c.counters.launches += 3;
+  }
+  else if (c.opt_seeding_mode == 0) {
     // direct: ASCII -> seeds (3 launches)
     const unsigned n_ctas = (unsigned)((n_reads + 1 + DIRECT_READS - 1) / DIRECT_READS);   // + 1: seed_first[n_reads] = total
     c.cta_first.ensure(2 * (size_t)n_ctas + 2, 1.25);

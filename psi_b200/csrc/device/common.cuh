@@ -96,13 +96,20 @@ __host__ __device__ __forceinline__ uint64_t mix_kb(uint64_t x, uint32_t kb)
 // sectors back to back (walkers) -- and only continue past a line without a free
 // slot.
 //
-// fmt 8 slot (64 bits), valid while kbits - line_bits <= 27:
-//   [63:37] remainder of the bijectively mixed k-mer (the line index holds the rest)
-//   [36:34] displacement from the home line (0..7)
-//   [33]    entry reaches only via an off-path walk      [32] payload is a locus list
-//   [31:0]  payload: global position, or offset of the list in the multi array,
-//           or (read index) head of the seed chain
-// fmt 16 slot: full k-mer, payload, flags (bit 0 list, bit 1 off-path; NIL32 = empty).
+// fmt 8 slot (64 bits), valid while R = kbits - line_bits <= 27; P = 27 - R spare bits widen the payload:
+//   [63:64-R]     remainder of the bijectively mixed k-mer (the line index holds the rest)
+//   next 3 bits   displacement from the home line (0..7)
+//   next 2 bits   flags: bit 1 = entry reached only via an off-path walk, bit 0 = payload is a locus list
+//   [31+P:0]      payload (32 + P bits): a LOCUS CODE (below), or the offset of the locus list in the multi
+//                 array, or (read index) the head of the seed chain
+//   An empty slot is all ones; no valid entry has both flag bits set.
+// fmt 16 slot: full k-mer (64 bits), payload low word, then flags in bits [1:0] and 30 more payload bits in
+//   [31:2] of the last word (NIL32 = empty).
+//
+// Locus code (path index, single-locus entries): everything a seed record needs from the graph side, so that a hit
+// costs NO further memory access: (node id << off_bits) | offset in the node when the ids fit the payload
+// (CODE_BY_ID), else (node rank << off_bits) | offset plus one gather of node_id[rank] (CODE_BY_RANK).
+// off_bits = bits of the longest node label - 1.  Locus LISTS (multi array) keep 32-bit global positions.
 
 constexpr uint32_t MAX_DISP = 7;
 // walk mode: the per-chunk bitmap of seed prefixes has 2 * min(k, FILTER_PFX) bits of index -- 8 MB at most, resident
@@ -125,10 +132,17 @@ struct KmerTable {
   uint32_t line_bits;   // log2(n_lines)
   uint32_t kbits;       // 2k
   uint32_t rem_bits;    // fmt 8 only: kbits - line_bits (<= 27)
+  uint32_t pay_hi;      // fmt 8 only: 27 - rem_bits payload bits above bit 31
   uint32_t fmt;         // 8 or 16 (bytes per slot)
   uint32_t stash_mask;
   uint32_t stash_nonempty;  // host-known: 0 lets lookups skip the stash entirely
 };
+
+// payload bits a slot of this table can hold
+__host__ __device__ __forceinline__ uint32_t table_payload_bits(const KmerTable& t)
+{
+  return t.fmt == 8 ? 32u + t.pay_hi : 62u;
+}
 
 struct Home {
   uint64_t line;
@@ -136,9 +150,21 @@ struct Home {
 };
 
 struct Found {
-  uint32_t payload;
+  uint64_t payload;
   uint32_t flags;
 };
+
+// ---- fmt 8 slot words ----
+__device__ __forceinline__ uint64_t slot8_make(const KmerTable& t, uint64_t want, uint32_t flags, uint64_t payload)
+{
+  return (want << (34u + t.pay_hi)) | ((uint64_t)(flags & 3u) << (32u + t.pay_hi)) | payload;
+}
+__device__ __forceinline__ uint64_t slot8_want(const KmerTable& t, uint64_t slot) { return slot >> (34u + t.pay_hi); }
+__device__ __forceinline__ uint32_t slot8_flags(const KmerTable& t, uint64_t slot) { return (uint32_t)(slot >> (32u + t.pay_hi)) & 3u; }
+__device__ __forceinline__ uint64_t slot8_payload(const KmerTable& t, uint64_t slot) { return slot & low_mask64(32u + t.pay_hi); }
+// ---- fmt 16 slot words ----
+__device__ __forceinline__ uint32_t slot16_flagword(uint32_t flags, uint64_t payload) { return (flags & 3u) | ((uint32_t)(payload >> 32) << 2); }
+__device__ __forceinline__ uint64_t slot16_payload(uint32_t payload_lo, uint32_t flagword) { return ((uint64_t)(flagword >> 2) << 32) | payload_lo; }
 
 __device__ __forceinline__ void ld_sector_nc(const void* p, uint64_t (&v)[4])
 {
@@ -202,14 +228,14 @@ __device__ __forceinline__ Home home_of(const KmerTable& t, uint64_t kmer)
 // Compare the slots of one 32-byte sector.  `want` = tag | displacement (fmt 8) or the k-mer (fmt 16).
 // Returns true on a match; `has_empty` reports a free slot in the sector.
 template <int FMT>
-__device__ __forceinline__ bool match_sector(const uint64_t (&v)[4], uint64_t want, Found& f, bool& has_empty)
+__device__ __forceinline__ bool match_sector(const KmerTable& t, const uint64_t (&v)[4], uint64_t want, Found& f, bool& has_empty)
 {
   bool hit = false;
   if (FMT == 8) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (v[j] == EMPTY8) has_empty = true;
-      else if ((v[j] >> 34) == want) { f.payload = (uint32_t)v[j]; f.flags = (uint32_t)(v[j] >> 32) & 3u; hit = true; }
+      else if (slot8_want(t, v[j]) == want) { f.payload = slot8_payload(t, v[j]); f.flags = slot8_flags(t, v[j]); hit = true; }
     }
   }
   else {
@@ -217,7 +243,7 @@ __device__ __forceinline__ bool match_sector(const uint64_t (&v)[4], uint64_t wa
     for (int j = 0; j < 2; ++j) {
       const uint32_t fl = (uint32_t)(v[2 * j + 1] >> 32);
       if (fl == NIL32) has_empty = true;
-      else if (v[2 * j] == want) { f.payload = (uint32_t)v[2 * j + 1]; f.flags = fl & 3u; hit = true; }
+      else if (v[2 * j] == want) { f.payload = slot16_payload((uint32_t)v[2 * j + 1], fl); f.flags = fl & 3u; hit = true; }
     }
   }
   return hit;
@@ -232,7 +258,7 @@ __device__ __forceinline__ bool stash_find(const KmerTable& t, uint64_t kmer, Fo
   for (uint32_t i = 0; i <= t.stash_mask; ++i) {
     const Slot16 s = ld_slot16_volatile(t.stash + p);
     if (s.flags == NIL32) return false;
-    if (s.key == kmer) { f.payload = s.payload; f.flags = s.flags & 3u; return true; }
+    if (s.key == kmer) { f.payload = slot16_payload(s.payload, s.flags); f.flags = s.flags & 3u; return true; }
     p = (p + 1) & t.stash_mask;
   }
   return false;
@@ -242,11 +268,13 @@ __device__ __forceinline__ bool stash_find(const KmerTable& t, uint64_t kmer, Fo
 // when the key exists and `chain` is set, the payload is swapped for
 // `payload` and the previous payload is returned in `prev`.  Returns false
 // when the stash is full.
-__device__ __forceinline__ bool stash_insert(const KmerTable& t, uint64_t kmer, uint32_t payload, uint32_t flags,
+__device__ __forceinline__ bool stash_insert(const KmerTable& t, uint64_t kmer, uint64_t payload64, uint32_t flags,
                                              bool chain, uint32_t& prev)
 {
   uint32_t p = (uint32_t)mix64(kmer ^ 0x5bd1e995u) & t.stash_mask;
   const Slot16 empty{ ~0ull, NIL32, NIL32 };
+  const uint32_t payload = (uint32_t)payload64;
+  flags = slot16_flagword(flags, payload64);
   for (uint32_t i = 0; i <= t.stash_mask; ++i) {
     Slot16 cur = ld_slot16_volatile(t.stash + p);
     while (true) {
@@ -289,7 +317,7 @@ __device__ __forceinline__ bool table_find_from(const KmerTable& t, const Home& 
     const uint64_t want = FMT == 8 ? ((h.tag | d) ) : kmer;
     bool has_empty = false, hit = false;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) hit |= match_sector<FMT>(v[i], want, f, has_empty);
+    for (int i = 0; i < 4; ++i) hit |= match_sector<FMT>(t, v[i], want, f, has_empty);
     if (hit) return true;
     if (has_empty) return false;
   }
@@ -314,8 +342,9 @@ __device__ __forceinline__ bool table_find_any(const KmerTable& t, uint64_t kmer
 // replaced by `payload` and the old payload is returned in `prev` (linked list
 // of read seeds); a fresh key returns NIL32.  Returns false when MAX_DISP + 1
 // lines and the stash are full (caller raises the overflow flag).
+// `payload` may use table_payload_bits(t) bits; chains (chain == true) keep 32-bit payloads (seed indices).
 template <int FMT>
-__device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, uint32_t payload, uint32_t flags,
+__device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, uint64_t payload, uint32_t flags,
                                              bool chain, uint32_t& prev)
 {
   const Home h = home_of<FMT>(t, kmer);
@@ -325,7 +354,7 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
     char* line = (char*)t.slots + (((h.line + d) & line_mask) << 7);
     if (FMT == 8) {
       const uint64_t want = h.tag | d;
-      const uint64_t fresh = (want << 34) | ((uint64_t)(flags & 3u) << 32) | payload;
+      const uint64_t fresh = slot8_make(t, want, flags, payload);
       unsigned long long* slot = (unsigned long long*)line;
 #pragma unroll 1
       for (int j = 0; j < 16; ++j) {
@@ -337,9 +366,9 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
             cur = old;
             continue;
           }
-          if ((cur >> 34) == want) {
+          if (slot8_want(t, cur) == want) {
             if (!chain) { prev = (uint32_t)cur; return true; }
-            const unsigned long long upd = (cur & 0xffffffff00000000ull) | payload;
+            const unsigned long long upd = (cur & 0xffffffff00000000ull) | (uint32_t)payload;
             const unsigned long long old = atomicCAS(slot + j, cur, upd);
             if (old == cur) { prev = (uint32_t)cur; return true; }
             cur = old;
@@ -358,14 +387,14 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
         while (true) {
           if (cur.flags == NIL32) {
             Slot16 old;
-            if (cas128(slot + j, empty, Slot16{ kmer, payload, flags & 3u }, old)) { prev = NIL32; return true; }
+            if (cas128(slot + j, empty, Slot16{ kmer, (uint32_t)payload, slot16_flagword(flags, payload) }, old)) { prev = NIL32; return true; }
             cur = old;
             continue;
           }
           if (cur.key == kmer) {
             if (!chain) { prev = cur.payload; return true; }
             Slot16 old;
-            if (cas128(slot + j, cur, Slot16{ kmer, payload, cur.flags }, old)) { prev = cur.payload; return true; }
+            if (cas128(slot + j, cur, Slot16{ kmer, (uint32_t)payload, cur.flags }, old)) { prev = cur.payload; return true; }
             cur = old;
             continue;
           }
@@ -375,25 +404,6 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
     }
   }
   return stash_insert(t, kmer, payload, flags, chain, prev);
-}
-
-// membership of (kmer, gpos) among the ON-PATH entries of the index.
-// multi list layout: [n_on, n_total, on-path loci (sorted)..., off-path loci (sorted)...]
-__device__ __forceinline__ bool index_contains(const KmerTable& t, const uint32_t* __restrict__ multi,
-                                               uint64_t kmer, uint32_t gpos)
-{
-  Found f;
-  if (!table_find_any(t, kmer, f)) return false;
-  if (!(f.flags & FLAG_MULTI)) return !(f.flags & FLAG_OFF) && f.payload == gpos;
-  const uint32_t cnt = __ldg(multi + f.payload);
-  uint32_t lo = 0, hi = cnt;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    const uint32_t v = __ldg(multi + f.payload + 2 + mid);
-    if (v == gpos) return true;
-    if (v < gpos) lo = mid + 1; else hi = mid;
-  }
-  return false;
 }
 
 // ------------------------------------------------------- warp helpers --

@@ -89,6 +89,8 @@ struct alignas(16) SlowItem {
   uint64_t kmer;
   uint32_t read;   // read index within the chunk
   uint32_t off;    // offset of the seed in the read
+  uint32_t seed;   // index of the seed within the chunk (dense results)
+  uint32_t pad;
 };
 
 struct HostTable {
@@ -114,6 +116,10 @@ struct Shared {
   DevBuf<uint32_t> nmask;        // 1 bit per base: not A/C/G/T
   DevBuf<uint64_t> node_id;
   uint64_t max_node_id = 0;      // PSI_B200_COMPACT records need it below 2^32
+  uint32_t max_node_len = 0;
+  // locus codes carried by single-locus index entries (common.cuh): (id or rank) << code_off_bits | offset
+  uint32_t code_off_bits = 0;
+  bool code_by_rank = false;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
   // rank16 and node_res live back to back in one allocation so that ONE L2 access-policy window can pin them
   // (they are gathered at random by every hit; together ~1.1 bytes per graph base)
@@ -163,7 +169,15 @@ struct Ctx {
   DevBuf<char> bases;            // owned copy for host submissions
   DevBuf<uint64_t> read_ptr;
   const char* d_bases = nullptr; // points to `bases` or to caller's device memory
-  const uint64_t* d_read_ptr = nullptr;
+  const uint64_t* d_read_ptr = nullptr;   // null: every read has `read_len` bases (packed chunks only)
+  // a chunk submitted as 2-bit words (psi_b200_submit_chunk_packed): d_words replaces d_bases
+  bool chunk_packed = false;
+  uint32_t read_len = 0;         // != 0: all reads of the chunk have this length
+  DevBuf<uint64_t> words;        // owned copy for host submissions
+  DevBuf<uint64_t> exc;
+  const uint64_t* d_words = nullptr;
+  const uint64_t* d_exc = nullptr;   // sorted base positions (within the chunk) of the characters outside A/C/G/T
+  uint64_t n_exc = 0;
   DevBuf<uint64_t> reads2;       // the chunk's bases, 2 bits each
   DevBuf<uint32_t> reads_n;      // 1 bit per base: not A/C/G/T
   DevBuf<uint32_t> cta_first;    // per CTA of the seeding kernels: first seed, then the raw counts
@@ -179,13 +193,14 @@ struct Ctx {
   uint64_t* h_pinned = nullptr;  // small pinned scratch for async counter read-back
 
   // ---- results ----
-  DevBuf<uint32_t> seed_hit;     // per seed: locus found by the probe
+  DevBuf<uint64_t> seed_hit;     // per seed: locus code found by the probe
   DevBuf<uint8_t> seed_kind;     // per seed: 0 none, 1 on an indexed path, 2 off-path, 3 queued for the slow kernel
   DevBuf<uint32_t> slow_queue;   // seeds the one-line probe could not settle
   DevBuf<SlowItem> slow_items;   // the same for the fused kernel
   DevBuf<Hit> hits;              // overflow hit list: locus lists, walker hits
   DevBuf<uint8_t> hit_kind;
-  DevBuf<Hit> sorted_hits;       // dense compact hits (PSI_B200_SORTED / NO_RESOLVE)
+  DevBuf<uint64_t> sorted_code;  // compacted hits (PSI_B200_SORTED / NO_RESOLVE): locus code and seed index
+  DevBuf<uint32_t> sorted_seed;
   DevBuf<uint8_t> rec_kind;      // per record: 1 on-path, 2 off-path
   bool kinds_valid = false;
   DevBuf<unsigned long long> dedup;  // off-path (chain head, gpos) set
@@ -194,6 +209,20 @@ struct Ctx {
   uint64_t n_hits = 0;
   bool records_valid = false;
   bool records_compact = false;  // records hold 4 x u32 per hit (PSI_B200_COMPACT)
+  // dense results (PSI_B200_DENSE): `records` holds one {node_id, node_off | off-path << 31} pair of u32 per seed, in
+  // seed order (NIL32 id = no hit); further hits of seeds with several loci are 4 x u32 records in `extra`
+  bool records_dense = false;
+  DevBuf<uint32_t> extra;
+  uint64_t n_dense_seeds = 0, n_extra = 0;
+  // ---- a step in flight (psi_b200_seeds_all_async .. psi_b200_wait) ----
+  bool pending = false;
+  int pending_out_kind = 0;               // 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense
+  unsigned pending_probe_mode = 0;
+  uint64_t pending_out_cap_want = 0;      // records: capacity learnt from an overflowed step
+  int pending_attempts = 0;
+  void* pending_dense_dst = nullptr;      // host destinations of the asynchronous dense fetch, if one was queued
+  void* pending_extra_dst = nullptr;
+  uint64_t pending_dense_cap = 0, pending_extra_cap = 0, pending_extra_copied = 0;
   uint32_t spill_items = 4096;   // per-warp global spill of the walker
   DevBuf<char> walk_spill;
 
@@ -203,8 +232,9 @@ struct Ctx {
   uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
   int opt_blocking_sync = 0;                   // 1: wait for a chunk on a blocking event (thread sleeps) instead of spinning
+  int opt_code_by_rank = 0;                    // 1: locus codes carry the node rank even when the ids would fit (tests)
+  int opt_timers = 1;                          // 0: no CUDA-event records around the kernels of a step
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)
-  int opt_fused_ctas = 4;                      // resident CTAs per SM the fused kernel is compiled for (3, 4 or 5)
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
   int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
   int opt_resolve_ctas = 6;                    // resident CTAs per SM the resolve kernel is compiled for (5 or 6)
@@ -224,7 +254,8 @@ enum {
   DC_AUX2 = 7,
   DC_OVF = 8,         // entries of the overflow hit list
   DC_SLOW = 9,        // seeds queued for seeds_slow_kernel
-  DC_COUNT = 10
+  DC_EXTRA = 10,      // dense results: records in the extra list
+  DC_COUNT = 12
 };
 
 }  // namespace psi_b200

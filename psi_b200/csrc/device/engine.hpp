@@ -21,7 +21,14 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
 void engine_seed_chunk(Ctx& c);   // the seeding kernels of the separate-kernel route (idempotent per chunk)
 void engine_seeds(Ctx& c, unsigned flags);
-void engine_seeds_fused(Ctx& c, unsigned probe_mode, bool compact);
+// out_kind: 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense per-seed results
+void engine_seeds_fused(Ctx& c, unsigned probe_mode, int out_kind);
+void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind);
+void engine_seeds_async(Ctx& c, unsigned flags);   // queues the step when the fused route serves it, else runs it synchronously
+void engine_wait(Ctx& c);
+void engine_fetch_dense(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+void engine_fetch_dense_async(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+void engine_submit_chunk_packed(Ctx& c, const psi_b200_packed_chunk& chunk, unsigned distance, bool on_device);
 void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);
 void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);
@@ -30,7 +37,11 @@ void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap);
 
 // Size a KmerTable for n_keys distinct k-mers of 2k = kbits bits; allocates and
 // clears the slots.  slack_bits: extra doublings of the line count (-1: auto).
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits = 0);
+// min_payload_bits: what a slot's payload must be able to hold (8-byte slots offer 32 + 27 - rem_bits, 16-byte slots 62).
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits = 0,
+                 uint32_t min_payload_bits = 32);
+// payload bits 8-byte slots would offer for this many keys (0: 8-byte slots are not possible)
+uint32_t table_fmt8_payload_bits(uint64_t n_keys, uint32_t kbits, int slack_bits);
 void table_clear(Ctx& c, HostTable& t);
 
 // CUDA-event timer slots (Ctx::ev holds a start/stop pair per slot)

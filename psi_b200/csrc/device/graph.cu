@@ -64,27 +64,23 @@ Ctx* engine_create(int device, unsigned seed_len)
   cudaDeviceProp prop;
   PSI_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) throw CudaError("libpsi_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
-  Ctx* c = new Ctx();
+  // owned by a guard until fully constructed: a failing CUDA call below must not leak the stream, events or buffers
+  struct Guard {
+    Ctx* c;
+    ~Guard() { if (c) engine_destroy(c); }
+  } guard{ new Ctx() };
+  Ctx* c = guard.c;
   c->device = device;
   c->k = seed_len;
   c->sm_count = prop.multiProcessorCount;
   PSI_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
-  // Index probes are single random 32-byte sectors: ask L2 not to promote a miss to
-  // a wider DRAM fetch.  Override for experiments with PSI_B200_L2_FETCH=32|64|128|0
-  // (0 = leave the device default).
-  {
-    size_t gran = 32;
-    if (const char* e = std::getenv("PSI_B200_L2_FETCH")) gran = (size_t)std::strtoul(e, nullptr, 10);
-    if (gran == 32 || gran == 64 || gran == 128) {
-      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) (void)cudaGetLastError();
-    }
-  }
   for (auto& ev : c->ev) PSI_CUDA(cudaEventCreate(&ev));
   PSI_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
   c->dev_counters.ensure(DC_COUNT);
   PSI_CUDA(cudaMemsetAsync(c->dev_counters.p, 0, DC_COUNT * sizeof(unsigned long long), c->stream));
   PSI_CUDA(cudaHostAlloc((void**)&c->h_pinned, (2 * DC_COUNT + 8) * sizeof(uint64_t), cudaHostAllocDefault));
+  guard.c = nullptr;
   return c;
 }
 
@@ -112,9 +108,10 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
   c->opt_fused = parent.opt_fused;
+  c->opt_timers = parent.opt_timers;
+  c->opt_code_by_rank = parent.opt_code_by_rank;
   c->opt_blocking_sync = parent.opt_blocking_sync;
   c->opt_index_slack = parent.opt_index_slack;
-  c->opt_fused_ctas = parent.opt_fused_ctas;
   c->opt_resolve_items = parent.opt_resolve_items;
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
   c->l2_window_bytes = parent.l2_window_bytes;
@@ -160,16 +157,19 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
   // rank structure for position -> node (zero-length nodes would share a start bit: fall back to pos2node then)
   bool zero_len = false;
   uint64_t max_id = 0;
+  uint32_t max_len = 0;
   std::vector<Rank16> rank16((n_bases >> 6) + 2, Rank16{ 0, 0, 0 });
   std::vector<NodeRes> node_res(n_nodes + 1);
   for (uint64_t v = 0; v < n_nodes; ++v) {
     node_res[v] = NodeRes{ rec[v].seq_start, 0, node_id[v] };
     if (node_id[v] > max_id) max_id = node_id[v];
+    if (rec[v].seq_len > max_len) max_len = rec[v].seq_len;
     if (rec[v].seq_len == 0) { zero_len = true; continue; }
     rank16[rec[v].seq_start >> 6].bits |= 1ull << (rec[v].seq_start & 63u);
   }
   node_res[n_nodes] = NodeRes{ (uint32_t)n_bases, 0, 0 };
   c.sh->max_node_id = max_id;
+  c.sh->max_node_len = max_len;
   {
     uint32_t run = 0;
     for (auto& r : rank16) { r.prefix = run; run += (uint32_t)__builtin_popcountll(r.bits); }
@@ -251,17 +251,25 @@ static uint32_t ceil_log2(uint64_t x)
   return b;
 }
 
-void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits)
+struct TablePlan {
+  uint32_t fmt, line_bits, rem_bits;
+};
+
+// A bucket is a 128-byte line.  Size for at most ~10 keys per 16-slot line
+// (fmt 8) or ~5 per 8-slot line (fmt 16): with a power-of-two line count the
+// mean load is 0.31-0.63, about 3 % of the lines overflow into their successor
+// at the upper end, and a lookup still reads exactly one line in ~97 % of the cases.
+// 8-byte slots need the k-mer's remainder to fit 27 bits AND the payload to fit the 32 + 27 - rem_bits left over.
+static TablePlan table_plan(uint64_t n_keys, uint32_t kbits, int& slack_bits, uint32_t min_payload_bits)
 {
-  // A bucket is a 128-byte line.  Size for at most ~10 keys per 16-slot line
-  // (fmt 8) or ~5 per 8-slot line (fmt 16): with a power-of-two line count the
-  // mean load is 0.31-0.63, about 3 % of the lines overflow into their successor
-  // at the upper end, and a lookup still reads exactly one line in ~97 % of the cases.
-  uint32_t fmt = 16, line_bits = ceil_log2((n_keys + 4) / 5 + 1), rem_bits = 0;
+  TablePlan p{ 16, ceil_log2((n_keys + 4) / 5 + 1), 0 };
   {
     uint32_t lb = ceil_log2((n_keys + 9) / 10 + 1);
     if (lb > kbits) lb = kbits;               // tiny k: at most one possible key per line
-    if (kbits - lb <= 27) { fmt = 8; line_bits = lb; rem_bits = kbits - lb; }
+    // extra line bits an explicit slack will add below also shorten the remainder
+    uint32_t lb_final = lb;
+    for (int i = 0; i < (slack_bits > 0 ? slack_bits : 0); ++i) if (lb_final < kbits) ++lb_final;
+    if (kbits - lb <= 27 && 32u + 27u - (kbits - lb_final) >= min_payload_bits) { p.fmt = 8; p.line_bits = lb; p.rem_bits = kbits - lb; }
   }
   // slack: 2^slack_bits times the lines.  Halving the load makes a full home line (and with it the slow path of the
   // probe) a rarity -- 1 % -> 0.001 % of the lines at 16 slots, 6 % -> 0.1 % at 8 slots -- for twice the memory.
@@ -271,15 +279,29 @@ void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t
   if (slack_bits < 0) {
     size_t free_b = 0, total_b = 0;
     slack_bits = 0;
-    if (fmt == 16 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (256ull << line_bits) <= total_b / 16 &&
-        (256ull << line_bits) <= free_b / 4)
+    if (p.fmt == 16 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (256ull << p.line_bits) <= total_b / 16 &&
+        (256ull << p.line_bits) <= free_b / 4)
       slack_bits = 1;
   }
   for (int i = 0; i < slack_bits; ++i) {
-    if (fmt == 8 && (rem_bits == 0 || line_bits + 1 > kbits)) break;
-    ++line_bits;
-    if (fmt == 8) --rem_bits;
+    if (p.fmt == 8 && (p.rem_bits == 0 || p.line_bits + 1 > kbits)) break;
+    ++p.line_bits;
+    if (p.fmt == 8) --p.rem_bits;
   }
+  return p;
+}
+
+uint32_t table_fmt8_payload_bits(uint64_t n_keys, uint32_t kbits, int slack_bits)
+{
+  const TablePlan p = table_plan(n_keys, kbits, slack_bits, 32);
+  return p.fmt == 8 ? 32u + 27u - p.rem_bits : 0u;
+}
+
+void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t stash_slots, int slack_bits, uint32_t min_payload_bits)
+{
+  if (min_payload_bits > 62) throw ArgError("table: payload wider than 62 bits");
+  const TablePlan p = table_plan(n_keys, kbits, slack_bits, min_payload_bits);
+  const uint32_t fmt = p.fmt, line_bits = p.line_bits, rem_bits = p.rem_bits;
   if (line_bits > 32) throw ArgError("table too large");   // line indices travel as 32-bit values
   const uint64_t n_lines = 1ull << line_bits;
   t.n_lines = n_lines;
@@ -294,6 +316,7 @@ void table_alloc(Ctx& c, HostTable& t, uint64_t n_keys, uint32_t kbits, uint64_t
   t.view.line_bits = line_bits;
   t.view.kbits = kbits;
   t.view.rem_bits = rem_bits;
+  t.view.pay_hi = fmt == 8 ? 27u - rem_bits : 0u;
   t.view.fmt = fmt;
   t.view.stash_mask = (uint32_t)(ss - 1);
   t.view.stash_nonempty = 1;  // until the build has been checked

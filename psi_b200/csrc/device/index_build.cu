@@ -181,7 +181,7 @@ run_multi_words_kernel(const uint32_t* __restrict__ run_start, uint32_t n_runs, 
 // the concatenation), each group ascending.
 template <int FMT>
 __global__ void __launch_bounds__(256)
-insert_runs_kernel(KmerTable t, const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
+insert_runs_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                    const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ multi_off,
                    uint32_t n_runs, uint32_t* __restrict__ multi, unsigned long long* __restrict__ err_flag)
 {
@@ -189,10 +189,12 @@ insert_runs_kernel(KmerTable t, const uint64_t* __restrict__ key, const uint64_t
   if (r >= n_runs) return;
   const uint32_t b = run_start[r], e = run_start[r + 1];
   const uint64_t kmer = key[b];
-  uint32_t payload, flags;
+  uint64_t payload;
+  uint32_t flags;
   if (e - b == 1) {
+    // single locus: the entry carries the locus code, so that a probe that finds it needs nothing else
     const uint64_t v = val[b];
-    payload = (uint32_t)v;
+    payload = code_of_gpos(g, (uint32_t)v);
     flags = (v >> 32) ? FLAG_OFF : 0u;
   }
   else {
@@ -321,11 +323,30 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   sh.multi.ensure((uint64_t)multi_words + 4);
 
-  table_alloc(c, sh.index, n_runs, 2 * c.k, (uint64_t)n_runs / 512 + 1024, c.opt_index_slack);
+  // Locus codes: (node id << off_bits) | offset when that fits the payload of 8-byte slots, else (node rank << off_bits)
+  // | offset (one gather of node_id per hit), else 16-byte slots (62 payload bits: by id unless the ids are wider still).
+  {
+    auto bits_of = [](uint64_t x) { uint32_t b = 0; while (x) { ++b; x >>= 1; } return b; };
+    const uint32_t off_bits = bits_of(sh.max_node_len ? sh.max_node_len - 1 : 0);
+    const uint32_t id_bits = bits_of(sh.max_node_id), rank_bits = bits_of(sh.n_nodes ? sh.n_nodes - 1 : 0);
+    const uint32_t list_bits = bits_of((uint64_t)multi_words + 4);
+    const uint32_t cap8 = table_fmt8_payload_bits(n_runs, 2 * c.k, c.opt_index_slack);
+    uint32_t need;
+    sh.code_off_bits = off_bits;
+    if (std::max(id_bits + off_bits, list_bits) <= cap8) { sh.code_by_rank = false; need = id_bits + off_bits; }
+    else if (std::max(rank_bits + off_bits, list_bits) <= cap8) { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    else if (id_bits + off_bits <= 62) { sh.code_by_rank = false; need = id_bits + off_bits; }
+    else { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    if (c.opt_code_by_rank) { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    need = std::max(need, list_bits);
+    if (need > 62) throw ArgError("index: node labels too long for the locus codes");
+    table_alloc(c, sh.index, n_runs, 2 * c.k, (uint64_t)n_runs / 512 + 1024, c.opt_index_slack, need);
+  }
+  const GraphView g = make_graph_view(c);   // after the code layout has been chosen
   if (sh.index.view.fmt == 8)
-    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
   else
-    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
   ++c.counters.launches;
   PSI_CUDA(cudaGetLastError());
   unsigned long long err = 0;
@@ -468,6 +489,7 @@ struct AllLociSource {
 };
 
 struct UncoveredSink {
+  GraphView g;
   KmerTable t;
   const uint32_t* multi;
   uint32_t* flags;   // bitmap over global positions
@@ -479,7 +501,7 @@ struct UncoveredSink {
   __device__ bool prune(uint64_t, uint32_t, uint32_t) const { return false; }
   __device__ void complete(uint64_t kmer, uint32_t origin)
   {
-    if (!has_index || !index_contains(t, multi, kmer, origin)) atomicOr(flags + (origin >> 5), 1u << (origin & 31u));
+    if (!has_index || !index_contains(g, t, multi, kmer, origin)) atomicOr(flags + (origin >> 5), 1u << (origin & 31u));
   }
   __device__ void finish() {}
 };
@@ -491,7 +513,7 @@ find_loci_kernel(GraphView g, uint32_t k, uint32_t step, KmerTable t, const uint
 {
   __shared__ WalkItem smem[WALK_WARPS * WALK_SMEM_ITEMS];
   AllLociSource src{ g, step };
-  UncoveredSink sink{ t, multi, flags, has_index };
+  UncoveredSink sink{ g, t, multi, flags, has_index };
   walk_all(g, k, g.n_bases, work, smem, spill, spill_items, err, src, sink);
 }
 
@@ -533,6 +555,7 @@ emit_loci_kernel(GraphView g, const uint32_t* __restrict__ flags, const uint32_t
 // of seeds.cu is used instead (offpath_mode 1); both give the same seed set.
 
 struct OffPathSink {
+  GraphView g;
   KmerTable t;
   const uint32_t* multi;
   uint32_t has_table;
@@ -544,7 +567,7 @@ struct OffPathSink {
   __device__ bool prune(uint64_t, uint32_t, uint32_t) const { return false; }
   __device__ void complete(uint64_t kmer, uint32_t origin)
   {
-    if (has_table && index_contains(t, multi, kmer, origin)) return;
+    if (has_table && index_contains(g, t, multi, kmer, origin)) return;
     const unsigned long long slot = atomicAdd(count, 1ull);
     if (out_kmer && slot < cap) { out_kmer[slot] = kmer; out_gpos[slot] = origin; }
   }
@@ -589,7 +612,7 @@ static void materialise_offpath(Ctx& c)
       PSI_CUDA(cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), c.stream));
       PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
       c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
-      OffPathSink sink{ sh.index.view, sh.multi.p, sh.has_table ? 1u : 0u, pass ? kmer_a.p : nullptr, gpos_a.p, n_walks, d_cnt };
+      OffPathSink sink{ g, sh.index.view, sh.multi.p, sh.has_table ? 1u : 0u, pass ? kmer_a.p : nullptr, gpos_a.p, n_walks, d_cnt };
       collect_offpath_kernel<<<grid, WALK_WARPS * 32, 0, c.stream>>>(g, c.k, sh.n_loci, sh.loci_node.p, sh.loci_off.p, sink,
                                                                     d_work, (WalkItem*)c.walk_spill.p, c.spill_items, d_err);
       ++c.counters.launches;
@@ -723,9 +746,11 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   else if (n == "fused") {
     c.opt_fused = value != 0;
   }
-  else if (n == "fused_ctas") {
-    if (value < 3 || value > 5) throw ArgError("set_option: fused_ctas is 3, 4 or 5");
-    c.opt_fused_ctas = (int)value;
+  else if (n == "timers") {
+    c.opt_timers = value != 0;
+  }
+  else if (n == "code_by_rank") {
+    c.opt_code_by_rank = value != 0;     // takes effect at the next set_paths / find_loci / set_loci
   }
   else if (n == "seeding_mode") {
     if (value < 0 || value > 1) throw ArgError("set_option: seeding_mode is 0 (direct from ASCII) or 1 (2-bit staging)");

@@ -21,9 +21,9 @@ struct Resolved {
 };
 
 // global graph position -> (node id, offset in the node); replaces position_to_id/offset(PathIndex)
-// (reference include/psi/pathindex.hpp:378-416)
-__device__ __forceinline__ void resolve_node(const GraphView& g, const uint64_t* __restrict__ node_id, uint32_t gpos,
-                                             uint64_t& id, uint64_t& off)
+// (reference include/psi/pathindex.hpp:378-416).  Only locus LISTS and walker hits carry positions; single-locus
+// index entries carry a locus code that decode_code (walker.cuh) turns into the same two fields without a gather.
+__device__ __forceinline__ void resolve_node(const GraphView& g, uint32_t gpos, uint64_t& id, uint64_t& off)
 {
   if (g.rank16) {
     // two dependent 16-byte gathers: start bits + prefix count of the 64 positions, then the node's record
@@ -37,20 +37,18 @@ __device__ __forceinline__ void resolve_node(const GraphView& g, const uint64_t*
   else {
     const uint32_t v = node_of_pos(g, gpos);
     off = gpos - __ldg(&g.rec[v].seq_start);
-    id = __ldg(node_id + v);
+    id = __ldg(g.node_id + v);
   }
 }
 
-__device__ __forceinline__ Resolved resolve_one(const GraphView& g, const uint64_t* __restrict__ node_id, uint32_t seed, uint32_t gpos,
-                                                const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
-                                                uint32_t d, uint64_t first_read_id)
+// seed index -> (read id, offset of the seed in the read); replaces Records::position_to_id/offset
+// (reference include/psi/sequence.hpp:1201-1213,1277-1289)
+__device__ __forceinline__ void resolve_read(uint32_t seed, const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
+                                             uint32_t d, uint64_t first_read_id, Resolved& o)
 {
-  Resolved o;
   const uint32_t r = __ldg(seed_read + seed);
   o.read_id = first_read_id + r;
   o.read_off = (uint64_t)(seed - __ldg(seed_first + r)) * d;
-  resolve_node(g, node_id, gpos, o.node_id, o.node_off);
-  return o;
 }
 
 // one 32-byte record per store instruction (STG.256): every 32-byte sector of the output is written exactly once

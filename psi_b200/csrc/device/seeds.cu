@@ -49,7 +49,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 seeds_on_paths_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const uint8_t* __restrict__ seed_valid,
                       const unsigned long long* __restrict__ n_seeds_p, uint32_t mode,
-                      uint32_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
+                      uint64_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
                       uint32_t* __restrict__ slow_queue, unsigned long long* __restrict__ slow_count)
 {
   __shared__ __align__(128) unsigned char s_lines[256 * 128];
@@ -80,32 +80,35 @@ seeds_on_paths_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const
 
   const uint4* ln = reinterpret_cast<const uint4*>(warp_lines + (lane << 7));
   bool hit = false, empty = false;
-  uint32_t pl = 0, fl = 0;
+  uint32_t pl = 0, ph = 0;                             // the matching slot's payload word and high word
   if (FMT == 8) {
-    const uint32_t want = (uint32_t)h.tag;             // tag | displacement 0 (30 bits)
+    const uint32_t want = (uint32_t)h.tag;             // tag | displacement 0 (<= 30 bits)
+    const uint32_t tsh = 2u + t.pay_hi;                // high word: [tag | disp][2 flag bits][pay_hi payload bits]
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint4 w = ln[(j + lane) & 7u];             // two slots: (w.x, w.y) and (w.z, w.w), high word second
-      empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has all of rem/disp/flags set
-      if ((w.y >> 2) == want) { hit = true; pl = w.x; fl = w.y & 3u; }
-      if ((w.w >> 2) == want) { hit = true; pl = w.z; fl = w.w & 3u; }
+      empty |= (w.y == 0xffffffffu) | (w.w == 0xffffffffu);   // no valid entry has both flag bits set
+      if ((w.y >> tsh) == want) { hit = true; pl = w.x; ph = w.y; }
+      if ((w.w >> tsh) == want) { hit = true; pl = w.z; ph = w.w; }
     }
   }
   else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint4 w = ln[(j + lane) & 7u];             // one slot: key (w.x, w.y), payload w.z, flags w.w
+      const uint4 w = ln[(j + lane) & 7u];             // one slot: key (w.x, w.y), payload w.z, flags + payload high bits w.w
       empty |= w.w == NIL32;
-      if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer) { hit = true; pl = w.z; fl = w.w & 3u; }
+      if (w.w != NIL32 && (((uint64_t)w.y << 32) | w.x) == kmer) { hit = true; pl = w.z; ph = w.w; }
     }
   }
+  const uint32_t fl = FMT == 8 ? (ph >> t.pay_hi) & 3u : ph & 3u;
+  const uint64_t payload = FMT == 8 ? ((uint64_t)(ph & ((1u << t.pay_hi) - 1u)) << 32) | pl : slot16_payload(pl, ph);
   if (s >= n_seeds) return;
   uint8_t kind = 0;
   if (ok) {
     if (hit) {
       kind = kind_of(fl, mode);
       if (fl & FLAG_MULTI) { kind = 3; slow_queue[atomicAdd(slow_count, 1ull)] = s; }
-      seed_hit[s] = pl;
+      seed_hit[s] = payload;
     }
     else if (!empty) {
       // the line is full and does not hold the key: it may sit in a following line (~1 % of the lines are full)
@@ -121,7 +124,7 @@ seeds_on_paths_kernel(KmerTable t, const uint64_t* __restrict__ seed_kmer, const
 __global__ void __launch_bounds__(256)
 seeds_slow_kernel(KmerTable t, const uint32_t* __restrict__ multi, const uint64_t* __restrict__ seed_kmer,
                   const uint32_t* __restrict__ slow_queue, const unsigned long long* __restrict__ slow_count, uint32_t mode,
-                  uint32_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
+                  uint64_t* __restrict__ seed_hit, uint8_t* __restrict__ seed_kind,
                   Hit* __restrict__ ovf, uint8_t* __restrict__ ovf_kind, uint64_t ovf_cap, unsigned long long* __restrict__ ovf_count)
 {
   const uint64_t n = *slow_count;
@@ -160,6 +163,7 @@ seeds_slow_kernel(KmerTable t, const uint32_t* __restrict__ multi, const uint64_
 //     claim (chain head, locus) in a device hash set reports, the others skip.
 
 struct ReadIndexSink {
+  GraphView g;
   const uint32_t* pfx_bits;     // bitmap of the first `pfx` bases of every read seed (2 pfx bits of index)
   uint32_t pfx;                 // 0: no prefix filter
   KmerTable rt;                 // chunk read index
@@ -207,8 +211,8 @@ struct ReadIndexSink {
     ++walks;
     Found f;
     if (!table_find_any(rt, kmer, f)) return;
-    const uint32_t head = f.payload;
-    if (has_index && index_contains(pt, multi, kmer, origin)) return;
+    const uint32_t head = (uint32_t)f.payload;
+    if (has_index && index_contains(g, pt, multi, kmer, origin)) return;
     if (!claim(((uint64_t)head << 32) | origin)) return;
     uint32_t n = 0;
     for (uint32_t s = head; s != NIL32; s = __ldg(next + s)) ++n;
@@ -242,22 +246,25 @@ seeds_off_paths_kernel(GraphView g, uint32_t k, uint64_t n_loci, const uint32_t*
 // (seed.hpp:32-46 as written by src/psikt.cpp:172-181): node_id, node_offset,
 // read_id, read_offset, 4 x u64.  read_id / read_offset replace
 // Records::position_to_id/offset (sequence.hpp:1201-1213,1277-1289); the node
-// lookup replaces position_to_id/offset(PathIndex) (pathindex.hpp:378-416).
+// half comes out of the locus code the probe found (no memory access for by-id
+// codes), or -- overflow entries: locus lists, walker hits -- from the global
+// position through the rank structure (pathindex.hpp:378-416).
 // A CTA takes 512 consecutive items (seeds first, then overflow entries), counts
 // its hits with ballots, reserves their output range with ONE atomic and writes
 // them in item order, so the output of a chunk is ordered by (read, offset) up
 // to the CTA granularity and the stores of a warp are contiguous.
-// RECORDS: 0 = dense compact hits only, 1 = 4 x u64 records, 2 = 4 x u32 records
+// RECORDS: 0 = (locus code, seed) pairs only, 1 = 4 x u64 records, 2 = 4 x u32 records
 template <int RECORDS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
-compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
-                       const uint32_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
+compact_resolve_kernel(GraphView g,
+                       const uint64_t* __restrict__ seed_hit, const uint8_t* __restrict__ seed_kind,
                        const unsigned long long* __restrict__ n_seeds_p,
                        const Hit* __restrict__ ovf, const uint8_t* __restrict__ ovf_kind,
                        const unsigned long long* __restrict__ n_ovf_p, uint64_t ovf_cap,
                        const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
                        uint32_t d, uint64_t first_read_id,
-                       uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind, Hit* __restrict__ out_hits, uint64_t cap,
+                       uint64_t* __restrict__ records, uint8_t* __restrict__ rec_kind,
+                       uint64_t* __restrict__ out_code, uint32_t* __restrict__ out_seed, uint64_t cap,
                        unsigned long long* __restrict__ total, unsigned long long* __restrict__ total_on)
 {
   __shared__ uint32_t s_cnt[8 * ITEMS];
@@ -272,22 +279,25 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
   // all independent loads first: kind and locus of every item (the locus is loaded whether or not it is a hit)
-  uint32_t seed[ITEMS], gpos[ITEMS];
+  uint32_t seed[ITEMS];
+  uint64_t code[ITEMS];     // per-seed items: the locus code; overflow items: the global position
   uint8_t kind[ITEMS];
+  bool is_ovf[ITEMS];
 #pragma unroll
   for (int h = 0; h < ITEMS; ++h) {
     const uint64_t i = base + h * 256u + threadIdx.x;
-    kind[h] = 0; seed[h] = 0; gpos[h] = 0;
+    kind[h] = 0; seed[h] = 0; code[h] = 0; is_ovf[h] = false;
     if (i < n_seeds) {
       kind[h] = __ldg(seed_kind + i);
-      gpos[h] = __ldg(seed_hit + i);
+      code[h] = __ldg(seed_hit + i);
       seed[h] = (uint32_t)i;
     }
     else if (i < n_items) {
       const Hit x = ovf[i - n_seeds];
       kind[h] = ovf_kind[i - n_seeds];
       seed[h] = x.seed;
-      gpos[h] = x.gpos;
+      code[h] = x.gpos;
+      is_ovf[h] = true;
     }
   }
 #pragma unroll
@@ -317,11 +327,18 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
     s_base = run ? atomicAdd(total, (unsigned long long)run) : 0ull;
     if (run_on) atomicAdd(total_on, (unsigned long long)run_on);
   }
-  // resolution of all items: ITEMS independent chains of gathers per thread
+  // resolution of all items: ITEMS independent chains per thread
   Resolved r[ITEMS];
 #pragma unroll
-  for (int h = 0; h < ITEMS; ++h)
-    if (RECORDS && kind[h]) r[h] = resolve_one(g, node_id, seed[h], gpos[h], seed_read, seed_first, d, first_read_id);
+  for (int h = 0; h < ITEMS; ++h) {
+    if (!kind[h]) continue;
+    if (RECORDS) {
+      resolve_read(seed[h], seed_read, seed_first, d, first_read_id, r[h]);
+      if (is_ovf[h]) resolve_node(g, (uint32_t)code[h], r[h].node_id, r[h].node_off);
+      else decode_code(g, code[h], r[h].node_id, r[h].node_off);
+    }
+    else if (is_ovf[h]) code[h] = code_of_gpos(g, (uint32_t)code[h]);
+  }
   __syncthreads();
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t run = 0;
@@ -341,21 +358,22 @@ compact_resolve_kernel(GraphView g, const uint64_t* __restrict__ node_id,
       else st_record(records + 4 * out, r[h]);
       rec_kind[out] = kind[h];
     }
-    else out_hits[out] = Hit{ seed[h], gpos[h] };
+    else { out_code[out] = code[h]; out_seed[out] = seed[h]; }
   }
 }
 
-// sorted compact hits -> records (only used with PSI_B200_SORTED)
+// sorted (locus code, seed) pairs -> records (only used with PSI_B200_SORTED)
 template <bool COMPACT>
 __global__ void __launch_bounds__(256)
-resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ node_id, const Hit* __restrict__ hits, uint64_t n_hits,
+resolve_hits_kernel(GraphView g, const uint64_t* __restrict__ codes, const uint32_t* __restrict__ seeds, uint64_t n_hits,
                     const uint32_t* __restrict__ seed_read, const uint32_t* __restrict__ seed_first,
                     uint32_t d, uint64_t first_read_id, uint64_t* __restrict__ records)
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_hits) return;
-  const Hit h = hits[i];
-  const Resolved r = resolve_one(g, node_id, h.seed, h.gpos, seed_read, seed_first, d, first_read_id);
+  Resolved r;
+  resolve_read(seeds[i], seed_read, seed_first, d, first_read_id, r);
+  decode_code(g, codes[i], r.node_id, r.node_off);
   if (COMPACT) { st_record32(records + 2 * i, r); return; }
   ulonglong2* o = reinterpret_cast<ulonglong2*>(records + 4 * i);
   o[0] = make_ulonglong2(r.node_id, r.node_off);
@@ -371,9 +389,18 @@ static uint64_t next_pow2(uint64_t x)
   return p;
 }
 
-void engine_seeds(Ctx& c, unsigned flags)
+static void engine_seeds_impl(Ctx& c, unsigned flags, bool async);
+
+void engine_seeds(Ctx& c, unsigned flags) { engine_seeds_impl(c, flags, false); }
+
+// Queues the step and returns when the fused kernel serves it; the other routes (walk mode, SORTED, NO_RESOLVE)
+// run to completion here, and psi_b200_wait then only reports.
+void engine_seeds_async(Ctx& c, unsigned flags) { engine_seeds_impl(c, flags, true); }
+
+static void engine_seeds_impl(Ctx& c, unsigned flags, bool async)
 {
   if (!c.has_chunk) throw StateError("seeds_all: no read chunk submitted");
+  if (c.pending) throw StateError("seeds_all: a step is in flight on this context (call psi_b200_wait first)");
   PSI_CUDA(cudaSetDevice(c.device));
   Shared& sh = *c.sh;
   // index mode: the off-path walks are entries of the table, one probe answers both questions.
@@ -386,16 +413,29 @@ void engine_seeds(Ctx& c, unsigned flags)
   const bool sorted = (flags & PSI_B200_SORTED) != 0;
   const bool resolve = !(flags & PSI_B200_NO_RESOLVE);
   const bool compact = (flags & PSI_B200_COMPACT) != 0;
-  if (compact && resolve) {
-    if (sh.max_node_id > 0xffffffffull) throw ArgError("seeds_all: PSI_B200_COMPACT needs node ids below 2^32");
-    if (c.first_read_id + c.n_reads > 0x100000000ull) throw ArgError("seeds_all: PSI_B200_COMPACT needs read ids below 2^32");
+  const bool dense = (flags & PSI_B200_DENSE) != 0;
+  if (dense && (sorted || !resolve || compact)) throw ArgError("seeds_all: PSI_B200_DENSE excludes SORTED, NO_RESOLVE and COMPACT");
+  if ((compact || dense) && resolve) {
+    if (sh.max_node_id >= 0xffffffffull) throw ArgError("seeds_all: PSI_B200_COMPACT / PSI_B200_DENSE need node ids below 2^32 - 1");
+    if (c.first_read_id + c.n_reads > 0x100000000ull) throw ArgError("seeds_all: PSI_B200_COMPACT / PSI_B200_DENSE need read ids below 2^32");
   }
   c.records_valid = false;
   c.kinds_valid = false;
+  c.records_dense = false;
   c.counters.fused = 0;
   // the usual case -- the index answers every requested phase, records wanted in emission order -- is ONE kernel
-  if (c.opt_fused && do_probe && !do_walk && !sorted && resolve) {
-    engine_seeds_fused(c, probe_mode, compact);
+  const bool probe_only = !do_walk && !sorted && resolve;
+  if ((c.opt_fused || dense) && do_probe && probe_only) {
+    if (async) engine_seeds_fused_async(c, probe_mode, compact ? 1 : dense ? 2 : 0);
+    else engine_seeds_fused(c, probe_mode, compact ? 1 : dense ? 2 : 0);
+    return;
+  }
+  if (dense) {
+    // dense results come from the fused kernel only; an index that cannot answer the requested phases hits nothing
+    if (do_walk) throw ArgError("seeds_all: PSI_B200_DENSE needs the off-path walks materialised in the index (offpath_mode 0 or 2)");
+    if (!sh.has_table) throw StateError("seeds_all: PSI_B200_DENSE needs an index (set_paths / set_loci first)");
+    if (async) engine_seeds_fused_async(c, 0, 2);
+    else engine_seeds_fused(c, 0, 2);
     return;
   }
   engine_seed_chunk(c);
@@ -419,13 +459,9 @@ void engine_seeds(Ctx& c, unsigned flags)
       if (do_probe) {
         const unsigned grid = grid_for(c.n_seeds_cap, 256);
         c.slow_queue.ensure(c.n_seeds_cap, 1.25);
-        static bool carveout_done[64] = {};   // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split
-        bool& carveout_set = carveout_done[c.device & 63];
-        if (!carveout_set) {
-          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-          carveout_set = true;
-        }
+        // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split (per device; benign when repeated)
+        PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         PhaseTimer t_probe(c, T_PROBE);
         if (sh.index.view.fmt == 8)
           seeds_on_paths_kernel<8><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,
@@ -453,6 +489,7 @@ void engine_seeds(Ctx& c, unsigned flags)
         const unsigned grid = (unsigned)c.sm_count * 8;
         c.walk_spill.ensure((size_t)grid * WALK_WARPS * c.spill_items * sizeof(WalkItem));
         ReadIndexSink sink;
+        sink.g = g;
         sink.pfx_bits = c.filter_bits.p;
         sink.pfx = c.filter_pfx;
         sink.rt = c.read_index.view;
@@ -484,45 +521,31 @@ void engine_seeds(Ctx& c, unsigned flags)
 
     // compaction (+ resolution unless the hits are to be sorted first)
     PhaseTimer t_res(c, T_RESOLVE);
-    const bool pin = c.l2_window_bytes != 0 && sh.has_rank16;
-    if (pin) {   // gathers of this kernel into rank16/node_res persist in the L2 set-aside, everything else streams
-      cudaStreamAttrValue attr{};
-      attr.accessPolicyWindow.base_ptr = sh.gather_pool.p;
-      attr.accessPolicyWindow.num_bytes = c.l2_window_bytes;
-      attr.accessPolicyWindow.hitRatio = c.l2_persist_bytes >= c.l2_window_bytes ? 1.0f : (float)c.l2_persist_bytes / (float)c.l2_window_bytes;
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    }
     uint64_t out_cap = 0;
     {
       const unsigned items = (unsigned)c.opt_resolve_items;
       const unsigned grid = grid_for(c.n_seeds_cap + c.hits.cap, 256, items);
-#define PSI_RESOLVE_ARGS(REC, KINDS, HITS) \
-  g, sh.node_id.p, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p, c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, \
-  c.seed_first.p, c.distance, c.first_read_id, REC, KINDS, HITS, out_cap, dc + DC_HITS, dc + DC_HITS_ON
+#define PSI_RESOLVE_ARGS(REC, KINDS, CODES, SEEDS) \
+  g, c.seed_hit.p, c.seed_kind.p, dc + DC_SEEDS, c.hits.p, c.hit_kind.p, dc + DC_OVF, c.hits.cap, c.seed_read.p, \
+  c.seed_first.p, c.distance, c.first_read_id, REC, KINDS, CODES, SEEDS, out_cap, dc + DC_HITS, dc + DC_HITS_ON
       if (sorted || !resolve) {
-        c.sorted_hits.ensure(out_cap_want);
-        out_cap = c.sorted_hits.cap;
-        if (items == 4) compact_resolve_kernel<0, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
-        else compact_resolve_kernel<0, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_hits.p));
+        c.sorted_code.ensure(out_cap_want);
+        c.sorted_seed.ensure(out_cap_want);
+        out_cap = std::min<uint64_t>(c.sorted_code.cap, c.sorted_seed.cap);
+        if (items == 4) compact_resolve_kernel<0, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_code.p, c.sorted_seed.p));
+        else compact_resolve_kernel<0, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(nullptr, nullptr, c.sorted_code.p, c.sorted_seed.p));
       }
       else {
         c.records.ensure(4 * out_cap_want);
         c.rec_kind.ensure(out_cap_want);
         out_cap = std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
-        if (compact) compact_resolve_kernel<2, 2, 6><<<grid_for(c.n_seeds_cap + c.hits.cap, 256, 2), 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else if (items == 4) compact_resolve_kernel<1, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else if (c.opt_resolve_ctas >= 6) compact_resolve_kernel<1, 2, 6><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
-        else compact_resolve_kernel<1, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr));
+        if (compact) compact_resolve_kernel<2, 2, 6><<<grid_for(c.n_seeds_cap + c.hits.cap, 256, 2), 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr, nullptr));
+        else if (items == 4) compact_resolve_kernel<1, 4, 4><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr, nullptr));
+        else if (c.opt_resolve_ctas >= 6) compact_resolve_kernel<1, 2, 6><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr, nullptr));
+        else compact_resolve_kernel<1, 2, 5><<<grid, 256, 0, c.stream>>>(PSI_RESOLVE_ARGS(c.records.p, c.rec_kind.p, nullptr, nullptr));
       }
 #undef PSI_RESOLVE_ARGS
       ++c.counters.launches;
-    }
-    if (pin) {
-      cudaStreamAttrValue attr{};
-      attr.accessPolicyWindow.num_bytes = 0;
-      PSI_CUDA(cudaStreamSetAttribute(c.stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     t_res.stop();
     PSI_CUDA(cudaGetLastError());
@@ -557,34 +580,33 @@ void engine_seeds(Ctx& c, unsigned flags)
   c.counters.n_on_probe_sectors = n_slow;   // seeds that needed more than their home line
   c.counters.offpath_mode = index_mode ? 2u : 1u;
 
+  const uint64_t* codes = c.sorted_code.p;
+  const uint32_t* seeds = c.sorted_seed.p;
   if (sorted && n_total > 1) {
     PhaseTimer t_sort(c, T_SORT);
-    // canonical order: (seed index, global position) ascending == (read_id, read_offset, node rank, node_offset)
-    DevBuf<unsigned long long> tmp_keys;
-    tmp_keys.ensure(n_total);
-    size_t tmp = 0;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(c.sorted_hits.p);
-    // Hit{seed, gpos} is little-endian (seed low, gpos high): sort by gpos bits first, then seed bits
-    cub::DoubleBuffer<unsigned long long> db(keys, tmp_keys.p);
-    PSI_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, db, (int64_t)n_total, 0, 64, c.stream));
-    c.scan_tmp.ensure(tmp);
-    // 64-bit value = gpos << 32 | seed; canonical order needs seed major: two stable passes
-    PSI_CUDA(cub::DeviceRadixSort::SortKeys(c.scan_tmp.p, tmp, db, (int64_t)n_total, 32, 64, c.stream));
-    PSI_CUDA(cub::DeviceRadixSort::SortKeys(c.scan_tmp.p, tmp, db, (int64_t)n_total, 0, 32, c.stream));
-    if (db.Current() != keys)
-      PSI_CUDA(cudaMemcpyAsync(keys, db.Current(), n_total * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c.stream));
+    // canonical order: (seed index, locus code) ascending == (read_id, read_offset, node id or rank, node_offset):
+    // LSD with two stable passes, by code, then by seed
+    DevBuf<uint64_t> code_b;
+    DevBuf<uint32_t> seed_b;
+    code_b.ensure(n_total); seed_b.ensure(n_total);
+    size_t tmp1 = 0, tmp2 = 0;
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, c.sorted_code.p, code_b.p, c.sorted_seed.p, seed_b.p, (int64_t)n_total, 0, 64, c.stream));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, seed_b.p, c.sorted_seed.p, code_b.p, c.sorted_code.p, (int64_t)n_total, 0, 32, c.stream));
+    c.scan_tmp.ensure(std::max(tmp1, tmp2));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(c.scan_tmp.p, tmp1, c.sorted_code.p, code_b.p, c.sorted_seed.p, seed_b.p, (int64_t)n_total, 0, 64, c.stream));
+    PSI_CUDA(cub::DeviceRadixSort::SortPairs(c.scan_tmp.p, tmp2, seed_b.p, c.sorted_seed.p, code_b.p, c.sorted_code.p, (int64_t)n_total, 0, 32, c.stream));
     t_sort.stop();
-    PSI_CUDA(cudaStreamSynchronize(c.stream));
-    c.counters.launches += 8;
+    PSI_CUDA(cudaStreamSynchronize(c.stream));   // the temporaries die here
+    c.counters.launches += 12;
   }
   if (sorted && resolve) {
     c.records.ensure(4 * std::max<uint64_t>(n_total, 1), 1.25);
     if (n_total) {
       if (compact)
-        resolve_hits_kernel<true><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
+        resolve_hits_kernel<true><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, codes, seeds, n_total, c.seed_read.p,
                                                                                 c.seed_first.p, c.distance, c.first_read_id, c.records.p);
       else
-        resolve_hits_kernel<false><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, sh.node_id.p, c.sorted_hits.p, n_total, c.seed_read.p,
+        resolve_hits_kernel<false><<<grid_for(n_total, 256), 256, 0, c.stream>>>(g, codes, seeds, n_total, c.seed_read.p,
                                                                                  c.seed_first.p, c.distance, c.first_read_id, c.records.p);
       ++c.counters.launches;
     }
@@ -597,7 +619,8 @@ void engine_seeds(Ctx& c, unsigned flags)
 
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact)
 {
-  if (!c.records_valid) throw StateError("fetch: no resolved seed records (call seeds_all without NO_RESOLVE first)");
+  if (c.pending) throw StateError("fetch: a step is in flight on this context (call psi_b200_wait first)");
+  if (!c.records_valid || c.records_dense) throw StateError("fetch: no resolved seed records (call seeds_all without NO_RESOLVE / DENSE first)");
   if (compact != c.records_compact)
     throw StateError(compact ? "fetch32: the last seeds_all was not run with PSI_B200_COMPACT"
                              : "fetch: the last seeds_all was run with PSI_B200_COMPACT (use psi_b200_fetch32)");
@@ -611,6 +634,7 @@ void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact)
 
 void engine_fetch_kinds(Ctx& c, uint8_t* kinds, uint64_t cap)
 {
+  if (c.pending) throw StateError("fetch_kinds: a step is in flight on this context (call psi_b200_wait first)");
   if (!c.kinds_valid) throw StateError("fetch_kinds: no unsorted resolved records");
   PSI_CUDA(cudaSetDevice(c.device));
   const uint64_t n = c.n_hits < cap ? c.n_hits : cap;

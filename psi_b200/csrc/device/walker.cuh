@@ -41,10 +41,14 @@ struct GraphView {
   const uint32_t* pos2node;
   const Rank16* rank16;      // null: use pos2node
   const NodeRes* node_res;
+  const uint64_t* node_id;   // the id reported in seed records, by rank
   uint32_t n_nodes;
   uint32_t pos2node_shift;
   uint64_t n_bases;
   uint32_t has_n;
+  // locus codes of the path index (common.cuh): (id or rank) << code_off_bits | offset in the node
+  uint32_t code_off_bits;
+  uint32_t code_by_rank;
 };
 
 inline GraphView make_graph_view(const Ctx& c)
@@ -57,6 +61,9 @@ inline GraphView make_graph_view(const Ctx& c)
   g.pos2node = c.sh->pos2node.p;
   g.rank16 = c.sh->has_rank16 ? c.sh->rank16 : nullptr;
   g.node_res = c.sh->node_res;
+  g.node_id = c.sh->node_id.p;
+  g.code_off_bits = c.sh->code_off_bits;
+  g.code_by_rank = c.sh->code_by_rank ? 1u : 0u;
   g.n_nodes = c.sh->n_nodes;
   g.pos2node_shift = Ctx::POS2NODE_SHIFT;
   g.n_bases = c.sh->n_bases;
@@ -70,6 +77,58 @@ __device__ __forceinline__ uint32_t node_of_pos(const GraphView& g, uint32_t pos
   uint32_t v = __ldg(g.pos2node + (pos >> g.pos2node_shift));
   while (__ldg(&g.rec[v + 1].seq_start) <= pos) ++v;
   return v;
+}
+
+// global position -> (node rank, offset in the node): two dependent 16-byte gathers (rank16, node_res), or the sampled
+// pos2node table when the graph has zero-length nodes
+__device__ __forceinline__ void rank_of_pos(const GraphView& g, uint32_t gpos, uint32_t& v, uint32_t& off)
+{
+  if (g.rank16) {
+    const uint4 rw = __ldg(reinterpret_cast<const uint4*>(g.rank16 + (gpos >> 6)));
+    const uint64_t bits = ((uint64_t)rw.y << 32) | rw.x;
+    v = rw.z + (uint32_t)__popcll(bits & (~0ull >> (63u - (gpos & 63u)))) - 1u;
+    off = gpos - __ldg(&g.node_res[v].seq_start);
+  }
+  else {
+    v = node_of_pos(g, gpos);
+    off = gpos - __ldg(&g.rec[v].seq_start);
+  }
+}
+
+// locus code of a global position (build time, walkers, locus lists: never on the one-line probe path)
+__device__ __forceinline__ uint64_t code_of_gpos(const GraphView& g, uint32_t gpos)
+{
+  uint32_t v, off;
+  rank_of_pos(g, gpos, v, off);
+  const uint64_t hi = g.code_by_rank ? (uint64_t)v : __ldg(g.node_id + v);
+  return (hi << g.code_off_bits) | off;
+}
+
+// locus code -> the graph half of a seed record; by-id codes need no memory access at all
+__device__ __forceinline__ void decode_code(const GraphView& g, uint64_t code, uint64_t& id, uint64_t& off)
+{
+  off = code & low_mask64(g.code_off_bits);
+  const uint64_t hi = code >> g.code_off_bits;
+  id = g.code_by_rank ? __ldg(g.node_id + hi) : hi;
+}
+
+// membership of (kmer, gpos) among the ON-PATH entries of the index.
+// multi list layout: [n_on, n_total, on-path loci (sorted)..., off-path loci (sorted)...]
+__device__ __forceinline__ bool index_contains(const GraphView& g, const KmerTable& t, const uint32_t* __restrict__ multi,
+                                               uint64_t kmer, uint32_t gpos)
+{
+  Found f;
+  if (!table_find_any(t, kmer, f)) return false;
+  if (!(f.flags & FLAG_MULTI)) return !(f.flags & FLAG_OFF) && f.payload == code_of_gpos(g, gpos);
+  const uint32_t cnt = __ldg(multi + f.payload);
+  uint32_t lo = 0, hi = cnt;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    const uint32_t v = __ldg(multi + f.payload + 2 + mid);
+    if (v == gpos) return true;
+    if (v < gpos) lo = mid + 1; else hi = mid;
+  }
+  return false;
 }
 
 constexpr int WALK_WARPS = 4;          // warps per CTA

@@ -97,15 +97,88 @@ bool ChunkReader::getline(std::string& out)
   return got;
 }
 
-uint64_t ChunkReader::next(uint64_t max_reads)
+// ------------------------------------------------------------ packing --
+
+namespace {
+
+// Eight characters (one per byte of c) -> 16 bits of 2-bit codes; `bad` gets a non-zero byte for every character
+// that is not A/C/G/T (either case).  Byte-parallel: x = (c >> 1) & 3; x ^= x >> 1 maps A, C, G, T to 0, 1, 2, 3;
+// the expected upper-case character is rebuilt from the code (0x41 + 2 b0 + 6 b1 + 11 b0 b1) and compared.
+inline uint64_t pack8(uint64_t c, uint64_t& bad)
 {
-  bases_.clear();
-  read_ptr_.assign(1, 0);
-  names_.clear();
-  name_ptr_.assign(1, 0);
+  const uint64_t ones = 0x0101010101010101ull;
+  uint64_t x = (c >> 1) & (3 * ones);
+  x ^= (x >> 1) & ones;
+  const uint64_t b0 = x & ones, b1 = (x >> 1) & ones, b01 = b0 & b1;
+  const uint64_t expect = 0x41 * ones + (b0 << 1) + (b1 << 1) + (b1 << 2) + (b01 << 3) + (b01 << 1) + b01;
+  bad = expect ^ (c & (0xdf * ones));
+  uint64_t t = (x | (x >> 6)) & 0x000f000f000f000full;
+  t = (t | (t >> 12)) & 0x000000ff000000ffull;
+  return (t | (t >> 24)) & 0xffffull;
+}
+
+template <class Sink>
+uint64_t pack_bases_impl(const char* bases, uint64_t n_bases, uint64_t* words, Sink&& on_exception)
+{
+  const uint64_t n_words = n_bases / 32 + 2;
+  uint64_t n_bad = 0, i = 0;
+  for (uint64_t w = 0; w < n_words; ++w) {
+    uint64_t word = 0;
+    for (int g = 0; g < 4 && i < n_bases; ++g) {
+      uint64_t c;
+      const uint64_t left = n_bases - i;
+      if (left >= 8) std::memcpy(&c, bases + i, 8);
+      else {
+        c = 0x4141414141414141ull;      // pad with 'A' (code 0, valid)
+        std::memcpy(&c, bases + i, left);
+      }
+      uint64_t bad;
+      uint64_t code = pack8(c, bad);
+      if (bad) {
+        for (int b = 0; b < 8; ++b)
+          if ((bad >> (8 * b)) & 0xff) {
+            on_exception(i + b);
+            ++n_bad;
+            code &= ~(3ull << (2 * b));   // stored as code 0
+          }
+      }
+      word |= code << (16 * g);
+      i += left >= 8 ? 8 : left;
+    }
+    words[w] = word;
+  }
+  return n_bad;
+}
+
+}  // namespace
+
+uint64_t pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, uint64_t* exc, uint64_t exc_cap)
+{
+  uint64_t stored = 0;
+  return pack_bases_impl(bases, n_bases, words, [&](uint64_t p) { if (exc && stored < exc_cap) exc[stored++] = p; });
+}
+
+uint64_t pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, std::vector<uint64_t>& exc)
+{
+  return pack_bases_impl(bases, n_bases, words, [&](uint64_t p) { exc.push_back(p); });
+}
+
+uint64_t ChunkReader::next(uint64_t max_reads, bool packed)
+{
+  cur_ ^= 1;            // the previous chunk's buffers stay untouched: its upload may still be in flight
+  Set& s = set();
+  s.bases.clear();
+  s.words.clear();
+  s.exc.clear();
+  s.read_ptr.assign(1, 0);
+  s.names.clear();
+  s.name_ptr.assign(1, 0);
+  staging_.clear();
   first_id_ = consumed_;  // sequence.hpp:1616
   std::string line, seq, tmp;
-  uint64_t n = 0;
+  uint64_t n = 0, total = 0;
+  bool uniform = true;
+  uint64_t len0 = 0;
   while (max_reads == 0 || n < max_reads) {
     if (has_pending_) { line.swap(pending_); has_pending_ = false; }
     else {
@@ -118,8 +191,8 @@ uint64_t ChunkReader::next(uint64_t max_reads)
     // name = header up to the first white space (kseq semantics)
     size_t e = 1;
     while (e < line.size() && line[e] != ' ' && line[e] != '\t') ++e;
-    names_.append(line, 1, e - 1);
-    name_ptr_.push_back(names_.size());
+    s.names.append(line, 1, e - 1);
+    s.name_ptr.push_back(s.names.size());
     seq.clear();
     while (getline(tmp)) {
       if (fastq && !tmp.empty() && tmp[0] == '+') break;
@@ -130,9 +203,20 @@ uint64_t ChunkReader::next(uint64_t max_reads)
       size_t q = 0;
       while (q < seq.size() && getline(tmp)) q += tmp.size();
     }
-    bases_.append(seq.data(), seq.size());
-    read_ptr_.push_back(bases_.size());
+    if (packed) staging_.insert(staging_.end(), seq.begin(), seq.end());
+    else s.bases.append(seq.data(), seq.size());
+    total += seq.size();
+    s.read_ptr.push_back(total);
+    if (n == 0) len0 = seq.size();
+    else if (seq.size() != len0) uniform = false;
     ++n;
+  }
+  uniform_len_ = (n && uniform && len0 && len0 <= 0xffffffffull) ? (uint32_t)len0 : 0u;
+  if (packed) {
+    const uint64_t n_words = total / 32 + 2;
+    s.words.reserve(n_words * sizeof(uint64_t));
+    s.words.resize(n_words * sizeof(uint64_t));
+    pack_bases(staging_.data(), total, reinterpret_cast<uint64_t*>(s.words.data()), s.exc);
   }
   consumed_ += n;
   return n;

@@ -134,25 +134,26 @@ def test_no_paths_all_loci_equals_closed_form(name, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("seeding,items,fused", [(1, 2, 0), (0, 4, 0), (1, 4, 0), (0, 3, 1), (0, 5, 1)],
-                         ids=["staged-2", "direct-4", "staged-4", "fused-3ctas", "fused-5ctas"])
+@pytest.mark.parametrize("seeding,items,fused", [(1, 2, 0), (0, 4, 0), (1, 4, 0), (0, 1, 1), (0, 1, 0)],
+                         ids=["staged-2", "direct-4", "staged-4", "fused-by-rank", "unfused-by-rank"])
 @pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "multi_k32", "fuzz_07", "fuzz_10", "fuzz_11"])
 def test_kernel_variants_give_the_same_set(name, seeding, items, fused):
     """The alternative kernels behind the tuning options (2-bit staged seeding, 4 items per thread in the resolve
-    kernel, the fused kernel compiled for 3 or 5 resident CTAs) must give the reference's set too; the defaults are
-    covered by every other test."""
+    kernel, index entries that carry (node rank, offset) instead of (node id, offset)) must give the reference's set
+    too; the defaults are covered by every other test."""
     c = CASES[name]
     g, rp, bases = load_case(c)
     ctx = capi.Context(c["k"], 0)
     ctx.set_option("fused", fused)
-    if fused:
-        ctx.set_option("fused_ctas", items)
+    if items == 1:
+        ctx.set_option("code_by_rank", 1)
     else:
         ctx.set_option("seeding_mode", seeding)
         ctx.set_option("resolve_items", items)
     ctx.set_graph(g, ids="coord")
     ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
     ctx.find_loci()
+    assert ctx.counters()["code_by_rank"] == (1 if items == 1 else 0)
     rec, total = run_chunks(ctx, rp, bases, c["d"], c["chunk"])
     got = capi.canonical(rec)
     assert total == len(got) == c["count"]
@@ -596,3 +597,224 @@ def test_forked_contexts_share_the_index_and_run_concurrently():
     child.submit_chunk(rp, bases, 0, c["d"])
     assert child.seeds_all() == c["count"]
     child.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 2-bit packed chunks in, dense per-seed results out, asynchronous steps (the formats the e2e path moves over PCIe)
+
+def run_chunks_packed(ctx, rp, bases, d, chunk, flags=capi.ALL, with_read_ptr=None):
+    n = len(rp) - 1
+    chunk = chunk or n
+    parts, total = [], 0
+    for b in range(0, max(n, 1), max(chunk, 1)):
+        e = min(n, b + chunk)
+        p = capi.Packed.pack(rp[b:e + 1] - rp[b], bases[int(rp[b]):int(rp[e])], b)
+        ctx.submit_chunk_packed(p, d, with_read_ptr)
+        cnt = ctx.seeds_all(flags)
+        rec = ctx.fetch()
+        assert len(rec) == cnt
+        parts.append(rec)
+        total += cnt
+    return np.concatenate(parts) if parts else np.zeros((0, 4), np.uint64), total
+
+
+@pytest.mark.parametrize("mode", ROUTES, ids=ROUTE_IDS)
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_packed_chunks_match_reference_golden(name, mode):
+    """The same golden seed sets when the chunk arrives as 2-bit words + exception list (psi_b200_submit_chunk_packed)."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"], mode=mode)
+    rec, total = run_chunks_packed(ctx, rp, bases, c["d"], c["chunk"])
+    assert ctx.counters()["fused"] == (1 if mode == (0, 1) else 0), "the route under test did not run"
+    got = capi.canonical(rec)
+    assert total == len(got) == c["count"]
+    assert util.md5_tuples(got) == c["md5"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("by_rank", [0, 1], ids=["by-id", "by-rank"])
+@pytest.mark.parametrize("packed", [0, 1], ids=["ascii", "packed"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_dense_results_match_reference_golden(name, packed, by_rank):
+    """PSI_B200_DENSE: one {node id, node offset | off-path bit} pair per seed + the extra list of multi-locus seeds
+    carry exactly the golden set, and the same on/off-path split as the records."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_option("code_by_rank", by_rank)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(g.pick_paths(c["n_paths"], seed=1))
+    ctx.find_loci()
+    n = len(rp) - 1
+    chunk = c["chunk"] or n
+    parts, kinds, parts_rec, kinds_rec = [], [], [], []
+    for b in range(0, n, chunk):
+        e = min(n, b + chunk)
+        sub_ptr, sub_bases = rp[b:e + 1] - rp[b], bases[int(rp[b]):int(rp[e])]
+        if packed:
+            ctx.submit_chunk_packed(capi.Packed.pack(sub_ptr, sub_bases, b), c["d"])
+        else:
+            ctx.submit_chunk(sub_ptr, sub_bases, b, c["d"])
+        cnt = ctx.seeds_all(capi.ALL | capi.DENSE)
+        dense, extra = ctx.fetch_dense()
+        rec, kd = capi.dense_to_records(dense, extra, sub_ptr, c["k"], c["d"], b)
+        assert cnt == len(rec)
+        parts.append(rec)
+        kinds.append(kd)
+        with pytest.raises(capi.PsiError):
+            ctx.fetch()                  # the resident results are dense
+        cnt2 = ctx.seeds_all(capi.ALL)
+        parts_rec.append(ctx.fetch())
+        kinds_rec.append(ctx.fetch_kinds())
+        assert cnt2 == cnt
+    rec, kd = np.concatenate(parts), np.concatenate(kinds)
+    got = capi.canonical(rec)
+    assert len(got) == len(rec) == c["count"]
+    assert util.md5_tuples(got) == c["md5"]
+    with_kind = lambda r, k_: np.unique(np.column_stack([r.astype(np.uint64), k_.astype(np.uint64)]), axis=0)
+    assert np.array_equal(with_kind(rec, kd), with_kind(np.concatenate(parts_rec), np.concatenate(kinds_rec)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+def test_packed_ragged_reads_every_alignment_and_k(fused):
+    """2-bit chunks: reads of every length 0..70 (seeds start at every 2-bit alignment of a word), N / lower case
+    sprinkled in (exception list), k from 3 to 32 and d from 1 to k + 3, records and dense results against the oracle."""
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    og = orc.OGraph.of(g)
+    _, full = util.read_fasta(util.GOLDEN / "inputs/reads_n10000l100e0i0.fa.gz")
+    rng = np.random.default_rng(6)
+    lens = np.concatenate([np.arange(0, 71), rng.integers(0, 71, 400)])
+    rng.shuffle(lens)
+    rp = np.zeros(len(lens) + 1, np.uint64)
+    rp[1:] = np.cumsum(lens)
+    starts = rng.integers(0, len(full) // 100 - 1, len(lens)) * 100 + rng.integers(0, 30, len(lens))
+    bases = np.concatenate([full[s:s + n] for s, n in zip(starts, lens)]).copy()
+    for i in rng.integers(0, len(bases), 60):
+        bases[i] = ord("N") if i % 2 else bases[i] | 0x20
+    p = capi.Packed.pack(rp, bases, 11)
+    assert p.read_len == 0 and len(p.exc) > 10
+    for k in (3, 4, 5, 12, 19, 20, 27, 28, 31, 32):
+        ctx = capi.Context(k, 0)
+        ctx.set_option("fused", fused)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(g.pick_paths(2, seed=3))
+        ctx.find_loci()
+        for d in sorted({1, 2, k, k + 3}):
+            if k < 8 and d < k:
+                continue
+            want, _ = orc.seeds_closed_form(og, orc.OReads(rp, bases, 11), k, d)
+            ctx.submit_chunk_packed(p, d)
+            n = ctx.seeds_all()
+            got = capi.canonical(ctx.fetch())
+            assert n == len(got), (k, d)
+            assert np.array_equal(got, want), (k, d)
+            n2 = ctx.seeds_all(capi.ALL | capi.DENSE)
+            dense, extra = ctx.fetch_dense()
+            rec, _ = capi.dense_to_records(dense, extra, rp, k, d, 11)
+            assert n2 == n and np.array_equal(capi.canonical(rec), want), (k, d)
+        ctx.close()
+
+
+def test_equal_length_packed_chunk_without_offsets():
+    """read_len != 0 and read_ptr == NULL: the chunk is words + a length; all routes, dense results and records."""
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    p = capi.Packed.pack(rp, bases, 0)
+    assert p.read_len == 100
+    for mode in ROUTES:
+        ctx, _ = make_ctx(g, c["k"], c["n_paths"], mode=mode)
+        ctx.submit_chunk_packed(p, c["d"], with_read_ptr=False)
+        n = ctx.seeds_all()
+        assert n == c["count"] and util.md5_tuples(capi.canonical(ctx.fetch())) == c["md5"]
+        if mode[0] == 0:
+            ctx.submit_chunk_packed(p, c["d"], with_read_ptr=False)
+            n = ctx.seeds_all(capi.ALL | capi.DENSE)
+            dense, extra = ctx.fetch_dense()
+            rec, _ = capi.dense_to_records(dense, extra, rp, c["k"], c["d"], 0)
+            assert n == c["count"] and util.md5_tuples(capi.canonical(rec)) == c["md5"]
+        ctx.close()
+
+
+def test_async_steps_over_forked_contexts_from_one_thread():
+    """psi_b200_seeds_all_async / fetch_dense_async / wait: ONE host thread keeps four pipelines in flight; the
+    results equal the synchronous ones.  Calls that need a finished step fail with ERR_STATE while one is in flight."""
+    import torch
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], c["n_paths"])
+    pipes = [ctx] + [ctx.fork() for _ in range(3)]
+    n = len(rp) - 1
+    bounds = np.linspace(0, n, 9).astype(int)
+    per_read = (100 - c["k"]) // c["d"] + 1
+    bufs = [(torch.empty((2500 * per_read, 2), dtype=torch.int32).pin_memory(), torch.empty((4096, 4), dtype=torch.int32).pin_memory())
+            for _ in pipes]
+    chunks = []
+    for i in range(8):
+        b, e = bounds[i], bounds[i + 1]
+        chunks.append((b, e, capi.Packed.pack(rp[b:e + 1] - rp[b], bases[int(rp[b]):int(rp[e])], b)))
+    recs = []
+
+    def finish(slot, job):
+        b, e, p = job
+        cnt = pipes[slot].wait()
+        ns, ne = pipes[slot].dense_counts()
+        assert ns == (e - b) * per_read
+        dense = bufs[slot][0].numpy().view(np.uint32)[:ns].copy()
+        extra = bufs[slot][1].numpy().view(np.uint32)[:ne].copy()
+        rec, _ = capi.dense_to_records(dense, extra, p.read_ptr, c["k"], c["d"], b)
+        assert len(rec) == cnt
+        recs.append(rec)
+
+    inflight = [None] * 4
+    for i, job in enumerate(chunks):
+        slot = i % 4
+        if inflight[slot] is not None:
+            finish(slot, inflight[slot])
+        cx = pipes[slot]
+        cx.submit_chunk_packed(job[2], c["d"], with_read_ptr=False)
+        cx.seeds_all_async(capi.ALL | capi.DENSE)
+        cx.fetch_dense_async(bufs[slot][0].data_ptr(), bufs[slot][0].shape[0], bufs[slot][1].data_ptr(), bufs[slot][1].shape[0])
+        if i == 0:
+            for call in (cx.seeds_all, cx.fetch_dense, cx.fetch, lambda: cx.submit_chunk_packed(job[2], c["d"])):
+                with pytest.raises(capi.PsiError) as e:
+                    call()
+                assert e.value.code == capi.ERR_STATE
+        inflight[slot] = job
+    for slot in range(4):
+        if inflight[slot] is not None:
+            finish(slot, inflight[slot])
+    got = capi.canonical(np.concatenate(recs))
+    assert len(got) == c["count"] and util.md5_tuples(got) == c["md5"]
+    # records (not dense) through the asynchronous pair as well
+    ctx.submit_chunk(rp, bases, 0, c["d"])
+    ctx.seeds_all_async(capi.ALL | capi.COMPACT)
+    assert ctx.wait() == c["count"]
+    assert util.md5_tuples(capi.canonical(ctx.fetch32().astype(np.uint64))) == c["md5"]
+    # a route the fused kernel does not serve completes inside seeds_all_async
+    ctx.seeds_all_async(capi.ALL | capi.SORTED)
+    assert ctx.wait() == c["count"]
+    for cx in pipes[1:]:
+        cx.close()
+    ctx.close()
+
+
+def test_dense_refuses_what_it_cannot_serve():
+    c = CASES["fuzz_00"]
+    g, rp, bases = load_case(c)
+    ctx, _ = make_ctx(g, c["k"], 2, mode=(1, 1))      # walk mode: the off-path hits are not in the index
+    ctx.submit_chunk(rp, bases, 0, c["d"])
+    with pytest.raises(capi.PsiError) as e:
+        ctx.seeds_all(capi.ALL | capi.DENSE)
+    assert e.value.code == capi.ERR_ARG
+    n_on = ctx.seeds_all(capi.ON_PATHS | capi.DENSE)   # the on-path phase alone is served by the index
+    dense, extra = ctx.fetch_dense()
+    rec, kinds = capi.dense_to_records(dense, extra, rp, c["k"], c["d"], 0)
+    assert len(rec) == n_on and (kinds == 1).all()
+    assert ctx.seeds_all(capi.ON_PATHS) == n_on
+    assert np.array_equal(capi.canonical(rec), capi.canonical(ctx.fetch()))
+    with pytest.raises(capi.PsiError) as e:
+        ctx.seeds_all(capi.ALL | capi.DENSE | capi.SORTED)
+    assert e.value.code == capi.ERR_ARG
+    ctx.close()
