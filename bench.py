@@ -37,8 +37,6 @@ sys.path.insert(0, os.fspath(ROOT))
 TRAFFIC = {
     "seeds_on_paths_kernel": (662.9e6, "profiles/r01i_kernels_ncu_raw.csv: seeds_on_paths_kernel<8>, dram__bytes_read.sum 635.3 MB + "
                                        "dram__bytes_write.sum 27.6 MB (mean of 2 launches)"),
-    "seeds_fused_kernel": (897.6e6, "profiles/r01zn_fused_ncu_raw.csv: seeds_fused_kernel<8, 5, 4>, dram__bytes_read.sum 780.6 MB + "
-                                    "dram__bytes_write.sum 117.0 MB (mean of 2 launches)"),
 }
 
 K = 20
@@ -216,11 +214,84 @@ def main_reference(args):
 
 # ------------------------------------------------------------ GPU arm --
 
+class Workload:
+    """One graph + index + read batches on this rank's GPU: the pipelines (a context and its forks sharing the resident
+    index), the batches as ASCII and as 2-bit words, resident in HBM and in pinned host memory."""
+
+    def __init__(self, torch, dev, rank, shape, k, read_len, n_reads, n_batches, n_paths, n_pipes, offpath_mode=0, opts=()):
+        from bench_support import synth
+        from psi_b200 import capi
+        self.torch, self.dev, self.rank, self.k, self.read_len, self.n_reads = torch, dev, rank, k, read_len, n_reads
+        t0 = time.time()
+        self.g = g = build_graph(shape)
+        ps = g.pick_paths(n_paths, seed=1)
+        self.ctx = ctx = capi.Context(k, dev.index)
+        ctx.set_option("offpath_mode", offpath_mode)
+        for kv in opts:
+            name, val = kv.split("=")
+            ctx.set_option(name, int(val))
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_graph(g, ids="internal")
+        ctx.set_paths(ps)
+        self.n_loci = ctx.find_loci()
+        self.c0 = c0 = ctx.counters()
+        if rank == 0:
+            log(f"[bench] {shape}: graph {g.n_nodes} nodes / {g.n_bases} bp; index {c0['n_index_kmers']} k-mers, "
+                f"{c0['index_bytes'] / 1e6:.0f} MB, slot {c0['index_slot_bytes']} B, locus codes by "
+                f"{'rank' if c0['code_by_rank'] else 'id'} ({c0['code_off_bits']} offset bits), build {c0['ms_index_build']:.0f} ms; "
+                f"{self.n_loci} starting loci, {c0['n_offpath_walks']} uncovered walks -> {c0['n_offpath_entries']} off-path entries "
+                f"(mode {c0['offpath_mode']}) in {c0['ms_find_loci']:.0f} ms; setup {time.time() - t0:.1f} s")
+        self.per_read = (read_len - k) // k + 1
+        self.n_seeds = n_reads * self.per_read
+        # distinct read batches per rank (weak scaling: every GPU processes its own shard of the read set)
+        self.ascii_h, self.ascii_d, self.words_h, self.words_d = [], [], [], []
+        t_pack = 0.0
+        for b in range(n_batches):
+            rp, bases = synth.reads(g, n_reads, read_len, 1002 + 1000 * rank + b)
+            hp = torch.from_numpy(rp.view(np.int64)).pin_memory()
+            hb = torch.from_numpy(bases).pin_memory()
+            t1 = time.perf_counter()
+            pk = capi.Packed.pack(rp, bases, rank * n_reads)       # what psi_b200_reader_next_packed does per chunk
+            t_pack += time.perf_counter() - t1
+            assert pk.read_len == read_len and len(pk.exc) == 0
+            hw = torch.from_numpy(pk.words.view(np.int64)).pin_memory()
+            self.ascii_h.append((hp, hb))
+            self.ascii_d.append((hp.to(dev), hb.to(dev)))
+            self.words_h.append(hw)
+            self.words_d.append(hw.to(dev))
+        self.pack_gbs = n_batches * n_reads * read_len / t_pack / 1e9 / 2   # pack_bases is run twice by Packed.pack (count, then fill)
+        self.n_batches = n_batches
+        self.pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
+        n_extra_cap = self.n_seeds // 8 + 4096
+        self.dense_h = [torch.empty((self.n_seeds, 2), dtype=torch.int32).pin_memory() for _ in self.pipes]
+        self.extra_h = [torch.empty((n_extra_cap, 4), dtype=torch.int32).pin_memory() for _ in self.pipes]
+        self.rec_h = [None] * len(self.pipes)
+        torch.cuda.synchronize()
+
+    # ---- one step on pipeline p: queue the chunk, the kernels and (e2e) the copy of the results ----
+    def submit(self, p, i, fmt, where):
+        cx, b, first = self.pipes[p], i % self.n_batches, self.rank * self.n_reads
+        if fmt == "packed":
+            w = (self.words_d if where == "device" else self.words_h)[b]
+            cx.submit_chunk_packed_raw(self.n_reads, self.n_reads * self.read_len, self.read_len, w.data_ptr(), first, self.k,
+                                       on_device=(where == "device"))
+        elif where == "device":
+            dp, db = self.ascii_d[b]
+            cx.submit_chunk_device(self.n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), first, self.k)
+        else:
+            hp, hb = self.ascii_h[b]
+            cx.submit_chunk_ptr(self.n_reads, hp.data_ptr(), hb.data_ptr(), first, self.k)
+
+    def close(self):
+        for cx in self.pipes[1:]:
+            cx.close()
+        self.ctx.close()
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
-    from bench_support import synth
-    from psi_b200 import capi
+    from psi_b200 import capi, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,81 +303,113 @@ def main_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    t0 = time.time()
-    g = build_graph(args.shape)
-    ps = g.pick_paths(N_PATHS, seed=1)
-    ctx = capi.Context(K, local)
-    ctx.set_option("offpath_mode", args.offpath_mode)
-    for kv in args.opt:
-        name, val = kv.split("=")
-        ctx.set_option(name, int(val))
-    if args.blocking_sync:
-        ctx.set_option("blocking_sync", 1)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    ctx.set_graph(g, ids="internal")
-    ctx.set_paths(ps)
-    n_loci = ctx.find_loci()
-    c0 = ctx.counters()
-    if rank == 0:
-        log(f"[bench] graph {g.n_nodes} nodes / {g.n_bases} bp; index {c0['n_index_kmers']} k-mers, "
-            f"{c0['index_bytes'] / 1e6:.0f} MB, slot {c0['index_slot_bytes']} B, build {c0['ms_index_build']:.0f} ms; "
-            f"{n_loci} starting loci, {c0['n_offpath_walks']} uncovered walks -> {c0['n_offpath_entries']} off-path entries "
-            f"(mode {c0['offpath_mode']}) in {c0['ms_find_loci']:.0f} ms; setup {time.time() - t0:.1f} s")
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    # distinct read batches per rank (weak scaling: every GPU processes its own shard of the read set)
-    n_reads = args.reads
-    batches_h, batches_d = [], []
-    for b in range(N_BATCHES):
-        rp, bases = synth.reads(g, n_reads, READ_LEN, 1002 + 1000 * rank + b)
-        hp = torch.from_numpy(rp.view(np.int64)).pin_memory()
-        hb = torch.from_numpy(bases).pin_memory()
-        batches_h.append((hp, hb))
-        batches_d.append((hp.to(dev), hb.to(dev)))
-    # e2e runs two pipelines (the context and a fork sharing its resident index) from two host threads, so that
-    # the upload of one batch overlaps the kernels and the download of the previous one (PCIe is full duplex)
-    n_pipes = max(1, args.pipelines)                 # e2e: two pipelines keep both PCIe directions busy; more only contend
-    # resident inputs: four pipelines let one chunk's kernel tail overlap the next one's head (5.4 vs 4.7 G reads/s on one
-    # GPU), but every pipeline is a host thread that spins in its stream synchronisation: with fewer than 8 host cores
-    # per rank (8 ranks on this 32-core box) four of them get in each other's way (35.2 vs 37.1 G reads/s at 8 GPUs)
-    n_vpipes = args.value_pipelines if args.value_pipelines > 0 else (4 if (os.cpu_count() or 1) // world >= 8 else 2)
-    pipes = [ctx] + [ctx.fork() for _ in range(max(n_pipes, n_vpipes) - 1)]
-    rec_hosts = [torch.empty((8 * n_reads, 4), dtype=torch.int64).pin_memory() for _ in range(n_pipes)]   # room for the seed records
-    torch.cuda.synchronize()
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
-    def step_device(i):
-        dp, db = batches_d[i % N_BATCHES]
-        ctx.submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
-        return ctx.seeds_all(capi.ALL)
+    def run_async(W, steps, warmup, n_pipes, fmt, where, flags, fetch):
+        """K steps through the C-ABI issued by ONE host thread round-robin over n_pipes contexts: submit_chunk* ->
+        seeds_all_async (-> fetch_dense_async); a context's previous step is completed (psi_b200_wait) only when the
+        context comes round again, so n_pipes chunks are in flight.  Timed with CUDA events after a barrier +
+        synchronize; every step has been waited for before the closing event.  Returns (ms, hits, launches, fused kernel
+        ms per step from the contexts' CUDA events)."""
+        pipes = W.pipes[:n_pipes]
+        busy = [False] * n_pipes
 
-    def step_e2e(i, p=0, compact=True):
-        hp, hb = batches_h[i % N_BATCHES]
-        cx, rec_host = pipes[p], rec_hosts[p]
-        cx.submit_chunk_ptr(n_reads, hp.data_ptr(), hb.data_ptr(), rank * n_reads, K)
-        if compact:      # 4 x u32 records: the same fields, half the bytes over PCIe
-            cx.seeds_all(capi.ALL | capi.COMPACT)
-            return cx.fetch32_into(rec_host.data_ptr(), rec_host.shape[0])
-        cx.seeds_all(capi.ALL)
-        return cx.fetch_into(rec_host.data_ptr(), rec_host.shape[0])
+        def issue(i):
+            p = i % n_pipes
+            n = 0
+            if busy[p]:
+                n = pipes[p].wait()
+            W.submit(p, i, fmt, where)
+            pipes[p].seeds_all_async(flags)
+            if fetch:
+                pipes[p].fetch_dense_async(W.dense_h[p].data_ptr(), W.n_seeds, W.extra_h[p].data_ptr(), W.extra_h[p].shape[0])
+            busy[p] = True
+            return n
 
-    def step_resident(i, p=0):
-        dp, db = batches_d[i % N_BATCHES]
-        pipes[p].submit_chunk_device(n_reads, dp.data_ptr(), db.data_ptr(), db.numel(), rank * n_reads, K)
-        return pipes[p].seeds_all(capi.ALL)
+        def drain():
+            n = 0
+            for p in range(n_pipes):
+                if busy[p]:
+                    n += pipes[p].wait()
+                    busy[p] = False
+            return n
 
-    def timed_e2e(steps, warmup, step_fn=step_e2e, n_pipes=n_pipes):
-        """K steps through the C-ABI, round-robin over the first n_pipes pipelines, one host thread each."""
         for i in range(max(warmup, n_pipes)):
-            step_fn(i, i % n_pipes)
+            issue(i)
+        drain()
         barrier()
         for cx in pipes:
             cx.reset_counters()
-        hits = [0] * n_pipes
-        errors = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hits = 0
+        e0.record()
+        for i in range(steps):
+            hits += issue(warmup + i)
+        hits += drain()
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        cs = [cx.counters() for cx in pipes]
+        launches = sum(c["launches"] for c in cs)
+        timed = sum(c["timed_steps"] for c in cs)
+        k_ms = sum(c["ms_probe_sum"] for c in cs) / timed if timed else 0.0
+        return ms, hits, launches, k_ms
+
+    def run_sync(W, steps, warmup, fmt, flags):
+        """The same K steps on ONE context, each completed before the next is issued."""
+        cx = W.pipes[0]
+        for i in range(warmup):
+            W.submit(0, i, fmt, "device")
+            cx.seeds_all(flags)
+        barrier()
+        cx.reset_counters()
+        acc = {"ms_on": 0.0, "ms_probe": 0.0, "ms_pack": 0.0, "ms_resolve": 0.0, "n_hits": 0, "n_hits_on": 0, "n_seeds": 0,
+               "n_on_probe_sectors": 0, "n_walks": 0, "ms_off": 0.0, "ms_read_index": 0.0}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        hits = 0
+        e0.record()
+        for i in range(steps):
+            W.submit(0, warmup + i, fmt, "device")
+            hits += cx.seeds_all(flags)
+            c = cx.counters()
+            for k_ in acc:
+                acc[k_] += c[k_]
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), hits, acc, cx.counters()["launches"]
+
+    def run_threads_ascii(W, steps, warmup, n_pipes, compact=True):
+        """Round 1's e2e arm, kept for comparison: ASCII chunk up, 16-byte records per hit down, one host thread per
+        pipeline, every call synchronous."""
+        def step(i, p):
+            cx = W.pipes[p]
+            if W.rec_h[p] is None:
+                W.rec_h[p] = torch.empty((2 * W.n_seeds, 4), dtype=torch.int32 if compact else torch.int64).pin_memory()
+            W.submit(p, i, "ascii", "host")
+            if compact:
+                cx.seeds_all(capi.ALL | capi.COMPACT)
+                return cx.fetch32_into(W.rec_h[p].data_ptr(), W.rec_h[p].shape[0])
+            cx.seeds_all(capi.ALL)
+            return cx.fetch_into(W.rec_h[p].data_ptr(), W.rec_h[p].shape[0])
+        for i in range(max(warmup, n_pipes)):
+            step(i, i % n_pipes)
+        barrier()
+        hits, errors = [0] * n_pipes, []
 
         def work(p):
             try:
                 for i in range(p, steps, n_pipes):
-                    hits[p] += step_fn(warmup + i, p)
+                    hits[p] += step(warmup + i, p)
             except Exception as e:   # surfaced after join
                 errors.append(e)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,172 +423,125 @@ def main_gpu(args):
         barrier()
         if errors:
             raise errors[0]
-        ms = e0.elapsed_time(e1)
-        launches = sum(cx.counters()["launches"] for cx in pipes)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, sum(hits), launches
+        return max_over_ranks(e0.elapsed_time(e1)), sum(hits)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(step_fn, steps, warmup):
-        for i in range(warmup):
-            step_fn(i)
-        barrier()
-        ctx.reset_counters()
-        acc = {"ms_on": 0.0, "ms_probe": 0.0, "ms_off": 0.0, "ms_pack": 0.0, "ms_read_index": 0.0, "ms_resolve": 0.0, "ms_h2d": 0.0,
-               "ms_d2h": 0.0, "n_hits_on": 0, "n_hits": 0, "n_seeds": 0, "n_walks": 0, "n_on_probe_sectors": 0}
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        hits = 0
-        for i in range(steps):
-            hits += step_fn(warmup + i)
-            c = ctx.counters()          # syncs the stream; per-kernel CUDA-event times of this step
-            for k_ in acc:
-                acc[k_] += c[k_]
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        launches = ctx.counters()["launches"]
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, hits, acc, launches
+    n_reads, steps, warmup = args.reads, args.steps, args.warmup
+    n_pipes = max(1, args.pipelines)
+    W = Workload(torch, dev, rank, args.shape, K, READ_LEN, n_reads, N_BATCHES, N_PATHS, n_pipes, args.offpath_mode, args.opt)
+    ctx, c0 = W.ctx, W.c0
+    DENSE = capi.ALL | capi.DENSE
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, hits_dev, acc, launches = timed(step_device, args.steps, args.warmup)
-    c_last = ctx.counters()
-    ms_e2e, hits_e2e, launches_e2e = timed_e2e(args.steps, args.warmup)
-    ms_e2e_wide, hits_e2e_wide, _ = timed_e2e(args.steps, args.warmup, lambda i, p=0: step_e2e(i, p, compact=False))
-    # the resident-input step again with the pipelines running concurrently (kernels of one chunk fill the launch and
-    # latency gaps of the other); `value` stays the single-pipeline figure the per-kernel timers belong to
-    ms_pipe, hits_pipe, launches_pipe = timed_e2e(args.steps, args.warmup, step_resident, n_vpipes)
-    assert hits_e2e == hits_e2e_wide == hits_pipe == hits_dev, (hits_e2e, hits_e2e_wide, hits_pipe, hits_dev)
-    # the same resident step through the separate seeding / probe / resolve kernels: per-kernel times, and the
-    # seeds_on_paths probe alone for its own roofline
-    fused_run = bool(c_last["fused"])
-    if fused_run:
-        ctx.set_option("fused", 0)
-        ms_sep, hits_sep, acc_sep, _ = timed(step_device, args.steps, args.warmup)
-        ctx.set_option("fused", 1)
-        assert hits_sep == hits_dev, (hits_sep, hits_dev)
-    else:
-        ms_sep, acc_sep = ms_dev, acc
+    # value: 2-bit chunks resident in HBM -> dense results resident in HBM, n_pipes chunks in flight from one host thread
+    ms_val, hits_val, launches_val, kms_val = run_async(W, steps, warmup, n_pipes, "packed", "device", DENSE, False)
+    # e2e: the same call sequence with pinned HOST buffers: 2-bit chunk up, dense results down, inside the timed region
+    ms_e2e, hits_e2e, launches_e2e, kms_e2e = run_async(W, steps, warmup, n_pipes, "packed", "host", DENSE, True)
     clocks = sampler.stop() if rank == 0 else None
+    # beside them: ASCII chunks (the packing then runs inside the fused kernel) and round 1's record formats
+    ms_val_ascii, hits_a, _, kms_ascii = run_async(W, steps, warmup, n_pipes, "ascii", "device", DENSE, False)
+    ms_val_rec, hits_r, _, kms_rec = run_async(W, steps, warmup, n_pipes, "ascii", "device", capi.ALL, False)
+    ms_e2e_ascii, hits_ea = run_threads_ascii(W, steps, warmup, 2, compact=True)
+    ms_one, hits_one, acc_one, launches_one = run_sync(W, steps, warmup, "packed", DENSE)
+    assert hits_val == hits_e2e == hits_a == hits_r == hits_ea == hits_one, (hits_val, hits_e2e, hits_a, hits_r, hits_ea, hits_one)
+    # the same resident step through the separate seeding / probe / resolve kernels: the seeds_on_paths probe alone
+    ctx.set_option("fused", 0)
+    ms_sep, hits_sep, acc_sep, _ = run_sync(W, steps, warmup, "ascii", capi.ALL)
+    ctx.set_option("fused", 1)
+    assert hits_sep == hits_val, (hits_sep, hits_val)
 
     # per-shard counts and a hits-per-read histogram, reduced with NCCL (the only collective on this path)
-    from psi_b200 import shard
+    W.submit(0, 0, "packed", "device")
+    ctx.seeds_all(DENSE)
+    dense, extra = ctx.fetch_dense()
+    per_read = (dense[:, 0] != capi.NIL32).reshape(n_reads, W.per_read).sum(axis=1)
+    if len(extra):
+        per_read += np.bincount(extra[:, 2].astype(np.int64) - rank * n_reads, minlength=n_reads)[:n_reads]
+    hist = np.bincount(np.minimum(per_read, shard.HIST_BINS - 1), minlength=shard.HIST_BINS)
+    counts, hist = shard.all_reduce_counts({"reads": n_reads * steps, "seeds": acc_one["n_seeds"], "hits": hits_val,
+                                            "hits_on": acc_one["n_hits_on"]}, hist, device=dev)
 
-    class _DevArray:   # view the device records of the last step as a torch tensor (no copy)
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<i8", "data": (ptr, False), "version": 2}
-    step_device(0)
-    ptr, n_rec = ctx.fetch_device()
-    if n_rec:
-        rec = torch.as_tensor(_DevArray(ptr, n_rec), device=dev)
-        per_read = torch.bincount(rec[:, 2] - rank * n_reads, minlength=n_reads)[:n_reads]
-        hist = torch.bincount(torch.clamp(per_read, max=shard.HIST_BINS - 1), minlength=shard.HIST_BINS).cpu().numpy()
-    else:
-        hist = np.zeros(shard.HIST_BINS, np.int64)
-        hist[0] = n_reads
-    counts, hist = shard.all_reduce_counts({"reads": n_reads * args.steps, "seeds": acc["n_seeds"], "hits": hits_dev,
-                                            "hits_on": acc["n_hits_on"], "walks": acc["n_walks"]}, hist, device=dev)
-    tot = [counts["reads"], counts["seeds"], counts["hits"], counts["hits_on"], counts["walks"]]
+    other = {}
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(torch, dev, run_async, run_sync, capi)
 
     if rank == 0:
         peak, peak_src = peaks()
-        reads_total, seeds_total, hits_total, hits_on_total, walks_total = tot
-        # value: K steps issued round-robin over --value-pipelines contexts (the context and its forks share one resident index; a
-        # pipeline's host-side launch and read-back gaps are filled by the other's kernels) -- the way the library is
-        # meant to be driven, and the way e2e is measured.  The one-pipeline loop, whose per-kernel CUDA-event times
-        # feed `kernel_ms_per_step` and `roofline`, is reported beside it.
-        ms_value = ms_pipe if n_vpipes > 1 else ms_dev
-        value = reads_total / (ms_value * 1e-3)
-        # roofline of the dominant kernel (seeds_on_paths probe), rank 0's launches.  Algorithmic bytes per launch =
-        # seeds x (8 B packed k-mer + 128 B = ONE index bucket line, the DRAM access unit: profiles/r01c_gather_peak.md)
-        # + hits x 8 B compact record.  The 32-B-sector accounting of SURVEY 8d (40 B per seed) is reported beside it.
-        n_probe_hits = acc_sep["n_hits"] if c_last["offpath_mode"] == 2 else acc_sep["n_hits_on"]
-        alg_bytes = (acc_sep["n_seeds"] * 136 + n_probe_hits * 8) / args.steps
-        alg_bytes_sector = (acc_sep["n_seeds"] * 40 + n_probe_hits * 8) / args.steps
-        on_ms = acc_sep["ms_probe"] / args.steps  # the probe kernel alone; ms_on = probe + slow-queue kernel
-        achieved = alg_bytes / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
-        achieved_sector = alg_bytes_sector / (on_ms * 1e-3) / 1e9 if on_ms > 0 else 0.0
-        per_step = {k_: acc[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_probe", "ms_read_index", "ms_off", "ms_resolve")}
-        probe_roof = {"bound": "hbm", "kernel": "seeds_on_paths_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                      "frac": achieved / peak, "traffic": TRAFFIC["seeds_on_paths_kernel"][0], "peak_source": peak_src,
-                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": on_ms,
-                      "bytes_per_seed": "8 B k-mer + 128 B bucket line + 8 B per hit",
-                      "sector_accounting": {"bytes_per_seed": "8 B k-mer + 32 B sector + 8 B per hit (SURVEY 8d, P=1)",
-                                            "achieved": achieved_sector, "frac": achieved_sector / peak},
-                      "probes_per_s": acc_sep["n_seeds"] / args.steps / (on_ms * 1e-3) if on_ms > 0 else 0.0,
-                      "random_line_ceiling_probes_per_s": 4.0e10,
-                      "traffic_source": TRAFFIC["seeds_on_paths_kernel"][1]}
-        if fused_run:
-            # the fused kernel is the step: chunk bytes + read offsets in, one bucket line per seed, one 32-byte record
-            # + 1 kind byte per hit out (the position -> node gathers hit L2-resident arrays and are not counted)
-            hb0 = batches_h[0][1]
-            f_bytes = hb0.numel() + 8 * (n_reads + 1) + (acc["n_seeds"] * 128 + acc["n_hits"] * 33) / args.steps
-            f_sector = hb0.numel() + 8 * (n_reads + 1) + (acc["n_seeds"] * 32 + acc["n_hits"] * 33) / args.steps
-            f_ms = acc["ms_probe"] / args.steps
-            f_ach = f_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0
-            roof = {"bound": "hbm", "kernel": "seeds_fused_kernel", "achieved": f_ach, "peak": peak, "unit": "GB/s",
-                    "frac": f_ach / peak, "traffic": TRAFFIC["seeds_fused_kernel"][0], "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": f_bytes, "launch_ms": f_ms,
-                    "bytes_per_read": "read bytes + 8 B offset + per seed one 128 B bucket line + per hit a 32 B record and 1 kind byte",
-                    "sector_accounting": {"bytes": "the same with 32 B per seed instead of the 128 B line (SURVEY 8d, P=1)",
-                                          "achieved": f_sector / (f_ms * 1e-3) / 1e9 if f_ms > 0 else 0.0,
-                                          "frac": f_sector / (f_ms * 1e-3) / 1e9 / peak if f_ms > 0 else 0.0},
-                    "probes_per_s": acc["n_seeds"] / args.steps / (f_ms * 1e-3) if f_ms > 0 else 0.0,
-                    "random_line_ceiling_probes_per_s": 4.0e10,
-                    "traffic_source": TRAFFIC["seeds_fused_kernel"][1]}
-        else:
-            roof = probe_roof
-        e2e_value = n_reads * args.steps * world / (ms_e2e * 1e-3)
-        hp, hb = batches_h[0]
+        reads_total, seeds_total, hits_total = counts["reads"], counts["seeds"], counts["hits"]
+        value = reads_total / (ms_val * 1e-3)
+        seeds_step, hits_step = acc_one["n_seeds"] / steps, acc_one["n_hits"] / steps
+        words_bytes = int(W.words_h[0].numel() * 8)
+        ascii_bytes = int(W.ascii_h[0][1].numel() + W.ascii_h[0][0].numel() * 8)
+        extra_copy = (6 * n_reads + 1) // 64 + 256       # speculative share of the extra list copied with every step
+
+        def roof_of(kernel, launch_ms, in_bytes, out_per_seed, traffic_key, what):
+            # per query seed 8 B (k-mer) + 32 B (P = 1: one index sector), per hit 8 + 16 B
+            alg = seeds_step * 40 + hits_step * 24
+            line = in_bytes + seeds_step * 128 + seeds_step * out_per_seed       # what the kernel must move at DRAM-line granularity
+            t = launch_ms * 1e-3
+            tr = TRAFFIC.get(traffic_key, (None, "no ncu --set full capture of this kernel yet"))
+            return {"bound": "hbm", "kernel": kernel, "achieved": alg / t / 1e9 if t > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                    "frac": alg / t / 1e9 / peak if t > 0 else 0.0, "traffic": tr[0], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
+                    "accounting": "SURVEY 8(d), P = 1: seeds x (8 B k-mer + 32 B index sector) + hits x (8 B locus + 16 B record)",
+                    "line_accounting": {"bytes": what, "bytes_per_launch": line, "achieved": line / t / 1e9 if t > 0 else 0.0,
+                                        "frac": line / t / 1e9 / peak if t > 0 else 0.0,
+                                        "why": "a random access costs one 128-byte DRAM line whatever part of it is used "
+                                               "(profiles/r01c_gather_peak.md): the reachable ceiling is the random-line rate"},
+                    "probes_per_s": seeds_step / t if t > 0 else 0.0, "random_line_ceiling_probes_per_s": 4.0e10,
+                    "timed_in": "the loop that yields `value` (CUDA events on each pipeline's stream around every launch)",
+                    "traffic_source": tr[1]}
+
+        roof = roof_of("seeds_fused_kernel<8, 1, 4, dense, packed>", kms_val, words_bytes, 8, "seeds_fused_kernel_dense_packed",
+                       "2-bit chunk in + per seed one 128 B bucket line + 8 B result out")
+        probe_ms = acc_sep["ms_probe"] / steps
+        probe_roof = roof_of("seeds_on_paths_kernel<8>", probe_ms, seeds_step * 9, 9, "seeds_on_paths_kernel",
+                             "per seed 8 B k-mer + 1 B validity in, one 128 B bucket line, 9 B result out")
         line = {
             "metric": f"reads/s (fully-sensitive seed finding, {args.shape}-shape graph, k={K})",
-            "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_val / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u64", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.shape}-shape graph ({g.n_bases} bp, {g.n_nodes} nodes, {N_PATHS} paths, "
-                                   f"{n_loci} starting loci), {n_reads} x {READ_LEN} bp reads per GPU per step, k={K}, d={K}",
-                       "l2": f"{N_BATCHES} distinct read batches cycled ({N_BATCHES * n_reads * READ_LEN / 1e6:.0f} MB) and a "
-                             f"{c0['index_bytes'] / 1e6:.0f} MB index: inputs larger than L2",
+            "config": {"workload": f"synthetic {args.shape}-shape graph ({W.g.n_bases} bp, {W.g.n_nodes} nodes, {N_PATHS} paths, "
+                                   f"{W.n_loci} starting loci), {n_reads} x {READ_LEN} bp reads per GPU per step, k={K}, d={K}",
+                       "l2": f"{N_BATCHES} distinct read batches cycled and a {c0['index_bytes'] / 1e6:.0f} MB index probed at random: "
+                             f"inputs larger than L2",
                        "sharding": "reads sharded by rank, graph + index replicated, NCCL all-reduce of counts only",
-                       "pipelines": f"contexts per GPU sharing one resident index, steps issued round-robin: {n_vpipes} for value "
-                                    f"(inputs resident), {n_pipes} for e2e (more only contend for PCIe)"},
-            "seeds_per_s": hits_total / (ms_value * 1e-3), "query_seeds_per_s": seeds_total / (ms_value * 1e-3),
-            "kernel_ms_per_step": per_step, "probe_slow_seeds_per_step": acc["n_on_probe_sectors"] / args.steps,
-            "e2e": {"value": e2e_value, "unit": "reads/s",
-                    "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
-                    "d2h_bytes_per_step": int(hits_e2e / args.steps * 16), "ms_per_step": ms_e2e / args.steps,
-                    "pipelines": n_pipes,
-                    "records": "4 x u32 {node_id, node_offset, read_id, read_offset} per hit (PSI_B200_COMPACT + psi_b200_fetch32)"},
-            "e2e_wide_records": {"value": n_reads * args.steps * world / (ms_e2e_wide * 1e-3), "unit": "reads/s",
-                                 "h2d_bytes_per_step": int(hb.numel() + hp.numel() * 8),
-                                 "d2h_bytes_per_step": int(hits_e2e_wide / args.steps * 32),
-                                 "ms_per_step": ms_e2e_wide / args.steps, "pipelines": n_pipes,
-                                 "records": "4 x u64 per hit, the byte layout psikt writes (psi_b200_fetch)"},
-            "value_one_pipeline": {"value": reads_total / (ms_dev * 1e-3), "unit": "reads/s", "ms_per_step": ms_dev / args.steps,
-                                   "note": "the same K steps on ONE context, each step synchronised before the next is issued; "
-                                           "kernel_ms_per_step and roofline are this loop's CUDA-event times"},
-            "gpu_launches": int(launches_pipe if n_vpipes > 1 else launches), "gpu_launches_e2e": int(launches_e2e),
-            "offpath_mode": "index (walks from the starting loci materialised into the index)" if c_last["offpath_mode"] == 2
-                            else "walk (graph walked from the starting loci for every chunk)",
+                       "formats": "chunk = 2-bit words (psi_b200_packed_chunk, what psi_b200_reader_next_packed hands over; "
+                                  f"the reader's packer ran at {W.pack_gbs:.2f} GB/s of characters on one host core here); "
+                                  "results = dense {node id, node offset} per seed (PSI_B200_DENSE)",
+                       "pipelines": f"{n_pipes} contexts per GPU sharing one resident index, all driven by ONE host thread through "
+                                    "psi_b200_seeds_all_async / psi_b200_wait"},
+            "seeds_per_s": hits_total / (ms_val * 1e-3), "query_seeds_per_s": seeds_total / (ms_val * 1e-3),
+            "gpu_launches": int(launches_val), "gpu_launches_e2e": int(launches_e2e),
+            "e2e": {"value": reads_total / (ms_e2e * 1e-3), "unit": "reads/s",
+                    "h2d_bytes_per_step": words_bytes, "d2h_bytes_per_step": int(8 * W.n_seeds + 16 * extra_copy + 8 * 12),
+                    "ms_per_step": ms_e2e / steps, "pipelines": n_pipes, "host_threads": 1,
+                    "fused_kernel_ms": kms_e2e,
+                    "formats": "up: 2-bit words of the chunk (pinned host memory); down: 8 bytes per seed {node id, node offset | "
+                               "off-path bit} + the extra list of multi-locus seeds + the step's counters"},
             "roofline": roof,
-            "route": "fused one-pass kernel (seeding + probe + records)" if fused_run else "separate seeding / probe / resolve kernels",
-            "separate_kernels": {"note": "the same resident step with set_option('fused', 0): per-kernel CUDA-event times and the "
-                                         "seeds_on_paths probe kernel's own roofline",
-                                 "ms_per_step": ms_sep / args.steps,
-                                 "kernel_ms_per_step": {k_: acc_sep[k_] / args.steps for k_ in ("ms_pack", "ms_on", "ms_probe", "ms_resolve")},
+            "value_ascii_chunks": {"value": reads_total / (ms_val_ascii * 1e-3), "unit": "reads/s", "ms_per_step": ms_val_ascii / steps,
+                                   "fused_kernel_ms": kms_ascii,
+                                   "note": "ASCII chunk resident in HBM (2-bit packing inside the fused kernel), dense results"},
+            "value_ascii_chunks_records": {"value": reads_total / (ms_val_rec * 1e-3), "unit": "reads/s", "ms_per_step": ms_val_rec / steps,
+                                           "fused_kernel_ms": kms_rec,
+                                           "note": "ASCII chunk in, 4 x u64 records per hit out: round 1's `value` configuration"},
+            "value_one_pipeline": {"value": reads_total / (ms_one * 1e-3), "unit": "reads/s", "ms_per_step": ms_one / steps,
+                                   "fused_kernel_ms": acc_one["ms_probe"] / steps, "step_kernels_ms": acc_one["ms_on"] / steps,
+                                   "note": "the same K steps on ONE context, each step waited for before the next is issued"},
+            "e2e_ascii_chunks_records": {"value": reads_total / (ms_e2e_ascii * 1e-3), "unit": "reads/s", "ms_per_step": ms_e2e_ascii / steps,
+                                         "h2d_bytes_per_step": ascii_bytes, "d2h_bytes_per_step": int(hits_step * 16),
+                                         "note": "round 1's e2e arm: ASCII chunk up, 16-byte records per hit down, two host threads"},
+            "probe_slow_seeds_per_step": acc_one["n_on_probe_sectors"] / steps,
+            "offpath_mode": "index (walks from the starting loci materialised into the index)" if c0["offpath_mode"] == 2
+                            else "walk (graph walked from the starting loci for every chunk)",
+            "route": "fused one-pass kernel (seeding + probe + results)",
+            "separate_kernels": {"note": "the same resident step (ASCII in, 32-byte records out) with set_option('fused', 0): "
+                                         "per-kernel CUDA-event times and the seeds_on_paths probe kernel's own roofline",
+                                 "ms_per_step": ms_sep / steps,
+                                 "kernel_ms_per_step": {k_: acc_sep[k_] / steps for k_ in ("ms_pack", "ms_on", "ms_probe", "ms_resolve")},
                                  "roofline_probe": probe_roof},
             "clocks": clocks,
             "hits_per_read_histogram": {"bins": "reads with h hits in one step, h = 0..62, last bin >= 63; summed over ranks",
@@ -493,8 +549,10 @@ def main_gpu(args):
             "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
                       "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"],
                       "offpath_entries": c0["n_offpath_entries"], "offpath_walks": c0["n_offpath_walks"],
-                      "stash_used": c0["index_stash_used"]},
+                      "stash_used": c0["index_stash_used"], "locus_codes": "by rank" if c0["code_by_rank"] else "by id"},
         }
+        if other:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             try:
                 r = reference_run(budget_s=8.0)
@@ -503,11 +561,41 @@ def main_gpu(args):
                 line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference",
                                         "sample": f"unavailable: {type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
-    for cx in pipes[1:]:
-        cx.close()
-    ctx.close()
+    W.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(torch, dev, run_async, run_sync, capi):
+    """The other single-GPU shapes BASELINE.json names, one short measurement each (resident 2-bit chunks -> dense
+    results, 4 chunks in flight): configs[2]'s read shape (150 bp) on the chr22-shape graph, configs[3] (MHC-like
+    region, k = 32) in index mode and in walk mode (the reference's scheme: graph walked per chunk)."""
+    out = {}
+    DENSE = capi.ALL | capi.DENSE
+    for name, shape, k, read_len, n_reads, mode in (("chr22_150bp", "chr22", 20, 150, 1_000_000, 0),
+                                                     ("mhc_k32", "mhc", 32, 150, 1_000_000, 0),
+                                                     ("mhc_k32_walk_mode", "mhc", 32, 150, 200_000, 1)):
+        try:
+            globals().update(K=k, READ_LEN=read_len)
+            W = Workload(torch, dev, 0, shape, k, read_len, n_reads, 2, N_PATHS, 4, mode)
+            if mode == 0:
+                ms, hits, launches, kms = run_async(W, 6, 3, 4, "packed", "device", DENSE, False)
+                ms_e, hits_e, _, _ = run_async(W, 6, 3, 4, "packed", "host", DENSE, True)
+                out[name] = {"value": n_reads * 6 / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms / 6, "fused_kernel_ms": kms,
+                             "query_seeds_per_s": W.n_seeds * 6 / (ms * 1e-3), "hits_per_step": hits / 6,
+                             "e2e": n_reads * 6 / (ms_e * 1e-3), "index_bytes": W.c0["index_bytes"], "slot_bytes": W.c0["index_slot_bytes"],
+                             "starting_loci": W.n_loci, "offpath_entries": W.c0["n_offpath_entries"],
+                             "workload": f"{shape}-shape graph, {n_reads} x {read_len} bp reads per step, k={k}"}
+            else:
+                ms, hits, acc, launches = run_sync(W, 4, 3, "packed", capi.ALL)
+                out[name] = {"value": n_reads * 4 / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms / 4,
+                             "kernel_ms_per_step": {k_: acc[k_] / 4 for k_ in ("ms_pack", "ms_read_index", "ms_on", "ms_off", "ms_resolve")},
+                             "walks_per_step": acc["n_walks"] / 4, "starting_loci": W.n_loci,
+                             "workload": f"{shape}-shape graph walked from its starting loci for every chunk of {n_reads} x {read_len} bp reads, k={k}"}
+            W.close()
+        except Exception as e:   # an extra line must not take the headline down
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def main():
@@ -521,10 +609,8 @@ def main():
     ap.add_argument("--k", type=int, default=K, help="seed length (other BASELINE configs: 32 with --shape mhc)")
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipelines", type=int, default=2, help="e2e: contexts (forks sharing one index) driven concurrently")
-    ap.add_argument("--value-pipelines", type=int, default=0,
-                    help="value (inputs resident in HBM): contexts driven concurrently; 0 = 4 with >= 8 host cores per rank, else 2")
-    ap.add_argument("--blocking-sync", type=int, default=0, help="1: pipelines sleep on a blocking event instead of spinning")
+    ap.add_argument("--pipelines", type=int, default=4, help="contexts (forks sharing one index) kept in flight by the one host thread")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs (N = 1 only)")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
     args = ap.parse_args()

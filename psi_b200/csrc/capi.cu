@@ -397,6 +397,7 @@ int psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits)
 int psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {
+    if (ctx->c->pending) throw StateError("fetch: a step is in flight on this context (call psi_b200_wait first)");
     if (n_hits) *n_hits = ctx->c->n_hits;
     if (cap && !hits) throw ArgError("fetch: null buffer");
     if (cap) engine_fetch(*ctx->c, hits, cap, false);
@@ -406,6 +407,7 @@ int psi_b200_fetch(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_
 int psi_b200_fetch32(psi_b200_ctx* ctx, uint32_t* hits, uint64_t cap, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {
+    if (ctx->c->pending) throw StateError("fetch32: a step is in flight on this context (call psi_b200_wait first)");
     if (n_hits) *n_hits = ctx->c->n_hits;
     if (cap && !hits) throw ArgError("fetch32: null buffer");
     if (cap) engine_fetch(*ctx->c, hits, cap, true);
@@ -415,6 +417,7 @@ int psi_b200_fetch32(psi_b200_ctx* ctx, uint32_t* hits, uint64_t cap, uint64_t* 
 int psi_b200_fetch_kinds(psi_b200_ctx* ctx, uint8_t* kinds, uint64_t cap, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {
+    if (ctx->c->pending) throw StateError("fetch_kinds: a step is in flight on this context (call psi_b200_wait first)");
     if (n_hits) *n_hits = ctx->c->n_hits;
     if (cap && !kinds) throw ArgError("fetch_kinds: null buffer");
     if (cap) engine_fetch_kinds(*ctx->c, kinds, cap);

@@ -58,6 +58,61 @@ def test_reader_fasta_fastq_gz_and_chunking(tmp_path):
     assert e.value.code == capi.ERR_IO
 
 
+def _unpack(words, n):
+    w = np.asarray(words, np.uint64)
+    idx = np.arange(n)
+    return ((w[idx // 32] >> ((idx % 32) * 2).astype(np.uint64)) & np.uint64(3)).astype(np.uint8)
+
+
+def test_pack_bases_matches_a_plain_restatement():
+    """psi_b200_pack_bases (byte-parallel packer of the chunk reader) against numpy: codes A,C,G,T = 0..3 of either
+    case, everything else code 0 + its position in the exception list; every length around the 8- and 32-base groups."""
+    rng = np.random.default_rng(1)
+    alphabet = np.frombuffer(b"ACGTacgtNn-*RYKM", np.uint8)
+    code = np.zeros(256, np.uint8)
+    for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        code[ch] = v
+    valid = np.zeros(256, bool)
+    valid[list(b"ACGTacgt")] = True
+    for n in list(range(0, 70)) + [127, 128, 129, 1000, 4097]:
+        b = alphabet[rng.choice(len(alphabet), n, p=[0.2] * 4 + [0.02] * 4 + [0.015] * 8)]
+        rp = np.array([0, n], np.uint64)
+        pk = capi.Packed.pack(rp, b)
+        assert len(pk.words) == n // 32 + 2
+        assert np.array_equal(_unpack(pk.words, n), code[b]), n
+        assert np.array_equal(pk.exc, np.flatnonzero(~valid[b]).astype(np.uint64)), n
+        tail = np.asarray(pk.words, np.uint64)
+        assert n % 32 == 0 or int(tail[n // 32]) >> (2 * (n % 32)) == 0      # zero filled past the last base
+        assert int(tail[-1]) == 0
+
+
+def test_reader_delivers_packed_chunks_and_alternates_its_buffers(tmp_path):
+    """psi_b200_reader_next_packed: the same records as the character reader, as 2-bit words; equal-length chunks
+    say so; what a call returned stays intact while the next chunk is parsed (two buffer sets alternate)."""
+    fq = tmp_path / "r.fastq"
+    reads = ["ACGTACGTAC", "GGNCCATTAG", "TTTTTTTTTT", "acgtnACGTA", "CCCCCCCCCC", "ACG"]
+    fq.write_text("".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(reads)))
+    r = capi.Reader(fq)
+    a = r.next_packed(2)
+    ref = capi.Packed.pack(np.array([0, 10, 20], np.uint64), np.frombuffer("".join(reads[:2]).encode(), np.uint8))
+    assert a.read_len == 10 and a.first_read_id == 0 and np.array_equal(a.read_ptr, ref.read_ptr)
+    assert np.array_equal(a.words, ref.words) and a.exc.tolist() == [12]
+    # raw view of the first chunk, then parse the second: the first chunk's buffers must not change
+    v1 = capi.PackedChunk()
+    r2 = capi.Reader(fq)
+    capi._check(capi.lib().psi_b200_reader_next_packed(r2._h, 2, C.byref(v1)))
+    w1 = np.ctypeslib.as_array(C.cast(v1.words, C.POINTER(C.c_uint64)), shape=(2,)).copy()
+    v2 = capi.PackedChunk()
+    capi._check(capi.lib().psi_b200_reader_next_packed(r2._h, 2, C.byref(v2)))
+    assert v2.first_read_id == 2 and v2.words != v1.words
+    assert np.array_equal(np.ctypeslib.as_array(C.cast(v1.words, C.POINTER(C.c_uint64)), shape=(2,)), w1)
+    b = r.next_packed(2)
+    assert b.first_read_id == 2 and b.read_len == 10 and b.exc.tolist() == [14]
+    c = r.next_packed(0)
+    assert c.first_read_id == 4 and c.read_len == 0 and c.read_ptr.tolist() == [0, 10, 13]     # ragged: offsets needed
+    assert r.next_packed(2) is None
+
+
 def test_gfa1_and_gfa2_load_the_same_graph(tmp_path):
     g2 = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
     p = tmp_path / "x1.gfa"
