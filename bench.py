@@ -473,31 +473,41 @@ def main_gpu(args):
         seeds_step, hits_step = acc_one["n_seeds"] / steps, acc_one["n_hits"] / steps
         words_bytes = int(W.words_h[0].numel() * 8)
         ascii_bytes = int(W.ascii_h[0][1].numel() + W.ascii_h[0][0].numel() * 8)
-        extra_copy = (6 * n_reads + 1) // 64 + 256       # speculative share of the extra list copied with every step
+        off_bytes = ctx.dense_off_bytes()
+        extra_copy = (n_reads * READ_LEN // K + n_reads + 1) // 256 + 256     # speculative share of the extra list copied with every step
 
-        def roof_of(kernel, launch_ms, in_bytes, out_per_seed, traffic_key, what):
-            # per query seed 8 B (k-mer) + 32 B (P = 1: one index sector), per hit 8 + 16 B
+        def roof_of(kernel, launch_ms, wall_ms, in_bytes, out_per_seed, traffic_key, what):
+            # per query seed 8 B (k-mer) + 32 B (P = 1: one index sector), per hit 8 + 16 B.
+            # launch_ms = mean CUDA-event duration of a launch; with several pipelines the launches overlap on the
+            # device (concurrency = launch_ms / wall time per launch), so what the GPU achieves is bytes per launch /
+            # WALL time per launch = bytes x concurrency / launch_ms.
             alg = seeds_step * 40 + hits_step * 24
             line = in_bytes + seeds_step * 128 + seeds_step * out_per_seed       # what the kernel must move at DRAM-line granularity
-            t = launch_ms * 1e-3
+            t = min(launch_ms, wall_ms) * 1e-3
             tr = TRAFFIC.get(traffic_key, (None, "no ncu --set full capture of this kernel yet"))
             return {"bound": "hbm", "kernel": kernel, "achieved": alg / t / 1e9 if t > 0 else 0.0, "peak": peak, "unit": "GB/s",
                     "frac": alg / t / 1e9 / peak if t > 0 else 0.0, "traffic": tr[0], "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms,
-                    "accounting": "SURVEY 8(d), P = 1: seeds x (8 B k-mer + 32 B index sector) + hits x (8 B locus + 16 B record)",
+                    "algorithmic_bytes_per_launch": alg, "launch_ms": launch_ms, "wall_ms_per_launch": wall_ms,
+                    "concurrency": launch_ms / wall_ms if wall_ms > 0 else 1.0,
+                    "accounting": "SURVEY 8(d), P = 1: seeds x (8 B k-mer + 32 B index sector) + hits x (8 B locus + 16 B record); "
+                                  "achieved = those bytes / min(launch_ms, wall time per launch)",
                     "line_accounting": {"bytes": what, "bytes_per_launch": line, "achieved": line / t / 1e9 if t > 0 else 0.0,
                                         "frac": line / t / 1e9 / peak if t > 0 else 0.0,
                                         "why": "a random access costs one 128-byte DRAM line whatever part of it is used "
                                                "(profiles/r01c_gather_peak.md): the reachable ceiling is the random-line rate"},
                     "probes_per_s": seeds_step / t if t > 0 else 0.0, "random_line_ceiling_probes_per_s": 4.0e10,
                     "timed_in": "the loop that yields `value` (CUDA events on each pipeline's stream around every launch)",
+                    "launch_ms_alone": acc_one["ms_probe"] / steps,
                     "traffic_source": tr[1]}
 
-        roof = roof_of("seeds_fused_kernel<8, 1, 4, dense, packed>", kms_val, words_bytes, 8, "seeds_fused_kernel_dense_packed",
-                       "2-bit chunk in + per seed one 128 B bucket line + 8 B result out")
+        roof = roof_of("seeds_fused_kernel<8, 1, 4, dense, packed>", kms_val, ms_val / steps, words_bytes, 4 + off_bytes,
+                       "seeds_fused_kernel_dense_packed",
+                       f"2-bit chunk in + per seed one 128 B bucket line + {4 + off_bytes} B result out")
         probe_ms = acc_sep["ms_probe"] / steps
-        probe_roof = roof_of("seeds_on_paths_kernel<8>", probe_ms, seeds_step * 9, 9, "seeds_on_paths_kernel",
+        probe_roof = roof_of("seeds_on_paths_kernel<8>", probe_ms, probe_ms, seeds_step * 9, 9, "seeds_on_paths_kernel",
                              "per seed 8 B k-mer + 1 B validity in, one 128 B bucket line, 9 B result out")
+        probe_roof["timed_in"] = "the one-context loop of separate_kernels"
+        probe_roof.pop("launch_ms_alone")
         line = {
             "metric": f"reads/s (fully-sensitive seed finding, {args.shape}-shape graph, k={K})",
             "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -516,11 +526,11 @@ def main_gpu(args):
             "seeds_per_s": hits_total / (ms_val * 1e-3), "query_seeds_per_s": seeds_total / (ms_val * 1e-3),
             "gpu_launches": int(launches_val), "gpu_launches_e2e": int(launches_e2e),
             "e2e": {"value": reads_total / (ms_e2e * 1e-3), "unit": "reads/s",
-                    "h2d_bytes_per_step": words_bytes, "d2h_bytes_per_step": int(8 * W.n_seeds + 16 * extra_copy + 8 * 12),
+                    "h2d_bytes_per_step": words_bytes, "d2h_bytes_per_step": int((4 + off_bytes) * W.n_seeds + 16 * extra_copy + 8 * 12),
                     "ms_per_step": ms_e2e / steps, "pipelines": n_pipes, "host_threads": 1,
                     "fused_kernel_ms": kms_e2e,
-                    "formats": "up: 2-bit words of the chunk (pinned host memory); down: 8 bytes per seed {node id, node offset | "
-                               "off-path bit} + the extra list of multi-locus seeds + the step's counters"},
+                    "formats": f"up: 2-bit words of the chunk (pinned host memory); down: {4 + off_bytes} bytes per seed (u32 node id, "
+                               f"u{8 * off_bytes} node offset | off-path bit) + the extra list of multi-locus seeds + the step's counters"},
             "roofline": roof,
             "value_ascii_chunks": {"value": reads_total / (ms_val_ascii * 1e-3), "unit": "reads/s", "ms_per_step": ms_val_ascii / steps,
                                    "fused_kernel_ms": kms_ascii,

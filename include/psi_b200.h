@@ -252,8 +252,8 @@ int  psi_b200_submit_chunk_packed(psi_b200_ctx* ctx, const psi_b200_packed_chunk
 #define PSI_B200_COMPACT   16u   /* resolve into 4 x u32 records (psi_b200_fetch32): same fields, half the bytes over PCIe;
                                     PSI_B200_ERR_ARG when a node id or a read id of the chunk does not fit 32 bits */
 
-#define PSI_B200_DENSE     32u   /* per-seed results instead of per-hit records (psi_b200_fetch_dense): one pair of u32
-                                    {node_id, node_off | off-path << 31} per seed, in seed order; 8 bytes per seed over
+#define PSI_B200_DENSE     32u   /* per-seed results instead of per-hit records (psi_b200_fetch_dense): a u32 node id
+                                    and a u16 / u32 node offset per seed, in seed order; 6 (or 8) bytes per seed over
                                     PCIe, read id / offset implied.  Needs the off-path walks in the index (offpath_mode
                                     0 or 2) and ids below 2^32 - 1; excludes SORTED, NO_RESOLVE, COMPACT */
 
@@ -274,17 +274,24 @@ int  psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits);
 int  psi_b200_seeds_all_async(psi_b200_ctx* ctx, unsigned flags);
 int  psi_b200_wait(psi_b200_ctx* ctx, uint64_t* n_hits);
 
-/* Results of a PSI_B200_DENSE step.  Seed s of the chunk (seeds in read order; read r of a chunk of equal-length
- * reads owns seeds r * per_read .. with per_read = (len - k) / d + 1, offset (s % per_read) * d; sequence.hpp:1712)
- * has dense[2 s] = node id (0xffffffff: no hit) and dense[2 s + 1] = node offset, bit 31 set when the hit was found
- * off the indexed paths (seeds_off_paths).  Seeds whose k-mer occurs at several loci have their further hits in
+/* Results of a PSI_B200_DENSE step: two planes in seed order.  Seed s of the chunk (seeds in read order; read r of a
+ * chunk of equal-length reads owns seeds r * per_read .. with per_read = (len - k) / d + 1, offset (s % per_read) * d;
+ * sequence.hpp:1712) has
+ *     ids[s]  (u32)  node id, 0xffffffff = no hit;
+ *     offs[s] (u16 when no node label is longer than 32 768 bases, else u32; psi_b200_dense_layout tells) node offset,
+ *             top bit set when the hit was found off the indexed paths (seeds_off_paths).
+ * `dense` receives ids[n_seeds] immediately followed by offs[n_seeds]: n_seeds * (4 + off_bytes) bytes; cap_seeds is
+ * the number of seeds the buffer has room for.  Seeds whose k-mer occurs at several loci have their further hits in
  * `extra`: 4 x u32 {node_id, node_off, read_id, read_off | off-path << 31} each.  n_hits of the step = dense hits +
  * n_extra.  fetch_dense copies after a completed step; fetch_dense_async queues the copies behind a step in flight
- * (the buffers -- pinned, for the copy to be asynchronous -- are valid after psi_b200_wait).  When more than
- * cap_extra extra records exist the first cap_extra are delivered and *n_extra tells (fetch again with more room). */
-int  psi_b200_fetch_dense(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
+ * (the buffers -- pinned, for the copy to be asynchronous -- are valid after psi_b200_wait; chunks with reads of
+ * several lengths make it wait for the step's seed count first).  When more than cap_extra extra records exist the
+ * first cap_extra are delivered and *n_extra tells (fetch again with more room). */
+int  psi_b200_fetch_dense(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
                           uint64_t* n_seeds, uint64_t* n_extra);
-int  psi_b200_fetch_dense_async(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+int  psi_b200_fetch_dense_async(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+/* Width in bytes (2 or 4) of the node-offset plane for the graph of this context. */
+int  psi_b200_dense_layout(psi_b200_ctx* ctx, unsigned* off_bytes);
 /* Counts of the last completed dense step. */
 int  psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra);
 

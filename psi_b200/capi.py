@@ -28,7 +28,7 @@ SYMBOLS = [
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
-    "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts",
+    "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout",
     "psi_b200_global_error",
     "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
@@ -130,6 +130,7 @@ def lib() -> C.CDLL:
     L.psi_b200_fetch_dense.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]
     L.psi_b200_fetch_dense_async.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
     L.psi_b200_dense_counts.argtypes = [vp, u64p, u64p]
+    L.psi_b200_dense_layout.argtypes = [vp, C.POINTER(C.c_uint)]
     L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
     L.psi_b200_fork.argtypes = [vp, C.POINTER(vp)]
     L.psi_b200_destroy.argtypes = [vp]
@@ -462,13 +463,20 @@ class Context:
         self._ck(lib().psi_b200_dense_counts(self._h, C.byref(ns), C.byref(ne)))
         return ns.value, ne.value
 
+    def dense_off_bytes(self) -> int:
+        b = C.c_uint()
+        self._ck(lib().psi_b200_dense_layout(self._h, C.byref(b)))
+        return b.value
+
     def fetch_dense(self):
-        """After seeds_all(flags | DENSE): (dense (n_seeds, 2) u32, extra (n_extra, 4) u32)."""
+        """After seeds_all(flags | DENSE): (dense (n_seeds, 2) u32 {node id, node offset | off-path << 31}, extra (n_extra, 4) u32).
+        The library delivers two planes (ids u32, offsets u16 or u32); they are widened into pairs here."""
         ns, ne = self.dense_counts()
-        dense = np.zeros((ns, 2), np.uint32)
+        ob = self.dense_off_bytes()
+        raw = np.zeros(ns * (4 + ob), np.uint8)
         extra = np.zeros((ne, 4), np.uint32)
-        self._ck(lib().psi_b200_fetch_dense(self._h, _ptr(dense), ns, _ptr(extra), ne, C.byref(C.c_uint64()), C.byref(C.c_uint64())))
-        return dense, extra
+        self._ck(lib().psi_b200_fetch_dense(self._h, _ptr(raw), ns, _ptr(extra), ne, C.byref(C.c_uint64()), C.byref(C.c_uint64())))
+        return dense_planes(raw, ns, ob), extra
 
     def fetch_dense_async(self, dense_addr: int, cap_seeds: int, extra_addr: int, cap_extra: int):
         self._ck(lib().psi_b200_fetch_dense_async(self._h, C.c_void_p(dense_addr), cap_seeds, C.c_void_p(extra_addr), cap_extra))
@@ -529,6 +537,18 @@ class Context:
 
     def reset_counters(self):
         self._ck(lib().psi_b200_reset_counters(self._h))
+
+
+def dense_planes(raw: np.ndarray, n_seeds: int, off_bytes: int) -> np.ndarray:
+    """ids[n_seeds] u32 + offs[n_seeds] u16/u32 (top bit = off-path) -> (n_seeds, 2) u32 {node id, offset | off-path << 31}."""
+    raw = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    ids = raw[: 4 * n_seeds].view(np.uint32)
+    if off_bytes == 2:
+        o = raw[4 * n_seeds: 6 * n_seeds].view(np.uint16).astype(np.uint32)
+        offs = (o & 0x7FFF) | ((o >> 15) << 31)
+    else:
+        offs = raw[4 * n_seeds: 8 * n_seeds].view(np.uint32)
+    return np.column_stack([ids, offs]).astype(np.uint32)
 
 
 def seed_layout(read_ptr, k: int, d: int):

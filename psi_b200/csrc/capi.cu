@@ -360,7 +360,7 @@ int psi_b200_wait(psi_b200_ctx* ctx, uint64_t* n_hits)
   })
 }
 
-int psi_b200_fetch_dense(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
+int psi_b200_fetch_dense(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra,
                          uint64_t* n_seeds, uint64_t* n_extra)
 {
   CTX_GUARD(ctx, {
@@ -370,9 +370,17 @@ int psi_b200_fetch_dense(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds,
   })
 }
 
-int psi_b200_fetch_dense_async(psi_b200_ctx* ctx, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
+int psi_b200_fetch_dense_async(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
 {
   CTX_GUARD(ctx, engine_fetch_dense_async(*ctx->c, dense, cap_seeds, extra, cap_extra))
+}
+
+int psi_b200_dense_layout(psi_b200_ctx* ctx, unsigned* off_bytes)
+{
+  CTX_GUARD(ctx, {
+    if (!ctx->c->sh->has_graph) throw StateError("dense_layout: no graph");
+    if (off_bytes) *off_bytes = ctx->c->sh->max_node_len <= 32768u ? 2u : 4u;
+  })
 }
 
 int psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra)

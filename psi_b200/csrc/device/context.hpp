@@ -209,9 +209,12 @@ struct Ctx {
   uint64_t n_hits = 0;
   bool records_valid = false;
   bool records_compact = false;  // records hold 4 x u32 per hit (PSI_B200_COMPACT)
-  // dense results (PSI_B200_DENSE): `records` holds one {node_id, node_off | off-path << 31} pair of u32 per seed, in
-  // seed order (NIL32 id = no hit); further hits of seeds with several loci are 4 x u32 records in `extra`
+  // dense results (PSI_B200_DENSE): `records` holds two planes in seed order -- node ids (u32, NIL32 = no hit) and node
+  // offsets with the off-path flag in the top bit (u16 or u32); further hits of seeds with several loci are 4 x u32
+  // records in `extra`
   bool records_dense = false;
+  uint32_t dense_off_bytes = 4;      // width of the node-offset plane: 2 when no node is longer than 32 768 bases
+  uint64_t dense_off_plane = 0;      // byte offset of the node-offset plane inside `records`
   DevBuf<uint32_t> extra;
   uint64_t n_dense_seeds = 0, n_extra = 0;
   // ---- a step in flight (psi_b200_seeds_all_async .. psi_b200_wait) ----

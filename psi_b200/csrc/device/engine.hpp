@@ -26,8 +26,8 @@ void engine_seeds_fused(Ctx& c, unsigned probe_mode, int out_kind);
 void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind);
 void engine_seeds_async(Ctx& c, unsigned flags);   // queues the step when the fused route serves it, else runs it synchronously
 void engine_wait(Ctx& c);
-void engine_fetch_dense(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
-void engine_fetch_dense_async(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+void engine_fetch_dense(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+void engine_fetch_dense_async(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
 void engine_submit_chunk_packed(Ctx& c, const psi_b200_packed_chunk& chunk, unsigned distance, bool on_device);
 void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);

@@ -23,9 +23,10 @@
 //   3. the characters of the NEXT batch are requested;
 //   4. wait for the lines only, every thread scans its own line (16 tag compares);
 //   5. results
-//      DENSE:   one coalesced 8-byte store per seed: {node id, node offset | off-path << 31}, NIL id = no hit.
+//      DENSE:   two coalesced stores per seed into two planes: node id (u32, NIL = no hit) and node offset with the
+//               off-path flag in its top bit (u16 when no node is longer than 32 768 bases, else u32).
 //               No atomics, no lists, no CTA-wide barrier in the loop.  Read id and offset are implied by the
-//               seed's position in the array (seed order of the chunk).
+//               seed's position in the planes (seed order of the chunk).
 //      RECORDS: the warp appends its hits (locus code, seed index) to a CTA-local list; every FUSED_FLUSH batches
 //               the list becomes 4 x u64 / 4 x u32 records behind ONE atomic reservation of the CTA's output range.
 // The ~0.3 % of the seeds one line cannot settle (locus lists, displaced keys) are queued with their k-mer and
@@ -76,7 +77,9 @@ struct FusedOut {
   uint8_t* rec_kind;
   uint64_t cap;
   uint32_t compact;
-  uint2* dense;                 // DENSE: one pair per seed
+  uint32_t* dense_id;           // DENSE: plane of node ids, one per seed (NIL32 = no hit)
+  void* dense_off;              //        plane of node offsets | off-path flag in the top bit: u16 (off16) or u32
+  uint32_t off16;
   SlowItem* slow_queue;
   uint64_t slow_cap;
   unsigned long long* dc;
@@ -366,15 +369,19 @@ seeds_fused_kernel(KmerTable t, GraphView g, FusedChunk ch, uint32_t mode, Fused
     // ---- 5. results ----
     if (DENSE) {
       if (active) {
-        uint2 v = make_uint2(NIL32, 0u);                   // also what a queued seed shows until the slow kernel has run
+        uint32_t vid = NIL32, voff = 0u;                   // also what a queued seed shows until the slow kernel has run
         if (kind) {
           uint64_t id, noff;
           decode_code(g, code, id, noff);
-          v = make_uint2((uint32_t)id, (uint32_t)noff | (kind == 2 ? 0x80000000u : 0u));
+          vid = (uint32_t)id;
+          voff = (uint32_t)noff;
           ++n_hit;
           n_on += kind == 1 ? 1u : 0u;
         }
-        out.dense[seed0 + base + threadIdx.x] = v;
+        const uint32_t s = seed0 + base + threadIdx.x;
+        out.dense_id[s] = vid;
+        if (out.off16) static_cast<uint16_t*>(out.dense_off)[s] = (uint16_t)(voff | (kind == 2 ? 0x8000u : 0u));
+        else static_cast<uint32_t*>(out.dense_off)[s] = voff | (kind == 2 ? 0x80000000u : 0u);
       }
     }
     else {
@@ -412,7 +419,7 @@ seeds_fused_kernel(KmerTable t, GraphView g, FusedChunk ch, uint32_t mode, Fused
 // reserves the output range of its 32 seeds with ONE atomic (same-address atomics serialise in L2: ~15 000 queued
 // seeds per 1 M reads would otherwise queue up there).
 //   RECORDS: the records are appended to the CTAs' output;
-//   DENSE:   the seed's first hit fills its slot of the dense array, further hits (locus lists) become 4 x u32
+//   DENSE:   the seed's first hit fills its slot of the dense planes, further hits (locus lists) become 4 x u32
 //            records {node_id, node_off, read_id, read_off | off-path << 31} in the extra list.
 template <bool DENSE>
 __global__ void __launch_bounds__(256)
@@ -464,7 +471,11 @@ seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphVi
       else resolve_node(g, __ldg(multi + f.payload + 2 + j), r.node_id, r.node_off);
       const uint32_t kind = single ? (n_on ? 1u : 2u) : (j - from < n_on ? 1u : 2u);
       if (DENSE) {
-        if (j == from) out.dense[it.seed] = make_uint2((uint32_t)r.node_id, (uint32_t)r.node_off | (kind == 2 ? 0x80000000u : 0u));
+        if (j == from) {
+          out.dense_id[it.seed] = (uint32_t)r.node_id;
+          if (out.off16) static_cast<uint16_t*>(out.dense_off)[it.seed] = (uint16_t)((uint32_t)r.node_off | (kind == 2 ? 0x8000u : 0u));
+          else static_cast<uint32_t*>(out.dense_off)[it.seed] = (uint32_t)r.node_off | (kind == 2 ? 0x80000000u : 0u);
+        }
         else {
           if (o < extra_cap)
             asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(extra + 4 * o), "r"((uint32_t)r.node_id), "r"((uint32_t)r.node_off),
@@ -597,7 +608,9 @@ static void fused_enqueue(Ctx& c)
   out.rec_kind = c.rec_kind.p;
   out.cap = dense ? 0 : std::min<uint64_t>(c.records.cap / 4, c.rec_kind.cap);
   out.compact = out_kind == 1 ? 1u : 0u;
-  out.dense = reinterpret_cast<uint2*>(c.records.p);
+  out.dense_id = reinterpret_cast<uint32_t*>(c.records.p);
+  out.dense_off = reinterpret_cast<char*>(c.records.p) + c.dense_off_plane;
+  out.off16 = c.dense_off_bytes == 2 ? 1u : 0u;
   out.slow_queue = c.slow_items.p;
   out.slow_cap = c.slow_items.cap;
   out.dc = dc;
@@ -629,13 +642,17 @@ static void fused_enqueue(Ctx& c)
 static void dense_copy_enqueue(Ctx& c)
 {
   if (c.pending_dense_dst && c.n_dense_seeds) {
-    const uint64_t n = std::min<uint64_t>(c.n_dense_seeds, c.pending_dense_cap);
-    PSI_CUDA(cudaMemcpyAsync(c.pending_dense_dst, c.records.p, n * 8, cudaMemcpyDeviceToHost, c.stream));
+    // the two planes, made adjacent on the host: ids[n_seeds], then offsets[n_seeds]
+    const uint64_t n = c.n_dense_seeds;
+    char* dst = static_cast<char*>(c.pending_dense_dst);
+    PSI_CUDA(cudaMemcpyAsync(dst, c.records.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(dst + n * 4, reinterpret_cast<const char*>(c.records.p) + c.dense_off_plane, n * c.dense_off_bytes,
+                             cudaMemcpyDeviceToHost, c.stream));
   }
   c.pending_extra_copied = 0;
   if (c.pending_extra_dst && c.pending_extra_cap) {
     // the length of the extra list is not known yet: copy a fixed share now, the rest (rarely any) at wait time
-    const uint64_t n = std::min<uint64_t>(std::min<uint64_t>(c.pending_extra_cap, c.extra.cap / 4), c.n_seeds_cap / 64 + 256);
+    const uint64_t n = std::min<uint64_t>(std::min<uint64_t>(c.pending_extra_cap, c.extra.cap / 4), c.n_seeds_cap / 256 + 256);
     PSI_CUDA(cudaMemcpyAsync(c.pending_extra_dst, c.extra.p, n * 16, cudaMemcpyDeviceToHost, c.stream));
     c.pending_extra_copied = n;
   }
@@ -651,7 +668,10 @@ void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind)
   c.ev_state[T_OFF] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
   c.n_dense_seeds = 0;
   if (dense) {
-    c.records.ensure(c.n_seeds_cap + 1);                       // one 8-byte pair per seed
+    // two planes in one buffer: 4 bytes of node id per seed, then 2 or 4 bytes of node offset per seed
+    c.dense_off_bytes = c.sh->max_node_len <= 32768u ? 2u : 4u;
+    c.dense_off_plane = ((c.n_seeds_cap + 1) * 4 + 255) & ~(uint64_t)255;
+    c.records.ensure((c.dense_off_plane + (c.n_seeds_cap + 1) * c.dense_off_bytes + 7) / 8);
     if (c.extra.cap == 0) c.extra.ensure(4 * std::max<uint64_t>(c.n_seeds_cap / 16, 1u << 16));
     // known now only when all reads have one length; otherwise the step's seed counter tells (engine_wait)
     if (c.read_len && !c.d_read_ptr)
@@ -671,7 +691,7 @@ void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind)
   c.pending = true;
 }
 
-void engine_fetch_dense_async(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
+void engine_fetch_dense_async(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
 {
   if (!c.pending || c.pending_out_kind != 2) throw StateError("fetch_dense_async: no PSI_B200_DENSE step in flight on this context");
   PSI_CUDA(cudaSetDevice(c.device));
@@ -762,15 +782,19 @@ void engine_seeds_fused(Ctx& c, unsigned probe_mode, int out_kind)
 }
 
 // Synchronous copy of the dense results of the last completed step.
-void engine_fetch_dense(Ctx& c, uint32_t* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
+void engine_fetch_dense(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
 {
   if (c.pending) throw StateError("fetch_dense: a step is in flight on this context (call psi_b200_wait first)");
   if (!c.records_valid || !c.records_dense) throw StateError("fetch_dense: the last seeds_all was not run with PSI_B200_DENSE");
   PSI_CUDA(cudaSetDevice(c.device));
   if (cap_seeds && c.n_dense_seeds > cap_seeds) throw ArgError("fetch_dense: the dense buffer is smaller than the chunk's seed count");
   PhaseTimer t(c, T_D2H);
-  if (dense && cap_seeds && c.n_dense_seeds)
-    PSI_CUDA(cudaMemcpyAsync(dense, c.records.p, c.n_dense_seeds * 8, cudaMemcpyDeviceToHost, c.stream));
+  if (dense && cap_seeds && c.n_dense_seeds) {
+    const uint64_t n = c.n_dense_seeds;
+    PSI_CUDA(cudaMemcpyAsync(dense, c.records.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaMemcpyAsync(static_cast<char*>(dense) + n * 4, reinterpret_cast<const char*>(c.records.p) + c.dense_off_plane,
+                             n * c.dense_off_bytes, cudaMemcpyDeviceToHost, c.stream));
+  }
   const uint64_t ne = std::min<uint64_t>(c.n_extra, cap_extra);
   if (extra && ne) PSI_CUDA(cudaMemcpyAsync(extra, c.extra.p, ne * 16, cudaMemcpyDeviceToHost, c.stream));
   t.stop();

@@ -761,7 +761,7 @@ def test_async_steps_over_forked_contexts_from_one_thread():
         cnt = pipes[slot].wait()
         ns, ne = pipes[slot].dense_counts()
         assert ns == (e - b) * per_read
-        dense = bufs[slot][0].numpy().view(np.uint32)[:ns].copy()
+        dense = capi.dense_planes(bufs[slot][0].numpy().copy(), ns, pipes[slot].dense_off_bytes())
         extra = bufs[slot][1].numpy().view(np.uint32)[:ne].copy()
         rec, _ = capi.dense_to_records(dense, extra, p.read_ptr, c["k"], c["d"], b)
         assert len(rec) == cnt
