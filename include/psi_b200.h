@@ -192,7 +192,7 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  *   "blocking_sync"     1: seeds_all / fetch wait on a blocking event (the host thread sleeps) instead of spinning in
  *                       cudaStreamSynchronize -- for more pipelines than host cores per GPU; default 0;
  *   "timers"            0: no CUDA-event records around the kernels of a step (default 1);
- *   "seeding_mode", "resolve_items", "resolve_ctas", "l2_persist": variants of the separate kernels. */
+ *   "seeding_mode", "resolve_items", "resolve_ctas": variants of the separate kernels. */
 int  psi_b200_set_option(psi_b200_ctx* ctx, const char* name, long long value);
 
 /* The graph the finder borrows (seed_finder.hpp:1747), flattened: CSR

@@ -121,8 +121,8 @@ struct Shared {
   uint32_t code_off_bits = 0;
   bool code_by_rank = false;
   DevBuf<uint32_t> pos2node;     // node rank containing position (i << POS2NODE_SHIFT)
-  // rank16 and node_res live back to back in one allocation so that ONE L2 access-policy window can pin them
-  // (they are gathered at random by every hit; together ~1.1 bytes per graph base)
+  // rank16 and node_res live back to back in one allocation (gathered by locus-list entries and walker hits only:
+  // single-locus index entries carry their locus code)
   DevBuf<char> gather_pool;
   Rank16* rank16 = nullptr;      // unused when the graph has zero-length nodes (then pos2node is used)
   NodeRes* node_res = nullptr;
@@ -230,8 +230,6 @@ struct Ctx {
   DevBuf<char> walk_spill;
 
   // ---- options (psi_b200_set_option) ----
-  int opt_l2_persist = 1;                      // pin the position->node gather arrays in L2 for the resolve kernel
-  size_t l2_window_bytes = 0, l2_persist_bytes = 0;
   uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
   int opt_blocking_sync = 0;                   // 1: wait for a chunk on a blocking event (thread sleeps) instead of spinning

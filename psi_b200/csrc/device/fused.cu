@@ -36,6 +36,7 @@
 #include "seeding.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 namespace psi_b200 {
 
@@ -529,10 +530,15 @@ static void launch_fused(Ctx& c, const GraphView& g, const FusedChunk& ch, unsig
   constexpr int MIN_CTAS = 4;
   auto kern = seeds_fused_kernel<FMT, K4, MIN_CTAS, DENSE, PACKED>;
   const size_t smem = FusedCfg<K4, PACKED>::SMEM;
-  // function attributes are per device and idempotent: setting them again from another thread or for another
-  // device is harmless, so no shared "done" flag is kept
-  PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // function attributes are per device: one bit per device ordinal and instantiation, set after the (idempotent)
+  // attribute calls have succeeded, so concurrent first launches from several host threads are harmless
+  static std::atomic<uint64_t> attr_done{ 0 };
+  const uint64_t bit = 1ull << (c.device & 63);
+  if (c.device >= 64 || !(attr_done.load(std::memory_order_acquire) & bit)) {
+    PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done.fetch_or(bit, std::memory_order_release);
+  }
   kern<<<grid, 256, smem, c.stream>>>(c.sh->index.view, g, ch, probe_mode, out);
 }
 

@@ -105,7 +105,6 @@ Ctx* engine_fork(Ctx& parent)
   c->counters.offpath_mode = pc.offpath_mode; c->counters.n_offpath_walks = pc.n_offpath_walks;
   c->spill_items = parent.spill_items;
   c->opt_offpath_mode = parent.opt_offpath_mode;
-  c->opt_l2_persist = parent.opt_l2_persist;
   c->opt_seeding_mode = parent.opt_seeding_mode;
   c->opt_fused = parent.opt_fused;
   c->opt_timers = parent.opt_timers;
@@ -114,8 +113,6 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_index_slack = parent.opt_index_slack;
   c->opt_resolve_items = parent.opt_resolve_items;
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
-  c->l2_window_bytes = parent.l2_window_bytes;
-  c->l2_persist_bytes = parent.l2_persist_bytes;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
   return c;
 }
@@ -196,17 +193,6 @@ void engine_set_graph(Ctx& c, uint64_t n_nodes, const uint64_t* seq_start, const
     c.sh->has_rank16 = !zero_len;
     PSI_CUDA(cudaMemcpyAsync(c.sh->rank16, rank16.data(), rank_bytes, cudaMemcpyHostToDevice, c.stream));
     PSI_CUDA(cudaMemcpyAsync(c.sh->node_res, node_res.data(), res_bytes, cudaMemcpyHostToDevice, c.stream));
-    // Let the gathered arrays persist in L2 across the streaming kernels of a chunk (set-aside capped by the device).
-    cudaDeviceProp prop;
-    PSI_CUDA(cudaGetDeviceProperties(&prop, c.device));
-    c.l2_window_bytes = 0;
-    if (c.opt_l2_persist && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-      const size_t want = std::min<size_t>(c.sh->gather_pool_bytes, (size_t)prop.persistingL2CacheMaxSize);
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-        c.l2_window_bytes = std::min<size_t>(c.sh->gather_pool_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-      else (void)cudaGetLastError();
-      c.l2_persist_bytes = want;
-    }
   }
 
   DevBuf<char> ascii;

@@ -384,6 +384,10 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   if (n_paths == 0) return;
   if (!path_ptr || !path_nodes) throw ArgError("set_paths: null arrays");
   if (n_paths >= 0x7fffffffull) throw ArgError("set_paths: too many paths");
+  // the C-ABI is public: nothing below may index outside what the caller handed over
+  if (path_ptr[0] != 0) throw ArgError("set_paths: path_ptr[0] must be 0");
+  for (uint64_t p = 0; p < n_paths; ++p)
+    if (path_ptr[p + 1] < path_ptr[p]) throw ArgError("set_paths: path_ptr is not monotone");
   const uint64_t n_entries = path_ptr[n_paths];
   for (uint64_t e = 0; e < n_entries; ++e)
     if (path_nodes[e] >= sh.n_nodes) throw ArgError("set_paths: node rank out of range");
@@ -416,6 +420,11 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   std::vector<NodeRec> h_rec(sh.n_nodes);
   PSI_CUDA(cudaMemcpyAsync(h_rec.data(), sh.node_rec.p, (size_t)sh.n_nodes * sizeof(NodeRec), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
+  for (uint64_t p = 0; p < n_paths; ++p) {
+    if (path_ptr[p + 1] == path_ptr[p]) continue;
+    if (head_off && head_off[p] > h_rec[path_nodes[path_ptr[p]]].seq_len) throw ArgError("set_paths: head offset beyond the first node's label");
+    if (tail_trim && tail_trim[p] > h_rec[path_nodes[path_ptr[p + 1] - 1]].seq_len) throw ArgError("set_paths: tail trim beyond the last node's label");
+  }
   uint64_t budget = c.opt_build_group_windows;
   if (budget == 0) {
     size_t free_b = 0, total_b = 0;
@@ -728,9 +737,6 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   else if (n == "offpath_max_pairs") {
     if (value < 0) throw ArgError("set_option: offpath_max_pairs must be >= 0");
     c.opt_offpath_max_pairs = (uint64_t)value;
-  }
-  else if (n == "l2_persist") {
-    c.opt_l2_persist = value != 0;     // takes effect at the next set_graph
   }
   else if (n == "build_group_windows") {
     if (value < 0) throw ArgError("set_option: build_group_windows must be >= 0 (0 = from the free device memory)");

@@ -5,6 +5,7 @@
 #include "records.cuh"
 
 #include <algorithm>
+#include <atomic>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -459,9 +460,14 @@ static void engine_seeds_impl(Ctx& c, unsigned flags, bool async)
       if (do_probe) {
         const unsigned grid = grid_for(c.n_seeds_cap, 256);
         c.slow_queue.ensure(c.n_seeds_cap, 1.25);
-        // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split (per device; benign when repeated)
-        PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // 6 CTAs x 32 KB of line buffers per SM need the large shared-memory split (an attribute per device)
+        static std::atomic<uint64_t> carveout_done{ 0 };
+        const uint64_t bit = 1ull << (c.device & 63);
+        if (c.device >= 64 || !(carveout_done.load(std::memory_order_acquire) & bit)) {
+          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          PSI_CUDA(cudaFuncSetAttribute(seeds_on_paths_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          carveout_done.fetch_or(bit, std::memory_order_release);
+        }
         PhaseTimer t_probe(c, T_PROBE);
         if (sh.index.view.fmt == 8)
           seeds_on_paths_kernel<8><<<grid, 256, 0, c.stream>>>(sh.index.view, c.seed_kmer.p, c.seed_valid.p, dc + DC_SEEDS,

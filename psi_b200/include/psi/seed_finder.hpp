@@ -13,8 +13,13 @@
 //   index_paths                        :1169-1176  psi_b200_set_paths
 //   add_uncovered_loci                 :1481-1541  psi_b200_find_loci / get_loci
 //   load_path_index/serialize_..       :1372-1413  pathset + loci files (own paths format, reference loci format)
-//   get_seeds + index_reads            :1089-1109  psi_b200_submit_chunk
-//   seeds_on_paths/off_paths/all       :1426-1457,1703-1743  psi_b200_seeds_all + psi_b200_fetch
+//   get_seeds + index_reads            :1089-1109  psi_b200_submit_chunk_packed
+//   seeds_on_paths/off_paths/all       :1426-1457,1703-1743  psi_b200_seeds_all_async + psi_b200_fetch_dense_async + psi_b200_wait
+//
+// Threads: like the reference's finder (seed_finder.hpp:386-399: one const finder, several threads, one chunk
+// each) the per-chunk calls may be made from several host threads at once; every thread drives its own pipeline
+// (psi_b200_fork: own stream and buffers over the one resident index).  The index-building calls are not
+// thread safe, as in the reference.
 //
 // Differences that are deliberate: callbacks see every hit of the
 // seed SET exactly once (the reference repeats a locus once per covering path
@@ -25,15 +30,20 @@
 #define PSI_B200_PSI_SEED_FINDER_HPP
 
 #include <atomic>
+#include <unistd.h>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -127,7 +137,16 @@ class SeedFinder {
     Timer::period_type get_timer(const std::string& name) const { return Timer::get(id + name); }
     Timer::period_type get_timer(const std::string& name, const std::string& tid) const { return Timer::get(id + name + tid); }
     void set_timer(const std::string& name, double seconds) const { Timer::set(id + name + get_thread_id(), seconds); }
-    static void signal_handler(int) {}
+    // SIGUSR1 (reference seed_finder.hpp:275-338): a one-line progress report on stderr; async-signal-safe (write only)
+    static std::atomic<unsigned long long>& chunks_done() { static std::atomic<unsigned long long> v{ 0 }; return v; }
+    static std::atomic<unsigned long long>& reads_done() { static std::atomic<unsigned long long> v{ 0 }; return v; }
+    static void signal_handler(int)
+    {
+      char buf[128];
+      int n = std::snprintf(buf, sizeof buf, "psi-b200: %llu chunks, %llu reads, %llu seeds off paths so far\n", chunks_done().load(),
+                            reads_done().load(), TraverserStats::seeds_off_paths().load());
+      if (n > 0) { ssize_t w = ::write(2, buf, (size_t)n); (void)w; }
+    }
     std::string id;
   };
 
@@ -145,13 +164,14 @@ class SeedFinder {
       device = e ? std::atoi(e) : 0;
     }
     if (psi_b200_create(device, len, &ctx) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
-    upload_graph();
+    try { upload_graph(); }
+    catch (...) { psi_b200_destroy(ctx); ctx = nullptr; throw; }
   }
   SeedFinder(const SeedFinder&) = delete;
   SeedFinder& operator=(const SeedFinder&) = delete;
   ~SeedFinder()
   {
-    if (host_records) psi_b200_host_free(host_records);
+    reset_pipes();
     if (pathset) psi_b200_pathset_free(pathset);
     if (ctx) psi_b200_destroy(ctx);
   }
@@ -217,6 +237,7 @@ class SeedFinder {
     if (!pathset) return;
     psi_b200_pathset_view v;
     if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
+    reset_pipes();     // the index is rebuilt: pipelines forked from the old one go
     check(psi_b200_set_paths(ctx, v.n_paths, v.path_ptr, v.nodes, v.head_off, v.tail_trim));
     has_index = v.n_paths != 0;
   }
@@ -225,6 +246,7 @@ class SeedFinder {
   {
     [[maybe_unused]] auto timer = stats_ptr->timeit_ts("find-uncovered");
     uint64_t n = 0;
+    reset_pipes();
     check(psi_b200_find_loci(ctx, step, &n));
     pull_loci(n);
   }
@@ -250,6 +272,9 @@ class SeedFinder {
 
   // files: <prefix>_paths.b200 (picked paths; the device index is rebuilt from them at load) and
   // <prefix>_loci_e<step>l<k> in the reference's own byte format (seed_finder.hpp:884-892,1659-1679).
+  // The paths file names the graph it belongs to (node count, base count, a checksum of the labels); a file written
+  // for another graph, or a damaged one, is refused (load returns false and the caller rebuilds, as the reference
+  // does for a missing piece, seed_finder.hpp:1396-1413).
   bool serialize_path_index(std::string const& fpath, unsigned int step_size = 1)
   {
     if (fpath.empty() || !pathset) return false;
@@ -259,7 +284,8 @@ class SeedFinder {
       if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) return false;
       std::ofstream ofs(fpath + "_paths.b200", std::ofstream::binary);
       if (!ofs) return false;
-      const uint64_t hdr[4] = { PATHS_MAGIC, context_, v.n_paths, v.path_ptr[v.n_paths] };
+      const psi_b200_graph_view& gv = graph_ptr->view();
+      const uint64_t hdr[8] = { PATHS_MAGIC, context_, v.n_paths, v.path_ptr[v.n_paths], gv.n_nodes, gv.n_bases, graph_checksum(), 0 };
       ofs.write(reinterpret_cast<const char*>(hdr), sizeof hdr);
       ofs.write(reinterpret_cast<const char*>(v.path_ptr), (v.n_paths + 1) * sizeof(uint64_t));
       // node ranks are stable for a given graph file (the load order is deterministic)
@@ -277,22 +303,38 @@ class SeedFinder {
     if (fpath.empty()) return false;
     {
       [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-pindex");
-      std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary);
+      std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary | std::ifstream::ate);
       if (!ifs) return false;
-      uint64_t hdr[4];
+      const uint64_t file_bytes = (uint64_t)ifs.tellg();
+      ifs.seekg(0);
+      uint64_t hdr[8];
       ifs.read(reinterpret_cast<char*>(hdr), sizeof hdr);
       if (!ifs || hdr[0] != PATHS_MAGIC) return false;
-      std::vector<uint64_t> path_ptr(hdr[2] + 1);
-      std::vector<uint32_t> nodes(hdr[3]), head(hdr[2]), tail(hdr[2]);
+      const psi_b200_graph_view& gv = graph_ptr->view();
+      const uint64_t n_paths = hdr[2], n_entries = hdr[3];
+      // the file must be exactly as long as its header says, and belong to this graph
+      if (n_paths > file_bytes || n_entries > file_bytes) return false;
+      if (file_bytes != sizeof hdr + (n_paths + 1) * 8 + n_entries * 4 + n_paths * 8) return false;
+      if (hdr[4] != gv.n_nodes || hdr[5] != gv.n_bases || hdr[6] != graph_checksum()) return false;
+      std::vector<uint64_t> path_ptr(n_paths + 1);
+      std::vector<uint32_t> nodes(n_entries), head(n_paths), tail(n_paths);
       ifs.read(reinterpret_cast<char*>(path_ptr.data()), path_ptr.size() * sizeof(uint64_t));
       ifs.read(reinterpret_cast<char*>(nodes.data()), nodes.size() * sizeof(uint32_t));
       ifs.read(reinterpret_cast<char*>(head.data()), head.size() * sizeof(uint32_t));
       ifs.read(reinterpret_cast<char*>(tail.data()), tail.size() * sizeof(uint32_t));
-      if (!ifs || path_ptr.back() != nodes.size()) return false;
-      for (uint32_t r : nodes) if (r >= graph_ptr->get_node_count()) return false;
+      if (!ifs || path_ptr.front() != 0 || path_ptr.back() != nodes.size()) return false;
+      for (uint64_t p = 0; p < n_paths; ++p) if (path_ptr[p + 1] < path_ptr[p]) return false;
+      for (uint32_t r : nodes) if (r >= gv.n_nodes) return false;
+      for (uint64_t p = 0; p < n_paths; ++p) {
+        if (path_ptr[p + 1] == path_ptr[p]) { if (head[p] || tail[p]) return false; continue; }
+        const uint32_t first = nodes[path_ptr[p]], last = nodes[path_ptr[p + 1] - 1];
+        if (head[p] > gv.seq_start[first + 1] - gv.seq_start[first]) return false;
+        if (tail[p] > gv.seq_start[last + 1] - gv.seq_start[last]) return false;
+      }
       context_ = context ? context : (unsigned)hdr[1];
-      check(psi_b200_set_paths(ctx, hdr[2], path_ptr.data(), nodes.data(), head.data(), tail.data()));
-      has_index = hdr[2] != 0;
+      reset_pipes();
+      check(psi_b200_set_paths(ctx, n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data()));
+      has_index = n_paths != 0;
     }
     if (!open_starts(fpath, seed_len, step_size)) {
       add_uncovered_loci(step_size);
@@ -327,6 +369,7 @@ class SeedFinder {
       if (!ifs) return false;
       auto it = by_coord.find(id);
       if (it == by_coord.end()) return false;
+      if (off >= graph_ptr->node_length(it->second)) return false;      // not a position of this graph
       loci.emplace_back(it->second, off);
     }
     set_starting_loci(std::move(loci));
@@ -357,17 +400,30 @@ class SeedFinder {
   }
 
   /* ---- per chunk ---- */
-  // seeding(): seeds at offsets 0, d, 2d, ... of every read (sequence.hpp:1688-1745).  Uploads the
-  // chunk and packs the seeds on the device; `seeds` becomes a view of `reads`.
+  // seeding(): seeds at offsets 0, d, 2d, ... of every read (sequence.hpp:1688-1745).  Uploads the chunk's 2-bit
+  // words to this thread's pipeline (asynchronously: `reads` must stay valid until the seeds have been found);
+  // the k-mers are cut on the device; `seeds` becomes a view of `reads`.
   template <typename T>
   void get_seeds(readsrecord_type& seeds, readsrecord_type const& reads, T distance) const
   {
     auto timer = stats_ptr->timeit_ts("seeding");
+    Pipe& p = pipe();
+    if (p.pending) throw std::runtime_error("a chunk is still in flight on this thread (seeds_all_wait first)");
     seeds = reads;
     seeds.seed_len = seed_len;
     seeds.distance = distance ? (unsigned)distance : seed_len;
-    seeds.serial = ++serial;
-    check(psi_b200_submit_chunk(ctx, reads.n_reads, reads.read_ptr, reads.bases, reads.rec_offset, seeds.distance));
+    seeds.serial = ++p.serial;
+    seeds.pipe = &p;
+    psi_b200_packed_chunk ch{};
+    ch.n_reads = reads.n_reads;
+    ch.first_read_id = reads.rec_offset;
+    ch.n_bases = reads.n_bases;
+    ch.read_len = reads.read_len;
+    ch.read_ptr = reads.read_len ? nullptr : reads.read_ptr;
+    ch.words = reads.words;
+    ch.exc = reads.exc;
+    ch.n_exc = reads.n_exc;
+    pcheck(p, psi_b200_submit_chunk_packed(p.ctx, &ch, seeds.distance, 0));
     timer.stop();
   }
 
@@ -395,7 +451,10 @@ class SeedFinder {
   void seeds_all(readsrecord_type const& seeds, readsindex_type& reads_index, traverser_type& traverser,
                  callback_type callback) const
   {
-    seeds_all(seeds, reads_index, traverser, callback, callback);
+    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
+    setup_traverser(traverser, seeds, reads_index);
+    sync_loci();
+    run(seeds, reads_index, PSI_B200_ALL, nullptr, callback, nullptr);
   }
 
   // callback1 receives the hits found on the indexed paths, callback2 the rest (seed_finder.hpp:1734-1743).
@@ -405,28 +464,82 @@ class SeedFinder {
     if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
     setup_traverser(traverser, seeds, reads_index);
     sync_loci();
-    run(seeds, reads_index, PSI_B200_ALL, nullptr, callback1, callback2);
+    run(seeds, reads_index, PSI_B200_ALL, nullptr, callback1, callback2 ? callback2 : [](output_type const&) {});
   }
+
+  // The same in two halves (not in the reference): seeds_all_begin queues the chunk's kernels and the copy of
+  // their results and returns; the caller does host work (parse the next chunk); seeds_all_wait / _wait_records
+  // blocks for the results and delivers them.  One chunk in flight per host thread.
+  void seeds_all_begin(readsrecord_type const& seeds, readsindex_type& reads_index) const
+  {
+    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
+    sync_loci();
+    begin(pipe(), seeds, reads_index, PSI_B200_ALL);
+  }
+  void seeds_all_wait(callback_type callback1, callback_type callback2 = nullptr) const { deliver(pipe(), callback1, callback2, nullptr); }
+  // bulk form: n records of 4 x u64 {node_id, node_offset, read_id, read_offset}, the CLI's byte layout
+  void seeds_all_wait_records(records_callback_type cb) const { deliver(pipe(), nullptr, nullptr, cb); }
 
   // Bulk variant used by the CLI: one call per chunk with all records in the output byte layout.
   void seeds_all_records(readsrecord_type const& seeds, readsindex_type& reads_index, records_callback_type cb) const
   {
-    if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
-    sync_loci();
-    check_serial(seeds, reads_index);
-    uint64_t n = 0;
-    check(psi_b200_seeds_all(ctx, PSI_B200_ALL, &n));
-    fetch(n);
-    account();
-    if (cb) cb(host_records, n);
+    seeds_all_begin(seeds, reads_index);
+    seeds_all_wait_records(cb);
   }
 
  private:
-  static constexpr uint64_t PATHS_MAGIC = 0x3130736874617042ull;  // "Bpaths01"
+  static constexpr uint64_t PATHS_MAGIC = 0x3230736874617042ull;  // "Bpaths02"
+
+  // One pipeline per host thread: a fork of the finder's context (own stream and device buffers over the shared
+  // resident index) plus the pinned host buffers its results arrive in.
+  struct Pipe {
+    psi_b200_ctx* ctx = nullptr;
+    uint64_t serial = 0;
+    void* dense = nullptr;         // ids[n_seeds] u32, then offsets[n_seeds] u16/u32
+    uint64_t dense_cap = 0;        // seeds
+    uint32_t* extra = nullptr;     // 4 x u32 per further hit of a multi-locus seed
+    uint64_t extra_cap = 0;
+    uint64_t* records = nullptr;   // per-hit records (routes without dense results) / the CLI's 4 x u64 staging
+    uint64_t rec_cap = 0;
+    // chunk in flight
+    bool pending = false, dense_mode = false, compact = false;
+    unsigned flags = 0;
+    readsrecord_type seeds;
+    ~Pipe()
+    {
+      if (dense) psi_b200_host_free(dense);
+      if (extra) psi_b200_host_free(extra);
+      if (records) psi_b200_host_free(records);
+      if (ctx) psi_b200_destroy(ctx);
+    }
+  };
+
+  Pipe& pipe() const
+  {
+    std::lock_guard<std::mutex> lk(pipes_mutex);
+    auto& slot = pipes[std::this_thread::get_id()];
+    if (!slot) {
+      auto p = std::make_unique<Pipe>();
+      if (psi_b200_fork(ctx, &p->ctx) != PSI_B200_OK) throw std::runtime_error(psi_b200_last_error(ctx));
+      slot = std::move(p);
+    }
+    return *slot;
+  }
+
+  // Pipelines share the index: before it is rebuilt they go (index building is single-threaded by contract).
+  void reset_pipes() const
+  {
+    std::lock_guard<std::mutex> lk(pipes_mutex);
+    pipes.clear();
+  }
 
   void check(int rc) const
   {
     if (rc != PSI_B200_OK) throw std::runtime_error(psi_b200_last_error(ctx));
+  }
+  static void pcheck(const Pipe& p, int rc)
+  {
+    if (rc != PSI_B200_OK) throw std::runtime_error(psi_b200_last_error(p.ctx));
   }
 
   void upload_graph()
@@ -436,6 +549,23 @@ class SeedFinder {
     check(psi_b200_set_graph(ctx, v.n_nodes, v.seq_start, v.seq, v.row_ptr, v.col, v.internal_id));
     max_node_id = 0;
     for (uint64_t i = 0; i < v.n_nodes; ++i) if (v.internal_id[i] > max_node_id) max_node_id = v.internal_id[i];
+    unsigned ob = 4;
+    check(psi_b200_dense_layout(ctx, &ob));
+    dense_off_bytes = ob;
+  }
+
+  // FNV-1a over the node labels and their boundaries: names the graph a saved path set belongs to
+  uint64_t graph_checksum() const
+  {
+    if (checksum_valid) return checksum;
+    const psi_b200_graph_view& v = graph_ptr->view();
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&h](const unsigned char* p, size_t n) { for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ull; } };
+    mix(reinterpret_cast<const unsigned char*>(v.seq), v.n_bases);
+    mix(reinterpret_cast<const unsigned char*>(v.seq_start), (v.n_nodes + 1) * sizeof(uint64_t));
+    checksum = h;
+    checksum_valid = true;
+    return h;
   }
 
   unsigned int set_context(unsigned int context, bool patched, std::function<void(std::string const&)> = nullptr,
@@ -475,35 +605,145 @@ class SeedFinder {
       node[i] = (uint32_t)(graph_ptr->id_to_rank(starting_loci[i].node_id()) - 1);
       off[i] = (uint32_t)starting_loci[i].offset();
     }
+    reset_pipes();
     check(psi_b200_set_loci(ctx, node.size(), node.data(), off.data()));
     loci_dirty = false;
   }
   void sync_loci() const { if (loci_dirty) push_loci(); }
 
-  void check_serial(readsrecord_type const& seeds, readsindex_type const& idx) const
+  static void grow(void*& p, uint64_t& cap, uint64_t want, uint64_t unit)
   {
-    if (seeds.serial == 0 || seeds.serial != serial || idx.serial != seeds.serial)
+    if (want <= cap) return;
+    if (p) psi_b200_host_free(p);
+    p = nullptr;
+    cap = 0;
+    const uint64_t n = want + want / 4 + 1024;
+    if (psi_b200_host_alloc(&p, n * unit) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
+    cap = n;
+  }
+
+  // Queue the chunk's step and the copy of its results on the pipeline.
+  void begin(Pipe& p, readsrecord_type const& seeds, readsindex_type const& idx, unsigned flags) const
+  {
+    if (p.pending) throw std::runtime_error("a chunk is still in flight on this thread (seeds_all_wait first)");
+    if (seeds.serial == 0 || seeds.pipe != &p || seeds.serial != p.serial || idx.serial != seeds.serial)
       throw std::runtime_error("seeds do not belong to the chunk last given to get_seeds()");
-  }
-
-  void fetch(uint64_t n, bool compact = false) const
-  {
-    if (n > host_cap) {
-      if (host_records) psi_b200_host_free(host_records);
-      host_cap = n + n / 4 + 1024;
-      void* p = nullptr;
-      if (psi_b200_host_alloc(&p, host_cap * 32) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
-      host_records = static_cast<uint64_t*>(p);
+    const bool ids32 = max_node_id < 0xffffffffull && seeds.rec_offset + seeds.n_reads <= 0x100000000ull;
+    p.flags = flags;
+    p.seeds = seeds;
+    p.dense_mode = false;
+    p.compact = ids32;
+    // dense per-seed results whenever the index serves them (walk mode and 64-bit ids keep per-hit records)
+    if (ids32 && dense_state != 2) {
+      const int rc = psi_b200_seeds_all_async(p.ctx, flags | PSI_B200_DENSE);
+      if (rc == PSI_B200_OK) {
+        dense_state = 1;
+        p.dense_mode = true;
+        uint64_t n_seeds = 0;
+        if (seeds.read_len) n_seeds = seeds.n_reads * (seeds.read_len >= seed_len ? (seeds.read_len - seed_len) / seeds.distance + 1 : 0);
+        else for (uint64_t r = 0; r < seeds.n_reads; ++r) n_seeds += seeds.seeds_of_read(r);
+        grow(p.dense, p.dense_cap, n_seeds, 8);
+        void* e = p.extra;
+        grow(e, p.extra_cap, n_seeds / 16 + 4096, 16);
+        p.extra = static_cast<uint32_t*>(e);
+        pcheck(p, psi_b200_fetch_dense_async(p.ctx, p.dense, p.dense_cap, p.extra, p.extra_cap));
+        p.pending = true;
+        return;
+      }
+      if (rc != PSI_B200_ERR_ARG && rc != PSI_B200_ERR_STATE) pcheck(p, rc);
+      if (dense_state == 0 && (flags & PSI_B200_ALL) == PSI_B200_ALL) dense_state = 2;   // this index never serves them
     }
-    uint64_t got = 0;
-    if (n && compact) check(psi_b200_fetch32(ctx, reinterpret_cast<uint32_t*>(host_records), n, &got));
-    else if (n) check(psi_b200_fetch(ctx, host_records, n, &got));
+    pcheck(p, psi_b200_seeds_all_async(p.ctx, ids32 ? flags | PSI_B200_COMPACT : flags));
+    p.pending = true;
   }
 
-  void account() const
+  // Wait for the chunk in flight and hand its hits to the callbacks (cb2 != null: off-path hits go there) or, as
+  // 4 x u64 records, to rcb.
+  void deliver(Pipe& p, const callback_type& cb1, const callback_type& cb2, const records_callback_type& rcb) const
+  {
+    if (!p.pending) throw std::runtime_error("no chunk in flight on this thread (seeds_all_begin first)");
+    p.pending = false;
+    uint64_t n_hits = 0;
+    pcheck(p, psi_b200_wait(p.ctx, &n_hits));
+    account(p);
+    const readsrecord_type& seeds = p.seeds;
+    Seed<> hit;
+    hit.match_len = seed_len;
+    hit.gocc = 0;
+    uint64_t* rec = nullptr;
+    uint64_t n_rec = 0;
+    if (rcb) {
+      void* r = p.records;
+      grow(r, p.rec_cap, n_hits, 32);
+      p.records = static_cast<uint64_t*>(r);
+      rec = p.records;
+    }
+    auto emit = [&](uint64_t node, uint64_t noff, uint64_t read, uint64_t roff, bool off_path) {
+      if (rec) {
+        uint64_t* o = rec + 4 * n_rec++;
+        o[0] = node; o[1] = noff; o[2] = read; o[3] = roff;
+        return;
+      }
+      hit.node_id = node; hit.node_offset = noff; hit.read_id = read; hit.read_offset = roff;
+      const callback_type& cb = (off_path && cb2) ? cb2 : cb1;
+      if (cb) cb(hit);
+    };
+    if (p.dense_mode) {
+      uint64_t n_seeds = 0, n_extra = 0;
+      pcheck(p, psi_b200_dense_counts(p.ctx, &n_seeds, &n_extra));
+      if (n_extra > p.extra_cap) {       // rare: more multi-locus hits than the buffer was sized for
+        void* e = p.extra;
+        grow(e, p.extra_cap, n_extra, 16);
+        p.extra = static_cast<uint32_t*>(e);
+        pcheck(p, psi_b200_fetch_dense(p.ctx, p.dense, p.dense_cap, p.extra, p.extra_cap, &n_seeds, &n_extra));
+      }
+      const uint32_t* ids = static_cast<const uint32_t*>(p.dense);
+      const uint16_t* off16 = reinterpret_cast<const uint16_t*>(ids + n_seeds);
+      const uint32_t* off32 = ids + n_seeds;
+      uint64_t s = 0;
+      for (uint64_t r = 0; r < seeds.n_reads; ++r) {
+        const uint64_t cnt = seeds.read_len ? (seeds.read_len >= seed_len ? (seeds.read_len - seed_len) / seeds.distance + 1 : 0)
+                                            : seeds.seeds_of_read(r);
+        for (uint64_t j = 0; j < cnt; ++j, ++s) {
+          if (ids[s] == 0xffffffffu) continue;
+          if (dense_off_bytes == 2) emit(ids[s], off16[s] & 0x7fffu, seeds.rec_offset + r, j * seeds.distance, (off16[s] >> 15) != 0);
+          else emit(ids[s], off32[s] & 0x7fffffffu, seeds.rec_offset + r, j * seeds.distance, (off32[s] >> 31) != 0);
+        }
+      }
+      if (s != n_seeds) throw std::runtime_error("dense results do not match the chunk's seed count");
+      for (uint64_t i = 0; i < n_extra; ++i) {
+        const uint32_t* x = p.extra + 4 * i;
+        emit(x[0], x[1], x[2], x[3] & 0x7fffffffu, (x[3] >> 31) != 0);
+      }
+    }
+    else if (n_hits) {
+      // per-hit records (walk mode / wide ids); the per-record kind routes the hit when there are two callbacks
+      void* raw = p.dense;
+      grow(raw, p.dense_cap, n_hits * 4, 8);     // room for n_hits x 32 bytes
+      p.dense = raw;
+      uint64_t got = 0;
+      if (p.compact) pcheck(p, psi_b200_fetch32(p.ctx, static_cast<uint32_t*>(raw), n_hits, &got));
+      else pcheck(p, psi_b200_fetch(p.ctx, static_cast<uint64_t*>(raw), n_hits, &got));
+      std::vector<uint8_t> kinds;
+      if (cb2) {
+        kinds.resize(n_hits);
+        pcheck(p, psi_b200_fetch_kinds(p.ctx, kinds.data(), n_hits, &got));
+      }
+      for (uint64_t i = 0; i < n_hits; ++i) {
+        const bool off_path = !kinds.empty() && kinds[i] == 2;
+        if (p.compact) { const uint32_t* x = static_cast<const uint32_t*>(raw) + 4 * i; emit(x[0], x[1], x[2], x[3], off_path); }
+        else { const uint64_t* x = static_cast<const uint64_t*>(raw) + 4 * i; emit(x[0], x[1], x[2], x[3], off_path); }
+      }
+    }
+    stats_type::chunks_done() += 1;
+    stats_type::reads_done() += seeds.n_reads;
+    if (rcb) rcb(rec, n_rec);
+  }
+
+  void account(const Pipe& p) const
   {
     psi_b200_counters_t c;
-    check(psi_b200_counters(ctx, &c));
+    pcheck(p, psi_b200_counters(p.ctx, &c));
     TraverserStats::seeds_off_paths() += c.n_hits_off;
     TraverserStats::nof_godowns() += c.n_walks;
     stats_ptr->set_timer("seeds-on-paths", (c.ms_on) * 1e-3);
@@ -515,38 +755,10 @@ class SeedFinder {
   void run(readsrecord_type const& seeds, readsindex_type const& idx, unsigned flags, const char* timer_name,
            const callback_type& cb1, const callback_type& cb2) const
   {
-    check_serial(seeds, idx);
     auto timer = timer_name ? std::make_unique<Timer>(stats_ptr->timeit_ts(timer_name)) : nullptr;
-    // 4 x u32 records (half the device-to-host bytes) whenever every id of this chunk fits 32 bits; the fields are
-    // widened into Seed<> below either way
-    const bool compact = max_node_id <= 0xffffffffull && seeds.rec_offset + seeds.n_reads <= 0x100000000ull;
-    uint64_t n = 0;
-    check(psi_b200_seeds_all(ctx, compact ? flags | PSI_B200_COMPACT : flags, &n));
-    fetch(n, compact);
-    account();
-    // with two callbacks the per-record kind (1 on an indexed path, 2 off-path) routes the hit
-    std::vector<uint8_t> kinds;
-    if (cb2 && n) {
-      kinds.resize(n);
-      uint64_t got = 0;
-      check(psi_b200_fetch_kinds(ctx, kinds.data(), n, &got));
-    }
-    Seed<> hit;
-    hit.match_len = seed_len;
-    hit.gocc = 0;
-    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(host_records);
-    for (uint64_t i = 0; i < n; ++i) {
-      if (compact) {
-        const uint32_t* r = r32 + 4 * i;
-        hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
-      }
-      else {
-        const uint64_t* r = host_records + 4 * i;
-        hit.node_id = r[0]; hit.node_offset = r[1]; hit.read_id = r[2]; hit.read_offset = r[3];
-      }
-      const callback_type& cb = (!kinds.empty() && kinds[i] == 2) ? cb2 : cb1;
-      if (cb) cb(hit);
-    }
+    Pipe& p = pipe();
+    begin(p, seeds, idx, flags);
+    deliver(p, cb1, cb2, nullptr);
   }
 
   const graph_type* graph_ptr;
@@ -557,14 +769,17 @@ class SeedFinder {
   unsigned int max_mem;
   unsigned int context_ = 0;
   std::unique_ptr<stats_type> stats_ptr;
-  psi_b200_ctx* ctx = nullptr;
+  psi_b200_ctx* ctx = nullptr;              // builds and owns the resident graph / index / loci
   psi_b200_pathset* pathset = nullptr;
   bool has_index = false;
   mutable bool loci_dirty = false;
-  mutable uint64_t serial = 0;
-  mutable uint64_t* host_records = nullptr;
-  mutable uint64_t host_cap = 0;
+  mutable std::mutex pipes_mutex;
+  mutable std::map<std::thread::id, std::unique_ptr<Pipe>> pipes;
+  mutable std::atomic<int> dense_state{ 0 };             // 0 unknown, 1 the index serves dense results, 2 it does not (walk mode)
   uint64_t max_node_id = 0;
+  unsigned dense_off_bytes = 4;
+  mutable uint64_t checksum = 0;
+  mutable bool checksum_valid = false;
 };
 
 }  // namespace psi

@@ -104,24 +104,31 @@ static void find_seeds(TGraph& graph, SeqStreamIn& reads_iss, std::FILE* output_
   unsigned long long found = 0, covered_reads = 0;
   std::vector<bool> covered;
   {
-    auto chunk = finder.create_readrecord();
+    // two chunk records alternate: while the GPU works on one chunk the next one is parsed from the reads file
+    // (the stream keeps two sets of page-locked buffers for exactly this)
+    decltype(finder.create_readrecord()) chunks[2] = { finder.create_readrecord(), finder.create_readrecord() };
     auto seeds = finder.create_readrecord();
     log->info("Finding seeds...");
     [[maybe_unused]] auto timer = timer_type("seed-finding");
-    while (true) {
+    auto load = [&](int slot) {
       log->info("Loading a read chunk...");
-      {
-        [[maybe_unused]] auto timer = timer_type("load-chunk");
-        if (!readRecords(chunk, reads_iss, params.chunk_size)) break;
-      }
+      [[maybe_unused]] auto timer = timer_type("load-chunk");
+      return readRecords(chunks[slot], reads_iss, params.chunk_size);
+    };
+    int cur = 0;
+    bool have = load(cur);
+    while (have) {
+      auto& chunk = chunks[cur];
       log->info("Fetched {} reads with total length of {}bp in {}.", length(chunk), lengthSum(chunk), timer_type::get_duration_str("load-chunk"));
       finder.get_seeds(seeds, chunk, params.distance);
       auto seeds_index = finder.index_reads(seeds);
       log->info("Seeding done in {}.", stats.get_timer("seeding", tid).str());
       log->info("Finding all seeds...");
+      finder.seeds_all_begin(seeds, seeds_index);
+      const bool have_next = load(cur ^ 1);
       covered.assign(chunk.size(), false);
       const uint64_t first = chunk.rec_offset;
-      finder.seeds_all_records(seeds, seeds_index, [&](const uint64_t* rec, uint64_t n) {
+      finder.seeds_all_wait_records([&](const uint64_t* rec, uint64_t n) {
         found += n;
         static_assert(sizeof(std::size_t) == sizeof(uint64_t), "the output format is 4 x size_t");
         if (n && std::fwrite(rec, 32, n, output_file) != n) throw std::runtime_error("could not write to the output file");
@@ -133,6 +140,8 @@ static void find_seeds(TGraph& graph, SeqStreamIn& reads_iss, std::FILE* output_
       log->info("Found seeds on paths in {}.", stats.get_timer("seeds-on-paths", tid).str());
       log->info("Found seeds off paths in {}.", stats.get_timer("seeds-off-paths", tid).str());
       log->info("Verified distance constraints in {}.", stats.get_timer("query-dindex", tid).str());
+      cur ^= 1;
+      have = have_next;
     }
   }
   log->info("Found seed in {}.", timer_type::get_duration_str("seed-finding"));

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -69,6 +71,32 @@ int main(int argc, char** argv)
     finder.seeds_off_paths(traverser, push(off));
     finder.seeds_all(seeds, index, traverser, push(all1), push(all2));
   }
+  // one const finder, several host threads, one chunk each (reference seed_finder.hpp:386-399): every thread gets
+  // its own pipeline over the shared index; the union of what the threads find is the same set
+  std::vector<uint64_t> mt[3];
+  {
+    const finder_type& cf = finder;
+    std::vector<std::thread> threads;
+    for (int t = 0; t < 3; ++t)
+      threads.emplace_back([&, t] {
+        // every thread reads the file through its own stream (a stream's chunk buffers belong to one consumer) and
+        // takes every third chunk
+        klibpp::SeqStreamIn iss_t(reads_path.c_str());
+        auto c = cf.create_readrecord();
+        auto s = cf.create_readrecord();
+        auto tr = cf.create_traverser();
+        for (unsigned long i = 0; readRecords(c, iss_t, chunk_size ? chunk_size : 1000); ++i) {
+          if (i % 3 != (unsigned long)t) continue;
+          cf.get_seeds(s, c, d);
+          auto ix = cf.index_reads(s);
+          cf.seeds_all(s, ix, tr, push(mt[t]));
+        }
+      });
+    for (auto& th : threads) th.join();
+  }
+  std::vector<uint64_t> mt_all;
+  for (auto& v : mt) mt_all.insert(mt_all.end(), v.begin(), v.end());
+  dump(out + ".mt", mt_all);
   dump(out + ".on", on);
   dump(out + ".off", off);
   dump(out + ".all1", all1);

@@ -30,7 +30,7 @@ def build_driver():
         return
     DRIVER.parent.mkdir(exist_ok=True)
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", os.fspath(DRIVER), os.fspath(DRIVER_SRC),
-                    "-L" + os.fspath(ROOT / "psi_b200"), "-lpsi_b200", "-Wl,-rpath," + os.fspath(ROOT / "psi_b200")], check=True)
+                    "-L" + os.fspath(ROOT / "psi_b200"), "-lpsi_b200", "-lpthread", "-Wl,-rpath," + os.fspath(ROOT / "psi_b200")], check=True)
 
 
 def gunzip_to(src, dst):
@@ -159,6 +159,16 @@ def test_psikt_saved_path_index_is_reloaded(tmp_path):
     g = capi.Graph.load_gfa(gfa)
     got = capi.canonical(load_psikt_output(tmp_path / "o1", g))
     assert util.md5_tuples(got) == c["md5"]
+    # a damaged paths file, or one written for another graph, is refused and the index is rebuilt
+    pf = Path(str(prefix) + "_paths.b200")
+    good = pf.read_bytes()
+    for bad in (good[:-7], good[:40] + b"\xff" * 8 + good[48:], good[:64] + b"\xff\xff\xff\x7f" + good[68:]):
+        pf.write_bytes(bad)
+        r = run([PSIKT, "-f", reads, "-l", c["k"], "-n", "4", "-I", prefix, "-L", tmp_path / "d.log", "-q", "-o", tmp_path / "o3", gfa])
+        assert r.returncode == 0, r.stderr
+        assert "No valid path index found. Creating the path index..." in (tmp_path / "d.log").read_text()
+        assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o3", g))) == c["md5"]
+        assert pf.read_bytes() != bad                  # rewritten by the rebuild
     # -n 0 and no index: nothing is found (src/psikt.cpp:121-123)
     r = run([PSIKT, "-f", reads, "-l", c["k"], "-L", tmp_path / "c.log", "-q", "-o", tmp_path / "o2", gfa])
     assert r.returncode == 0
@@ -189,7 +199,8 @@ def test_seed_finder_api_matches_oracle(tmp_path, name, chunk):
 
     def load(ext):
         return np.fromfile(str(tmp_path / "out") + ext, dtype="<u8").reshape(-1, 4)
-    on, off, all1, all2 = load(".on"), load(".off"), load(".all1"), load(".all2")
+    on, off, all1, all2, mt = load(".on"), load(".off"), load(".all1"), load(".all2"), load(".mt")
+    assert len(mt) == c["count"] and util.md5_tuples(np.unique(mt, axis=0)) == c["md5"], "three threads over one const finder"
     for part in (on, off, all1, all2):
         assert len(np.unique(part, axis=0)) == len(part), "callbacks see each hit once"
     sep = np.unique(np.concatenate([on, off]), axis=0)
