@@ -420,11 +420,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   std::vector<NodeRec> h_rec(sh.n_nodes);
   PSI_CUDA(cudaMemcpyAsync(h_rec.data(), sh.node_rec.p, (size_t)sh.n_nodes * sizeof(NodeRec), cudaMemcpyDeviceToHost, c.stream));
   PSI_CUDA(cudaStreamSynchronize(c.stream));
-  for (uint64_t p = 0; p < n_paths; ++p) {
-    if (path_ptr[p + 1] == path_ptr[p]) continue;
-    if (head_off && head_off[p] > h_rec[path_nodes[path_ptr[p]]].seq_len) throw ArgError("set_paths: head offset beyond the first node's label");
-    if (tail_trim && tail_trim[p] > h_rec[path_nodes[path_ptr[p + 1] - 1]].seq_len) throw ArgError("set_paths: tail trim beyond the last node's label");
-  }
+  // (head offsets / tail trims longer than their node are clamped by path_windows_kernel: such a path end is empty)
   uint64_t budget = c.opt_build_group_windows;
   if (budget == 0) {
     size_t free_b = 0, total_b = 0;
