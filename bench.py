@@ -37,6 +37,9 @@ sys.path.insert(0, os.fspath(ROOT))
 TRAFFIC = {
     "seeds_on_paths_kernel": (662.9e6, "profiles/r01i_kernels_ncu_raw.csv: seeds_on_paths_kernel<8>, dram__bytes_read.sum 635.3 MB + "
                                        "dram__bytes_write.sum 27.6 MB (mean of 2 launches)"),
+    "seeds_fused_kernel_dense_packed": (645.3e6, "profiles/r02c_fused_ncu_raw.csv: seeds_fused_kernel<8, 1, 4, dense, packed>, "
+                                                 "dram__bytes_read.sum 614.0 MB + dram__bytes_write.sum 31.3 MB (mean of 3 launches; "
+                                                 "below the line accounting because 40 % of the sectors hit L2)"),
 }
 
 K = 20
@@ -261,7 +264,7 @@ class Workload:
             self.words_d.append(hw.to(dev))
         self.pack_gbs = n_batches * n_reads * read_len / t_pack / 1e9 / 2   # pack_bases is run twice by Packed.pack (count, then fill)
         self.n_batches = n_batches
-        self.pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
+        self.pipes = [ctx] + [ctx.fork() for _ in range(max(n_pipes, 2) - 1)]     # the ASCII comparison arm drives two
         n_extra_cap = self.n_seeds // 8 + 4096
         self.dense_h = [torch.empty((self.n_seeds, 2), dtype=torch.int32).pin_memory() for _ in self.pipes]
         self.extra_h = [torch.empty((n_extra_cap, 4), dtype=torch.int32).pin_memory() for _ in self.pipes]
@@ -462,6 +465,8 @@ def main_gpu(args):
     counts, hist = shard.all_reduce_counts({"reads": n_reads * steps, "seeds": acc_one["n_seeds"], "hits": hits_val,
                                             "hits_on": acc_one["n_hits_on"]}, hist, device=dev)
 
+    pcie = pcie_ceiling(torch, dev, int(W.words_h[0].numel() * 8), int((4 + ctx.dense_off_bytes()) * W.n_seeds))
+    drop_in = psikt_drop_in(W) if (world == 1 and rank == 0 and not args.no_other_configs) else None
     other = {}
     if world == 1 and not args.no_other_configs:
         other = other_configs(torch, dev, run_async, run_sync, capi)
@@ -529,6 +534,8 @@ def main_gpu(args):
                     "h2d_bytes_per_step": words_bytes, "d2h_bytes_per_step": int((4 + off_bytes) * W.n_seeds + 16 * extra_copy + 8 * 12),
                     "ms_per_step": ms_e2e / steps, "pipelines": n_pipes, "host_threads": 1,
                     "fused_kernel_ms": kms_e2e,
+                    "pcie": dict(pcie, floor_ms_per_step=max(words_bytes / (pcie["h2d_bidir_gbs"] * 1e6), (4 + off_bytes) * W.n_seeds / (pcie["d2h_bidir_gbs"] * 1e6)),
+                                 note="rank 0's link, measured while the other ranks are idle at N > 1"),
                     "formats": f"up: 2-bit words of the chunk (pinned host memory); down: {4 + off_bytes} bytes per seed (u32 node id, "
                                f"u{8 * off_bytes} node offset | off-path bit) + the extra list of multi-locus seeds + the step's counters"},
             "roofline": roof,
@@ -561,6 +568,8 @@ def main_gpu(args):
                       "offpath_entries": c0["n_offpath_entries"], "offpath_walks": c0["n_offpath_walks"],
                       "stash_used": c0["index_stash_used"], "locus_codes": "by rank" if c0["code_by_rank"] else "by id"},
         }
+        if drop_in:
+            line["drop_in_psikt"] = drop_in
         if other:
             line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
@@ -576,12 +585,89 @@ def main_gpu(args):
         dist.destroy_process_group()
 
 
+def pcie_ceiling(torch, dev, up_bytes, down_bytes, reps=12):
+    """What the host link of this GPU sustains for the e2e step's transfer sizes: pinned-memory copies alone and in both
+    directions at once (two streams).  GB/s; the e2e step cannot beat max(up / h2d_bidir, down / d2h_bidir)."""
+    hu = torch.empty(up_bytes, dtype=torch.uint8).pin_memory()
+    hd = torch.empty(down_bytes, dtype=torch.uint8).pin_memory()
+    du = torch.empty(up_bytes, dtype=torch.uint8, device=dev)
+    dd = torch.empty(down_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(do_up, do_down):
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        if do_up:
+            with torch.cuda.stream(s1):
+                ev[0].record()
+                for _ in range(reps):
+                    du.copy_(hu, non_blocking=True)
+                ev[1].record()
+        if do_down:
+            with torch.cuda.stream(s2):
+                ev[2].record()
+                for _ in range(reps):
+                    hd.copy_(dd, non_blocking=True)
+                ev[3].record()
+        torch.cuda.synchronize()
+        up = up_bytes * reps / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9 if do_up else None
+        down = down_bytes * reps / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9 if do_down else None
+        return up, down
+    timed(True, True)
+    h2d, _ = timed(True, False)
+    _, d2h = timed(False, True)
+    h2d_b, d2h_b = timed(True, True)
+    return {"h2d_gbs": h2d, "d2h_gbs": d2h, "h2d_bidir_gbs": h2d_b, "d2h_bidir_gbs": d2h_b,
+            "how": f"{reps} pinned-memory copies of {up_bytes} B up / {down_bytes} B down on two streams, CUDA events"}
+
+
+def psikt_drop_in(W, n_reads=2_000_000, chunk=500_000):
+    """The drop-in itself: psi_b200/bin/psikt from a reads file to the seed file (graph load and index build excluded:
+    the CLI's own 'seed-finding' timer brackets the chunk loop: parse -> GPU -> write)."""
+    import re
+    import shutil
+    from bench_support import synth
+    psikt = ROOT / "psi_b200" / "bin" / "psikt"
+    if not psikt.exists():
+        return {"error": "psi_b200/bin/psikt not built"}
+    td = tempfile.mkdtemp(prefix="psikt_bench_")
+    try:
+        gfa, fa, out, logf = (os.path.join(td, x) for x in ("g.gfa", "r.fa", "seeds.bin", "psikt.log"))
+        W.g.write_gfa(gfa)
+        rp, bases = synth.reads(W.g, n_reads, W.read_len, 4242)
+        rec = np.empty((n_reads, 10 + W.read_len + 1), np.uint8)     # ">r0000000\n" + bases + "\n"
+        rec[:, 0], rec[:, 1], rec[:, 9], rec[:, -1] = ord(">"), ord("r"), 10, 10
+        ids = np.arange(n_reads)
+        for c in range(7):
+            rec[:, 8 - c] = 48 + (ids // 10 ** c) % 10
+        rec[:, 10:-1] = bases.reshape(n_reads, W.read_len)
+        rec.tofile(fa)
+        t0 = time.time()
+        p = subprocess.run([os.fspath(psikt), "-f", fa, "-l", str(W.k), "-n", str(N_PATHS), "-c", str(chunk), "-o", out, "-L", logf, "-q", gfa],
+                           capture_output=True, text=True, timeout=900)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            return {"error": (p.stderr or "").strip()[-300:]}
+        text = open(logf).read()
+        m = re.search(r"Found seed in ([0-9.]+) s", text)
+        t_find = float(m.group(1)) if m else None
+        n_found = int(re.search(r"Total number of seeds found: (\d+)", text).group(1))
+        return {"reads_per_s": n_reads / t_find if t_find else None, "seed_finding_s": t_find, "wall_s_with_graph_load_and_index": wall,
+                "reads": n_reads, "chunk": chunk, "seeds_written": n_found, "output_bytes": os.path.getsize(out),
+                "input_bytes": os.path.getsize(fa),
+                "what": "psikt -f reads.fa -l K -n 16 -c CHUNK -o seeds.bin graph.gfa: FASTA parsing + 2-bit packing (one host thread), "
+                        "GPU step, 32-byte records expanded and written, next chunk parsed while the GPU works"}
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def other_configs(torch, dev, run_async, run_sync, capi):
     """The other single-GPU shapes BASELINE.json names, one short measurement each (resident 2-bit chunks -> dense
     results, 4 chunks in flight): configs[2]'s read shape (150 bp) on the chr22-shape graph, configs[3] (MHC-like
     region, k = 32) in index mode and in walk mode (the reference's scheme: graph walked per chunk)."""
     out = {}
     DENSE = capi.ALL | capi.DENSE
+    k0, len0 = K, READ_LEN
     for name, shape, k, read_len, n_reads, mode in (("chr22_150bp", "chr22", 20, 150, 1_000_000, 0),
                                                      ("mhc_k32", "mhc", 32, 150, 1_000_000, 0),
                                                      ("mhc_k32_walk_mode", "mhc", 32, 150, 200_000, 1)):
@@ -605,6 +691,7 @@ def other_configs(torch, dev, run_async, run_sync, capi):
             W.close()
         except Exception as e:   # an extra line must not take the headline down
             out[name] = {"error": f"{type(e).__name__}: {e}"}
+    globals().update(K=k0, READ_LEN=len0)
     return out
 
 

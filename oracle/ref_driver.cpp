@@ -21,6 +21,10 @@
  *                  as native size_t, in emission order (multiset, path dependent).
  *    --nodes FILE  per rank (1..n): internal id, coordinate id, label length (3 x u64).
  *    --loci FILE   starting loci: internal id, offset (2 x u64).
+ *    --paths FILE  the paths the reference picked and indexed (SeedFinder::pick_paths, seed_finder.hpp:1138-1167):
+ *                  u64 n_paths, then per path u64 n_nodes, u64 head offset (bases cut from the first node),
+ *                  u64 tail trim (bases cut from the last node), u64 text length, the node ids (internal, u64
+ *                  each) and the path's forward text padded to a multiple of 8 bytes.
  *  and one JSON line on stdout with counts and timings.
  */
 #include <cstdio>
@@ -44,7 +48,7 @@
 using namespace psi;
 
 struct Args {
-  std::string gfa, fastq, out, raw, nodes, loci;
+  std::string gfa, fastq, out, raw, nodes, loci, paths;
   unsigned k = 0, d = 0, n = 0, context = 0, step = 1;
   unsigned long chunk = 0, first_read = 0, max_reads = 0;
   bool patched = true;
@@ -74,6 +78,7 @@ int main( int argc, char** argv )
     else if ( s == "--raw" ) a.raw = next();
     else if ( s == "--nodes" ) a.nodes = next();
     else if ( s == "--loci" ) a.loci = next();
+    else if ( s == "--paths" ) a.paths = next();
     else if ( s == "-k" ) a.k = std::stoul( next() );
     else if ( s == "-d" ) a.d = std::stoul( next() );
     else if ( s == "-n" ) a.n = std::stoul( next() );
@@ -128,6 +133,30 @@ int main( int argc, char** argv )
     for ( auto const& l : finder.get_starting_loci() ) {
       uint64_t rec[2] = { (uint64_t)l.node_id(), (uint64_t)l.offset() };
       write_u64s( f, rec, 2 );
+    }
+    std::fclose( f );
+  }
+
+  if ( !a.paths.empty() ) {
+    std::FILE* f = std::fopen( a.paths.c_str(), "wb" );
+    auto const& pset = finder.get_pindex().get_paths_set();
+    uint64_t n = pset.size();
+    write_u64s( f, &n, 1 );
+    for ( auto it = pset.begin(); it != pset.end(); ++it ) {
+      auto const& p = *it;
+      std::vector< uint64_t > ids;
+      for ( auto id : p.get_nodes() ) ids.push_back( (uint64_t)id );
+      std::string text = sequence( p, Forward() );
+      uint64_t head = ids.empty() ? 0 : (uint64_t)p.get_head_offset();
+      /* bases of the last node that the path does not cover */
+      uint64_t tail = 0;
+      if ( ids.size() == 1 ) tail = (uint64_t)graph.node_length( ids.back() ) - head - (uint64_t)p.get_sequence_len();
+      else if ( !ids.empty() ) tail = (uint64_t)graph.node_length( ids.back() ) - (uint64_t)p.get_seqlen_tail();
+      uint64_t hdr[4] = { (uint64_t)ids.size(), head, tail, (uint64_t)text.size() };
+      write_u64s( f, hdr, 4 );
+      if ( !ids.empty() ) write_u64s( f, ids.data(), ids.size() );
+      text.resize( ( text.size() + 7 ) / 8 * 8, '\0' );
+      if ( !text.empty() && std::fwrite( text.data(), 1, text.size(), f ) != text.size() ) { std::perror( "fwrite" ); std::exit( 3 ); }
     }
     std::fclose( f );
   }
