@@ -818,3 +818,53 @@ def test_dense_refuses_what_it_cannot_serve():
         ctx.seeds_all(capi.ALL | capi.DENSE | capi.SORTED)
     assert e.value.code == capi.ERR_ARG
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# starting loci on the reference's own paths (tests/golden/loci/*.npz, written by make_loci_golden.py)
+
+import glob as _glob
+import os as _os
+
+LOCI_FIXTURES = sorted(f for f in _glob.glob(_os.fspath(util.GOLDEN / "loci" / "*.npz")) if "_e" not in _os.path.basename(f))
+
+
+@pytest.mark.parametrize("fixture", LOCI_FIXTURES, ids=lambda f: _os.path.basename(f)[:-4])
+def test_device_loci_on_the_reference_paths(fixture):
+    """The paths the reference picked (patches with trimmed ends included) go through psi_b200_set_paths; the device's
+    starting loci equal the oracle's, are a subset of the reference's own (node-level coverage, seed_finder.hpp:1481-1541;
+    relation pinned on the CPU in tests/test_oracle.py), and loading the REFERENCE's loci instead (psi_b200_set_loci,
+    what a shared _loci_e1l<k> file does) gives the very same seed set: the extra loci are redundant."""
+    z = np.load(fixture)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    k = int(z["k"])
+    ps = capi.PathSet(path_ptr=z["path_ptr"], nodes=z["nodes"], head_off=z["head"], tail_trim=z["tail"])
+    _, full = util.read_fasta(util.GOLDEN / "inputs/reads_n10000l100e0i0.fa.gz")
+    rp, bases = util.random_walk_reads(g, 400, max(k + 8, 60), seed=9) if g.n_nodes != 210 else (np.arange(0, 1501, dtype=np.uint64) * np.uint64(100), full[:150000])
+    want, _ = orc.seeds_closed_form(orc.OGraph.of(g), orc.OReads(rp, bases), k, k)
+    sets = []
+    for mode in ((0, 1), (1, 1)):
+        ctx = capi.Context(k, 0)
+        ctx.set_option("offpath_mode", mode[0])
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(ps)
+        ctx.find_loci()
+        ln, lo = ctx.get_loci()
+        wn, wo = orc.uncovered_loci(orc.OGraph.of(g), orc.OPaths(z["path_ptr"], z["nodes"], z["head"], z["tail"]), k)
+        assert np.array_equal(ln, wn) and np.array_equal(lo, wo)
+        ours = set(zip(ln.tolist(), lo.tolist()))
+        ref = set(zip(z["loci_rank"].tolist(), z["loci_off"].tolist()))
+        assert ours <= ref
+        ctx.submit_chunk(rp, bases, 0, k)
+        n = ctx.seeds_all()
+        got = capi.canonical(ctx.fetch())
+        assert n == len(got) and np.array_equal(got, want)
+        # the reference's loci, as a shared loci file would hand them over
+        ctx.set_loci(z["loci_rank"], z["loci_off"])
+        ctx.submit_chunk(rp, bases, 0, k)
+        n2 = ctx.seeds_all()
+        got2 = capi.canonical(ctx.fetch())
+        assert n2 == len(got2) and np.array_equal(got2, want)
+        sets.append(got)
+        ctx.close()
+    assert np.array_equal(sets[0], sets[1])

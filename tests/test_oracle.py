@@ -181,3 +181,88 @@ def test_chunking_does_not_change_the_set():
         parts.append(t)
     t = np.concatenate(parts)
     assert util.md5_tuples(t) == c["md5"]   # disjoint read ranges: concatenation is already canonical
+
+
+# ---- starting loci pinned to the reference (tests/golden/make_loci_golden.py) ----
+#
+# The reference derives its starting loci from NODE-level coverage: a k-walk is covered when the sequence of nodes it
+# runs through is a contiguous piece of some indexed path (add_uncovered_loci + covered_by, reference
+# seed_finder.hpp:1481-1541, pathset.hpp:205-218,389-395).  This build (oracle psi_oracle_uncovered_loci = the device's
+# find_loci_kernel, compared with each other in tests/test_gpu_parity.py) uses the k-MER level: a locus starts a walk
+# iff some k-walk from it spells a k-mer w with (w, locus) absent from the path index.  On the same paths the two
+# relate as: ours is a subset of the reference's, and every locus only the reference has is redundant -- all its
+# k-walks are already on-path entries (the walk leaves the path's nodes but spells what the path spells there).
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+LOCI_FIXTURES = sorted(glob.glob(os.fspath(util.GOLDEN / "loci" / "*.npz")))
+
+
+def _load_loci_fixture(path):
+    z = np.load(path)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    return z, g, orc.OPaths(z["path_ptr"], z["nodes"], z["head"], z["tail"])
+
+
+def _path_pairs(g, z, k):
+    """{(k-mer bytes, global position)} of all k-windows of the fixture's paths."""
+    pairs = set()
+    for p in range(len(z["head"])):
+        nodes = z["nodes"][int(z["path_ptr"][p]):int(z["path_ptr"][p + 1])]
+        seq = np.concatenate([g.seq[int(g.seq_start[v]):int(g.seq_start[v + 1])] for v in nodes])
+        gpos = np.concatenate([np.arange(int(g.seq_start[v]), int(g.seq_start[v + 1])) for v in nodes])
+        lo, hi = int(z["head"][p]), len(seq) - int(z["tail"][p])
+        text, gp = seq[lo:hi].tobytes().upper(), gpos[lo:hi]
+        for i in range(len(text) - k + 1):
+            w = text[i:i + k]
+            if set(w) <= set(b"ACGT"):
+                pairs.add((w, int(gp[i])))
+    return pairs
+
+
+def _walks_from(g, v, off, k):
+    """All k-mers spelt by forward walks from (node rank v, offset off); N stops a walk (traverser_bfs.hpp:114-161)."""
+    out, stack = [], [(v, off, b"")]
+    while stack:
+        v, o, acc = stack.pop()
+        lab = g.seq[int(g.seq_start[v]) + o:int(g.seq_start[v + 1])].tobytes().upper()
+        acc += lab[:k - len(acc)]
+        if not set(acc) <= set(b"ACGT"):
+            continue
+        if len(acc) == k:
+            out.append(acc)
+            continue
+        for e in range(int(g.row_ptr[v]), int(g.row_ptr[v + 1])):
+            stack.append((int(g.col[e]), 0, acc))
+    return out
+
+
+@pytest.mark.parametrize("fixture", [f for f in LOCI_FIXTURES if "_e" not in os.path.basename(f)], ids=lambda f: os.path.basename(f)[:-4])
+def test_starting_loci_against_the_reference_on_its_own_paths(fixture):
+    z, g, op = _load_loci_fixture(fixture)
+    k = int(z["k"])
+    n, o = orc.uncovered_loci(orc.OGraph.of(g), op, k)
+    ours = set(zip(n.tolist(), o.tolist()))
+    ref = set(zip(z["loci_rank"].tolist(), z["loci_off"].tolist()))
+    assert ours <= ref, sorted(ours - ref)[:5]
+    extra = ref - ours
+    assert len(extra) <= 0.02 * max(len(ref), 1) + 4, "the two definitions differ on a handful of loci only"
+    if extra and g.n_nodes < 1000:
+        pairs = _path_pairs(g, z, k)
+        for v, off in extra:
+            gp = int(g.seq_start[v]) + off
+            for w in _walks_from(g, v, off, k):
+                assert (w, gp) in pairs, "a locus only the reference starts from must be fully served by the path index"
+
+
+def test_reference_known_answer_for_the_tiny_graph():
+    """reference test/src/test_seedfinder.cpp:102-126: tiny graph, k = 12, 4 paths -> loci (1, 2..7), (2, 0), (3, 0);
+    8 (and 32) paths -> none.  The fixtures were produced by the reference itself and carry exactly that."""
+    z, g, op = _load_loci_fixture(util.GOLDEN / "loci" / "tiny_k12_n4.npz")
+    got = sorted((int(g.coord_id[v]), int(o)) for v, o in zip(z["loci_rank"], z["loci_off"]))
+    assert got == [(1, 2), (1, 3), (1, 4), (1, 5), (1, 6), (1, 7), (2, 0), (3, 0)]
+    n, o = orc.uncovered_loci(orc.OGraph.of(g), op, 12)
+    assert sorted((int(g.coord_id[v]), int(x)) for v, x in zip(n, o)) == got
+    z8, g8, op8 = _load_loci_fixture(util.GOLDEN / "loci" / "tiny_k12_n8.npz")
+    assert len(z8["loci_rank"]) == 0 and len(orc.uncovered_loci(orc.OGraph.of(g8), op8, 12)[0]) == 0
