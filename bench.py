@@ -109,7 +109,8 @@ class ClockSampler:
 def build_graph(shape: str):
     from bench_support import synth
     from psi_b200 import capi
-    a = synth.graph_arrays(**synth.SHAPES[shape])
+    spec = synth.SHAPES[shape]
+    a = synth.graph_arrays_multi(spec["components"]) if "components" in spec else synth.graph_arrays(**spec)
     return capi.Graph.from_arrays(a["ids"], a["seq_start"], a["seq"], a["row_ptr"], a["col"], a["path_ptr"],
                                   a["path_nodes"], sort=True)
 
@@ -661,6 +662,182 @@ def psikt_drop_in(W, n_reads=2_000_000, chunk=500_000):
         shutil.rmtree(td, ignore_errors=True)
 
 
+def main_sharded(args):
+    """BASELINE configs[2] / configs[4]: ONE read set sharded by read across the ranks (psi_b200/shard.py), graph and
+    index replicated on every GPU, no data-path collective; NCCL only sums the counts.  Strong scaling: the read set is
+    fixed (--reads-total), every rank takes a contiguous range holding the same number of bases and works through it
+    in chunks of --reads.  Every rank checks its own results: completeness (reads are error-free walks of the graph, so
+    every seed must hit) and soundness of a sample of records against the graph's labels."""
+    import torch
+    import torch.distributed as dist
+    from bench_support import synth
+    from psi_b200 import capi, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    k, L, total, chunk = K, READ_LEN, args.reads_total, args.reads
+    t0 = time.time()
+    g = build_graph(args.shape)
+    ps = g.pick_paths(N_PATHS, seed=1)
+    t_host = time.time() - t0
+    ctx = capi.Context(k, local)
+    ctx.set_option("offpath_mode", args.offpath_mode)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ctx.set_option(name, int(val))
+    ctx.set_graph(g, ids="internal")
+    ctx.set_paths(ps)
+    n_loci = ctx.find_loci()
+    c0 = ctx.counters()
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    if rank == 0:
+        log(f"[sharded] {args.shape}: graph {g.n_nodes} nodes / {g.n_bases} bp / {g.n_paths} components, host build {t_host:.0f} s; "
+            f"index {c0['n_index_kmers']} k-mers at {c0['n_index_entries']} loci, {c0['index_bytes'] / 1e9:.2f} GB, slot "
+            f"{c0['index_slot_bytes']} B, built in {c0['ms_index_build']:.0f} ms; {n_loci} starting loci, {c0['n_offpath_entries']} "
+            f"off-path entries (mode {c0['offpath_mode']}) in {c0['ms_find_loci']:.0f} ms; device memory in use "
+            f"{(total_b - free_b) / 1e9:.1f} of {total_b / 1e9:.0f} GB")
+    # the ONE read set: blocks of a million reads, block b drawn with seed 7000 + b; a rank materialises only the blocks its
+    # shard touches (shard_bounds cuts the whole set's offsets)
+    read_ptr = np.arange(total + 1, dtype=np.uint64) * np.uint64(L)
+    bounds = shard.shard_bounds(read_ptr, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    BLOCK = 1_000_000
+    parts = []
+    for b in range(lo // BLOCK, (hi + BLOCK - 1) // BLOCK):
+        nb = min(BLOCK, total - b * BLOCK)
+        _, bases = synth.reads(g, nb, L, 7000 + b)
+        s, e = max(lo, b * BLOCK) - b * BLOCK, min(hi, b * BLOCK + nb) - b * BLOCK
+        parts.append(bases[s * L:e * L])
+    bases = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+    n_mine = hi - lo
+    per_read = (L - k) // k + 1
+    chunks = []       # (first read id, n reads, pinned words)
+    for s in range(0, n_mine, chunk):
+        e = min(n_mine, s + chunk)
+        pk = capi.Packed.pack(np.arange(e - s + 1, dtype=np.uint64) * np.uint64(L), bases[s * L:e * L], lo + s)
+        chunks.append((lo + s, e - s, torch.from_numpy(pk.words.view(np.int64)).pin_memory()))
+    n_pipes = 3
+    pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
+    ob = ctx.dense_off_bytes()
+    dense_h = [torch.empty(chunk * per_read * (4 + ob), dtype=torch.uint8).pin_memory() for _ in pipes]
+    extra_h = [torch.empty((chunk * per_read // 8 + 4096, 4), dtype=torch.int32).pin_memory() for _ in pipes]
+    DENSE = capi.ALL | capi.DENSE
+    stats = {"hits": 0, "seeds_hit": 0, "checked": 0}
+    rng = np.random.default_rng(5 + rank)
+
+    def check(first, n, p):
+        # completeness + soundness of a sample, straight from what arrived in pinned host memory
+        ns, ne = pipes[p].dense_counts()
+        assert ns == n * per_read, (ns, n, per_read)
+        dense = capi.dense_planes(dense_h[p].numpy()[:ns * (4 + ob)], ns, ob)
+        hit = dense[:, 0] != capi.NIL32
+        stats["seeds_hit"] += int(hit.sum())
+        assert hit.all(), f"{int((~hit).sum())} seeds of error-free reads found nothing"
+        if stats["checked"] < 4000:
+            idx = rng.integers(0, ns, 500)
+            ranks = np.searchsorted(g.internal_id, dense[idx, 0].astype(np.uint64))      # gum's internal ids grow with the rank
+            assert np.array_equal(g.internal_id[ranks], dense[idx, 0].astype(np.uint64))
+            for s_i, v in zip(idx, ranks):
+                r, j = divmod(int(s_i), per_read)
+                want = bases[((first - lo) + r) * L + j * k:((first - lo) + r) * L + j * k + k].tobytes()
+                off = int(dense[s_i, 1] & 0x7FFFFFFF)
+                assert want in _walks_from(g, int(v), off, k), "a record does not spell its seed in the graph"
+            stats["checked"] += len(idx)
+
+    def run(verify, resident):
+        busy = [None] * n_pipes
+        words_d = [w.to(dev) for _, _, w in chunks] if resident else None
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i, (first, n, w) in enumerate(chunks):
+            p = i % n_pipes
+            if busy[p] is not None:
+                stats["hits"] += pipes[p].wait()
+                if verify:
+                    check(*busy[p], p)
+            pipes[p].submit_chunk_packed_raw(n, n * L, L, (words_d[i] if resident else w).data_ptr(), first, k, on_device=resident)
+            pipes[p].seeds_all_async(DENSE)
+            if not resident:
+                pipes[p].fetch_dense_async(dense_h[p].data_ptr(), chunk * per_read, extra_h[p].data_ptr(), extra_h[p].shape[0])
+            busy[p] = (first, n)
+        for p in range(n_pipes):
+            if busy[p] is not None:
+                stats["hits"] += pipes[p].wait()
+                if verify:
+                    check(*busy[p], p)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    run(True, False)                  # warm-up pass that also verifies every chunk
+    hits_verified = stats["hits"]
+    stats["hits"] = 0
+    ms_e2e = run(False, False)
+    hits_e2e = stats["hits"]
+    stats["hits"] = 0
+    ms_res = run(False, True) if n_mine * L / 4 < 0.25 * free_b else None
+    counts, _ = shard.all_reduce_counts({"reads": n_mine, "hits": hits_e2e, "seeds": n_mine * per_read, "checked": stats["checked"]},
+                                        np.zeros(shard.HIST_BINS, np.int64), device=dev)
+    assert hits_e2e == hits_verified
+    if rank == 0:
+        assert counts["reads"] == total
+        line = {"metric": f"reads/s (fully-sensitive seed finding, {args.shape}-shape graph, k={k})",
+                "value": total / (ms_res * 1e-3) if ms_res else None, "unit": "reads/s", "n_gpus": world, "steps": len(chunks), "warmup": len(chunks),
+                "ms_per_step": (ms_res or ms_e2e) / max(len(chunks), 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8/u64", "data": "synthetic",
+                "config": {"workload": f"synthetic {args.shape}-shape graph ({g.n_bases} bp, {g.n_nodes} nodes, {g.n_paths} components, "
+                                       f"{N_PATHS} paths each, {n_loci} starting loci), ONE set of {total} x {L} bp reads sharded by read over "
+                                       f"{world} GPU(s) (psi_b200/shard.py), chunks of {chunk} reads, k={k}, d={k}",
+                           "sharding": "contiguous read ranges of equal base count per rank, graph + index replicated, NCCL all-reduce of counts only"},
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "reads/s", "ms_total": ms_e2e,
+                        "h2d_bytes_per_step": int(chunks[0][2].numel() * 8) if chunks else 0,
+                        "d2h_bytes_per_step": int(chunk * per_read * (4 + ob))},
+                "seeds_per_s": counts["hits"] / ((ms_res or ms_e2e) * 1e-3), "hits": counts["hits"], "query_seeds": counts["seeds"],
+                "verified": f"every seed of every (error-free) read hit; {counts['checked']} sampled records spell their seed in the graph",
+                "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
+                          "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"],
+                          "offpath_entries": c0["n_offpath_entries"], "device_bytes_in_use": int(total_b - free_b)}}
+        print(json.dumps(line), flush=True)
+    for cx in pipes[1:]:
+        cx.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _walks_from(g, v, off, k):
+    """All k-mers spelt by forward walks from (node rank v, offset off) -- the soundness check of main_sharded."""
+    out, stack = [], [(v, off, b"")]
+    while stack:
+        v, o, acc = stack.pop()
+        acc += g.seq[int(g.seq_start[v]) + o:int(g.seq_start[v + 1])].tobytes()[:k - len(acc)]
+        if len(acc) == k:
+            out.append(acc)
+            continue
+        for e in range(int(g.row_ptr[v]), int(g.row_ptr[v + 1])):
+            stack.append((int(g.col[e]), 0, acc))
+    return out
+
+
 def other_configs(torch, dev, run_async, run_sync, capi):
     """The other single-GPU shapes BASELINE.json names, one short measurement each (resident 2-bit chunks -> dense
     results, 4 chunks in flight): configs[2]'s read shape (150 bp) on the chr22-shape graph, configs[3] (MHC-like
@@ -707,6 +884,9 @@ def main():
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipelines", type=int, default=4, help="contexts (forks sharing one index) kept in flight by the one host thread")
+    ap.add_argument("--reads-total", type=int, default=0,
+                    help="> 0: strong scaling -- ONE read set of this many reads sharded over the ranks in chunks of --reads "
+                         "(BASELINE configs[2]: --reads-total 10000000 --read-len 150; configs[4]: --shape wg_1_4 ...)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs (N = 1 only)")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to psi_b200_set_option (tuning experiments)")
     ap.add_argument("--offpath-mode", type=int, default=0, help="0 auto, 1 walk per chunk, 2 materialise (psi_b200_set_option)")
@@ -715,6 +895,8 @@ def main():
     globals().update(K=args.k, READ_LEN=args.read_len)
     if args.impl == "reference":
         main_reference(args)
+    elif args.reads_total > 0:
+        main_sharded(args)
     else:
         main_gpu(args)
 

@@ -39,6 +39,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def whole_genome_components(total_bp, total_sites, n_components=24):
+    """BASELINE configs[4]'s recipe: n components of equal size, the chr22 site mix, seeds 100 + c."""
+    return [dict(backbone=total_bp // n_components, sites=total_sites // n_components, p_snp=0.90, p_ins=0.05, tri_frac=0.0,
+                 seeds=(100 + c, 200 + c)) for c in range(n_components)]
+
+
 # named shapes of BASELINE.json / SURVEY 8d
 SHAPES = {
     # backbone, sites, p_snp, p_ins, tri_frac, seeds
@@ -47,6 +53,9 @@ SHAPES = {
     # a chromosome-1-sized instance of the chr22 recipe (5x): exercises the grouped index build (16 paths x 255 Mbp = 4 G
     # path windows) and a 5.4 GB index
     "chr1": dict(backbone=250_000_000, sites=4_900_000, p_snp=0.90, p_ins=0.05, tri_frac=0.0, seeds=(1, 2)),
+    # BASELINE configs[4] (3.1 Gbp, 80 M sites, 24 components) at 1/4 and 1/16 of its size
+    "wg_1_4": dict(components=whole_genome_components(775_000_000, 20_000_000)),
+    "wg_1_16": dict(components=whole_genome_components(193_750_000, 5_000_000)),
     "mhc": dict(backbone=5_000_000, sites=416_667, p_snp=1.0, p_ins=0.0, tri_frac=0.10, seeds=(6, 7)),
 }
 
@@ -67,6 +76,26 @@ def graph_arrays(backbone, sites, p_snp=0.9, p_ins=0.05, tri_frac=0.0, seeds=(22
     L.psi_synth_graph_free(h)
     return dict(ids=ids, seq_start=seq_start, seq=seq, row_ptr=row_ptr, col=col[: m.value],
                 path_ptr=np.array([0, pl.value], np.uint64), path_nodes=path[: pl.value])
+
+
+def graph_arrays_multi(components):
+    """Several independent components (one embedded path each) as ONE graph: `components` is a list of graph_arrays
+    keyword dicts.  Node ids continue from component to component; there is no edge between components."""
+    parts = [graph_arrays(**c) for c in components]
+    ids, seq_start, seq, row_ptr, col, path_ptr, path_nodes = [], [np.zeros(1, np.uint64)], [], [np.zeros(1, np.uint64)], [], [0], []
+    n0 = b0 = m0 = 0
+    for a in parts:
+        n, b, m = len(a["ids"]), len(a["seq"]), len(a["col"])
+        ids.append(a["ids"] + np.uint64(n0))
+        seq_start.append(a["seq_start"][1:] + np.uint64(b0))
+        seq.append(a["seq"])
+        row_ptr.append(a["row_ptr"][1:] + np.uint64(m0))
+        col.append(a["col"] + np.uint32(n0))
+        path_nodes.append(a["path_nodes"] + np.uint32(n0))
+        path_ptr.append(path_ptr[-1] + len(a["path_nodes"]))
+        n0, b0, m0 = n0 + n, b0 + b, m0 + m
+    return dict(ids=np.concatenate(ids), seq_start=np.concatenate(seq_start), seq=np.concatenate(seq), row_ptr=np.concatenate(row_ptr),
+                col=np.concatenate(col), path_ptr=np.array(path_ptr, np.uint64), path_nodes=np.concatenate(path_nodes))
 
 
 def reads(g, n_reads, length, seed):
