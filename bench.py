@@ -536,7 +536,7 @@ def main_gpu(args):
                     "ms_per_step": ms_e2e / steps, "pipelines": n_pipes, "host_threads": 1,
                     "fused_kernel_ms": kms_e2e,
                     "pcie": dict(pcie, floor_ms_per_step=max(words_bytes / (pcie["h2d_bidir_gbs"] * 1e6), (4 + off_bytes) * W.n_seeds / (pcie["d2h_bidir_gbs"] * 1e6)),
-                                 note="rank 0's link, measured while the other ranks are idle at N > 1"),
+                                 note="rank 0's link; at N > 1 every rank runs the same copies at the same moment, so this is one GPU's share of the box's host bandwidth"),
                     "formats": f"up: 2-bit words of the chunk (pinned host memory); down: {4 + off_bytes} bytes per seed (u32 node id, "
                                f"u{8 * off_bytes} node offset | off-path bit) + the extra list of multi-locus seeds + the step's counters"},
             "roofline": roof,
