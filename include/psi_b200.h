@@ -177,7 +177,12 @@ const char* psi_b200_last_error(const psi_b200_ctx* ctx);
  * non-blocking stream). */
 int  psi_b200_set_stream(psi_b200_ctx* ctx, void* cuda_stream);
 int  psi_b200_sync(psi_b200_ctx* ctx);
-/* Tuning knobs.  Set before set_paths / find_loci / set_loci:
+/* Options.  Set before set_paths:
+ *   "gocc_threshold"    -r of the CLI / gocc_threshold of SeedFinder(graph, len, gocc_threshold, ...) (seed_finder.hpp:930-942):
+ *                       seeds_on_paths skips every k-mer that occurs more often than this in the text of the indexed paths
+ *                       (index_iter.hpp:842-848; 0 = no threshold).  seeds_off_paths is unaffected, so hits at starting loci
+ *                       survive.  Needs the off-path walks in the index (PSI_B200_ERR_ARG from find_loci / set_loci otherwise).
+ * Set before set_paths / find_loci / set_loci:
  *   "code_by_rank"      1: index entries carry (node rank, offset) even when (node id, offset) would fit (test hook);
  *   "offpath_mode"      0 auto (default), 1 walk the graph from the starting loci for every chunk
  *                       (the reference's scheme), 2 always materialise those walks into the index;
@@ -342,6 +347,7 @@ typedef struct {
   /* sums over the fused steps completed since create / reset (CUDA events on the context's stream; "timers" option) */
   double ms_probe_sum, ms_on_sum;
   uint64_t timed_steps;
+  uint64_t n_gocc_dropped;     /* on-path entries the gocc threshold removed from the index */
   uint32_t code_by_rank;       /* 1: index entries carry (node rank, offset), 0: (node id, offset) -- no gather per hit */
   uint32_t code_off_bits;
 } psi_b200_counters_t;

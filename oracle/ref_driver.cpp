@@ -23,8 +23,8 @@
  *    --loci FILE   starting loci: internal id, offset (2 x u64).
  *    --paths FILE  the paths the reference picked and indexed (SeedFinder::pick_paths, seed_finder.hpp:1138-1167):
  *                  u64 n_paths, then per path u64 n_nodes, u64 head offset (bases cut from the first node),
- *                  u64 tail trim (bases cut from the last node), u64 text length, the node ids (internal, u64
- *                  each) and the path's forward text padded to a multiple of 8 bytes.
+ *                  u64 tail trim (bases cut from the last node), u64 text length, the node RANKS (0-based, u64
+ *                  each; flattened by include/psi_b200_gum.hpp) and the path's forward text padded to 8 bytes.
  *  and one JSON line on stdout with counts and timings.
  */
 #include <cstdio>
@@ -45,11 +45,13 @@
 #include <gum/io_utils.hpp>
 #include <kseq++/seqio.hpp>
 
+#include "../include/psi_b200_gum.hpp"
+
 using namespace psi;
 
 struct Args {
   std::string gfa, fastq, out, raw, nodes, loci, paths;
-  unsigned k = 0, d = 0, n = 0, context = 0, step = 1;
+  unsigned k = 0, d = 0, n = 0, context = 0, step = 1, gocc = 0;
   unsigned long chunk = 0, first_read = 0, max_reads = 0;
   bool patched = true;
   bool on_only = false, off_only = false;
@@ -84,6 +86,7 @@ int main( int argc, char** argv )
     else if ( s == "-n" ) a.n = std::stoul( next() );
     else if ( s == "-t" ) a.context = std::stoul( next() );
     else if ( s == "-e" ) a.step = std::stoul( next() );
+    else if ( s == "-r" ) a.gocc = std::stoul( next() );   /* seed genome occurrence count threshold (src/psikt.cpp -r) */
     else if ( s == "-c" ) a.chunk = std::stoul( next() );
     else if ( s == "--first-read" ) a.first_read = std::stoul( next() );
     else if ( s == "--max-reads" ) a.max_reads = std::stoul( next() );
@@ -121,7 +124,7 @@ int main( int argc, char** argv )
     std::fclose( f );
   }
 
-  finder_type finder( graph, a.k );
+  finder_type finder( graph, a.k, a.gocc );
   t0 = now_s();
   if ( a.n != 0 ) {
     finder.create_path_index( a.n, a.patched, a.context, a.step );
@@ -138,23 +141,23 @@ int main( int argc, char** argv )
   }
 
   if ( !a.paths.empty() ) {
+    /* the flat arrays come from the adapter the C-ABI ships for the reference's types (include/psi_b200_gum.hpp):
+     * dumping through it pins the adapter's rank / head / tail arithmetic to the reference's own path text */
     std::FILE* f = std::fopen( a.paths.c_str(), "wb" );
     auto const& pset = finder.get_pindex().get_paths_set();
-    uint64_t n = pset.size();
+    psi_b200::FlatPaths fp = psi_b200::flatten_paths( graph, pset );
+    uint64_t n = fp.head_off.size();
     write_u64s( f, &n, 1 );
-    for ( auto it = pset.begin(); it != pset.end(); ++it ) {
-      auto const& p = *it;
-      std::vector< uint64_t > ids;
-      for ( auto id : p.get_nodes() ) ids.push_back( (uint64_t)id );
-      std::string text = sequence( p, Forward() );
-      uint64_t head = ids.empty() ? 0 : (uint64_t)p.get_head_offset();
-      /* bases of the last node that the path does not cover */
-      uint64_t tail = 0;
-      if ( ids.size() == 1 ) tail = (uint64_t)graph.node_length( ids.back() ) - head - (uint64_t)p.get_sequence_len();
-      else if ( !ids.empty() ) tail = (uint64_t)graph.node_length( ids.back() ) - (uint64_t)p.get_seqlen_tail();
-      uint64_t hdr[4] = { (uint64_t)ids.size(), head, tail, (uint64_t)text.size() };
+    uint64_t pi = 0;
+    for ( auto it = pset.begin(); it != pset.end(); ++it, ++pi ) {
+      std::string text = sequence( *it, Forward() );
+      uint64_t nn = fp.path_ptr[ pi + 1 ] - fp.path_ptr[ pi ];
+      uint64_t hdr[4] = { nn, fp.head_off[ pi ], fp.tail_trim[ pi ], (uint64_t)text.size() };
       write_u64s( f, hdr, 4 );
-      if ( !ids.empty() ) write_u64s( f, ids.data(), ids.size() );
+      for ( uint64_t e = fp.path_ptr[ pi ]; e < fp.path_ptr[ pi + 1 ]; ++e ) {
+        uint64_t r = fp.nodes[ e ];
+        write_u64s( f, &r, 1 );
+      }
       text.resize( ( text.size() + 7 ) / 8 * 8, '\0' );
       if ( !text.empty() && std::fwrite( text.data(), 1, text.size(), f ) != text.size() ) { std::perror( "fwrite" ); std::exit( 3 ); }
     }

@@ -84,7 +84,7 @@ class Counters(C.Structure):
                 ("ms_off", C.c_float), ("ms_resolve", C.c_float), ("ms_sort", C.c_float), ("ms_d2h", C.c_float),
                 ("launches", C.c_uint32), ("ms_probe", C.c_float),
                 ("ms_probe_sum", C.c_double), ("ms_on_sum", C.c_double), ("timed_steps", C.c_uint64),
-                ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32)]
+                ("n_gocc_dropped", C.c_uint64), ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}

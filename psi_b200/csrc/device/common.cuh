@@ -343,9 +343,10 @@ __device__ __forceinline__ bool table_find_any(const KmerTable& t, uint64_t kmer
 // of read seeds); a fresh key returns NIL32.  Returns false when MAX_DISP + 1
 // lines and the stash are full (caller raises the overflow flag).
 // `payload` may use table_payload_bits(t) bits; chains (chain == true) keep 32-bit payloads (seed indices).
+// where: if not null, receives the address of the slot's low payload word (for counters kept in the payload).
 template <int FMT>
 __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, uint64_t payload, uint32_t flags,
-                                             bool chain, uint32_t& prev)
+                                             bool chain, uint32_t& prev, unsigned int** where = nullptr)
 {
   const Home h = home_of<FMT>(t, kmer);
   const uint64_t line_mask = (1ull << t.line_bits) - 1ull;
@@ -362,11 +363,12 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
         while (true) {
           if (cur == EMPTY8) {
             const unsigned long long old = atomicCAS(slot + j, EMPTY8, fresh);
-            if (old == EMPTY8) { prev = NIL32; return true; }
+            if (old == EMPTY8) { prev = NIL32; if (where) *where = reinterpret_cast<unsigned int*>(slot + j); return true; }
             cur = old;
             continue;
           }
           if (slot8_want(t, cur) == want) {
+            if (where) *where = reinterpret_cast<unsigned int*>(slot + j);
             if (!chain) { prev = (uint32_t)cur; return true; }
             const unsigned long long upd = (cur & 0xffffffff00000000ull) | (uint32_t)payload;
             const unsigned long long old = atomicCAS(slot + j, cur, upd);
@@ -387,11 +389,16 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
         while (true) {
           if (cur.flags == NIL32) {
             Slot16 old;
-            if (cas128(slot + j, empty, Slot16{ kmer, (uint32_t)payload, slot16_flagword(flags, payload) }, old)) { prev = NIL32; return true; }
+            if (cas128(slot + j, empty, Slot16{ kmer, (uint32_t)payload, slot16_flagword(flags, payload) }, old)) {
+              prev = NIL32;
+              if (where) *where = &slot[j].payload;
+              return true;
+            }
             cur = old;
             continue;
           }
           if (cur.key == kmer) {
+            if (where) *where = &slot[j].payload;
             if (!chain) { prev = cur.payload; return true; }
             Slot16 old;
             if (cas128(slot + j, cur, Slot16{ kmer, (uint32_t)payload, cur.flags }, old)) { prev = cur.payload; return true; }
@@ -403,7 +410,20 @@ __device__ __forceinline__ bool table_insert(const KmerTable& t, uint64_t kmer, 
       }
     }
   }
-  return stash_insert(t, kmer, payload, flags, chain, prev);
+  if (where) *where = nullptr;      // counters are not kept in the stash: the caller treats this as an overflow
+  return where ? false : stash_insert(t, kmer, payload, flags, chain, prev);
+}
+
+// Counting table: find-or-insert `kmer` and add 1 to the 32-bit counter in its payload.  False when the key found no
+// slot in MAX_DISP + 1 lines (the caller raises the overflow flag; the host retries with a larger table).
+template <int FMT>
+__device__ __forceinline__ bool table_count(const KmerTable& t, uint64_t kmer)
+{
+  uint32_t prev;
+  unsigned int* where = nullptr;
+  if (!table_insert<FMT>(t, kmer, 0, 0, false, prev, &where) || !where) return false;
+  atomicAdd(where, 1u);
+  return true;
 }
 
 // ------------------------------------------------------- warp helpers --

@@ -140,6 +140,14 @@ struct Shared {
   DevBuf<uint32_t> on_gpos;
   uint64_t n_on_pairs = 0, n_off_pairs = 0;
 
+  // ---- gocc threshold (-r): the picked paths stay on the device so that the k-mers' occurrence counts can be taken
+  // when the final table is built ----
+  uint32_t gocc_threshold = 0;
+  bool paths_kept = false, table_filtered = false;
+  DevBuf<uint64_t> path_ptr;
+  DevBuf<uint32_t> path_nodes, path_head, path_tail;
+  uint64_t n_paths = 0, n_path_entries = 0;
+
   // ---- starting loci ----
   uint64_t n_loci = 0;
   DevBuf<uint32_t> loci_node, loci_off;
@@ -233,6 +241,7 @@ struct Ctx {
   uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
   int opt_blocking_sync = 0;                   // 1: wait for a chunk on a blocking event (thread sleeps) instead of spinning
+  uint32_t opt_gocc_threshold = 0;             // seeds_on_paths skips k-mers with more occurrences in the path text (0: none)
   int opt_code_by_rank = 0;                    // 1: locus codes carry the node rank even when the ids would fit (tests)
   int opt_timers = 1;                          // 0: no CUDA-event records around the kernels of a step
   int opt_fused = 1;                           // 1: index-mode steps run the fused one-pass kernel (fused.cu)

@@ -109,6 +109,7 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_fused = parent.opt_fused;
   c->opt_timers = parent.opt_timers;
   c->opt_code_by_rank = parent.opt_code_by_rank;
+  c->opt_gocc_threshold = parent.opt_gocc_threshold;
   c->opt_blocking_sync = parent.opt_blocking_sync;
   c->opt_index_slack = parent.opt_index_slack;
   c->opt_resolve_items = parent.opt_resolve_items;

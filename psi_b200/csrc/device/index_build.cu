@@ -50,12 +50,16 @@ __device__ __forceinline__ uint32_t path_of_entry(const PathsView& p, uint64_t e
 // One warp per path entry (a node visit); lanes stride over the offsets inside
 // the node.  For every offset the k-window that starts there is gathered along
 // the PATH's successors.  count_only: just count valid windows.
-template <bool COUNT_ONLY>
+// MODE 0: emit (k-mer, locus) pairs; 1: count the valid windows; 2: count the windows PER K-MER in a counting table
+// (the k-mer's number of occurrences in the path text, what the reference compares with its gocc threshold,
+// index_iter.hpp:842-848)
+template <int MODE>
 __global__ void __launch_bounds__(256)
 path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint64_t e_end,
                     uint64_t* __restrict__ out_kmer, uint32_t* __restrict__ out_gpos,
-                    unsigned long long* __restrict__ out_count)
+                    unsigned long long* __restrict__ out_count, KmerTable counts, unsigned long long* __restrict__ err_flag)
 {
+  constexpr bool COUNT_ONLY = MODE == 1;
   const uint32_t lane = lane_id();
   const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -98,6 +102,9 @@ path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint
         }
       }
       if (COUNT_ONLY) local_count += ok;
+      else if (MODE == 2) {
+        if (ok && !(counts.fmt == 8 ? table_count<8>(counts, kmer) : table_count<16>(counts, kmer))) atomicOr(err_flag, 2ull);
+      }
       else {
         const uint64_t slot = warp_reserve(out_count, ok ? 1u : 0u);
         if (ok) { out_kmer[slot] = kmer; out_gpos[slot] = r.seq_start + o; }
@@ -214,6 +221,56 @@ insert_runs_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ key, c
   if (!table_insert<FMT>(t, kmer, payload, flags, false, prev)) atomicOr(err_flag, 2ull);
 }
 
+// ------------------------------------------------ gocc threshold (-r) --
+//
+// The reference skips, in seeds_on_paths, every k-mer that occurs more than gocc_threshold times in the path text
+// (kmer_exact_matches, index_iter.hpp:842-848); seeds_off_paths is not affected and still reports every k-walk from a
+// starting locus.  With the off-path walks materialised that is a filter on the index: the on-path entries of such a
+// k-mer go, except those at a starting locus, which stay as off-path entries.
+
+__global__ void __launch_bounds__(256)
+mark_loci_kernel(const NodeRec* __restrict__ rec, const uint32_t* __restrict__ loci_node, const uint32_t* __restrict__ loci_off,
+                 uint64_t n_loci, uint32_t n_nodes, uint32_t* __restrict__ bits)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_loci) return;
+  const uint32_t v = loci_node[i];
+  if (v >= n_nodes || loci_off[i] >= rec[v].seq_len) return;
+  const uint32_t gpos = rec[v].seq_start + loci_off[i];
+  atomicOr(bits + (gpos >> 5), 1u << (gpos & 31u));
+}
+
+// keep[i] = 0 for the on-path pairs of over-represented k-mers that are not at a starting locus; those at one become
+// off-path entries (bit 32 of the value).
+__global__ void __launch_bounds__(256)
+gocc_filter_kernel(const uint64_t* __restrict__ key, uint64_t* __restrict__ val, uint64_t n, KmerTable counts, uint32_t threshold,
+                   const uint32_t* __restrict__ loci_bits, uint32_t* __restrict__ keep)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k_ = 1;
+  const uint64_t v = val[i];
+  if (!(v >> 32)) {
+    Found f{};
+    if (table_find_any(counts, key[i], f) && (uint32_t)f.payload > threshold) {
+      const uint32_t gpos = (uint32_t)v;
+      if ((loci_bits[gpos >> 5] >> (gpos & 31u)) & 1u) val[i] = v | (1ull << 32);
+      else k_ = 0;
+    }
+  }
+  keep[i] = k_;
+}
+
+__global__ void __launch_bounds__(256)
+compact_kv_kernel(const uint64_t* __restrict__ key, const uint64_t* __restrict__ val, const uint32_t* __restrict__ keep,
+                  const uint32_t* __restrict__ scan, uint64_t n, uint64_t* __restrict__ okey, uint64_t* __restrict__ oval)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  okey[scan[i]] = key[i];
+  oval[scan[i]] = val[i];
+}
+
 // ------------------------------------------------------------ host side --
 
 static void exclusive_scan_u32(Ctx& c, const uint32_t* in, uint32_t* out, uint64_t n)
@@ -262,12 +319,14 @@ static uint64_t sort_unique_pairs(Ctx& c, DevBuf<uint64_t>& kmer_a, DevBuf<uint3
 }
 
 // (Re)build the device index from the resident on-path pairs plus `n_off` off-path pairs
-// (both sorted by (kmer, gpos) and duplicate free).
-static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gpos, uint64_t n_off)
+// (both sorted by (kmer, gpos) and duplicate free).  final: the starting loci are known and this is the table the
+// chunks will probe -- the gocc threshold, if one is set, is applied here (never to the table the loci are derived from).
+static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gpos, uint64_t n_off, bool final = false)
 {
   Shared& sh = *c.sh;
   const uint64_t n_on = sh.n_on_pairs;
-  const uint64_t n = n_on + n_off;
+  uint64_t n = n_on + n_off;
+  sh.table_filtered = false;
   unsigned long long* d_err = c.dev_counters.p + DC_ERR;
   sh.has_table = false;
   sh.n_off_pairs = n_off;
@@ -286,8 +345,8 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
   key_a.ensure(n); val_a.ensure(n);
   concat_pairs_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(sh.on_kmer.p, sh.on_gpos.p, n_on, off_kmer, off_gpos, n_off, key_a.p, val_a.p);
   ++c.counters.launches;
-  const uint64_t* key = key_a.p;
-  const uint64_t* val = val_a.p;
+  uint64_t* key = key_a.p;
+  uint64_t* val = val_a.p;
   if (n_off && n_on) {  // stable sort by k-mer keeps on-path loci ahead of off-path loci, each group ascending
     key_b.ensure(n); val_b.ensure(n);
     size_t tmp_bytes = 0;
@@ -299,6 +358,62 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
     PSI_CUDA(cudaStreamSynchronize(c.stream));
     key = key_b.p;
     val = val_b.p;
+  }
+
+  DevBuf<uint64_t> key_f, val_f;
+  if (final && sh.gocc_threshold && n_on) {
+    // occurrences of every k-mer in the path text, counted over the retained paths
+    if (!sh.paths_kept) throw StateError("gocc threshold: the paths were indexed before the threshold was set");
+    HostTable counts;
+    for (int grow = 0;; ++grow) {
+      table_alloc(c, counts, n_on, 2 * c.k, 1024, grow);
+      PSI_CUDA(cudaMemsetAsync(counts.slots.p, 0xff, counts.n_lines * 128, c.stream));
+      PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+      const GraphView g0 = make_graph_view(c);
+      PathsView pv{ sh.path_ptr.p, sh.path_nodes.p, sh.path_head.p, sh.path_tail.p, (uint32_t)sh.n_paths };
+      const uint64_t n_entries = sh.n_path_entries;
+      const unsigned wgrid = (unsigned)std::min<uint64_t>((n_entries + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
+      path_windows_kernel<2><<<wgrid, 256, 0, c.stream>>>(g0, pv, c.k, 0, n_entries, nullptr, nullptr, nullptr, counts.view, d_err);
+      ++c.counters.launches;
+      unsigned long long err = 0;
+      PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      if (!(err & 2ull)) break;
+      if (grow >= 3) throw OverflowError("gocc threshold: counting table overflow");
+    }
+    counts.view.stash_nonempty = 0;
+    const uint64_t n_words = (sh.n_bases + 31) >> 5;
+    DevBuf<uint32_t> loci_bits, keep, kscan;
+    loci_bits.ensure(n_words + 1);
+    PSI_CUDA(cudaMemsetAsync(loci_bits.p, 0, (n_words + 1) * sizeof(uint32_t), c.stream));
+    if (sh.n_loci)
+      mark_loci_kernel<<<grid_for(sh.n_loci, 256), 256, 0, c.stream>>>(sh.node_rec.p, sh.loci_node.p, sh.loci_off.p, sh.n_loci, sh.n_nodes, loci_bits.p);
+    keep.ensure(n + 1); kscan.ensure(n + 1);
+    gocc_filter_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(key, val, n, counts.view, sh.gocc_threshold, loci_bits.p, keep.p);
+    PSI_CUDA(cudaMemsetAsync(keep.p + n, 0, sizeof(uint32_t), c.stream));
+    exclusive_scan_u32(c, keep.p, kscan.p, n + 1);
+    uint32_t n_kept = 0;
+    PSI_CUDA(cudaMemcpyAsync(&n_kept, kscan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    key_f.ensure((uint64_t)n_kept + 1); val_f.ensure((uint64_t)n_kept + 1);
+    compact_kv_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(key, val, keep.p, kscan.p, n, key_f.p, val_f.p);
+    c.counters.launches += 3;
+    PSI_CUDA(cudaGetLastError());
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    c.counters.n_gocc_dropped = n - n_kept;
+    key = key_f.p;
+    val = val_f.p;
+    n = n_kept;
+    sh.table_filtered = true;
+    if (n == 0) {
+      table_alloc(c, sh.index, 1, 2 * c.k, 1024);
+      sh.index.view.stash_nonempty = 0;
+      sh.multi.ensure(4);
+      sh.has_table = true;
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      c.counters.n_index_entries = c.counters.n_index_kmers = 0;
+      return;
+    }
   }
 
   // k-mer runs
@@ -429,6 +544,21 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   }
   sh.on_kmer.release(); sh.on_gpos.release();
   sh.n_on_pairs = 0;
+  sh.gocc_threshold = c.opt_gocc_threshold;
+  sh.paths_kept = false;
+  if (sh.gocc_threshold) {
+    // the k-mer occurrence counts are taken when the final table is built (the loci are known then): keep the paths
+    sh.path_ptr.ensure(n_paths + 1); sh.path_nodes.ensure(n_entries + 1); sh.path_head.ensure(n_paths + 1); sh.path_tail.ensure(n_paths + 1);
+    PSI_CUDA(cudaMemcpyAsync(sh.path_ptr.p, d_path_ptr.p, (n_paths + 1) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c.stream));
+    if (n_entries) PSI_CUDA(cudaMemcpyAsync(sh.path_nodes.p, d_nodes.p, n_entries * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+    if (head_off) PSI_CUDA(cudaMemcpyAsync(sh.path_head.p, d_head.p, n_paths * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+    else PSI_CUDA(cudaMemsetAsync(sh.path_head.p, 0, n_paths * sizeof(uint32_t), c.stream));
+    if (tail_trim) PSI_CUDA(cudaMemcpyAsync(sh.path_tail.p, d_tail.p, n_paths * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+    else PSI_CUDA(cudaMemsetAsync(sh.path_tail.p, 0, n_paths * sizeof(uint32_t), c.stream));
+    sh.n_paths = n_paths;
+    sh.n_path_entries = n_entries;
+    sh.paths_kept = true;
+  }
   uint64_t n_windows_total = 0;
   for (uint64_t g0 = 0; g0 < n_paths;) {
     uint64_t g1 = g0, bases = 0;
@@ -445,7 +575,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
     // pass 1: count valid windows
     const unsigned wgrid = (unsigned)std::min<uint64_t>((e1 - e0 + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
     PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-    path_windows_kernel<true><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, nullptr, nullptr, d_cnt);
+    path_windows_kernel<1><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, nullptr, nullptr, d_cnt, KmerTable{}, nullptr);
     ++c.counters.launches;
     unsigned long long n_pairs = 0;
     PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
@@ -459,7 +589,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
     DevBuf<uint32_t> gpos_a;
     kmer_a.ensure(n_pairs + n_acc); gpos_a.ensure(n_pairs + n_acc);
     PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-    path_windows_kernel<false><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt);
+    path_windows_kernel<0><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt, KmerTable{}, nullptr);
     ++c.counters.launches;
     if (n_acc) {
       PSI_CUDA(cudaMemcpyAsync(kmer_a.p + n_pairs, sh.on_kmer.p, n_acc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c.stream));
@@ -597,10 +727,16 @@ static void materialise_offpath(Ctx& c)
   c.counters.n_offpath_walks = 0;
   c.counters.offpath_mode = 1;
   const bool had_off = sh.n_off_pairs != 0;
-  auto drop_off = [&] { if (had_off || !sh.has_table) build_table(c, nullptr, nullptr, 0); };
-  if (sh.n_loci == 0) { drop_off(); sh.offpath_indexed = true; c.counters.offpath_mode = 2; return; }
-  if (c.opt_offpath_mode == 1) { drop_off(); return; }
-  if (!sh.has_table) build_table(c, nullptr, nullptr, 0);
+  const bool gocc = sh.gocc_threshold != 0 && sh.has_index;
+  c.counters.n_gocc_dropped = 0;
+  auto walk_mode_refused = [&] {
+    if (gocc) throw ArgError("a gocc threshold needs the off-path walks materialised in the index (offpath_mode 0 or 2 and a budget that holds them)");
+  };
+  auto drop_off = [&](bool final) { if (had_off || !sh.has_table || sh.table_filtered || (final && gocc)) build_table(c, nullptr, nullptr, 0, final); };
+  if (sh.n_loci == 0) { drop_off(true); sh.offpath_indexed = true; c.counters.offpath_mode = 2; return; }
+  if (c.opt_offpath_mode == 1) { walk_mode_refused(); drop_off(false); return; }
+  // the walks are compared with the UNFILTERED path index
+  if (!sh.has_table || sh.table_filtered) build_table(c, nullptr, nullptr, 0);
 
   const GraphView g = make_graph_view(c);
   const unsigned grid = (unsigned)c.sm_count * 8;
@@ -637,7 +773,7 @@ static void materialise_offpath(Ctx& c)
     }
     if (pass == 0) {
       c.counters.n_offpath_walks = n_walks;
-      if (n_walks >= 0xfffffff0ull || (c.opt_offpath_mode == 0 && n_walks > c.opt_offpath_max_pairs)) { drop_off(); return; }
+      if (n_walks >= 0xfffffff0ull || (c.opt_offpath_mode == 0 && n_walks > c.opt_offpath_max_pairs)) { walk_mode_refused(); drop_off(false); return; }
       if (n_walks == 0) break;
       kmer_a.ensure(n_walks); gpos_a.ensure(n_walks);
     }
@@ -646,7 +782,7 @@ static void materialise_offpath(Ctx& c)
   DevBuf<uint32_t> off_gpos;
   const uint64_t n_off = sort_unique_pairs(c, kmer_a, gpos_a, n_walks, off_kmer, off_gpos);
   kmer_a.release(); gpos_a.release();
-  if (n_off || had_off) build_table(c, off_kmer.p, off_gpos.p, n_off);
+  if (n_off || had_off || gocc) build_table(c, off_kmer.p, off_gpos.p, n_off, true);
   sh.offpath_indexed = true;
   c.counters.offpath_mode = 2;
 }
@@ -750,6 +886,10 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   }
   else if (n == "timers") {
     c.opt_timers = value != 0;
+  }
+  else if (n == "gocc_threshold") {
+    if (value < 0 || value > 0xffffffffll) throw ArgError("set_option: gocc_threshold must be in [0, 2^32)");
+    c.opt_gocc_threshold = (uint32_t)value;     // takes effect at the next set_paths
   }
   else if (n == "code_by_rank") {
     c.opt_code_by_rank = value != 0;     // takes effect at the next set_paths / find_loci / set_loci

@@ -23,9 +23,12 @@
 //
 // Differences that are deliberate: callbacks see every hit of the
 // seed SET exactly once (the reference repeats a locus once per covering path
-// and per walk); `gocc` is not tracked (0); the distance index, approximate
-// matching, MEM mode and a non-zero gocc threshold are outside this build and
-// throw std::runtime_error when requested.
+// and per walk); Seed<>::gocc is not filled (0); the distance index, approximate
+// matching and MEM mode are outside this build and throw std::runtime_error when
+// requested.  A gocc threshold (-r) and a step size (-e) make the reference's seed
+// set depend on its (randomly) picked paths and on the loci it derived from them:
+// with the same paths and loci (psi_b200_set_paths / set_loci, a shared loci file)
+// this build gives the same set (tests/golden/loci, written by the reference).
 #ifndef PSI_B200_PSI_SEED_FINDER_HPP
 #define PSI_B200_PSI_SEED_FINDER_HPP
 
@@ -158,13 +161,16 @@ class SeedFinder {
         stats_ptr(std::make_unique<stats_type>(this))
   {
     if (mismatches != 0) throw std::runtime_error("approximate seed matching is not implemented");
-    if (gocc_thr != 0) throw std::runtime_error("a seed genome occurrence threshold makes the seed set path dependent; not supported");
     if (device < 0) {
       const char* e = std::getenv("PSI_B200_DEVICE");
       device = e ? std::atoi(e) : 0;
     }
     if (psi_b200_create(device, len, &ctx) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
-    try { upload_graph(); }
+    try {
+      upload_graph();
+      // seeds_on_paths skips k-mers with more occurrences in the path text (index_iter.hpp:842-848); applied to the index
+      if (gocc_thr != 0) check(psi_b200_set_option(ctx, "gocc_threshold", gocc_thr));
+    }
     catch (...) { psi_b200_destroy(ctx); ctx = nullptr; throw; }
   }
   SeedFinder(const SeedFinder&) = delete;

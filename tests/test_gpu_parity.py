@@ -868,3 +868,56 @@ def test_device_loci_on_the_reference_paths(fixture):
         sets.append(got)
         ctx.close()
     assert np.array_equal(sets[0], sets[1])
+
+
+PATH_DEPENDENT_FIXTURES = sorted(f for f in _glob.glob(_os.fspath(util.GOLDEN / "loci" / "*.npz")) if len(np.load(f)["seeds"]))
+
+
+@pytest.mark.parametrize("fixture", PATH_DEPENDENT_FIXTURES, ids=lambda f: _os.path.basename(f)[:-4])
+def test_gocc_threshold_and_step_size_on_the_reference_paths_and_loci(fixture):
+    """-r (gocc threshold) and -e (step size) make the reference's seed set depend on the paths it picked and the loci
+    it derived from them.  The fixture holds one run of the unmodified reference: its paths, its loci and the seeds it
+    found; the same paths (psi_b200_set_paths) and loci (psi_b200_set_loci -- what a shared _loci_e<step>l<k> file
+    hands over) must give the same set: records and dense results, 2-bit and ASCII chunks."""
+    z = np.load(fixture)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    k, thr = int(z["k"]), int(z["gocc"])
+    rp, bases = util.read_fasta(util.GOLDEN / str(z["reads"]))
+    n = int(z["max_reads"])
+    rp, bases = rp[:n + 1], bases[:int(rp[n])]
+    want = z["seeds"]          # canonical: (read id, read offset, coordinate node id, node offset)
+    ctx = capi.Context(k, 0)
+    ctx.set_option("gocc_threshold", thr)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(capi.PathSet(path_ptr=z["path_ptr"], nodes=z["nodes"], head_off=z["head"], tail_trim=z["tail"]))
+    ctx.set_loci(z["loci_rank"], z["loci_off"])
+    cn = ctx.counters()
+    assert cn["offpath_mode"] == 2 and (cn["n_gocc_dropped"] > 0) == (thr > 0)
+    ctx.submit_chunk(rp, bases, 0, k)
+    cnt = ctx.seeds_all()
+    got = capi.canonical(ctx.fetch())
+    assert cnt == len(got) and np.array_equal(got, want)
+    ctx.submit_chunk_packed(capi.Packed.pack(rp, bases, 0), k)
+    cnt = ctx.seeds_all(capi.ALL | capi.DENSE)
+    dense, extra = ctx.fetch_dense()
+    rec, _ = capi.dense_to_records(dense, extra, rp, k, k, 0)
+    assert cnt == len(rec) and np.array_equal(capi.canonical(rec), want)
+    ctx.set_option("fused", 0)
+    ctx.submit_chunk(rp, bases, 0, k)
+    assert ctx.seeds_all() == len(want) and np.array_equal(capi.canonical(ctx.fetch()), want)
+    # the loci may be set again (the table is rebuilt from the unfiltered pairs first)
+    ctx.set_loci(z["loci_rank"], z["loci_off"])
+    ctx.submit_chunk(rp, bases, 0, k)
+    assert ctx.seeds_all() == len(want)
+    ctx.close()
+    if thr:
+        # walk mode cannot serve a threshold: refused, not ignored
+        ctx = capi.Context(k, 0)
+        ctx.set_option("gocc_threshold", thr)
+        ctx.set_option("offpath_mode", 1)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(capi.PathSet(path_ptr=z["path_ptr"], nodes=z["nodes"], head_off=z["head"], tail_trim=z["tail"]))
+        with pytest.raises(capi.PsiError) as e:
+            ctx.set_loci(z["loci_rank"], z["loci_off"])
+        assert e.value.code == capi.ERR_ARG
+        ctx.close()
