@@ -169,8 +169,11 @@ def reference_run(n_reads_per_core=None, cores=None, shape="chr22_1_51", budget_
                 last_err = (err or "").strip().splitlines()[-1:] or [f"exit code {p.returncode}"]
         if len(stats) == used:
             break
-        # the reference picks its paths with std::random_device, so a crash need not repeat: one more try at the same
-        # process count, then halve
+        # The reference's TraverserBFS::advance pushes a copy of a state onto the vector the state lives in and keeps using
+        # the reference afterwards (traverser_bfs.hpp:147-158): a heap use-after-free whenever the vector grows at a node
+        # with three or more successors (AddressSanitizer report: profiles/r02_reference_asan_use_after_free.txt).  Whether
+        # it crashes depends on the heap and on the randomly picked paths, so one more try at the same process count,
+        # then halve (a process may also have run out of memory on a box with many cores)
         tries += 1
         nxt = used if tries % 2 == 1 else used // 2
         log(f"[bench] reference: {used - len(stats)} of {used} processes failed ({last_err}); retrying with {nxt}")
@@ -195,6 +198,10 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the inputs (synthetic graph -> GFA, reads -> FASTA) are built with the host half of the library only: this process
+    # never maps the CUDA library
+    from psi_b200 import capi
+    capi.use_host_library()
     try:
         vals = []
         for i in range(args.warmup + args.steps):

@@ -91,6 +91,19 @@ class Counters(C.Structure):
 
 
 _lib = None
+HOST_LIB_PATH = _HERE / "libpsi_b200_host.so"
+# the host half of the C-ABI (graphs, paths, reads): what libpsi_b200_host.so exports
+HOST_SYMBOLS = [s_ for s_ in SYMBOLS if s_.startswith(("psi_b200_graph_", "psi_b200_pick_paths", "psi_b200_pathset_", "psi_b200_reader_",
+                                                       "psi_b200_pack_bases", "psi_b200_global_error"))]
+_host_only = False
+
+
+def use_host_library():
+    """Bind libpsi_b200_host.so instead of libpsi_b200.so: graphs, paths and reads only, no CUDA runtime mapped into the
+    process (bench.py's reference arm builds its inputs with it).  Must be called before the first lib()."""
+    global _host_only
+    assert _lib is None, "use_host_library() must come before the first call into the library"
+    _host_only = True
 
 
 def lib() -> C.CDLL:
@@ -98,15 +111,28 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise PsiError(ERR_IO, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = HOST_LIB_PATH if _host_only else LIB_PATH
+    if not path.exists():
+        raise PsiError(ERR_IO, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)")
-    L = C.CDLL(os.fspath(LIB_PATH))
+    L = C.CDLL(os.fspath(path))
+    if _host_only:
+        _bind_host(L)
+        _lib = L
+        return L
     u64p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p
+    _bind_host(L)
     L.psi_b200_version.restype = C.c_char_p
-    L.psi_b200_global_error.restype = C.c_char_p
     L.psi_b200_last_error.restype = C.c_char_p
     L.psi_b200_last_error.argtypes = [vp]
+    _bind_device(L, u64p, u32p, vp)
+    _lib = L
+    return L
+
+
+def _bind_host(L):
+    u64p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p
+    L.psi_b200_global_error.restype = C.c_char_p
     L.psi_b200_graph_load_gfa.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.psi_b200_graph_from_arrays.argtypes = [C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]
     L.psi_b200_graph_free.argtypes = [vp]
@@ -124,6 +150,9 @@ def lib() -> C.CDLL:
     L.psi_b200_reader_close.restype = None
     L.psi_b200_reader_next_packed.argtypes = [vp, C.c_uint64, C.POINTER(PackedChunk)]
     L.psi_b200_pack_bases.argtypes = [vp, C.c_uint64, vp, vp, C.c_uint64, u64p]
+
+
+def _bind_device(L, u64p, u32p, vp):
     L.psi_b200_submit_chunk_packed.argtypes = [vp, C.POINTER(PackedChunk), C.c_uint, C.c_int]
     L.psi_b200_seeds_all_async.argtypes = [vp, C.c_uint]
     L.psi_b200_wait.argtypes = [vp, u64p]
@@ -155,8 +184,6 @@ def lib() -> C.CDLL:
     L.psi_b200_host_free.restype = None
     L.psi_b200_counters.argtypes = [vp, C.POINTER(Counters)]
     L.psi_b200_reset_counters.argtypes = [vp]
-    _lib = L
-    return L
 
 
 def _check(rc: int, ctx=None):

@@ -4,6 +4,8 @@
 
 #include "context.hpp"
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace psi_b200 {
 
 Ctx* engine_create(int device, unsigned seed_len);
@@ -48,18 +50,34 @@ void table_clear(Ctx& c, HostTable& t);
 enum { T_INDEX = 0, T_LOCI = 1, T_H2D = 2, T_PACK = 3, T_READ_INDEX = 4, T_ON = 5, T_OFF = 6, T_RESOLVE = 7,
        T_SORT = 8, T_D2H = 9, T_USER = 10, T_PROBE = 11, T_COUNT = 12 };
 
+// NVTX range names: the reference's timer names (seed_finder.hpp:427-456) where a phase has one
+inline const char* phase_name(int slot)
+{
+  static const char* const names[T_COUNT] = { "index-paths", "find-uncovered", "seeding (upload)", "seeding", "index-reads", "seeds-on-paths",
+                                              "seeds-off-path", "seeds-on-paths (records)", "sort-seeds", "fetch-seeds", "user", "seeds-on-paths (probe)" };
+  return slot >= 0 && slot < T_COUNT ? names[slot] : "psi_b200";
+}
+
+// A phase of a step: a pair of CUDA events on the context's stream (device time, read by psi_b200_counters) and an
+// NVTX range on the host thread (what nsys / ncu --nvtx group by).
 struct PhaseTimer {
   Ctx& c;
   int i;
+  bool open = true;
   PhaseTimer(Ctx& ctx, int slot) : c(ctx), i(slot)
   {
+    nvtxRangePushA(phase_name(slot));
     cudaEventRecord(c.ev[2 * i], c.stream);
     c.ev_state[i] = 1;
   }
+  PhaseTimer(const PhaseTimer&) = delete;
+  PhaseTimer& operator=(const PhaseTimer&) = delete;
+  ~PhaseTimer() { if (open) nvtxRangePop(); }
   void stop()
   {
     cudaEventRecord(c.ev[2 * i + 1], c.stream);
     c.ev_state[i] = 2;
+    if (open) { nvtxRangePop(); open = false; }
   }
   // valid after the stream has been synchronised
   float ms() const { return timer_ms(c, i); }

@@ -595,6 +595,8 @@ static void fused_enqueue(Ctx& c)
   ch.d = c.distance;
   ch.cta_first = nullptr;
   ch.seeds_per_read = 0;
+  nvtxRangePushA("seeds-on-paths + seeds-off-path (fused)");
+  struct Pop { ~Pop() { nvtxRangePop(); } } pop_range;
   PSI_CUDA(cudaMemsetAsync(dc, 0, DC_COUNT * sizeof(unsigned long long), c.stream));
   if (dense) {
     if (c.read_len && !c.d_read_ptr) ch.seeds_per_read = c.read_len >= c.k ? (c.read_len - c.k) / c.distance + 1 : 0;

@@ -5,7 +5,9 @@
 #include <cstring>
 #include <stdexcept>
 
+#ifndef PSI_B200_HOST_ONLY
 #include <cuda_runtime_api.h>
+#endif
 #include <zlib.h>
 
 namespace psi_b200 {
@@ -15,8 +17,10 @@ namespace psi_b200 {
 HostBuffer::~HostBuffer()
 {
   if (!data_) return;
-  if (pinned_) cudaFreeHost(data_);
-  else std::free(data_);
+#ifndef PSI_B200_HOST_ONLY
+  if (pinned_) { cudaFreeHost(data_); return; }
+#endif
+  std::free(data_);
 }
 
 void HostBuffer::reserve(size_t bytes)
@@ -26,18 +30,25 @@ void HostBuffer::reserve(size_t bytes)
   while (ncap < bytes) ncap *= 2;
   char* nd = nullptr;
   bool pinned = false;
+#ifndef PSI_B200_HOST_ONLY
   void* p = nullptr;
   if (cudaHostAlloc(&p, ncap, cudaHostAllocDefault) == cudaSuccess) {
     nd = (char*)p;
     pinned = true;
   }
-  else {
-    (void)cudaGetLastError();  // no device: page-able memory is fine for host-only use
+  else (void)cudaGetLastError();  // no device: page-able memory is fine for host-only use
+#endif
+  if (!nd) {
     nd = (char*)std::malloc(ncap);
     if (!nd) throw std::bad_alloc();
   }
   if (size_) std::memcpy(nd, data_, size_);
-  if (data_) { if (pinned_) cudaFreeHost(data_); else std::free(data_); }
+  if (data_) {
+#ifndef PSI_B200_HOST_ONLY
+    if (pinned_) cudaFreeHost(data_); else
+#endif
+    std::free(data_);
+  }
   data_ = nd;
   cap_ = ncap;
   pinned_ = pinned;

@@ -271,6 +271,9 @@ class SeedFinder {
     if (info) info("Indexing the selected paths...");
     index_paths();
     if (info) info("Detecting uncovered loci...");
+    if (step_size > 1 && warn)
+      warn("Step size > 1: the starting loci are sampled on this build's own lattice (node offsets divisible by the step), "
+           "not on the reference's per-walk lattice; share a loci file (-I) for identical seed sets.");
     add_uncovered_loci(step_size);
     if (info) info("Constructing distance index for pair distance queries...");
     create_distance_index(dmin, dmax);

@@ -16,6 +16,11 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session", autouse=True)
 def _built():
-    """Build the shared libraries once per session (cheap no-op when up to date)."""
+    """Build the shared libraries once per session (cheap no-op when up to date).  Without the CUDA toolkit only the
+    host half and the oracle are built: the CPU-only suites still run, tests that need libpsi_b200.so say so."""
+    import shutil
     import __graft_entry__ as ge
-    ge.build()
+    if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists() or (ROOT / "psi_b200" / "libpsi_b200.so").exists():
+        ge.build()
+    else:
+        ge.build_host_only()

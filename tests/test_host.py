@@ -22,6 +22,27 @@ def test_library_exports_every_declared_symbol():
     assert L.psi_b200_version().decode().endswith("sm_100a")
 
 
+def test_host_library_has_the_host_half_only_and_maps_no_cuda():
+    """libpsi_b200_host.so: graphs, paths and reads without the CUDA runtime (what bench.py's reference arm binds)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from psi_b200 import capi\n"
+        "capi.use_host_library()\n"
+        "L = capi.lib()\n"
+        "assert all(hasattr(L, s) for s in capi.HOST_SYMBOLS)\n"
+        "assert not hasattr(L, 'psi_b200_create') and not hasattr(L, 'psi_b200_seeds_all')\n"
+        "g = capi.Graph.load_gfa(%r)\n"
+        "ps = g.pick_paths(2)\n"
+        "assert g.n_nodes == 210 and ps.n_paths == 2\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libpsi_b200_host.so' in maps and 'libpsi_b200.so' not in maps and 'libcudart' not in maps, 'CUDA mapped'\n"
+        "print('ok')\n") % (os.fspath(util.ROOT), os.fspath(util.GOLDEN / "inputs/x.gfa.gz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-1000:]
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
