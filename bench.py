@@ -473,7 +473,9 @@ def main_gpu(args):
     counts, hist = shard.all_reduce_counts({"reads": n_reads * steps, "seeds": acc_one["n_seeds"], "hits": hits_val,
                                             "hits_on": acc_one["n_hits_on"]}, hist, device=dev)
 
+    barrier()      # every rank copies at the same moment: the figure is one GPU's share of the box's host bandwidth
     pcie = pcie_ceiling(torch, dev, int(W.words_h[0].numel() * 8), int((4 + ctx.dense_off_bytes()) * W.n_seeds))
+    barrier()
     drop_in = psikt_drop_in(W) if (world == 1 and rank == 0 and not args.no_other_configs) else None
     other = {}
     if world == 1 and not args.no_other_configs:

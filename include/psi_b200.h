@@ -316,6 +316,21 @@ int  psi_b200_fetch_kinds(psi_b200_ctx* ctx, uint8_t* kinds, uint64_t cap, uint6
 /* Device pointer to the same records (valid until the next seeds_all). */
 int  psi_b200_fetch_device(psi_b200_ctx* ctx, const uint64_t** d_hits, uint64_t* n_hits);
 
+/* ---- MEM mode: SeedFinder::seeds_on_paths(sequence, callback) -> find_mems (seed_finder.hpp:1459-1479,
+ * index_iter.hpp:854-906) ----
+ * build_mem_index: the index those queries need -- the sorted suffix table of the text of the given paths (the same
+ * arrays as psi_b200_set_paths; stands behind PathIndex::create_index, pathindex.hpp:235-243).  Before the first fork.
+ * find_mems: the reference's scan over every read of the submitted chunk (any submit_chunk* call): extend
+ * read[start : start + len] while it occurs in the path text; once len >= seed length and it occurs at most
+ * gocc_threshold times ("gocc_threshold" option, 0 = no limit), report all its occurrences and restart behind it; a
+ * read stops after max_mem raw hits (0 = no limit).  The result is the SET of hits, 6 x u64 each:
+ * {node_id, node_off, read_id, read_off, match_len, gocc}; gocc = occurrences in the path text, counted per path like
+ * the reference's.  Reads longer than 65 535 bases are not supported. */
+int  psi_b200_build_mem_index(psi_b200_ctx* ctx, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                              const uint32_t* head_off, const uint32_t* tail_trim);
+int  psi_b200_find_mems(psi_b200_ctx* ctx, unsigned max_mem, uint64_t* n_hits);
+int  psi_b200_fetch_mems(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits);
+
 /* Pinned host memory for chunk / result buffers. */
 int  psi_b200_host_alloc(void** p, size_t bytes);
 void psi_b200_host_free(void* p);

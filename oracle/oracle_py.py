@@ -216,3 +216,63 @@ def run_reference(gfa, fastq, k, d=0, n_paths=16, patched=True, context=0, chunk
         stats = json.loads(pr.stdout.strip().splitlines()[-1])
         tuples = np.fromfile(out, np.uint64).reshape(-1, 4) if want_out else None
         return tuples, stats
+
+
+# ---------------------------------------------------------------- MEM mode --
+
+def path_texts(g, path_ptr, nodes, head, tail):
+    """Forward text of every indexed path and, per text position, the global graph position it comes from
+    (sequence(path, Forward), reference include/psi/path_interface.hpp:207-255)."""
+    texts, gpos = [], []
+    for p in range(len(head)):
+        ns = nodes[int(path_ptr[p]):int(path_ptr[p + 1])]
+        seq = np.concatenate([g.seq[int(g.seq_start[v]):int(g.seq_start[v + 1])] for v in ns]) if len(ns) else np.zeros(0, np.uint8)
+        gp = np.concatenate([np.arange(int(g.seq_start[v]), int(g.seq_start[v + 1]), dtype=np.int64) for v in ns]) if len(ns) else np.zeros(0, np.int64)
+        lo, hi = int(head[p]), len(seq) - int(tail[p])
+        texts.append(seq[lo:hi].tobytes().upper())
+        gpos.append(gp[lo:hi])
+    return texts, gpos
+
+
+def _occurrences(texts, pat):
+    out = []
+    for ti, t in enumerate(texts):
+        i = t.find(pat)
+        while i != -1:
+            out.append((ti, i))
+            i = t.find(pat, i + 1)
+    return out
+
+
+def find_mems(texts, pattern: bytes, minlen: int, gocc_threshold=0, max_mem=0):
+    """Restatement of find_mems (reference include/psi/index_iter.hpp:854-906) as called by
+    SeedFinder::seeds_on_paths(sequence, callback) (seed_finder.hpp:1459-1479): a greedy left-to-right scan that
+    extends pattern[start : start + plen] while it still occurs in the path text, reports ALL its occurrences as soon as
+    it is at least minlen long and occurs at most gocc_threshold times, then restarts one character further on; a
+    character that cannot be appended (or an 'N') also restarts the scan behind it.  Returns the raw hits in emission
+    order: (start, plen, gocc, text index, text offset)."""
+    if gocc_threshold == 0:
+        gocc_threshold = 2 ** 32 - 1
+    if max_mem == 0:
+        max_mem = 2 ** 32 - 1
+    pattern = pattern.upper()
+    hits, start, plen, has_hit, nof = [], 0, 0, False, 0
+    occ = None                                    # occurrences of pattern[start:start+plen]; None = all positions (plen 0)
+    while start + plen < len(pattern):
+        if plen >= minlen and len(occ) <= gocc_threshold:
+            has_hit = True
+            for ti, o in occ:
+                hits.append((start, plen, len(occ), ti, o))
+                nof += 1
+            if nof >= max_mem:
+                break
+        c = pattern[start + plen:start + plen + 1]
+        nxt = None
+        if not has_hit and c != b"N":
+            nxt = _occurrences(texts, pattern[start:start + plen + 1])
+        if has_hit or c == b"N" or not nxt:
+            start, plen, has_hit, occ = start + plen + 1, 0, False, None
+            continue
+        occ = nxt
+        plen += 1
+    return hits

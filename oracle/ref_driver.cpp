@@ -25,6 +25,10 @@
  *                  u64 n_paths, then per path u64 n_nodes, u64 head offset (bases cut from the first node),
  *                  u64 tail trim (bases cut from the last node), u64 text length, the node RANKS (0-based, u64
  *                  each; flattened by include/psi_b200_gum.hpp) and the path's forward text padded to 8 bytes.
+ *    --mems FILE   MEM mode (SeedFinder::seeds_on_paths(sequence, callback) -> find_mems, seed_finder.hpp:1459-1479,
+ *                  index_iter.hpp:854-906) on every read of --fastq instead of the k-mer path: per hit 6 x u64
+ *                  read ordinal, read offset, match length, gocc, node id (coordinate), node offset, in emission order
+ *                  (raw: one hit per occurrence in the path text).  -E sets max_mem, -r the gocc threshold.
  *  and one JSON line on stdout with counts and timings.
  */
 #include <cstdio>
@@ -50,7 +54,8 @@
 using namespace psi;
 
 struct Args {
-  std::string gfa, fastq, out, raw, nodes, loci, paths;
+  std::string gfa, fastq, out, raw, nodes, loci, paths, mems;
+  unsigned max_mem = 0;
   unsigned k = 0, d = 0, n = 0, context = 0, step = 1, gocc = 0;
   unsigned long chunk = 0, first_read = 0, max_reads = 0;
   bool patched = true;
@@ -81,6 +86,8 @@ int main( int argc, char** argv )
     else if ( s == "--nodes" ) a.nodes = next();
     else if ( s == "--loci" ) a.loci = next();
     else if ( s == "--paths" ) a.paths = next();
+    else if ( s == "--mems" ) a.mems = next();
+    else if ( s == "-E" ) a.max_mem = std::stoul( next() );
     else if ( s == "-k" ) a.k = std::stoul( next() );
     else if ( s == "-d" ) a.d = std::stoul( next() );
     else if ( s == "-n" ) a.n = std::stoul( next() );
@@ -124,7 +131,7 @@ int main( int argc, char** argv )
     std::fclose( f );
   }
 
-  finder_type finder( graph, a.k, a.gocc );
+  finder_type finder( graph, a.k, a.gocc, a.max_mem );
   t0 = now_s();
   if ( a.n != 0 ) {
     finder.create_path_index( a.n, a.patched, a.context, a.step );
@@ -185,7 +192,27 @@ int main( int argc, char** argv )
 
   double t_seeding = 0, t_on = 0, t_off = 0;
   unsigned long n_reads = 0, n_seeds = 0, n_chunks = 0;
-  if ( !a.fastq.empty() ) {
+  if ( !a.mems.empty() && !a.fastq.empty() ) {
+    std::FILE* f = std::fopen( a.mems.c_str(), "wb" );
+    klibpp::SeqStreamIn iss( a.fastq.c_str() );
+    klibpp::KSeq rec;
+    uint64_t ordinal = 0;
+    t0 = now_s();
+    while ( ( a.max_reads == 0 || ordinal < a.max_reads ) && ( iss >> rec ) ) {
+      std::string const& sequence = rec.seq;
+      finder.seeds_on_paths( sequence, [&]( typename traverser_type::output_type const& h ) {
+        uint64_t out6[6] = { ordinal, (uint64_t)h.read_offset, (uint64_t)h.match_len, (uint64_t)h.gocc,
+                             (uint64_t)graph.coordinate_id( h.node_id ), (uint64_t)h.node_offset };
+        write_u64s( f, out6, 6 );
+        ++raw_on;
+      } );
+      ++ordinal;
+    }
+    t_on = now_s() - t0;
+    n_reads = ordinal;
+    std::fclose( f );
+  }
+  else if ( !a.fastq.empty() ) {
     klibpp::SeqStreamIn iss( a.fastq.c_str() );
     if ( !iss ) { std::fprintf( stderr, "cannot open %s\n", a.fastq.c_str() ); return 2; }
     /* Skip to the first read of this shard; read ids stay global (sequence.hpp:1616). */

@@ -29,6 +29,7 @@ SYMBOLS = [
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
     "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout",
+    "psi_b200_build_mem_index", "psi_b200_find_mems", "psi_b200_fetch_mems",
     "psi_b200_global_error",
     "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
@@ -160,6 +161,9 @@ def _bind_device(L, u64p, u32p, vp):
     L.psi_b200_fetch_dense_async.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
     L.psi_b200_dense_counts.argtypes = [vp, u64p, u64p]
     L.psi_b200_dense_layout.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.psi_b200_build_mem_index.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
+    L.psi_b200_find_mems.argtypes = [vp, C.c_uint, u64p]
+    L.psi_b200_fetch_mems.argtypes = [vp, vp, C.c_uint64, u64p]
     L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
     L.psi_b200_fork.argtypes = [vp, C.POINTER(vp)]
     L.psi_b200_destroy.argtypes = [vp]
@@ -507,6 +511,18 @@ class Context:
 
     def fetch_dense_async(self, dense_addr: int, cap_seeds: int, extra_addr: int, cap_extra: int):
         self._ck(lib().psi_b200_fetch_dense_async(self._h, C.c_void_p(dense_addr), cap_seeds, C.c_void_p(extra_addr), cap_extra))
+
+    def build_mem_index(self, p: PathSet):
+        self._ck(lib().psi_b200_build_mem_index(self._h, p.n_paths, _ptr(p.path_ptr), _ptr(p.nodes), _ptr(p.head_off), _ptr(p.tail_trim)))
+
+    def find_mems(self, max_mem=0) -> np.ndarray:
+        """MEM mode over the submitted chunk: (n, 6) u64 {node_id, node_off, read_id, read_off, match_len, gocc}."""
+        n = C.c_uint64()
+        self._ck(lib().psi_b200_find_mems(self._h, max_mem, C.byref(n)))
+        out = np.zeros((n.value, 6), np.uint64)
+        if n.value:
+            self._ck(lib().psi_b200_fetch_mems(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
 
     def seeds_all(self, flags=ALL) -> int:
         n = C.c_uint64()

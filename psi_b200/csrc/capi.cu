@@ -205,6 +205,29 @@ int psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extr
   })
 }
 
+int psi_b200_build_mem_index(psi_b200_ctx* ctx, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                             const uint32_t* head_off, const uint32_t* tail_trim)
+{
+  CTX_GUARD(ctx, engine_build_mem_index(*ctx->c, n_paths, path_ptr, path_nodes, head_off, tail_trim))
+}
+
+int psi_b200_find_mems(psi_b200_ctx* ctx, unsigned max_mem, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    engine_find_mems(*ctx->c, max_mem);
+    if (n_hits) *n_hits = ctx->c->n_mems;
+  })
+}
+
+int psi_b200_fetch_mems(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits)
+{
+  CTX_GUARD(ctx, {
+    if (n_hits) *n_hits = ctx->c->n_mems;
+    if (cap && !hits) throw ArgError("fetch_mems: null buffer");
+    if (cap) engine_fetch_mems(*ctx->c, hits, cap);
+  })
+}
+
 int psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {

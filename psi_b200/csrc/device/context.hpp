@@ -148,6 +148,14 @@ struct Shared {
   DevBuf<uint32_t> path_nodes, path_head, path_tail;
   uint64_t n_paths = 0, n_path_entries = 0;
 
+  // ---- MEM mode (mems.cu): the suffix table of the path text ----
+  bool has_mem_index = false;
+  uint64_t mem_n = 0;              // text positions in the table
+  uint32_t mem_paths_n = 0;
+  DevBuf<uint64_t> mem_path_ptr, mem_entry_start, mem_key;
+  DevBuf<uint32_t> mem_nodes, mem_head, mem_tail, mem_gpos, mem_ent, mem_pstart;
+  DevBuf<uint8_t> mem_vlen;
+
   // ---- starting loci ----
   uint64_t n_loci = 0;
   DevBuf<uint32_t> loci_node, loci_off;
@@ -225,6 +233,11 @@ struct Ctx {
   uint64_t dense_off_plane = 0;      // byte offset of the node-offset plane inside `records`
   DevBuf<uint32_t> extra;
   uint64_t n_dense_seeds = 0, n_extra = 0;
+  // ---- MEM mode results ----
+  DevBuf<uint4> mem_raw;             // raw hits of find_mems_kernel (16 bytes each)
+  DevBuf<uint64_t> mem_records;      // 6 x u64 per hit: node_id, node_off, read_id, read_off, match_len, gocc
+  bool mem_valid = false;
+  uint64_t n_mems = 0, n_mems_raw = 0;
   // ---- a step in flight (psi_b200_seeds_all_async .. psi_b200_wait) ----
   bool pending = false;
   int pending_out_kind = 0;               // 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense

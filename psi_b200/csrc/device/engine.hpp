@@ -30,6 +30,10 @@ void engine_seeds_async(Ctx& c, unsigned flags);   // queues the step when the f
 void engine_wait(Ctx& c);
 void engine_fetch_dense(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
 void engine_fetch_dense_async(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
+void engine_build_mem_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* path_nodes,
+                            const uint32_t* head_off, const uint32_t* tail_trim);
+void engine_find_mems(Ctx& c, unsigned max_mem);
+void engine_fetch_mems(Ctx& c, uint64_t* hits, uint64_t cap);
 void engine_submit_chunk_packed(Ctx& c, const psi_b200_packed_chunk& chunk, unsigned distance, bool on_device);
 void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);

@@ -921,3 +921,45 @@ def test_gocc_threshold_and_step_size_on_the_reference_paths_and_loci(fixture):
             ctx.set_loci(z["loci_rank"], z["loci_off"])
         assert e.value.code == capi.ERR_ARG
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MEM mode (psi_b200_build_mem_index / psi_b200_find_mems) against the reference's own hits on its own paths
+
+MEM_FIXTURES = sorted(_glob.glob(_os.fspath(util.GOLDEN / "mems" / "*.npz")))
+
+
+@pytest.mark.parametrize("packed", [0, 1], ids=["ascii", "packed"])
+@pytest.mark.parametrize("fixture", MEM_FIXTURES, ids=lambda f: _os.path.basename(f)[:-4])
+def test_find_mems_against_the_reference(fixture, packed):
+    """SeedFinder::seeds_on_paths(sequence, cb) -> find_mems (seed_finder.hpp:1459-1479, index_iter.hpp:854-906): the
+    device scan over the suffix table of the reference's own paths gives the reference's hits -- read offsets, match
+    lengths (extended past 32 characters by a gocc threshold), occurrence counts, loci -- as a set; chunked = unchunked."""
+    z = np.load(fixture)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    rp, bases = util.read_fasta(util.GOLDEN / str(z["reads"]))
+    n = min(int(z["max_reads"]), len(rp) - 1)
+    rp, bases = rp[:n + 1], bases[:int(rp[n])]
+    ctx = capi.Context(int(z["k"]), 0)
+    ctx.set_option("gocc_threshold", int(z["gocc"]))
+    ctx.set_graph(g, ids="coord")
+    with pytest.raises(capi.PsiError) as e:
+        ctx.submit_chunk(rp, bases, 0, 0)
+        ctx.find_mems()                       # no MEM index yet
+    assert e.value.code == capi.ERR_STATE
+    ctx.build_mem_index(capi.PathSet(path_ptr=z["path_ptr"], nodes=z["nodes"], head_off=z["head"], tail_trim=z["tail"]))
+
+    def run(lo, hi):
+        sub_ptr, sub = rp[lo:hi + 1] - rp[lo], bases[int(rp[lo]):int(rp[hi])]
+        if packed:
+            ctx.submit_chunk_packed(capi.Packed.pack(sub_ptr, sub, lo), 0)
+        else:
+            ctx.submit_chunk(sub_ptr, sub, lo, 0)
+        m = ctx.find_mems(int(z["max_mem"]))     # node_id, node_off, read_id, read_off, match_len, gocc
+        return m[:, [2, 3, 4, 5, 0, 1]]
+    got = run(0, n)
+    assert len(np.unique(got, axis=0)) == len(got), "the device result is a set"
+    assert np.array_equal(np.unique(got, axis=0), z["mems"])
+    parts = np.concatenate([run(b, min(n, b + 97)) for b in range(0, n, 97)])
+    assert np.array_equal(np.unique(parts, axis=0), z["mems"])
+    ctx.close()

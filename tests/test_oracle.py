@@ -266,3 +266,35 @@ def test_reference_known_answer_for_the_tiny_graph():
     assert sorted((int(g.coord_id[v]), int(x)) for v, x in zip(n, o)) == got
     z8, g8, op8 = _load_loci_fixture(util.GOLDEN / "loci" / "tiny_k12_n8.npz")
     assert len(z8["loci_rank"]) == 0 and len(orc.uncovered_loci(orc.OGraph.of(g8), op8, 12)[0]) == 0
+
+
+# ---- MEM mode pinned to the reference (tests/golden/make_mem_golden.py) ----
+
+MEM_FIXTURES = sorted(glob.glob(os.fspath(util.GOLDEN / "mems" / "*.npz")))
+
+
+def load_mem_fixture(path):
+    z = np.load(path)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    rp, bases = util.read_fasta(util.GOLDEN / str(z["reads"]))
+    n = min(int(z["max_reads"]), len(rp) - 1)
+    return z, g, rp[:n + 1], bases[:int(rp[n])]
+
+
+@pytest.mark.parametrize("fixture", MEM_FIXTURES, ids=lambda f: os.path.basename(f)[:-4])
+def test_find_mems_restatement_against_the_reference(fixture):
+    """oracle_py.find_mems (restatement of index_iter.hpp:854-906) on the reference's own paths gives the hits the
+    reference's seeds_on_paths(sequence, cb) gave: offsets, lengths (a gocc threshold extends them, up to 63 here),
+    occurrence counts, loci; max_mem cuts a read off after that many raw hits."""
+    z, g, rp, bases = load_mem_fixture(fixture)
+    texts, gpos = orc.path_texts(g, z["path_ptr"], z["nodes"], z["head"], z["tail"])
+    rows = []
+    for r in range(len(rp) - 1):
+        pat = bases[int(rp[r]):int(rp[r + 1])].tobytes()
+        for st, pl, go, ti, o in orc.find_mems(texts, pat, int(z["k"]), int(z["gocc"]), int(z["max_mem"])):
+            gp = int(gpos[ti][o])
+            v = int(np.searchsorted(g.seq_start, gp, side="right") - 1)
+            rows.append((r, st, pl, go, int(g.coord_id[v]), gp - int(g.seq_start[v])))
+    assert len(rows) == int(z["n_raw"])
+    got = np.unique(np.array(rows, np.uint64).reshape(-1, 6), axis=0)
+    assert np.array_equal(got, z["mems"])
