@@ -23,8 +23,8 @@
 //
 // Differences that are deliberate: callbacks see every hit of the
 // seed SET exactly once (the reference repeats a locus once per covering path
-// and per walk); Seed<>::gocc is not filled (0); the distance index, approximate
-// matching and MEM mode are outside this build and throw std::runtime_error when
+// and per walk); Seed<>::gocc is filled in MEM mode only; the distance index and
+// approximate matching are outside this build and throw std::runtime_error when
 // requested.  A gocc threshold (-r) and a step size (-e) make the reference's seed
 // set depend on its (randomly) picked paths and on the loci it derived from them:
 // with the same paths and loci (psi_b200_set_paths / set_loci, a shared loci file)
@@ -245,6 +245,7 @@ class SeedFinder {
     if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
     reset_pipes();     // the index is rebuilt: pipelines forked from the old one go
     check(psi_b200_set_paths(ctx, v.n_paths, v.path_ptr, v.nodes, v.head_off, v.tail_trim));
+    remember_paths(v.n_paths, v.path_ptr, v.nodes, v.head_off, v.tail_trim);
     has_index = v.n_paths != 0;
   }
 
@@ -343,6 +344,7 @@ class SeedFinder {
       context_ = context ? context : (unsigned)hdr[1];
       reset_pipes();
       check(psi_b200_set_paths(ctx, n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data()));
+      remember_paths(n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data());
       has_index = n_paths != 0;
     }
     if (!open_starts(fpath, seed_len, step_size)) {
@@ -447,6 +449,33 @@ class SeedFinder {
     if (context_ != 0 && context_ < seed_len) throw std::runtime_error("seed length should not be larger than context size");
     if (!has_index) return;
     run(seeds, reads_index, PSI_B200_ON_PATHS, "seeds-on-paths", callback, nullptr);
+  }
+
+  // MEM mode (seed_finder.hpp:1459-1479 -> find_mems, index_iter.hpp:854-906): the greedy scan of one sequence
+  // against the text of the indexed paths; hits carry match_len and gocc (occurrences in the path text), read_id is
+  // not set by the reference either.  The device index for it (suffix table of the path text) is built on first use.
+  template <typename TString>
+  void seeds_on_paths(TString const& sequence, callback_type callback) const
+  {
+    if (!has_index) return;
+    ensure_mem_index();
+    auto timer = stats_ptr->timeit_ts("query-paths");
+    Pipe& p = pipe();
+    if (p.pending) throw std::runtime_error("a chunk is still in flight on this thread (seeds_all_wait first)");
+    const std::string text(sequence.begin(), sequence.end());
+    const uint64_t rp[2] = { 0, text.size() };
+    ++p.serial;          // whatever get_seeds submitted to this pipeline is gone
+    pcheck(p, psi_b200_submit_chunk(p.ctx, 1, rp, text.data(), 0, 0));
+    uint64_t n = 0;
+    pcheck(p, psi_b200_find_mems(p.ctx, max_mem == UINT_MAX ? 0u : max_mem, &n));
+    std::vector<uint64_t> rec(6 * n);
+    if (n) pcheck(p, psi_b200_fetch_mems(p.ctx, rec.data(), n, &n));
+    Seed<> hit;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t* x = rec.data() + 6 * i;
+      hit.node_id = x[0]; hit.node_offset = x[1]; hit.read_id = 0; hit.read_offset = x[3]; hit.match_len = x[4]; hit.gocc = x[5];
+      if (callback) callback(hit);
+    }
   }
 
   void seeds_off_paths(traverser_type& traverser, callback_type callback) const
@@ -561,6 +590,27 @@ class SeedFinder {
     unsigned ob = 4;
     check(psi_b200_dense_layout(ctx, &ob));
     dense_off_bytes = ob;
+  }
+
+  void remember_paths(uint64_t n_paths, const uint64_t* path_ptr, const uint32_t* nodes, const uint32_t* head, const uint32_t* tail)
+  {
+    std::lock_guard<std::mutex> lk(mem_mutex);
+    mem_built = false;
+    kept_ptr.assign(path_ptr, path_ptr + n_paths + 1);
+    kept_nodes.assign(nodes, nodes + path_ptr[n_paths]);
+    kept_head.assign(head, head + n_paths);
+    kept_tail.assign(tail, tail + n_paths);
+  }
+
+  // the MEM index is built when the first MEM query comes (before any other thread has a pipeline of its own:
+  // building is single-threaded by contract, like the rest of the index construction)
+  void ensure_mem_index() const
+  {
+    std::lock_guard<std::mutex> lk(mem_mutex);
+    if (mem_built) return;
+    reset_pipes();
+    check(psi_b200_build_mem_index(ctx, kept_head.size(), kept_ptr.data(), kept_nodes.data(), kept_head.data(), kept_tail.data()));
+    mem_built = true;
   }
 
   // FNV-1a over the node labels and their boundaries: names the graph a saved path set belongs to
@@ -784,7 +834,11 @@ class SeedFinder {
   mutable bool loci_dirty = false;
   mutable std::mutex pipes_mutex;
   mutable std::map<std::thread::id, std::unique_ptr<Pipe>> pipes;
-  mutable std::atomic<int> dense_state{ 0 };             // 0 unknown, 1 the index serves dense results, 2 it does not (walk mode)
+  mutable std::atomic<int> dense_state{ 0 };
+  mutable std::mutex mem_mutex;
+  mutable bool mem_built = false;
+  std::vector<uint64_t> kept_ptr{ 0 };
+  std::vector<uint32_t> kept_nodes, kept_head, kept_tail;             // 0 unknown, 1 the index serves dense results, 2 it does not (walk mode)
   uint64_t max_node_id = 0;
   unsigned dense_off_bytes = 4;
   mutable uint64_t checksum = 0;

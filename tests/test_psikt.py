@@ -211,6 +211,20 @@ def test_seed_finder_api_matches_oracle(tmp_path, name, chunk):
     assert np.array_equal(np.unique(on, axis=0), np.unique(all1, axis=0))
     assert np.array_equal(np.unique(off, axis=0), np.unique(all2, axis=0))
     g = capi.Graph.load_gfa(gfa)
+    # MEM mode through the mirror (seeds_on_paths(sequence, cb)): the restatement of find_mems on the very paths the
+    # mirror picked (psi_b200_pick_paths is seeded, so they can be drawn again here)
+    mems = np.fromfile(str(tmp_path / "out") + ".mems", dtype="<u8").reshape(-1, 6)
+    ps = g.pick_paths(c["n_paths"], True, c["k"], seed=0x9e3779b97f4a7c15)
+    texts, gpos = orc.path_texts(g, ps.path_ptr, ps.nodes, ps.head_off, ps.tail_trim)
+    rp, bases = util.read_fasta(util.GOLDEN / c["reads"])
+    rows = []
+    for r in range(min(40, len(rp) - 1, chunk or 40)):
+        for st, pl, go, ti, o in orc.find_mems(texts, bases[int(rp[r]):int(rp[r + 1])].tobytes(), c["k"]):
+            gp = int(gpos[ti][o])
+            v = int(np.searchsorted(g.seq_start, gp, side="right") - 1)
+            rows.append((r, st, pl, go, int(g.coord_id[v]), gp - int(g.seq_start[v])))
+    want = np.unique(np.array(rows, np.uint64).reshape(-1, 6), axis=0)
+    assert len(mems) == len(want) and np.array_equal(np.unique(mems, axis=0), want)
     loci = np.fromfile(str(tmp_path / "out") + ".loci", dtype="<u8").reshape(-1, 2)
     assert info["loci"] == len(loci) and info["uniq_nodes"] == len(np.unique(loci[:, 0]))
     assert set(loci[:, 0].tolist()) <= set(g.coord_id.tolist())
