@@ -892,7 +892,7 @@ def main():
     ap.add_argument("--k", type=int, default=K, help="seed length (other BASELINE configs: 32 with --shape mhc)")
     ap.add_argument("--read-len", type=int, default=READ_LEN, help="read length (150 for BASELINE configs[2..4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipelines", type=int, default=4, help="contexts (forks sharing one index) kept in flight by the one host thread")
+    ap.add_argument("--pipelines", type=int, default=6, help="contexts (forks sharing one index) kept in flight by the one host thread")
     ap.add_argument("--reads-total", type=int, default=0,
                     help="> 0: strong scaling -- ONE read set of this many reads sharded over the ranks in chunks of --reads "
                          "(BASELINE configs[2]: --reads-total 10000000 --read-len 150; configs[4]: --shape wg_1_4 ...)")
