@@ -198,3 +198,50 @@ def test_mhc_shape_k32_equals_oracle():
         c = ctx.counters()
         assert c["n_hits_off"] > 0
         ctx.close()
+
+
+def test_chr22_shape_one_chunk_of_configs2_size(chr22):
+    """BASELINE configs[2] as ONE chunk: 10 M x 150 bp reads (70 M seeds, 375 MB of 2-bit words) through the measured
+    path -- 2-bit chunk, fused kernel, dense per-seed results, asynchronous step.  Completeness on the whole chunk;
+    soundness of a sample; the dense planes equal what four chunks of 2.5 M give, seed for seed; and the per-hit
+    records of a 1 M-read slice carry the same loci as its dense results."""
+    g, k, n, L = chr22, 20, 10_000_000, 150
+    per_read = (L - k) // k + 1
+    parts = [synth.reads(g, 1_000_000, L, 3000 + b)[1] for b in range(10)]
+    bases = np.concatenate(parts)
+    del parts
+    rp = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    ctx = make_ctx(g, k, 16, 0)
+    ctx.submit_chunk_packed(capi.Packed.pack(rp, bases, 0), k, with_read_ptr=False)
+    ctx.seeds_all_async(capi.ALL | capi.DENSE)
+    cnt = ctx.wait()
+    dense, extra = ctx.fetch_dense()
+    assert len(dense) == n * per_read and ctx.counters()["n_seeds"] == n * per_read
+    hit = dense[:, 0] != capi.NIL32
+    assert hit.all(), f"{int((~hit).sum())} seeds of error-free reads found nothing"
+    assert cnt == int(hit.sum()) + len(extra)
+    # soundness of sampled seeds
+    order = np.argsort(g.coord_id, kind="stable")
+    ids_sorted = g.coord_id[order]
+    rng = np.random.default_rng(11)
+    for s in rng.integers(0, len(dense), 2000):
+        r, j = divmod(int(s), per_read)
+        v = int(order[np.searchsorted(ids_sorted, int(dense[s, 0]))])
+        want = bases[r * L + j * k:r * L + j * k + k].tobytes()
+        assert spells(g, v, int(dense[s, 1] & 0x7FFFFFFF), want)
+    # four chunks give the same planes
+    q = n // 4
+    for b in range(4):
+        sub = bases[b * q * L:(b + 1) * q * L]
+        ctx.submit_chunk_packed(capi.Packed.pack(rp[:q + 1], sub, b * q), k, with_read_ptr=False)
+        ctx.seeds_all(capi.ALL | capi.DENSE)
+        d2, e2 = ctx.fetch_dense()
+        assert np.array_equal(d2, dense[b * q * per_read:(b + 1) * q * per_read]), f"chunk {b}"
+    # records of the first million reads against their dense results
+    m = 1_000_000
+    ctx.submit_chunk(rp[:m + 1], bases[:m * L], 0, k)
+    ctx.seeds_all(capi.ALL)
+    rows = sort_rows(ctx.fetch())
+    rec, _ = capi.dense_to_records(dense[:m * per_read], extra[extra[:, 2] < m] if len(extra) else extra, rp[:m + 1], k, k, 0)
+    assert np.array_equal(sort_rows(rec), rows)
+    ctx.close()
