@@ -103,6 +103,13 @@ typedef struct {
 } psi_b200_pathset_view;
 int  psi_b200_pick_paths(const psi_b200_graph* g, unsigned n, int patched,
                          unsigned context, uint64_t seed, psi_b200_pathset** out);
+/* The path set of a path index SAVED BY THE REFERENCE (psikt -I <prefix>): reads `<prefix>_paths` as written by
+ * PathIndex::save_paths_set / PathSet::serialize / Path<graph, Compact>::serialize (pathindex.hpp:313-332,
+ * pathset.hpp:261-273, path_base.hpp:552-560: coordinate node ids as sdsl enc_vector<elias_delta>, left, right, node
+ * breaks).  Together with `<prefix>_loci_e<step>l<k>` (same format in both builds) a saved index is shared: the
+ * device index is rebuilt from the paths.  PSI_B200_ERR_IO when the file is missing, malformed or belongs to another
+ * graph.  *context receives the patch context stored in the file. */
+int  psi_b200_pathset_load_reference(const psi_b200_graph* g, const char* paths_file, psi_b200_pathset** out, uint64_t* context);
 void psi_b200_pathset_free(psi_b200_pathset* p);
 int  psi_b200_pathset_get_view(const psi_b200_pathset* p, psi_b200_pathset_view* view);
 

@@ -29,6 +29,7 @@
  *                  index_iter.hpp:854-906) on every read of --fastq instead of the k-mer path: per hit 6 x u64
  *                  read ordinal, read offset, match length, gocc, node id (coordinate), node offset, in emission order
  *                  (raw: one hit per occurrence in the path text).  -E sets max_mem, -r the gocc threshold.
+ *    --save-index P  SeedFinder::serialize_path_index(P, step): the files psikt -I writes (P, P_paths, P_loci_e<step>l<k>).
  *  and one JSON line on stdout with counts and timings.
  */
 #include <cstdio>
@@ -54,7 +55,7 @@
 using namespace psi;
 
 struct Args {
-  std::string gfa, fastq, out, raw, nodes, loci, paths, mems;
+  std::string gfa, fastq, out, raw, nodes, loci, paths, mems, save_index;
   unsigned max_mem = 0;
   unsigned k = 0, d = 0, n = 0, context = 0, step = 1, gocc = 0;
   unsigned long chunk = 0, first_read = 0, max_reads = 0;
@@ -87,6 +88,7 @@ int main( int argc, char** argv )
     else if ( s == "--loci" ) a.loci = next();
     else if ( s == "--paths" ) a.paths = next();
     else if ( s == "--mems" ) a.mems = next();
+    else if ( s == "--save-index" ) a.save_index = next();   /* SeedFinder::serialize_path_index (psikt -I) */
     else if ( s == "-E" ) a.max_mem = std::stoul( next() );
     else if ( s == "-k" ) a.k = std::stoul( next() );
     else if ( s == "-d" ) a.d = std::stoul( next() );
@@ -137,6 +139,11 @@ int main( int argc, char** argv )
     finder.create_path_index( a.n, a.patched, a.context, a.step );
   }
   double t_index = now_s() - t0;
+
+  if ( !a.save_index.empty() && !finder.serialize_path_index( a.save_index, a.step ) ) {
+    std::fprintf( stderr, "could not save the path index to %s\n", a.save_index.c_str() );
+    return 3;
+  }
 
   if ( !a.loci.empty() ) {
     std::FILE* f = std::fopen( a.loci.c_str(), "wb" );

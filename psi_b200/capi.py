@@ -25,7 +25,7 @@ NIL32 = 0xFFFFFFFF
 SYMBOLS = [
     "psi_b200_graph_load_gfa", "psi_b200_graph_from_arrays", "psi_b200_graph_free",
     "psi_b200_graph_get_view", "psi_b200_graph_path", "psi_b200_graph_write_gfa",
-    "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view",
+    "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view", "psi_b200_pathset_load_reference",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
     "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout",
@@ -142,6 +142,7 @@ def _bind_host(L):
     L.psi_b200_graph_path.argtypes = [vp, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(u32p), u64p]
     L.psi_b200_graph_write_gfa.argtypes = [vp, C.c_char_p]
     L.psi_b200_pick_paths.argtypes = [vp, C.c_uint, C.c_int, C.c_uint, C.c_uint64, C.POINTER(vp)]
+    L.psi_b200_pathset_load_reference.argtypes = [vp, C.c_char_p, C.POINTER(vp), u64p]
     L.psi_b200_pathset_free.argtypes = [vp]
     L.psi_b200_pathset_free.restype = None
     L.psi_b200_pathset_get_view.argtypes = [vp, C.POINTER(PathSetView)]
@@ -256,6 +257,12 @@ class Graph:
 
     def write_gfa(self, path):
         _check(lib().psi_b200_graph_write_gfa(self._h, os.fspath(path).encode()))
+
+    def load_reference_paths(self, paths_file):
+        """(PathSet, context) from a `<prefix>_paths` file saved by the reference."""
+        h, ctx = C.c_void_p(), C.c_uint64()
+        _check(lib().psi_b200_pathset_load_reference(self._h, os.fspath(paths_file).encode(), C.byref(h), C.byref(ctx)))
+        return PathSet(h), ctx.value
 
     def pick_paths(self, n, patched=True, context=0, seed=1) -> "PathSet":
         h = C.c_void_p()

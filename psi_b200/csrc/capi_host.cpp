@@ -141,6 +141,22 @@ int psi_b200_pick_paths(const psi_b200_graph* g, unsigned n, int patched, unsign
   catch (...) { delete p; return translate(g_error); }
 }
 
+int psi_b200_pathset_load_reference(const psi_b200_graph* g, const char* paths_file, psi_b200_pathset** out, uint64_t* context)
+{
+  if (!g || !paths_file || !out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  psi_b200_pathset* p = nullptr;
+  try {
+    p = new psi_b200_pathset();
+    uint64_t ctx = 0;
+    load_reference_paths(g->g, paths_file, p->p, ctx);
+    if (context) *context = ctx;
+    *out = p;
+    return PSI_B200_OK;
+  }
+  catch (...) { delete p; translate(g_error); return PSI_B200_ERR_IO; }
+}
+
 void psi_b200_pathset_free(psi_b200_pathset* p) { delete p; }
 
 int psi_b200_pathset_get_view(const psi_b200_pathset* p, psi_b200_pathset_view* v)

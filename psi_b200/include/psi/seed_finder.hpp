@@ -314,7 +314,7 @@ class SeedFinder {
     {
       [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-pindex");
       std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary | std::ifstream::ate);
-      if (!ifs) return false;
+      if (!ifs) return load_reference_path_index(fpath, context, step_size, dmin, dmax);
       const uint64_t file_bytes = (uint64_t)ifs.tellg();
       ifs.seekg(0);
       uint64_t hdr[8];
@@ -347,6 +347,30 @@ class SeedFinder {
       remember_paths(n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data());
       has_index = n_paths != 0;
     }
+    if (!open_starts(fpath, seed_len, step_size)) {
+      add_uncovered_loci(step_size);
+      save_starts(fpath, seed_len, step_size);
+    }
+    create_distance_index(dmin, dmax);
+    return true;
+  }
+
+  // An index saved by the REFERENCE (psikt -I of cartoonist/psi): `<prefix>_paths` holds its picked paths (coordinate
+  // node ids as an sdsl enc_vector, left / right trims; pathindex.hpp:313-332, path_base.hpp:552-560) and
+  // `<prefix>_loci_e<step>l<k>` its starting loci in the format both builds share.  The device index is rebuilt from
+  // the paths; the reference's serialised FM-index (`<prefix>`) is not needed.
+  bool load_reference_path_index(std::string const& fpath, unsigned int context, unsigned int step_size, unsigned int dmin,
+                                 unsigned int dmax)
+  {
+    psi_b200_pathset* ps = nullptr;
+    uint64_t file_context = 0;
+    if (psi_b200_pathset_load_reference(graph_ptr->handle(), (fpath + "_paths").c_str(), &ps, &file_context) != PSI_B200_OK) return false;
+    // the reference refuses an index saved with another context (pathindex.hpp:289-291)
+    if (context != 0 && file_context != context) { psi_b200_pathset_free(ps); return false; }
+    if (pathset) psi_b200_pathset_free(pathset);
+    pathset = ps;
+    context_ = (unsigned)file_context;
+    index_paths();
     if (!open_starts(fpath, seed_len, step_size)) {
       add_uncovered_loci(step_size);
       save_starts(fpath, seed_len, step_size);

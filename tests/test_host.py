@@ -189,3 +189,34 @@ def test_pick_paths_requires_an_embedded_path(tmp_path):
     with pytest.raises(capi.PsiError) as e:       # reference seed_finder.hpp:1145-1147 throws
         g.pick_paths(2)
     assert e.value.code == capi.ERR_ARG
+
+
+@pytest.mark.parametrize("name", ["x_k12_n16", "x_k20_n8", "multi_k32_n4", "m_k20_n4", "fuzz02_k12_n3_full"])
+def test_paths_of_an_index_saved_by_the_reference_are_read_back(name):
+    """psi_b200_pathset_load_reference decodes `<prefix>_paths` as the unmodified reference wrote it
+    (tests/golden/make_refindex_golden.py): sdsl enc_vector<elias_delta, 128> of coordinate ids (samples + delta codes,
+    paths of up to 3 400 nodes), left / right trims -> the same ranks, head offsets and tail trims the driver dumped."""
+    z = np.load(util.GOLDEN / "refindex" / f"{name}.npz")
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    ps, context = g.load_reference_paths(util.GOLDEN / "refindex" / f"{name}_paths")
+    assert context == (int(z["k"]) if bool(z["patched"]) else 0)
+    assert np.array_equal(ps.path_ptr, z["path_ptr"]) and np.array_equal(ps.nodes, z["nodes"])
+    assert np.array_equal(ps.head_off, z["head"]) and np.array_equal(ps.tail_trim, z["tail"])
+    # a file for another graph, a truncated file, a missing file: refused
+    other = capi.Graph.load_gfa(util.GOLDEN / "inputs/tiny.gfa.gz")
+    with pytest.raises(capi.PsiError) as e:
+        other.load_reference_paths(util.GOLDEN / "refindex" / f"{name}_paths")
+    assert e.value.code == capi.ERR_IO
+    with pytest.raises(capi.PsiError):
+        g.load_reference_paths(util.GOLDEN / "refindex" / "no_such_paths")
+
+
+def test_truncated_reference_paths_file_is_refused(tmp_path):
+    raw = (util.GOLDEN / "refindex" / "x_k20_n8_paths").read_bytes()
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/x.gfa.gz")
+    for cut in (5, 24, 100, 700):                 # inside the paths section (what follows it is not read)
+        p = tmp_path / "cut_paths"
+        p.write_bytes(raw[:cut])
+        with pytest.raises(capi.PsiError) as e:
+            g.load_reference_paths(p)
+        assert e.value.code == capi.ERR_IO

@@ -177,6 +177,31 @@ def test_psikt_saved_path_index_is_reloaded(tmp_path):
 
 
 @pytest.mark.gpu
+def test_psikt_loads_a_path_index_saved_by_the_reference(tmp_path):
+    """`psikt -I <prefix>` with the files the REFERENCE's psikt -I wrote (tests/golden/refindex: `<prefix>_paths` and
+    `<prefix>_loci_e1l<k>`, byte for byte): the index is found and loaded -- paths decoded from sdsl's enc_vector, loci in
+    the shared format -- and the seed set is the golden one."""
+    import shutil
+    c = G["x_k12"]
+    gfa = gunzip_to(util.GOLDEN / c["gfa"], tmp_path / "g.gfa")
+    for f in ("x_k12_n16_paths", "x_k12_n16_loci_e1l12"):
+        shutil.copy(util.GOLDEN / "refindex" / f, tmp_path / f.replace("x_k12_n16", "idx"))
+    r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", c["k"], "-I", tmp_path / "idx", "-L", tmp_path / "a.log", "-q", "-o", tmp_path / "o", gfa])
+    assert r.returncode == 0, r.stderr
+    text = (tmp_path / "a.log").read_text()
+    assert "The path index has been found and loaded." in text and "No valid path index found" not in text
+    z = np.load(util.GOLDEN / "refindex" / "x_k12_n16.npz")
+    assert "Total number of starting loci: %d" % int(z["n_loci"]) in text      # the reference's own loci were loaded
+    g = capi.Graph.load_gfa(gfa)
+    assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o", g))) == c["md5"]
+    # another seed length: the paths are loaded, the loci (none saved for this k) are computed and saved beside them
+    r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", "20", "-I", tmp_path / "idx", "-L", tmp_path / "b.log", "-q", "-o", tmp_path / "o2", gfa])
+    assert r.returncode == 0, r.stderr
+    assert "The path index has been found and loaded." in (tmp_path / "b.log").read_text() and (tmp_path / "idx_loci_e1l20").exists()
+    assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o2", g))) == G["x_k20_c1000"]["md5"]
+
+
+@pytest.mark.gpu
 def test_psikt_graph_without_embedded_path_is_an_error(tmp_path):
     gfa = tmp_path / "nopath.gfa"
     gfa.write_text("H\tVN:Z:1.0\nS\t1\tACGTACGTACGTAAACCCGGGTTT\nS\t2\tACGT\nL\t1\t+\t2\t+\t0M\n")
