@@ -194,11 +194,15 @@ def test_psikt_loads_a_path_index_saved_by_the_reference(tmp_path):
     assert "Total number of starting loci: %d" % int(z["n_loci"]) in text      # the reference's own loci were loaded
     g = capi.Graph.load_gfa(gfa)
     assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o", g))) == c["md5"]
-    # another seed length: the paths are loaded, the loci (none saved for this k) are computed and saved beside them
-    r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", "20", "-I", tmp_path / "idx", "-L", tmp_path / "b.log", "-q", "-o", tmp_path / "o2", gfa])
+    # a shorter seed length: the paths are loaded, the loci (none saved for this k) are computed and saved beside them
+    c10 = G["x_k10_tiny_reads"]
+    r = run([PSIKT, "-f", util.GOLDEN / c10["reads"], "-l", "10", "-I", tmp_path / "idx", "-L", tmp_path / "b.log", "-q", "-o", tmp_path / "o2", gfa])
     assert r.returncode == 0, r.stderr
-    assert "The path index has been found and loaded." in (tmp_path / "b.log").read_text() and (tmp_path / "idx_loci_e1l20").exists()
-    assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o2", g))) == G["x_k20_c1000"]["md5"]
+    assert "The path index has been found and loaded." in (tmp_path / "b.log").read_text() and (tmp_path / "idx_loci_e1l10").exists()
+    assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o2", g))) == c10["md5"]
+    # a seed longer than the context the index was patched with is refused, as by the reference (seed_finder.hpp:1434-1437)
+    r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", "20", "-I", tmp_path / "idx", "-Q", "-q", "-o", tmp_path / "o3", gfa])
+    assert r.returncode == 1 and "seed length should not be larger than context size" in r.stderr
 
 
 @pytest.mark.gpu
