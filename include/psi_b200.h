@@ -198,6 +198,11 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  *                       default 0 = what the free device memory allows, at most 2^30) and merges the groups' distinct pairs;
  *   "index_slack"       extra doublings of the index's bucket count: fewer full buckets (slow-path probes) for twice
  *                       the memory each; -1 (default) = 1 for 16-byte slots (k > ~27) while the index stays small, else 0.
+ * Set before create_distance_index:
+ *   "dindex_mode"       0 auto (default), 1 keep no rows (every query enumerates), 2 always materialise the rows;
+ *   "dindex_max_bytes"  auto mode materialises when the rows take at most this (0 = half of the free device memory);
+ *   "dindex_list_cap"   (node, distance) states a warp holds in shared memory (power of two, 64..1024; default 256):
+ *                       nodes / queries with more are served from a global scratch region (test hook).
  * Any time (they select among kernels that produce the same records):
  *   "fused"             1 (default): when the index answers the requested phases by itself, a chunk is ONE kernel
  *                       (seeding + probe + records); 0: separate seeding / probe / resolve kernels;
@@ -338,6 +343,20 @@ int  psi_b200_build_mem_index(psi_b200_ctx* ctx, uint64_t n_paths, const uint64_
 int  psi_b200_find_mems(psi_b200_ctx* ctx, unsigned max_mem, uint64_t* n_hits);
 int  psi_b200_fetch_mems(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_t* n_hits);
 
+/* ---- Paired-end distance verification: SeedFinder::create_distance_index / verify_distance (seed_finder.hpp:1193-1265,
+ * 1300-1317; DiVerG's distance index, ext/diverg/include/diverg/dindex.hpp:767-914) ----
+ * create_distance_index: prepares the queries for the window dmin <= l <= dmax (characters walked from the first locus
+ * to the second).  As in the reference nothing is built when dmin == 0 or dmax < dmin, and verify_distance then fails
+ * with PSI_B200_ERR_STATE.  The device keeps, per node, the (node, distance) pairs reachable inside the window (8 bytes
+ * each; "dindex_max_bytes" option, default half of the free device memory) -- or nothing at all when they would not
+ * fit ("dindex_mode" 1), in which case every query enumerates the walks from its first locus.  Before the first fork.
+ * verify_distance: n queries of 4 x u32 {rank of v, offset in v, rank of u, offset in u}; ok[i] = 1 when the reference's
+ * verify_distance(v, o, u, p) holds: v != u and some walk of dmin..dmax characters leads from (v, o) to (u, p), or v == u
+ * and dmin <= p - o <= dmax (seed_finder.hpp:1306-1309).  Loci that do not exist answer 0.  on_device != 0: pairs and ok
+ * are device pointers (pairs 16-byte aligned).  Synchronous. */
+int  psi_b200_create_distance_index(psi_b200_ctx* ctx, unsigned dmin, unsigned dmax);
+int  psi_b200_verify_distance(psi_b200_ctx* ctx, uint64_t n, const uint32_t* pairs, uint8_t* ok, int on_device);
+
 /* Pinned host memory for chunk / result buffers. */
 int  psi_b200_host_alloc(void** p, size_t bytes);
 void psi_b200_host_free(void* p);
@@ -372,6 +391,10 @@ typedef struct {
   uint64_t n_gocc_dropped;     /* on-path entries the gocc threshold removed from the index */
   uint32_t code_by_rank;       /* 1: index entries carry (node rank, offset), 0: (node id, offset) -- no gather per hit */
   uint32_t code_off_bits;
+  uint64_t n_dindex_entries;   /* (node, distance) pairs of the distance index (counted even when they are not kept) */
+  uint64_t dindex_bytes;       /* device bytes of the materialised rows */
+  uint32_t dindex_mode;        /* 0 none, 1 queries enumerate, 2 rows materialised */
+  float ms_dindex_build;
 } psi_b200_counters_t;
 int  psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out);
 int  psi_b200_reset_counters(psi_b200_ctx* ctx);

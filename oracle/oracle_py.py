@@ -276,3 +276,34 @@ def find_mems(texts, pattern: bytes, minlen: int, gocc_threshold=0, max_mem=0):
         occ = nxt
         plen += 1
     return hits
+
+
+# ---------------------------------------------------- distance verification --
+
+def verify_distance(g, v: int, o: int, u: int, p: int, dmin: int, dmax: int) -> bool:
+    """Restatement of SeedFinder::verify_distance over DiVerG's distance index (reference seed_finder.hpp:1300-1317;
+    index built by create_distance_index :1193-1265 = diverg::util::create_distance_index, dindex.hpp:767-914:
+    D = A^dmin (A + I)^(dmax - dmin) over the character-level adjacency A, i.e. D[x][y] is set iff some walk of
+    dmin <= l <= dmax character steps leads from character x to character y): is there such a walk from locus (v, o)
+    to locus (u, p)?  v, u are 0-based node ranks.  Inside one node only the offsets count (:1306-1309).  Across nodes:
+    breadth-first over (node, distance at which its first character is reached) states, bounded by dmax -- any graph,
+    cycles included."""
+    if v == u:
+        return o <= p and dmin <= p - o <= dmax
+    def length(x):
+        return int(g.seq_start[x + 1] - g.seq_start[x])
+    seen = set()
+    todo = []
+    def push(x, s):
+        if s <= dmax and (x, s) not in seen:
+            seen.add((x, s))
+            todo.append((x, s))
+    for e in range(int(g.row_ptr[v]), int(g.row_ptr[v + 1])):
+        push(int(g.col[e]), length(v) - o)
+    while todo:
+        x, s = todo.pop()
+        if x == u and dmin <= s + p <= dmax:
+            return True
+        for e in range(int(g.row_ptr[x]), int(g.row_ptr[x + 1])):
+            push(int(g.col[e]), s + length(x))
+    return False

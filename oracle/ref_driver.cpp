@@ -29,6 +29,10 @@
  *                  index_iter.hpp:854-906) on every read of --fastq instead of the k-mer path: per hit 6 x u64
  *                  read ordinal, read offset, match length, gocc, node id (coordinate), node offset, in emission order
  *                  (raw: one hit per occurrence in the path text).  -E sets max_mem, -r the gocc threshold.
+ *    --dist FILE   paired-end distance verification (SeedFinder::create_distance_index + verify_distance,
+ *                  seed_finder.hpp:1193-1317; DiVerG's range sparse boolean matrix powers on Kokkos' Serial backend) for
+ *                  the insert sizes -m DMIN -M DMAX: pseudo-random pairs of loci at most DMAX + 8 characters apart in
+ *                  rank order, per pair 5 x u64: rank of v (0-based), offset, rank of u, offset, answer (0 / 1).
  *    --save-index P  SeedFinder::serialize_path_index(P, step): the files psikt -I writes (P, P_paths, P_loci_e<step>l<k>).
  *  and one JSON line on stdout with counts and timings.
  */
@@ -55,7 +59,9 @@
 using namespace psi;
 
 struct Args {
-  std::string gfa, fastq, out, raw, nodes, loci, paths, mems, save_index;
+  std::string gfa, fastq, out, raw, nodes, loci, paths, mems, save_index, dist;
+  unsigned dmin = 0, dmax = 0;
+  unsigned long dist_queries = 20000;
   unsigned max_mem = 0;
   unsigned k = 0, d = 0, n = 0, context = 0, step = 1, gocc = 0;
   unsigned long chunk = 0, first_read = 0, max_reads = 0;
@@ -88,6 +94,10 @@ int main( int argc, char** argv )
     else if ( s == "--loci" ) a.loci = next();
     else if ( s == "--paths" ) a.paths = next();
     else if ( s == "--mems" ) a.mems = next();
+    else if ( s == "--dist" ) a.dist = next();
+    else if ( s == "-m" ) a.dmin = std::stoul( next() );
+    else if ( s == "-M" ) a.dmax = std::stoul( next() );
+    else if ( s == "--dist-queries" ) a.dist_queries = std::stoul( next() );
     else if ( s == "--save-index" ) a.save_index = next();   /* SeedFinder::serialize_path_index (psikt -I) */
     else if ( s == "-E" ) a.max_mem = std::stoul( next() );
     else if ( s == "-k" ) a.k = std::stoul( next() );
@@ -139,6 +149,40 @@ int main( int argc, char** argv )
     finder.create_path_index( a.n, a.patched, a.context, a.step );
   }
   double t_index = now_s() - t0;
+
+  if ( !a.dist.empty() ) {
+    finder.create_distance_index( a.dmin, a.dmax, PerComponent{} );
+    /* global character order of every node start (gum::util::id_to_charorder): rank order */
+    std::vector< uint64_t > start, ids, lens;
+    uint64_t total = 0;
+    graph.for_each_node( [&]( auto rank, auto id ) {
+      (void)rank;
+      start.push_back( total ); ids.push_back( (uint64_t)id ); lens.push_back( (uint64_t)graph.node_length( id ) );
+      total += graph.node_length( id );
+      return true;
+    } );
+    auto locate = [&]( uint64_t pos, uint64_t& r, uint64_t& o ) {
+      r = std::upper_bound( start.begin(), start.end(), pos ) - start.begin() - 1;
+      o = pos - start[ r ];
+    };
+    std::FILE* f = std::fopen( a.dist.c_str(), "wb" );
+    uint64_t x = 0x9e3779b97f4a7c15ull;
+    auto rnd = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for ( unsigned long q = 0; q < a.dist_queries; ++q ) {
+      uint64_t pa = rnd() % total;
+      uint64_t span = 3ull * a.dmax + 24;            /* rank order interleaves alleles: look well beyond dmax */
+      uint64_t pb = pa + rnd() % span;
+      if ( q % 7 == 0 && pa >= 5 ) pb = pa - rnd() % 5;   /* some targets behind the source */
+      if ( pb >= total ) pb = total - 1;
+      uint64_t rv, ov, ru, ou;
+      locate( pa, rv, ov );
+      locate( pb, ru, ou );
+      bool ok = finder.verify_distance( (graph_type::id_type)ids[ rv ], ov, (graph_type::id_type)ids[ ru ], ou );
+      uint64_t row[5] = { rv, ov, ru, ou, ok ? 1ull : 0ull };
+      write_u64s( f, row, 5 );
+    }
+    std::fclose( f );
+  }
 
   if ( !a.save_index.empty() && !finder.serialize_path_index( a.save_index, a.step ) ) {
     std::fprintf( stderr, "could not save the path index to %s\n", a.save_index.c_str() );

@@ -30,6 +30,7 @@ SYMBOLS = [
     "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
     "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout",
     "psi_b200_build_mem_index", "psi_b200_find_mems", "psi_b200_fetch_mems",
+    "psi_b200_create_distance_index", "psi_b200_verify_distance",
     "psi_b200_global_error",
     "psi_b200_create", "psi_b200_fork", "psi_b200_destroy", "psi_b200_last_error", "psi_b200_set_stream", "psi_b200_sync", "psi_b200_set_option",
     "psi_b200_set_graph", "psi_b200_set_paths", "psi_b200_find_loci", "psi_b200_get_loci", "psi_b200_set_loci",
@@ -85,7 +86,8 @@ class Counters(C.Structure):
                 ("ms_off", C.c_float), ("ms_resolve", C.c_float), ("ms_sort", C.c_float), ("ms_d2h", C.c_float),
                 ("launches", C.c_uint32), ("ms_probe", C.c_float),
                 ("ms_probe_sum", C.c_double), ("ms_on_sum", C.c_double), ("timed_steps", C.c_uint64),
-                ("n_gocc_dropped", C.c_uint64), ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32)]
+                ("n_gocc_dropped", C.c_uint64), ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32),
+                ("n_dindex_entries", C.c_uint64), ("dindex_bytes", C.c_uint64), ("dindex_mode", C.c_uint32), ("ms_dindex_build", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
@@ -165,6 +167,8 @@ def _bind_device(L, u64p, u32p, vp):
     L.psi_b200_build_mem_index.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
     L.psi_b200_find_mems.argtypes = [vp, C.c_uint, u64p]
     L.psi_b200_fetch_mems.argtypes = [vp, vp, C.c_uint64, u64p]
+    L.psi_b200_create_distance_index.argtypes = [vp, C.c_uint, C.c_uint]
+    L.psi_b200_verify_distance.argtypes = [vp, C.c_uint64, vp, vp, C.c_int]
     L.psi_b200_create.argtypes = [C.c_int, C.c_uint, C.POINTER(vp)]
     L.psi_b200_fork.argtypes = [vp, C.POINTER(vp)]
     L.psi_b200_destroy.argtypes = [vp]
@@ -530,6 +534,19 @@ class Context:
         if n.value:
             self._ck(lib().psi_b200_fetch_mems(self._h, _ptr(out), n.value, C.byref(n)))
         return out
+
+    def create_distance_index(self, dmin: int, dmax: int):
+        self._ck(lib().psi_b200_create_distance_index(self._h, dmin, dmax))
+
+    def verify_distance(self, pairs) -> np.ndarray:
+        """pairs: (n, 4) u32 {rank of v, offset, rank of u, offset}; returns n booleans."""
+        q = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 4)
+        out = np.zeros(len(q), np.uint8)
+        self._ck(lib().psi_b200_verify_distance(self._h, len(q), _ptr(q), _ptr(out), 0))
+        return out.astype(bool)
+
+    def verify_distance_device(self, n: int, d_pairs: int, d_out: int):
+        self._ck(lib().psi_b200_verify_distance(self._h, n, C.c_void_p(d_pairs), C.c_void_p(d_out), 1))
 
     def seeds_all(self, flags=ALL) -> int:
         n = C.c_uint64()

@@ -228,6 +228,16 @@ int psi_b200_fetch_mems(psi_b200_ctx* ctx, uint64_t* hits, uint64_t cap, uint64_
   })
 }
 
+int psi_b200_create_distance_index(psi_b200_ctx* ctx, unsigned dmin, unsigned dmax)
+{
+  CTX_GUARD(ctx, engine_create_distance_index(*ctx->c, dmin, dmax))
+}
+
+int psi_b200_verify_distance(psi_b200_ctx* ctx, uint64_t n, const uint32_t* pairs, uint8_t* ok, int on_device)
+{
+  CTX_GUARD(ctx, engine_verify_distance(*ctx->c, n, pairs, ok, on_device != 0))
+}
+
 int psi_b200_seeds_all(psi_b200_ctx* ctx, unsigned flags, uint64_t* n_hits)
 {
   CTX_GUARD(ctx, {

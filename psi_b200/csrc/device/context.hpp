@@ -156,6 +156,14 @@ struct Shared {
   DevBuf<uint32_t> mem_nodes, mem_head, mem_tail, mem_gpos, mem_ent, mem_pstart;
   DevBuf<uint8_t> mem_vlen;
 
+  // ---- paired-end distance index (distance.cu): per node, the (node, distance) pairs inside the window ----
+  bool has_dindex = false;         // create_distance_index was given a constructible window
+  bool dist_rows = false;          // the rows are materialised (else queries enumerate)
+  uint32_t dist_dmin = 0, dist_dmax = 0;
+  DevBuf<uint32_t> dist_row_len;
+  DevBuf<unsigned long long> dist_row_start, dist_entries;   // entry = node rank << 32 | distance between first characters
+  uint64_t n_dist_entries = 0;
+
   // ---- starting loci ----
   uint64_t n_loci = 0;
   DevBuf<uint32_t> loci_node, loci_off;
@@ -238,6 +246,10 @@ struct Ctx {
   DevBuf<uint64_t> mem_records;      // 6 x u64 per hit: node_id, node_off, read_id, read_off, match_len, gocc
   bool mem_valid = false;
   uint64_t n_mems = 0, n_mems_raw = 0;
+  // ---- distance queries (distance.cu) ----
+  DevBuf<uint32_t> dist_q, dist_queue;
+  DevBuf<uint8_t> dist_out;
+  DevBuf<unsigned long long> dist_counters, dist_big;
   // ---- a step in flight (psi_b200_seeds_all_async .. psi_b200_wait) ----
   bool pending = false;
   int pending_out_kind = 0;               // 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense
@@ -261,6 +273,9 @@ struct Ctx {
   int opt_seeding_mode = 0;                     // 0 seeds straight from the ASCII chunk, 1 via a 2-bit copy of the reads
   int opt_resolve_items = 2;                   // items per thread of the resolve kernel (2 or 4)
   int opt_resolve_ctas = 6;                    // resident CTAs per SM the resolve kernel is compiled for (5 or 6)
+  int opt_dindex_mode = 0;                     // distance index: 0 auto, 1 never materialise the rows (queries enumerate), 2 always
+  uint32_t opt_dindex_list_cap = 256;          // (node, distance) states a warp keeps in shared memory before the global scratch serves it (test hook)
+  uint64_t opt_dindex_max_bytes = 0;           // auto: materialise when the rows take at most this (0: half of the free memory)
   int opt_offpath_mode = 0;                    // 0 auto, 1 walk per chunk, 2 always materialise
   uint64_t opt_offpath_max_pairs = 1ull << 28; // auto: materialise when the k-walks number at most this
 };

@@ -34,6 +34,8 @@ void engine_build_mem_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, 
                             const uint32_t* head_off, const uint32_t* tail_trim);
 void engine_find_mems(Ctx& c, unsigned max_mem);
 void engine_fetch_mems(Ctx& c, uint64_t* hits, uint64_t cap);
+void engine_create_distance_index(Ctx& c, unsigned dmin, unsigned dmax);
+void engine_verify_distance(Ctx& c, uint64_t n, const uint32_t* pairs, uint8_t* out, bool on_device);
 void engine_submit_chunk_packed(Ctx& c, const psi_b200_packed_chunk& chunk, unsigned distance, bool on_device);
 void engine_set_option(Ctx& c, const char* name, long long value);
 void engine_fetch(Ctx& c, void* hits, uint64_t cap, bool compact);

@@ -103,6 +103,8 @@ Ctx* engine_fork(Ctx& parent)
   c->counters.n_loci = pc.n_loci; c->counters.ms_index_build = pc.ms_index_build; c->counters.ms_find_loci = pc.ms_find_loci;
   c->counters.n_offpath_entries = pc.n_offpath_entries; c->counters.index_stash_used = pc.index_stash_used;
   c->counters.offpath_mode = pc.offpath_mode; c->counters.n_offpath_walks = pc.n_offpath_walks;
+  c->counters.n_dindex_entries = pc.n_dindex_entries; c->counters.dindex_bytes = pc.dindex_bytes;
+  c->counters.dindex_mode = pc.dindex_mode; c->counters.ms_dindex_build = pc.ms_dindex_build;
   c->spill_items = parent.spill_items;
   c->opt_offpath_mode = parent.opt_offpath_mode;
   c->opt_seeding_mode = parent.opt_seeding_mode;
@@ -115,6 +117,9 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_resolve_items = parent.opt_resolve_items;
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
+  c->opt_dindex_mode = parent.opt_dindex_mode;
+  c->opt_dindex_list_cap = parent.opt_dindex_list_cap;
+  c->opt_dindex_max_bytes = parent.opt_dindex_max_bytes;
   return c;
 }
 

@@ -870,6 +870,18 @@ void engine_set_option(Ctx& c, const char* name, long long value)
     if (value < 0) throw ArgError("set_option: offpath_max_pairs must be >= 0");
     c.opt_offpath_max_pairs = (uint64_t)value;
   }
+  else if (n == "dindex_mode") {
+    if (value < 0 || value > 2) throw ArgError("set_option: dindex_mode is 0 (auto), 1 (queries enumerate) or 2 (rows materialised)");
+    c.opt_dindex_mode = (int)value;     // takes effect at the next create_distance_index
+  }
+  else if (n == "dindex_list_cap") {
+    if (value < 64 || value > 1024 || (value & (value - 1))) throw ArgError("set_option: dindex_list_cap is a power of two in [64, 1024]");
+    c.opt_dindex_list_cap = (uint32_t)value;
+  }
+  else if (n == "dindex_max_bytes") {
+    if (value < 0) throw ArgError("set_option: dindex_max_bytes must be >= 0 (0 = half of the free device memory)");
+    c.opt_dindex_max_bytes = (uint64_t)value;
+  }
   else if (n == "build_group_windows") {
     if (value < 0) throw ArgError("set_option: build_group_windows must be >= 0 (0 = from the free device memory)");
     c.opt_build_group_windows = (uint64_t)value;     // takes effect at the next set_paths

@@ -10,8 +10,10 @@
 #ifndef PSI_B200_PSI_GRAPH_HPP
 #define PSI_B200_PSI_GRAPH_HPP
 
+#include <atomic>
 #include <cstdint>
 #include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -66,6 +68,7 @@ class SeqGraph {
     psi_b200_graph_free(h_);
     h_ = h;
     by_id_.clear();
+    by_id_ready_.store(false);
     if (h_ && psi_b200_graph_get_view(h_, &v_) != PSI_B200_OK) throw std::runtime_error(psi_b200_global_error());
   }
   const psi_b200_graph* handle() const { return h_; }
@@ -78,12 +81,26 @@ class SeqGraph {
   id_type rank_to_id(rank_type rank) const { check_rank(rank); return (id_type)v_.internal_id[rank - 1]; }
   rank_type id_to_rank(id_type id) const
   {
-    if (by_id_.empty()) for (uint64_t r = 0; r < v_.n_nodes; ++r) by_id_.emplace(v_.internal_id[r], r + 1);
+    if (!by_id_ready_.load(std::memory_order_acquire)) {     // built once, by whichever thread asks first
+      std::lock_guard<std::mutex> lk(by_id_mutex_);
+      if (!by_id_ready_.load(std::memory_order_relaxed)) {
+        by_id_.clear();
+        by_id_.reserve(v_.n_nodes);
+        for (uint64_t r = 0; r < v_.n_nodes; ++r) by_id_.emplace(v_.internal_id[r], r + 1);
+        by_id_ready_.store(true, std::memory_order_release);
+      }
+    }
     auto it = by_id_.find((uint64_t)id);
     if (it == by_id_.end()) throw std::runtime_error("node id not found");
     return it->second;
   }
   id_type coordinate_id(id_type id) const { return (id_type)v_.coord_id[id_to_rank(id) - 1]; }
+  // external (coordinate) id -> internal id (gum id_by_coordinate); linear scan: a test / tooling accessor
+  id_type id_by_coordinate(id_type cid) const
+  {
+    for (uint64_t r = 0; r < v_.n_nodes; ++r) if (v_.coord_id[r] == (uint64_t)cid) return (id_type)v_.internal_id[r];
+    throw std::runtime_error("coordinate id not found");
+  }
   offset_type node_length(id_type id) const { rank_type r = id_to_rank(id); return v_.seq_start[r] - v_.seq_start[r - 1]; }
   std::string node_sequence(id_type id) const
   {
@@ -123,10 +140,17 @@ class SeqGraph {
 
  private:
   void check_rank(rank_type rank) const { if (rank == 0 || rank > v_.n_nodes) throw std::runtime_error("rank out of range"); }
-  void swap(SeqGraph& o) { std::swap(h_, o.h_); std::swap(v_, o.v_); by_id_.swap(o.by_id_); }
+  void swap(SeqGraph& o)
+  {
+    std::swap(h_, o.h_); std::swap(v_, o.v_); by_id_.swap(o.by_id_);
+    const bool a = by_id_ready_.load(), b = o.by_id_ready_.load();
+    by_id_ready_.store(b); o.by_id_ready_.store(a);
+  }
   psi_b200_graph* h_ = nullptr;
   psi_b200_graph_view v_{};
   mutable std::unordered_map<uint64_t, uint64_t> by_id_;
+  mutable std::atomic<bool> by_id_ready_{ false };
+  mutable std::mutex by_id_mutex_;
 };
 
 namespace util {

@@ -32,6 +32,7 @@
 #ifndef PSI_B200_PSI_SEED_FINDER_HPP
 #define PSI_B200_PSI_SEED_FINDER_HPP
 
+#include <array>
 #include <atomic>
 #include <unistd.h>
 #include <climits>
@@ -46,6 +47,8 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
+#include <utility>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -180,6 +183,87 @@ class SeedFinder {
     reset_pipes();
     if (pathset) psi_b200_pathset_free(pathset);
     if (ctx) psi_b200_destroy(ctx);
+  }
+
+  /* ---- paired-end distance verification (reference seed_finder.hpp:1193-1317) ----
+   * The reference materialises DiVerG's boolean matrix of all locus pairs whose distance lies in [dmin, dmax] and looks
+   * a pair up; here the device keeps the same relation per node (psi_b200_create_distance_index) and answers queries in
+   * bulk.  Whole / PerComponent only choose how the reference assembles its matrix: the relation is the same. */
+  template <typename TDIndexMode = PerComponent>
+  void create_distance_index(unsigned int dmin, unsigned int dmax, TDIndexMode = {},
+                             std::function<void(std::string const&)> info = nullptr,
+                             std::function<void(std::string const&)> = nullptr)
+  {
+    if (dmin == 0 || dmax < dmin) return;   // not constructible (seed_finder.hpp:1198)
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("index-distances");
+    if (info) info(std::is_same<TDIndexMode, Whole>::value ? "Constructing distance index for the whole graph..."
+                                                            : "Constructing distance index on the device...");
+    reset_pipes();
+    check(psi_b200_create_distance_index(ctx, dmin, dmax));
+    d = std::make_pair(dmin, dmax);
+  }
+
+  static std::string get_distance_index_path(std::string prefix, unsigned int dmin, unsigned int dmax)
+  {
+    return prefix + "_dist_mat_m" + std::to_string(dmin) + "M" + std::to_string(dmax);
+  }
+
+  // The device rebuilds its rows from the graph in milliseconds, so the file only records WHICH index was saved (window
+  // and graph); `.b200` keeps it apart from the reference's serialised matrix of the same prefix, which is not read.
+  bool save_distance_index(std::string prefix) const
+  {
+    if (d.first == 0) return true;   // empty distance index (seed_finder.hpp:1270)
+    std::ofstream ofs(get_distance_index_path(prefix, d.first, d.second) + ".b200", std::ofstream::binary);
+    if (!ofs) return false;
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("save-dindex");
+    const psi_b200_graph_view& gv = graph_ptr->view();
+    const uint64_t hdr[6] = { DIST_MAGIC, d.first, d.second, gv.n_nodes, gv.n_bases, graph_checksum() };
+    ofs.write(reinterpret_cast<const char*>(hdr), sizeof hdr);
+    return (bool)ofs;
+  }
+
+  bool open_distance_index(std::string prefix, unsigned int dmin = 0, unsigned int dmax = 0)
+  {
+    if (dmax == 0) dmax = dmin;
+    std::ifstream ifs(get_distance_index_path(prefix, dmin, dmax) + ".b200", std::ifstream::binary);
+    if (!ifs) return false;
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-dindex");
+    uint64_t hdr[6] = { 0, 0, 0, 0, 0, 0 };
+    ifs.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+    const psi_b200_graph_view& gv = graph_ptr->view();
+    if (!ifs || hdr[0] != DIST_MAGIC || hdr[1] != dmin || hdr[2] != dmax || hdr[3] != gv.n_nodes || hdr[4] != gv.n_bases ||
+        hdr[5] != graph_checksum())
+      return false;
+    create_distance_index(dmin, dmax);
+    return d.first == dmin && d.second == dmax && dmin != 0;
+  }
+
+  bool verify_distance(id_type v, offset_type o, id_type u, offset_type p) const
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("query-dindex");
+    const uint32_t q[4] = { (uint32_t)(graph_ptr->id_to_rank(v) - 1), clamp32(o), (uint32_t)(graph_ptr->id_to_rank(u) - 1), clamp32(p) };
+    uint8_t ok = 0;
+    Pipe& pp = pipe();
+    pcheck(pp, psi_b200_verify_distance(pp.ctx, 1, q, &ok, 0));
+    return ok != 0;
+  }
+
+  // Bulk form -- what a paired-end caller uses: n quadruples {v, o, u, p} (node ids as in verify_distance), one answer
+  // each, one device pass for all of them.
+  std::vector<uint8_t> verify_distances(const std::vector<std::array<uint64_t, 4>>& ends) const
+  {
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("query-dindex");
+    std::vector<uint32_t> q(4 * ends.size());
+    for (size_t i = 0; i < ends.size(); ++i) {
+      q[4 * i] = (uint32_t)(graph_ptr->id_to_rank((id_type)ends[i][0]) - 1);
+      q[4 * i + 1] = clamp32(ends[i][1]);
+      q[4 * i + 2] = (uint32_t)(graph_ptr->id_to_rank((id_type)ends[i][2]) - 1);
+      q[4 * i + 3] = clamp32(ends[i][3]);
+    }
+    std::vector<uint8_t> ok(ends.size());
+    Pipe& pp = pipe();
+    pcheck(pp, psi_b200_verify_distance(pp.ctx, ends.size(), q.data(), ok.data(), 0));
+    return ok;
   }
 
   /* ---- accessors ---- */
@@ -551,6 +635,8 @@ class SeedFinder {
 
  private:
   static constexpr uint64_t PATHS_MAGIC = 0x3230736874617042ull;  // "Bpaths02"
+  static constexpr uint64_t DIST_MAGIC = 0x3130747369644242ull;   // "BBdist01"
+  static uint32_t clamp32(uint64_t x) { return x > 0xffffffffull ? 0xffffffffu : (uint32_t)x; }
 
   // One pipeline per host thread: a fork of the finder's context (own stream and device buffers over the shared
   // resident index) plus the pinned host buffers its results arrive in.
@@ -660,13 +746,6 @@ class SeedFinder {
       context = seed_len;
     }
     return context;
-  }
-
-  void create_distance_index(unsigned int dmin, unsigned int dmax)
-  {
-    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("index-distances");
-    if (dmin == 0 && dmax == 0) return;   // reference: no-op when dmin == 0 (seed_finder.hpp:1198)
-    throw std::runtime_error("the paired-end distance index is outside this build's scope (use -m 0 -M 0)");
   }
 
   void pull_loci(uint64_t n)
@@ -851,6 +930,7 @@ class SeedFinder {
   unsigned int gocc_threshold;
   unsigned int max_mem;
   unsigned int context_ = 0;
+  std::pair<unsigned int, unsigned int> d{ 0, 0 };   // distance window of the index (reference: SeedFinder::d)
   std::unique_ptr<stats_type> stats_ptr;
   psi_b200_ctx* ctx = nullptr;              // builds and owns the resident graph / index / loci
   psi_b200_pathset* pathset = nullptr;

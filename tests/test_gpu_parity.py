@@ -963,3 +963,105 @@ def test_find_mems_against_the_reference(fixture, packed):
     parts = np.concatenate([run(b, min(n, b + 97)) for b in range(0, n, 97)])
     assert np.array_equal(np.unique(parts, axis=0), z["mems"])
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Paired-end distance verification (psi_b200_create_distance_index / psi_b200_verify_distance) against the reference
+
+DIST_FIXTURES = sorted(_glob.glob(_os.fspath(util.GOLDEN / "dist" / "*.npz")))
+TINY_DISTANT = [(1, 0, 1, 0), (1, 0, 1, 1), (1, 0, 1, 3), (1, 0, 1, 6), (1, 0, 1, 7), (1, 0, 7, 0), (2, 0, 9, 10), (9, 1, 9, 14),
+                (9, 5, 9, 18), (9, 18, 11, 0), (9, 18, 11, 3), (9, 18, 15, 0), (9, 18, 15, 6)]
+TINY_CLOSED = [(1, 0, 2, 0), (1, 0, 6, 0), (1, 0, 6, 2), (9, 0, 9, 8), (9, 1, 9, 13), (9, 10, 9, 18), (9, 6, 9, 18), (9, 18, 15, 1),
+               (9, 18, 15, 5)]
+# rows kept in HBM, no rows (every query enumerates), and both with a shared-memory capacity small enough that the
+# global scratch region serves part of the nodes / queries
+DIST_MODES = [(2, 256), (1, 256), (2, 64), (1, 64)]
+DIST_MODE_IDS = ["rows", "walk", "rows-spill", "walk-spill"]
+
+
+@pytest.mark.parametrize("mode", DIST_MODES, ids=DIST_MODE_IDS)
+@pytest.mark.parametrize("fixture", DIST_FIXTURES, ids=lambda f: _os.path.basename(f)[:-4])
+def test_verify_distance_against_the_reference(fixture, mode):
+    """SeedFinder::create_distance_index + verify_distance (seed_finder.hpp:1193-1317): every locus pair the compiled
+    reference answered gets the same answer from the device, from the materialised rows and by enumeration."""
+    z = np.load(fixture)
+    g = capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"]))
+    ctx = capi.Context(12, 0)
+    ctx.set_graph(g, ids="coord")
+    rows = z["rows"]
+    with pytest.raises(capi.PsiError) as e:
+        ctx.verify_distance(rows[:, :4])          # no index yet
+    assert e.value.code == capi.ERR_STATE
+    ctx.set_option("dindex_mode", mode[0])
+    ctx.set_option("dindex_list_cap", mode[1])
+    ctx.create_distance_index(int(z["dmin"]), int(z["dmax"]))
+    c = ctx.counters()
+    assert c["dindex_mode"] == mode[0]
+    assert (c["n_dindex_entries"] > 0 and c["dindex_bytes"] > 0) if mode[0] == 2 else c["dindex_bytes"] == 0
+    got = ctx.verify_distance(rows[:, :4])
+    assert np.array_equal(got, rows[:, 4].astype(bool))
+    # a fork shares the index; loci that do not exist answer "no"
+    f = ctx.fork()
+    assert np.array_equal(f.verify_distance(rows[:97, :4]), rows[:97, 4].astype(bool))
+    n = len(g.coord_id)
+    bad = np.array([[n, 0, 0, 0], [0, 0, n + 5, 0], [0, 1 << 20, 1, 0], [0, 0, 1, 1 << 20]], np.uint32)
+    assert not f.verify_distance(bad).any()
+    f.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode", DIST_MODES, ids=DIST_MODE_IDS)
+def test_verify_distance_known_answers_of_the_reference_test(mode):
+    """test/src/test_seedfinder.cpp:225-312 on the device: tiny graph, window 8..12."""
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/tiny.gfa.gz")
+    r = {int(c): i for i, c in enumerate(g.coord_id)}
+    ctx = capi.Context(30, 0)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_option("dindex_mode", mode[0])
+    ctx.set_option("dindex_list_cap", mode[1])
+    ctx.create_distance_index(8, 12)
+    q = lambda rows: np.array([[r[a], b, r[c], d] for a, b, c, d in rows], np.uint32)
+    assert not ctx.verify_distance(q(TINY_DISTANT)).any()
+    assert ctx.verify_distance(q(TINY_CLOSED)).all()
+    # "not constructible" windows leave no index behind (seed_finder.hpp:1198)
+    ctx.create_distance_index(0, 12)
+    with pytest.raises(capi.PsiError):
+        ctx.verify_distance(q(TINY_CLOSED))
+    ctx.create_distance_index(9, 8)
+    with pytest.raises(capi.PsiError):
+        ctx.verify_distance(q(TINY_CLOSED))
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_verify_distance_fuzz_fresh_graphs_vs_oracle(seed):
+    """Fresh bubble graphs, windows of several widths: rows = enumeration = oracle restatement, on pairs drawn close
+    enough to each other that about half of them fall inside the window."""
+    import tempfile
+    text = util.random_bubble_gfa(4000 + seed, backbone=2500, sites=160, p_snp=0.6, p_ins=0.2, max_indel=9)
+    with tempfile.TemporaryDirectory() as td:
+        open(_os.path.join(td, "f.gfa"), "w").write(text)
+        g = capi.Graph.load_gfa(_os.path.join(td, "f.gfa"))
+    og = orc.OGraph.of(g)
+    rng = util.SplitMix(77 + seed)
+    n = len(g.coord_id)
+    start = np.asarray(g.seq_start, np.int64)
+    total = int(start[-1])
+    dmin, dmax = [(1, 3), (7, 7), (30, 90), (120, 400), (15, 16), (200, 210)][seed]
+    pairs = []
+    for _ in range(1500):
+        a = rng.below(total)
+        b = min(total - 1, a + rng.below(2 * dmax + 20))
+        rv, ru = int(np.searchsorted(start, a, side="right")) - 1, int(np.searchsorted(start, b, side="right")) - 1
+        pairs.append((rv, a - int(start[rv]), ru, b - int(start[ru])))
+    pairs = np.array(pairs, np.uint32)
+    want = np.array([orc.verify_distance(og, int(v), int(o), int(u), int(p), dmin, dmax) for v, o, u, p in pairs])
+    assert want.any() and not want.all()
+    for mode, cap in DIST_MODES:
+        ctx = capi.Context(12, 0)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_option("dindex_mode", mode)
+        ctx.set_option("dindex_list_cap", cap)
+        ctx.create_distance_index(dmin, dmax)
+        assert np.array_equal(ctx.verify_distance(pairs), want), (mode, cap)
+        ctx.close()

@@ -299,3 +299,41 @@ def test_find_mems_restatement_against_the_reference(fixture):
     got = np.unique(np.array(rows, np.uint64).reshape(-1, 6), axis=0)
     want = z["mems"][z["mems"][:, 0] < n_check]
     assert len(want) > 50 and np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Paired-end distance verification: the restatement against the unmodified reference (tests/golden/make_dist_golden.py)
+
+DIST_FIXTURES = sorted(glob.glob(os.fspath(util.GOLDEN / "dist" / "*.npz")))
+
+
+def test_distance_fixtures_exist():
+    assert len(DIST_FIXTURES) >= 8
+
+
+@pytest.mark.parametrize("fixture", DIST_FIXTURES, ids=lambda f: os.path.basename(f)[:-4])
+def test_verify_distance_restatement_against_the_reference(fixture):
+    """oracle_py.verify_distance (walks of dmin..dmax characters between two loci) answers every locus pair like
+    SeedFinder::verify_distance over DiVerG's matrix index (seed_finder.hpp:1193-1317) did in the compiled reference."""
+    z = np.load(fixture)
+    og = orc.OGraph.of(capi.Graph.load_gfa(util.GOLDEN / str(z["gfa"])))
+    dmin, dmax = int(z["dmin"]), int(z["dmax"])
+    rows = z["rows"]
+    assert rows[:, 4].any() and not rows[:, 4].all()
+    got = np.array([orc.verify_distance(og, int(v), int(o), int(u), int(p), dmin, dmax) for v, o, u, p, _ in rows])
+    assert np.array_equal(got, rows[:, 4].astype(bool))
+
+
+def test_verify_distance_known_answers_of_the_reference_test():
+    """test/src/test_seedfinder.cpp:225-268: tiny graph, window 8..12, the pairs the reference lists as distant / closed."""
+    g = capi.Graph.load_gfa(util.GOLDEN / "inputs/tiny.gfa.gz")
+    og = orc.OGraph.of(g)
+    r = {int(c): i for i, c in enumerate(g.coord_id)}
+    distant = [(1, 0, 1, 0), (1, 0, 1, 1), (1, 0, 1, 3), (1, 0, 1, 6), (1, 0, 1, 7), (1, 0, 7, 0), (2, 0, 9, 10), (9, 1, 9, 14),
+               (9, 5, 9, 18), (9, 18, 11, 0), (9, 18, 11, 3), (9, 18, 15, 0), (9, 18, 15, 6)]
+    closed = [(1, 0, 2, 0), (1, 0, 6, 0), (1, 0, 6, 2), (9, 0, 9, 8), (9, 1, 9, 13), (9, 10, 9, 18), (9, 6, 9, 18), (9, 18, 15, 1),
+              (9, 18, 15, 5)]
+    for a, b, c, d in distant:
+        assert not orc.verify_distance(og, r[a], b, r[c], d, 8, 12)
+    for a, b, c, d in closed:
+        assert orc.verify_distance(og, r[a], b, r[c], d, 8, 12)

@@ -25,12 +25,17 @@ def run(cmd, **kw):
     return subprocess.run([str(c) for c in cmd], capture_output=True, text=True, timeout=600, **kw)
 
 
-def build_driver():
-    if DRIVER.exists() and DRIVER.stat().st_mtime > DRIVER_SRC.stat().st_mtime:
+def build_driver(src=DRIVER_SRC, exe=DRIVER):
+    hdrs = list((ROOT / "psi_b200" / "include" / "psi").glob("*.hpp"))
+    if exe.exists() and exe.stat().st_mtime > max(f.stat().st_mtime for f in [src] + hdrs):
         return
-    DRIVER.parent.mkdir(exist_ok=True)
-    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", os.fspath(DRIVER), os.fspath(DRIVER_SRC),
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", os.fspath(exe), os.fspath(src),
                     "-L" + os.fspath(ROOT / "psi_b200"), "-lpsi_b200", "-lpthread", "-Wl,-rpath," + os.fspath(ROOT / "psi_b200")], check=True)
+
+
+DIST_DRIVER_SRC = ROOT / "tests" / "cpp" / "distance_driver.cpp"
+DIST_DRIVER = ROOT / "tests" / "cpp" / "build" / "distance_driver"
 
 
 def gunzip_to(src, dst):
@@ -257,3 +262,33 @@ def test_seed_finder_api_matches_oracle(tmp_path, name, chunk):
     loci = np.fromfile(str(tmp_path / "out") + ".loci", dtype="<u8").reshape(-1, 2)
     assert info["loci"] == len(loci) and info["uniq_nodes"] == len(np.unique(loci[:, 0]))
     assert set(loci[:, 0].tolist()) <= set(g.coord_id.tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny_8_12", "x_10_40", "multi_20_60", "m_50_150"])
+def test_seed_finder_distance_api_matches_the_reference(tmp_path, name):
+    """The reference's own scenario (test/src/test_seedfinder.cpp:225-312) through the mirror: create_distance_index,
+    verify_distance one by one, in bulk and from three threads, save_distance_index, a second finder that opens the saved
+    index -- every answer equal to the one the compiled reference gave (tests/golden/dist)."""
+    build_driver(DIST_DRIVER_SRC, DIST_DRIVER)
+    z = np.load(util.GOLDEN / "dist" / f"{name}.npz")
+    gz = util.GOLDEN / str(z["gfa"])
+    gfa = gunzip_to(gz, tmp_path / "g.gfa") if str(gz).endswith(".gz") else gz
+    g = capi.Graph.load_gfa(gfa)
+    rows = z["rows"].astype(np.uint64)
+    pairs = rows[:, :4].copy()
+    pairs[:, 0] = g.coord_id[rows[:, 0]]
+    pairs[:, 2] = g.coord_id[rows[:, 2]]
+    pairs.astype("<u8").tofile(tmp_path / "pairs")
+    r = run([DIST_DRIVER, gfa, int(z["dmin"]), int(z["dmax"]), tmp_path / "pairs", tmp_path / "out", tmp_path / "idx"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["threw_without_index"] and info["infos"] == 1 and info["saved"] and info["opened"] and not info["wrong_window"]
+    assert info["mt_ok"] and info["entries"] > 0
+    out = np.fromfile(tmp_path / "out", np.uint8)
+    n, ns = len(rows), info["single"]
+    want = rows[:, 4].astype(np.uint8)
+    assert len(out) == ns + 2 * n
+    assert np.array_equal(out[:ns], want[:ns]), "single queries"
+    assert np.array_equal(out[ns:ns + n], want), "bulk query"
+    assert np.array_equal(out[ns + n:], want), "index reopened by a second finder"
