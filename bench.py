@@ -874,11 +874,56 @@ def other_configs(torch, dev, run_async, run_sync, capi):
                              "kernel_ms_per_step": {k_: acc[k_] / 4 for k_ in ("ms_pack", "ms_read_index", "ms_on", "ms_off", "ms_resolve")},
                              "walks_per_step": acc["n_walks"] / 4, "starting_loci": W.n_loci,
                              "workload": f"{shape}-shape graph walked from its starting loci for every chunk of {n_reads} x {read_len} bp reads, k={k}"}
+            if name == "chr22_150bp":
+                out["distance_index_300_500"] = distance_bench(torch, dev, capi, W.g, 300, 500)
             W.close()
         except Exception as e:   # an extra line must not take the headline down
             out[name] = {"error": f"{type(e).__name__}: {e}"}
     globals().update(K=k0, READ_LEN=len0)
     return out
+
+
+def distance_bench(torch, dev, capi, g, dmin, dmax, n_pairs=4_000_000):
+    """Paired-end distance verification (SeedFinder::create_distance_index / verify_distance, SURVEY 8 f4) on the same
+    graph: index build, then n_pairs locus pairs resident in HBM answered against the materialised rows and by
+    enumeration; pairs are drawn so that roughly a third fall inside the window."""
+    try:
+        rng = np.random.default_rng(5)
+        start = np.asarray(g.seq_start, np.int64)
+        a = rng.integers(0, int(start[-1]) - 2 * dmax - 64, n_pairs)
+        b = a + rng.integers(0, int(1.5 * dmax), n_pairs)
+        rv, ru = np.searchsorted(start, a, side="right") - 1, np.searchsorted(start, b, side="right") - 1
+        pairs = np.stack([rv, a - start[rv], ru, b - start[ru]], axis=1).astype(np.uint32)
+        d_pairs = torch.from_numpy(pairs.view(np.int32)).to(dev)
+        d_out = torch.zeros(n_pairs, dtype=torch.uint8, device=dev)
+        res = {"workload": f"chr22-shape graph, window {dmin}..{dmax}, {n_pairs} locus pairs resident in HBM"}
+        for mode, key in ((2, "rows"), (1, "enumerate")):
+            ctx = capi.Context(K, dev.index)
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            ctx.set_graph(g, ids="internal")
+            ctx.set_option("dindex_mode", mode)
+            t0 = time.perf_counter()
+            ctx.create_distance_index(dmin, dmax)
+            build_s = time.perf_counter() - t0
+            c = ctx.counters()
+            n_q = n_pairs if mode == 2 else n_pairs // 8
+            ctx.verify_distance_device(n_q, d_pairs.data_ptr(), d_out.data_ptr())      # warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ctx.verify_distance_device(n_q, d_pairs.data_ptr(), d_out.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            res[key] = {"queries_per_s": n_q / (ms * 1e-3), "ms_per_call": ms, "queries_per_call": n_q,
+                        "inside_window": int(d_out[:n_q].sum().item())}
+            if mode == 2:
+                res["index"] = {"entries": c["n_dindex_entries"], "bytes": c["dindex_bytes"], "build_ms_device": c["ms_dindex_build"],
+                                "build_s_wall": build_s, "bytes_per_query": 16 + 1 + 12 + 8 * c["n_dindex_entries"] / max(c["n_nodes"], 1)}
+            ctx.close()
+        return res
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def main():

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 #include <algorithm>
 
@@ -264,6 +265,73 @@ gather_occ_kernel(const char* __restrict__ table, uint64_t n_sectors_mask, const
   if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
 }
 
+// sm_100 TMA gather: cp.async.bulk.tensor.2d.tile::gather4 copies FOUR rows of a [n_lines, 128 B] tensor map into shared
+// memory with one instruction (one column coordinate, four row coordinates), completion on an mbarrier.  Lanes 0..7 of
+// each warp issue one gather4 for four probes each, ITEMS rounds; dynamic shared memory ITEMS * 256 * 128 bytes + 8.
+#include <cuda.h>
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+gather4_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t n_sectors_mask, const uint64_t* __restrict__ keys, uint32_t n,
+               unsigned long long* __restrict__ sink)
+{
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"((uint32_t)(ITEMS * 256 * 128)) : "memory");
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const uint32_t p0 = blockIdx.x * (256u * ITEMS) + i * 256u + warp * 32u + lane * 4u;
+      int32_t row[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t key = p0 + j < n ? keys[p0 + j] : 0;
+        row[j] = (int32_t)((mix64(key) & n_sectors_mask) >> 2);
+      }
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dyn + ((size_t)(i * 256 + warp * 32 + lane * 4) << 7));
+      asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                   :: "r"(dst), "l"(&tmap), "r"(0), "r"(row[0]), "r"(row[1]), "r"(row[2]), "r"(row[3]), "r"(bar_a) : "memory");
+    }
+  }
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar_a) : "memory");
+  uint64_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    const uint4* ln = reinterpret_cast<const uint4*>(dyn + ((size_t)(i * 256 + threadIdx.x) << 7));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const uint4 w = ln[(j + threadIdx.x) & 7]; acc ^= w.x ^ w.y ^ w.z ^ w.w; }
+  }
+  if (acc == 0x1234567ull) atomicAdd(sink, 1ull);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+static bool make_line_tensor_map(CUtensorMap* out, void* table, uint64_t n_lines, unsigned box_rows)
+{
+  typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+  const cuuint64_t dims[2] = { 128, n_lines };
+  const cuuint64_t strides[1] = { 128 };
+  const cuuint32_t box[2] = { 128, box_rows };
+  const cuuint32_t estr[2] = { 1, 1 };
+  const CUresult r = ((encode_t)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, table, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) std::fprintf(stderr, "cuTensorMapEncodeTiled(box rows %u): error %d\n", box_rows, (int)r);
+  return r == CUDA_SUCCESS;
+}
+
 template <class F>
 static float time_launch(F launch, int reps, char* flush, size_t flush_bytes)
 {
@@ -346,6 +414,29 @@ int main(int argc, char** argv)
 
   size_t g = 0;
   CK(cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity));
+  const char* only = argc > 4 ? argv[4] : "";
+  if (std::string(only) == "gather4") {
+    // ./gather_peak MiB probes reps gather4 [box rows = 4]: the TMA gather4 variants alone (a faulting variant must
+    // not take the other measurements down, so this mode runs in a process of its own)
+    const unsigned box_rows = argc > 5 ? (unsigned)std::atoi(argv[5]) : 4u;
+    CUtensorMap tmap;
+    if (!make_line_tensor_map(&tmap, table, bytes >> 7, box_rows)) { std::printf("{\"test\": \"random_gather\", \"variant\": \"tma_gather4\", \"error\": \"tensor map\"}\n"); return 0; }
+    auto rep4 = [&](const char* name, float ms) {
+      std::printf("{\"test\": \"random_gather\", \"variant\": \"%s_box%u\", \"table_bytes\": %llu, \"probes\": %u, \"bytes_per_probe\": 128, "
+                  "\"ms\": %.4f, \"Gprobes_per_s\": %.2f, \"useful_GBps\": %.1f}\n", name, box_rows, (unsigned long long)table_bytes, n, ms,
+                  n / (ms * 1e-3) / 1e9, (double)n * 128 / (ms * 1e-3) / 1e9);
+    };
+    CK(cudaFuncSetAttribute(gather4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 * 256 * 128));
+    CK(cudaFuncSetAttribute(gather4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 128));
+    CK(cudaFuncSetAttribute(gather4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 128));
+    rep4("tma_gather4_128B_items1", time_launch([&] { gather4_kernel<1><<<(n + 255) / 256, 256, 1 * 256 * 128>>>(tmap, mask, keys, n, sink); }, reps, flush, flush_bytes));
+    rep4("tma_gather4_128B_items2", time_launch([&] { gather4_kernel<2><<<(n + 511) / 512, 256, 2 * 256 * 128>>>(tmap, mask, keys, n, sink); }, reps, flush, flush_bytes));
+    rep4("tma_gather4_128B_items4", time_launch([&] { gather4_kernel<4><<<(n + 1023) / 1024, 256, 4 * 256 * 128>>>(tmap, mask, keys, n, sink); }, reps, flush, flush_bytes));
+    // the LDGSTS variant the product kernel uses, in the same process for a like-for-like number
+    CK(cudaFuncSetAttribute(gather_ldgsts_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * 16));
+    rep4("ldgsts_128B_items8", time_launch([&] { gather_ldgsts_kernel<8><<<(n + 255) / 256, 256, 8 * 256 * 16>>>(table, mask, keys, n, sink); }, reps, flush, flush_bytes));
+    return 0;
+  }
   auto report = [&](const char* name, float ms, int bytes, double probes) {
     std::printf("{\"test\": \"random_gather\", \"variant\": \"%s\", \"table_bytes\": %llu, \"probes\": %.0f, \"bytes_per_probe\": %d, "
                 "\"ms\": %.4f, \"Gprobes_per_s\": %.2f, \"useful_GBps\": %.1f, \"useful_plus_key_GBps\": %.1f}\n",

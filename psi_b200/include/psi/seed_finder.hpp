@@ -388,7 +388,8 @@ class SeedFinder {
       ofs.write(reinterpret_cast<const char*>(v.tail_trim), v.n_paths * sizeof(uint32_t));
       if (!ofs) return false;
     }
-    return save_starts(fpath, seed_len, step_size);
+    // like the reference (seed_finder.hpp:1372-1378): paths, starting loci, distance index
+    return save_starts(fpath, seed_len, step_size) && save_distance_index(fpath);
   }
 
   bool load_path_index(std::string const& fpath, unsigned int context = 0, unsigned int step_size = 1,
@@ -435,7 +436,10 @@ class SeedFinder {
       add_uncovered_loci(step_size);
       save_starts(fpath, seed_len, step_size);
     }
-    create_distance_index(dmin, dmax);
+    if (!open_distance_index(fpath, dmin, dmax)) {   // seed_finder.hpp:1405-1411
+      create_distance_index(dmin, dmax);
+      save_distance_index(fpath);
+    }
     return true;
   }
 
@@ -459,7 +463,10 @@ class SeedFinder {
       add_uncovered_loci(step_size);
       save_starts(fpath, seed_len, step_size);
     }
-    create_distance_index(dmin, dmax);
+    if (!open_distance_index(fpath, dmin, dmax)) {   // seed_finder.hpp:1405-1411
+      create_distance_index(dmin, dmax);
+      save_distance_index(fpath);
+    }
     return true;
   }
 

@@ -150,7 +150,11 @@ int main(int argc, char** argv)
   }
   ok &= throws_runtime_error([&] { finder_type f3(graph, 33); }, "seed length");
   ok &= throws_runtime_error([&] { finder_type f4(graph, k, 0, 0, 1); }, "approximate");
-  ok &= throws_runtime_error([&] { finder_type f5(graph, k); f5.create_path_index(1, true, 0, 1, 100, 300); }, "distance index");
+  {  // insert sizes given to create_path_index build the distance index too (seed_finder.hpp:1341-1343)
+    finder_type f5(graph, k);
+    f5.create_path_index(1, true, 0, 1, 100, 300);
+    ok &= f5.get_counters().dindex_mode != 0;
+  }
   std::printf("{\"chunks\": %lu, \"reads\": %lu, \"loci\": %zu, \"uniq_nodes\": %zu, \"on\": %zu, \"off\": %zu, \"all1\": %zu, \"all2\": %zu, "
               "\"infos\": %zu, \"errors_ok\": %s}\n",
               n_chunks, n_reads, finder.get_starting_loci().size(), finder.get_nof_uniq_nodes(), on.size() / 4, off.size() / 4,

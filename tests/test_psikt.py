@@ -174,6 +174,18 @@ def test_psikt_saved_path_index_is_reloaded(tmp_path):
         assert "No valid path index found. Creating the path index..." in (tmp_path / "d.log").read_text()
         assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o3", g))) == c["md5"]
         assert pf.read_bytes() != bad                  # rewritten by the rebuild
+    # insert sizes (-m / -M): the distance index is created with the path index, noted beside it, and found again
+    p2 = tmp_path / "idx2"
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-n", "4", "-I", p2, "-m", "100", "-M", "300", "-x", "-L", tmp_path / "e.log", "-q", "-o",
+             tmp_path / "o4", gfa])
+    assert r.returncode == 0, r.stderr
+    text = (tmp_path / "e.log").read_text()
+    assert "Constructing distance index" in text and "Created distance index in" in text and "Saved distance index in" in text
+    assert Path(str(p2) + "_dist_mat_m100M300.b200").exists()
+    r = run([PSIKT, "-f", reads, "-l", c["k"], "-I", p2, "-m", "100", "-M", "300", "-L", tmp_path / "f.log", "-q", "-o", tmp_path / "o5", gfa])
+    assert r.returncode == 0, r.stderr
+    assert "The path index has been found and loaded." in (tmp_path / "f.log").read_text()
+    assert util.md5_tuples(capi.canonical(load_psikt_output(tmp_path / "o5", g))) == c["md5"]
     # -n 0 and no index: nothing is found (src/psikt.cpp:121-123)
     r = run([PSIKT, "-f", reads, "-l", c["k"], "-L", tmp_path / "c.log", "-q", "-o", tmp_path / "o2", gfa])
     assert r.returncode == 0
