@@ -824,7 +824,8 @@ def main_sharded(args):
                 "verified": f"every seed of every (error-free) read hit; {counts['checked']} sampled records spell their seed in the graph",
                 "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
                           "slot_bytes": c0["index_slot_bytes"], "build_ms": c0["ms_index_build"], "find_loci_ms": c0["ms_find_loci"],
-                          "offpath_entries": c0["n_offpath_entries"], "device_bytes_in_use": int(total_b - free_b)}}
+                          "offpath_entries": c0["n_offpath_entries"], "device_bytes_in_use": int(total_b - free_b),
+                          "build_slices": c0["index_build_slices"], "host_graph_and_paths_s": t_host}}
         print(json.dumps(line), flush=True)
     for cx in pipes[1:]:
         cx.close()

@@ -53,7 +53,9 @@ SHAPES = {
     # a chromosome-1-sized instance of the chr22 recipe (5x): exercises the grouped index build (16 paths x 255 Mbp = 4 G
     # path windows) and a 5.4 GB index
     "chr1": dict(backbone=250_000_000, sites=4_900_000, p_snp=0.90, p_ins=0.05, tri_frac=0.0, seeds=(1, 2)),
-    # BASELINE configs[4] (3.1 Gbp, 80 M sites, 24 components) at 1/4 and 1/16 of its size
+    # BASELINE configs[4] as written: 3.1 Gbp, 80 M sites, 24 components (a sliced index build: more than 2^32 pairs)
+    "wg": dict(components=whole_genome_components(3_100_000_000, 80_000_000)),
+    # ... and at 1/4 and 1/16 of its size
     "wg_1_4": dict(components=whole_genome_components(775_000_000, 20_000_000)),
     "wg_1_16": dict(components=whole_genome_components(193_750_000, 5_000_000)),
     "mhc": dict(backbone=5_000_000, sites=416_667, p_snp=1.0, p_ins=0.0, tri_frac=0.10, seeds=(6, 7)),

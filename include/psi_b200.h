@@ -196,6 +196,11 @@ int  psi_b200_sync(psi_b200_ctx* ctx);
  *   "offpath_max_pairs" auto mode materialises when the walks number at most this (default 2^28);
  *   "build_group_windows" set_paths indexes the paths in groups of at most this many k-windows (32 B of scratch each;
  *                       default 0 = what the free device memory allows, at most 2^30) and merges the groups' distinct pairs;
+ *   "build_slices"      set_paths builds the index in this many slices of the k-mer space (1, 4, 16, 64 or 256; 0 = auto:
+ *                       one slice unless the graph may hold more than ~3 * 2^30 distinct (k-mer, locus) pairs).  A sliced
+ *                       build has no 2^32 limit on the number of pairs, releases its sorted pairs once the starting loci
+ *                       are set (find_loci / set_loci once; set_paths again before changing them) and does not serve a
+ *                       gocc threshold;
  *   "index_slack"       extra doublings of the index's bucket count: fewer full buckets (slow-path probes) for twice
  *                       the memory each; -1 (default) = 1 for 16-byte slots (k > ~27) while the index stays small, else 0.
  * Set before create_distance_index:
@@ -395,6 +400,8 @@ typedef struct {
   uint64_t dindex_bytes;       /* device bytes of the materialised rows */
   uint32_t dindex_mode;        /* 0 none, 1 queries enumerate, 2 rows materialised */
   float ms_dindex_build;
+  uint32_t index_build_slices; /* slices of the k-mer space the index was built in (1: one-shot build) */
+  uint32_t reserved0;
 } psi_b200_counters_t;
 int  psi_b200_counters(psi_b200_ctx* ctx, psi_b200_counters_t* out);
 int  psi_b200_reset_counters(psi_b200_ctx* ctx);

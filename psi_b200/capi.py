@@ -87,7 +87,8 @@ class Counters(C.Structure):
                 ("launches", C.c_uint32), ("ms_probe", C.c_float),
                 ("ms_probe_sum", C.c_double), ("ms_on_sum", C.c_double), ("timed_steps", C.c_uint64),
                 ("n_gocc_dropped", C.c_uint64), ("code_by_rank", C.c_uint32), ("code_off_bits", C.c_uint32),
-                ("n_dindex_entries", C.c_uint64), ("dindex_bytes", C.c_uint64), ("dindex_mode", C.c_uint32), ("ms_dindex_build", C.c_float)]
+                ("n_dindex_entries", C.c_uint64), ("dindex_bytes", C.c_uint64), ("dindex_mode", C.c_uint32), ("ms_dindex_build", C.c_float),
+                ("index_build_slices", C.c_uint32), ("reserved0", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}

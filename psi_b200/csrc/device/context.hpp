@@ -7,6 +7,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -139,6 +140,17 @@ struct Shared {
   DevBuf<uint64_t> on_kmer;      // distinct on-path (k-mer, locus) pairs, sorted: kept to re-merge when the loci change
   DevBuf<uint32_t> on_gpos;
   uint64_t n_on_pairs = 0, n_off_pairs = 0;
+  // Sliced build (graphs whose distinct pairs outgrow 32-bit counts, index_build.cu): the distinct on-path pairs are
+  // kept per slice of the k-mer space (a k-mer belongs to the slice its first slice_bits / 2 bases spell), each slice
+  // sorted by (k-mer, locus); on_kmer / on_gpos stay empty.  The slices are released once the final table stands.
+  struct PairSlice {
+    DevBuf<uint64_t> kmer;
+    DevBuf<uint32_t> gpos;
+    uint64_t n = 0, n_kmers = 0;
+  };
+  std::vector<std::unique_ptr<PairSlice>> slices;
+  uint32_t slice_bits = 0;
+  bool pairs_released = false;
 
   // ---- gocc threshold (-r): the picked paths stay on the device so that the k-mers' occurrence counts can be taken
   // when the final table is built ----
@@ -263,6 +275,7 @@ struct Ctx {
   DevBuf<char> walk_spill;
 
   // ---- options (psi_b200_set_option) ----
+  int opt_build_slices = 0;                    // set_paths: slices of the k-mer space the index is built in (0 auto, else a power of 4 up to 256)
   uint64_t opt_build_group_windows = 0;        // set_paths: path windows materialised at a time (0: from the free memory, <= 2^30)
   int opt_index_slack = -1;                    // extra doublings of the path index's bucket count (-1 auto: 1 for 16-byte slots)
   int opt_blocking_sync = 0;                   // 1: wait for a chunk on a blocking event (thread sleeps) instead of spinning

@@ -118,6 +118,8 @@ Ctx* engine_fork(Ctx& parent)
   c->opt_resolve_ctas = parent.opt_resolve_ctas;
   c->opt_offpath_max_pairs = parent.opt_offpath_max_pairs;
   c->opt_dindex_mode = parent.opt_dindex_mode;
+  c->opt_build_slices = parent.opt_build_slices;
+  c->counters.index_build_slices = pc.index_build_slices;
   c->opt_dindex_list_cap = parent.opt_dindex_list_cap;
   c->opt_dindex_max_bytes = parent.opt_dindex_max_bytes;
   return c;

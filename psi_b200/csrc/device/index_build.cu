@@ -53,11 +53,20 @@ __device__ __forceinline__ uint32_t path_of_entry(const PathsView& p, uint64_t e
 // MODE 0: emit (k-mer, locus) pairs; 1: count the valid windows; 2: count the windows PER K-MER in a counting table
 // (the k-mer's number of occurrences in the path text, what the reference compares with its gocc threshold,
 // index_iter.hpp:842-848)
+// A slice (sliced builds of very large graphs): only the windows whose FIRST slice_bits / 2 bases spell slice_id are
+// taken; a window whose first bases lie inside its node is rejected before anything else is read.
+struct WindowSlice {
+  uint32_t bits;   // 0: every window
+  uint32_t id;
+  uint64_t cap;    // MODE 0: room in out_kmer / out_gpos (the count goes on beyond it; nothing is written)
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint64_t e_end,
                     uint64_t* __restrict__ out_kmer, uint32_t* __restrict__ out_gpos,
-                    unsigned long long* __restrict__ out_count, KmerTable counts, unsigned long long* __restrict__ err_flag)
+                    unsigned long long* __restrict__ out_count, KmerTable counts, unsigned long long* __restrict__ err_flag,
+                    WindowSlice slice)
 {
   constexpr bool COUNT_ONLY = MODE == 1;
   const uint32_t lane = lane_id();
@@ -78,6 +87,8 @@ path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint
       const uint32_t o = o0 + lane;
       bool ok = o < to;
       uint64_t kmer = 0;
+      if (ok && slice.bits && to - o >= (slice.bits >> 1))
+        ok = (uint32_t)extract_bases(g.seq2, (uint64_t)r.seq_start + o, slice.bits >> 1) == slice.id;
       if (ok) {
         uint32_t depth = 0, off = o;
         uint64_t ce = e;
@@ -100,6 +111,7 @@ path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint
           cto = cr.seq_len;
           if (ce + 1 == pend) cto = tail < cto ? cto - tail : 0;
         }
+        if (ok && slice.bits && (uint32_t)(kmer & ((1ull << slice.bits) - 1ull)) != slice.id) ok = false;
       }
       if (COUNT_ONLY) local_count += ok;
       else if (MODE == 2) {
@@ -107,7 +119,7 @@ path_windows_kernel(GraphView g, PathsView p, uint32_t k, uint64_t e_begin, uint
       }
       else {
         const uint64_t slot = warp_reserve(out_count, ok ? 1u : 0u);
-        if (ok) { out_kmer[slot] = kmer; out_gpos[slot] = r.seq_start + o; }
+        if (ok && slot < slice.cap) { out_kmer[slot] = kmer; out_gpos[slot] = r.seq_start + o; }
       }
     }
   }
@@ -190,7 +202,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 insert_runs_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ key, const uint64_t* __restrict__ val,
                    const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ multi_off,
-                   uint32_t n_runs, uint32_t* __restrict__ multi, unsigned long long* __restrict__ err_flag)
+                   uint32_t n_runs, uint32_t* __restrict__ multi, unsigned long long* __restrict__ err_flag, uint32_t multi_base)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_runs) return;
@@ -205,7 +217,7 @@ insert_runs_kernel(KmerTable t, GraphView g, const uint64_t* __restrict__ key, c
     flags = (v >> 32) ? FLAG_OFF : 0u;
   }
   else {
-    const uint32_t m = multi_off[r];
+    const uint32_t m = multi_base + multi_off[r];
     uint32_t n_on = 0;
     for (uint32_t i = b; i < e; ++i) {
       const uint64_t v = val[i];
@@ -318,12 +330,180 @@ static uint64_t sort_unique_pairs(Ctx& c, DevBuf<uint64_t>& kmer_a, DevBuf<uint3
   return n_unique;
 }
 
+// ------------------------------------------------------------ sliced build --
+//
+// The one-shot build above counts pairs, runs and list words in 32 bits.  A graph with more than ~4 G distinct
+// (k-mer, locus) pairs (BASELINE configs[4]: 3.1 Gbp) is built in slices of the k-mer space instead: a k-mer belongs to
+// the slice its first slice_bits / 2 bases spell, every slice holds its own sorted distinct pairs (Shared::slices) and
+// is run-length grouped and inserted into the ONE table by itself, so that every count is per slice.
+
+template <class T>
+static void grow_preserve(Ctx& c, DevBuf<T>& b, size_t used, size_t want)
+{
+  if (want <= b.cap) return;
+  T* np = nullptr;
+  PSI_CUDA(cudaMalloc((void**)&np, want * sizeof(T)));
+  if (used && b.p) PSI_CUDA(cudaMemcpyAsync(np, b.p, used * sizeof(T), cudaMemcpyDeviceToDevice, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  if (b.p) cudaFree(b.p);
+  b.p = np;
+  b.cap = want;
+}
+
+__global__ void __launch_bounds__(256)
+flag_slice_kernel(const uint64_t* __restrict__ kmer, uint64_t n, uint64_t mask, uint32_t id, uint32_t* __restrict__ flag)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (kmer[i] & mask) == id ? 1u : 0u;
+}
+
+static void empty_table(Ctx& c)
+{
+  Shared& sh = *c.sh;
+  table_alloc(c, sh.index, 1, 2 * c.k, 1024);
+  sh.index.view.stash_nonempty = 0;
+  sh.multi.ensure(4);
+  sh.has_table = true;
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  c.counters.n_index_entries = c.counters.n_index_kmers = 0;
+}
+
+static void build_table_sliced(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gpos, uint64_t n_off)
+{
+  Shared& sh = *c.sh;
+  if (sh.pairs_released)
+    throw StateError("index: the sorted pairs of a sliced build were released when the starting loci were set; call set_paths again");
+  if (sh.gocc_threshold) throw ArgError("index: a gocc threshold is not served by a sliced build (build_slices)");
+  if (n_off >= 0xfffffff0ull) throw ArgError("index: more than 2^32 off-path pairs");
+  const uint32_t n_slices = (uint32_t)sh.slices.size();
+  const uint64_t slice_mask = (1ull << sh.slice_bits) - 1ull;
+  sh.table_filtered = false;
+  sh.has_table = false;
+  sh.n_off_pairs = n_off;
+  unsigned long long* d_err = c.dev_counters.p + DC_ERR;
+  uint64_t runs_bound = n_off;
+  for (auto& sl : sh.slices) runs_bound += sl->n_kmers;
+  if (runs_bound == 0) { empty_table(c); return; }
+  PSI_CUDA(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), c.stream));
+  // locus codes as in build_table; list offsets are taken as 32 bits wide (the lists are not known yet)
+  {
+    auto bits_of = [](uint64_t x) { uint32_t b = 0; while (x) { ++b; x >>= 1; } return b; };
+    const uint32_t off_bits = bits_of(sh.max_node_len ? sh.max_node_len - 1 : 0);
+    const uint32_t id_bits = bits_of(sh.max_node_id), rank_bits = bits_of(sh.n_nodes ? sh.n_nodes - 1 : 0);
+    const uint32_t list_bits = 32;
+    const uint32_t cap8 = table_fmt8_payload_bits(runs_bound, 2 * c.k, c.opt_index_slack);
+    uint32_t need;
+    sh.code_off_bits = off_bits;
+    if (std::max(id_bits + off_bits, list_bits) <= cap8) { sh.code_by_rank = false; need = id_bits + off_bits; }
+    else if (std::max(rank_bits + off_bits, list_bits) <= cap8) { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    else if (id_bits + off_bits <= 62) { sh.code_by_rank = false; need = id_bits + off_bits; }
+    else { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    if (c.opt_code_by_rank) { sh.code_by_rank = true; need = rank_bits + off_bits; }
+    need = std::max(need, list_bits);
+    if (need > 62) throw ArgError("index: node labels too long for the locus codes");
+    table_alloc(c, sh.index, runs_bound, 2 * c.k, runs_bound / 512 + 1024, c.opt_index_slack, need);
+  }
+  const GraphView g = make_graph_view(c);   // after the code layout has been chosen
+  if (sh.multi.cap < (1u << 20)) sh.multi.ensure(1u << 20);
+  uint64_t multi_used = 0, n_total = 0, n_runs_total = 0;
+  DevBuf<uint32_t> oflag, oscan, offs_g;
+  DevBuf<uint64_t> offs_k;
+  if (n_off) { oflag.ensure(n_off + 1); oscan.ensure(n_off + 1); }
+  for (uint32_t si = 0; si < n_slices; ++si) {
+    const Shared::PairSlice& sl = *sh.slices[si];
+    uint32_t n_off_s = 0;
+    if (n_off) {   // the off-path pairs of this slice (the input is sorted, so is the selection)
+      flag_slice_kernel<<<grid_for(n_off, 256), 256, 0, c.stream>>>(off_kmer, n_off, slice_mask, si, oflag.p);
+      PSI_CUDA(cudaMemsetAsync(oflag.p + n_off, 0, sizeof(uint32_t), c.stream));
+      exclusive_scan_u32(c, oflag.p, oscan.p, n_off + 1);
+      PSI_CUDA(cudaMemcpyAsync(&n_off_s, oscan.p + n_off, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      if (n_off_s) {
+        offs_k.ensure(n_off_s); offs_g.ensure(n_off_s);
+        compact_pairs_kernel<<<grid_for(n_off, 256), 256, 0, c.stream>>>(off_kmer, off_gpos, oflag.p, oscan.p, n_off, offs_k.p, offs_g.p);
+      }
+      c.counters.launches += 2;
+    }
+    const uint64_t n = sl.n + n_off_s;
+    if (n == 0) continue;
+    if (n >= 0xfffffff0ull) throw ArgError("index: more than 2^32 pairs in one slice (raise build_slices)");
+    DevBuf<uint64_t> key_a, val_a, key_b, val_b;
+    key_a.ensure(n); val_a.ensure(n);
+    concat_pairs_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(sl.kmer.p, sl.gpos.p, sl.n, offs_k.p, offs_g.p, n_off_s, key_a.p, val_a.p);
+    ++c.counters.launches;
+    uint64_t* key = key_a.p;
+    uint64_t* val = val_a.p;
+    if (n_off_s && sl.n) {
+      key_b.ensure(n); val_b.ensure(n);
+      size_t tmp_bytes = 0;
+      PSI_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_a.p, key_b.p, val_a.p, val_b.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+      DevBuf<char> tmp;
+      tmp.ensure(tmp_bytes);
+      PSI_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key_a.p, key_b.p, val_a.p, val_b.p, (int64_t)n, 0, (int)(2 * c.k), c.stream));
+      c.counters.launches += 6;
+      PSI_CUDA(cudaStreamSynchronize(c.stream));
+      key = key_b.p;
+      val = val_b.p;
+    }
+    DevBuf<uint32_t> flag, scan;
+    flag.ensure(n + 1); scan.ensure(n + 1);
+    flag_run_heads_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(key, n, flag.p);
+    ++c.counters.launches;
+    PSI_CUDA(cudaMemsetAsync(flag.p + n, 0, sizeof(uint32_t), c.stream));
+    exclusive_scan_u32(c, flag.p, scan.p, n + 1);
+    uint32_t n_runs = 0;
+    PSI_CUDA(cudaMemcpyAsync(&n_runs, scan.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    DevBuf<uint32_t> run_start, words, multi_off;
+    run_start.ensure((uint64_t)n_runs + 2); words.ensure((uint64_t)n_runs + 2); multi_off.ensure((uint64_t)n_runs + 2);
+    scatter_run_starts_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(flag.p, scan.p, n, n_runs, run_start.p);
+    run_multi_words_kernel<<<grid_for(n_runs, 256), 256, 0, c.stream>>>(run_start.p, n_runs, words.p);
+    c.counters.launches += 2;
+    PSI_CUDA(cudaMemsetAsync(words.p + n_runs, 0, sizeof(uint32_t), c.stream));
+    exclusive_scan_u32(c, words.p, multi_off.p, (uint64_t)n_runs + 1);
+    uint32_t multi_words = 0;
+    PSI_CUDA(cudaMemcpyAsync(&multi_words, multi_off.p + n_runs, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    PSI_CUDA(cudaStreamSynchronize(c.stream));
+    if (multi_used + multi_words + 4 >= 0xfffffff0ull) throw ArgError("index: locus lists beyond 2^32 words");
+    if (multi_used + multi_words + 4 > sh.multi.cap)
+      grow_preserve(c, sh.multi, multi_used, std::max<uint64_t>(2 * sh.multi.cap, multi_used + multi_words + 4));
+    if (sh.index.view.fmt == 8)
+      insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err,
+                                                                        (uint32_t)multi_used);
+    else
+      insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err,
+                                                                         (uint32_t)multi_used);
+    ++c.counters.launches;
+    PSI_CUDA(cudaGetLastError());
+    PSI_CUDA(cudaStreamSynchronize(c.stream));     // the slice's temporaries die here
+    multi_used += multi_words;
+    n_total += n;
+    n_runs_total += n_runs;
+  }
+  unsigned long long err = 0;
+  uint32_t stash_used = 0;
+  PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaMemcpyAsync(&stash_used, sh.index.stash_used.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  if (err & 2ull) throw OverflowError("path index: hash stash exhausted");
+  sh.index.view.stash_nonempty = stash_used ? 1u : 0u;
+  sh.has_table = true;
+  c.counters.n_index_entries = n_total;
+  c.counters.n_index_kmers = n_runs_total;
+  c.counters.n_offpath_entries = n_off;
+  c.counters.index_buckets = sh.index.n_lines;
+  c.counters.index_bytes = sh.index.n_lines * 128 + (multi_used + 4) * 4 + ((uint64_t)sh.index.view.stash_mask + 1) * sizeof(Slot16);
+  c.counters.index_slot_bytes = sh.index.view.fmt;
+  c.counters.index_stash_used = stash_used;
+}
+
 // (Re)build the device index from the resident on-path pairs plus `n_off` off-path pairs
 // (both sorted by (kmer, gpos) and duplicate free).  final: the starting loci are known and this is the table the
 // chunks will probe -- the gocc threshold, if one is set, is applied here (never to the table the loci are derived from).
 static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gpos, uint64_t n_off, bool final = false)
 {
   Shared& sh = *c.sh;
+  if (!sh.slices.empty() || sh.pairs_released) { build_table_sliced(c, off_kmer, off_gpos, n_off); return; }
   const uint64_t n_on = sh.n_on_pairs;
   uint64_t n = n_on + n_off;
   sh.table_filtered = false;
@@ -373,7 +553,7 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
       PathsView pv{ sh.path_ptr.p, sh.path_nodes.p, sh.path_head.p, sh.path_tail.p, (uint32_t)sh.n_paths };
       const uint64_t n_entries = sh.n_path_entries;
       const unsigned wgrid = (unsigned)std::min<uint64_t>((n_entries + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
-      path_windows_kernel<2><<<wgrid, 256, 0, c.stream>>>(g0, pv, c.k, 0, n_entries, nullptr, nullptr, nullptr, counts.view, d_err);
+      path_windows_kernel<2><<<wgrid, 256, 0, c.stream>>>(g0, pv, c.k, 0, n_entries, nullptr, nullptr, nullptr, counts.view, d_err, WindowSlice{ 0, 0, 0 });
       ++c.counters.launches;
       unsigned long long err = 0;
       PSI_CUDA(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
@@ -459,9 +639,9 @@ static void build_table(Ctx& c, const uint64_t* off_kmer, const uint32_t* off_gp
   }
   const GraphView g = make_graph_view(c);   // after the code layout has been chosen
   if (sh.index.view.fmt == 8)
-    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+    insert_runs_kernel<8><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err, 0u);
   else
-    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err);
+    insert_runs_kernel<16><<<grid_for(n_runs, 256), 256, 0, c.stream>>>(sh.index.view, g, key, val, run_start.p, multi_off.p, n_runs, sh.multi.p, d_err, 0u);
   ++c.counters.launches;
   PSI_CUDA(cudaGetLastError());
   unsigned long long err = 0;
@@ -493,6 +673,9 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
   sh.has_table = false;
   sh.offpath_indexed = false;
   sh.n_on_pairs = sh.n_off_pairs = 0;
+  sh.slices.clear();
+  sh.slice_bits = 0;
+  sh.pairs_released = false;
   c.counters.n_path_bases = c.counters.n_index_entries = c.counters.n_index_kmers = c.counters.n_offpath_entries = 0;
   c.counters.index_bytes = c.counters.index_buckets = 0;
   c.counters.ms_index_build = 0;
@@ -560,6 +743,97 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
     sh.paths_kept = true;
   }
   uint64_t n_windows_total = 0;
+  sh.slices.clear();
+  sh.slice_bits = 0;
+  sh.pairs_released = false;
+  c.counters.index_build_slices = 1;
+  // one-shot or sliced?  The bases of the paths bound their k-windows, twice the graph's bases is a generous estimate of
+  // the distinct (k-mer, locus) pairs among them.
+  std::vector<uint64_t> path_bases(n_paths, 0);
+  uint64_t bases_total = 0;
+  for (uint64_t p = 0; p < n_paths; ++p) {
+    uint64_t b = 0;
+    for (uint64_t e = path_ptr[p]; e < path_ptr[p + 1]; ++e) b += h_rec[path_nodes[e]].seq_len;
+    path_bases[p] = b;
+    bases_total += b;
+  }
+  uint32_t n_slices = 1;
+  if (c.opt_build_slices > 0) n_slices = (uint32_t)c.opt_build_slices;
+  else {
+    const uint64_t est = std::min<uint64_t>(bases_total, 2 * sh.n_bases);
+    if (est > (3ull << 30)) { n_slices = 4; while (n_slices < 256 && est / n_slices > (1ull << 29)) n_slices *= 4; }
+  }
+  if (n_slices > 1) {
+    if (sh.gocc_threshold) throw ArgError("set_paths: a gocc threshold is not served by a sliced index build (build_slices)");
+    uint32_t sb = 0;
+    while ((1u << sb) < n_slices) sb += 2;     // whole bases: n_slices is a power of 4
+    if (sb > 2 * c.k) throw ArgError("set_paths: more build slices than k-mers");
+    sh.slice_bits = sb;
+    c.counters.index_build_slices = n_slices;
+    const uint64_t group_bases = std::max<uint64_t>(budget, 1u << 20) * n_slices / 2;
+    uint64_t n_on_total = 0;
+    for (uint32_t si = 0; si < n_slices; ++si) {
+      auto sl = std::make_unique<Shared::PairSlice>();
+      uint64_t n_acc = 0;
+      for (uint64_t g0 = 0; g0 < n_paths;) {
+        uint64_t g1 = g0, bases = 0;
+        while (g1 < n_paths) {
+          if (g1 > g0 && bases + path_bases[g1] > group_bases) break;
+          bases += path_bases[g1];
+          ++g1;
+        }
+        const uint64_t e0 = path_ptr[g0], e1 = path_ptr[g1];
+        g0 = g1;
+        if (e1 == e0) continue;
+        const unsigned wgrid = (unsigned)std::min<uint64_t>((e1 - e0 + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
+        // no counting pass: the slice's share of the group is guessed and the group redone if it holds more
+        uint64_t cap = bases / n_slices + bases / (4ull * n_slices) + (1u << 16);
+        unsigned long long n_pairs = 0;
+        DevBuf<uint64_t> kmer_a;
+        DevBuf<uint32_t> gpos_a;
+        for (;;) {
+          if (cap + n_acc >= 0xfffffff0ull) throw ArgError("set_paths: more than 2^32 path windows in one slice of one group (raise build_slices)");
+          kmer_a.ensure(cap + n_acc); gpos_a.ensure(cap + n_acc);
+          PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+          path_windows_kernel<0><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt, KmerTable{}, nullptr,
+                                                             WindowSlice{ sb, si, cap });
+          ++c.counters.launches;
+          PSI_CUDA(cudaGetLastError());
+          PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
+          PSI_CUDA(cudaStreamSynchronize(c.stream));
+          if (n_pairs <= cap) break;
+          cap = n_pairs;        // the kernel counted on beyond the capacity: exact now
+        }
+        n_windows_total += n_pairs;
+        if (n_pairs == 0) continue;
+        if (n_acc) {
+          PSI_CUDA(cudaMemcpyAsync(kmer_a.p + n_pairs, sl->kmer.p, n_acc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c.stream));
+          PSI_CUDA(cudaMemcpyAsync(gpos_a.p + n_pairs, sl->gpos.p, n_acc * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+          PSI_CUDA(cudaStreamSynchronize(c.stream));
+          sl->kmer.release(); sl->gpos.release();
+        }
+        n_acc = sort_unique_pairs(c, kmer_a, gpos_a, n_pairs + n_acc, sl->kmer, sl->gpos);
+      }
+      sl->n = n_acc;
+      if (n_acc) {   // distinct k-mers of the slice: sizes the table before the slices are grouped into runs
+        DevBuf<uint32_t> flag, scan;
+        flag.ensure(n_acc + 1); scan.ensure(n_acc + 1);
+        flag_run_heads_kernel<<<grid_for(n_acc, 256), 256, 0, c.stream>>>(sl->kmer.p, n_acc, flag.p);
+        ++c.counters.launches;
+        PSI_CUDA(cudaMemsetAsync(flag.p + n_acc, 0, sizeof(uint32_t), c.stream));
+        exclusive_scan_u32(c, flag.p, scan.p, n_acc + 1);
+        uint32_t n_k = 0;
+        PSI_CUDA(cudaMemcpyAsync(&n_k, scan.p + n_acc, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+        PSI_CUDA(cudaStreamSynchronize(c.stream));
+        sl->n_kmers = n_k;
+      }
+      n_on_total += n_acc;
+      sh.slices.push_back(std::move(sl));
+    }
+    sh.n_on_pairs = n_on_total;
+    d_nodes.release(); d_path_ptr.release(); d_head.release(); d_tail.release();   // room for the table
+  }
+  else
   for (uint64_t g0 = 0; g0 < n_paths;) {
     uint64_t g1 = g0, bases = 0;
     while (g1 < n_paths) {
@@ -575,7 +849,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
     // pass 1: count valid windows
     const unsigned wgrid = (unsigned)std::min<uint64_t>((e1 - e0 + 7) / 8 + 1, (uint64_t)c.sm_count * 32);
     PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-    path_windows_kernel<1><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, nullptr, nullptr, d_cnt, KmerTable{}, nullptr);
+    path_windows_kernel<1><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, nullptr, nullptr, d_cnt, KmerTable{}, nullptr, WindowSlice{ 0, 0, 0 });
     ++c.counters.launches;
     unsigned long long n_pairs = 0;
     PSI_CUDA(cudaMemcpyAsync(&n_pairs, d_cnt, sizeof(n_pairs), cudaMemcpyDeviceToHost, c.stream));
@@ -589,7 +863,7 @@ void engine_build_index(Ctx& c, uint64_t n_paths, const uint64_t* path_ptr, cons
     DevBuf<uint32_t> gpos_a;
     kmer_a.ensure(n_pairs + n_acc); gpos_a.ensure(n_pairs + n_acc);
     PSI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
-    path_windows_kernel<0><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt, KmerTable{}, nullptr);
+    path_windows_kernel<0><<<wgrid, 256, 0, c.stream>>>(g, pv, c.k, e0, e1, kmer_a.p, gpos_a.p, d_cnt, KmerTable{}, nullptr, WindowSlice{ 0, 0, n_pairs });
     ++c.counters.launches;
     if (n_acc) {
       PSI_CUDA(cudaMemcpyAsync(kmer_a.p + n_pairs, sh.on_kmer.p, n_acc * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c.stream));
@@ -787,6 +1061,16 @@ static void materialise_offpath(Ctx& c)
   c.counters.offpath_mode = 2;
 }
 
+// A large sliced build gives its sorted pairs back once the table that the chunks will probe stands (12 bytes per pair:
+// 60 GB at whole-genome scale); changing the loci afterwards needs set_paths again.
+static void release_sliced_pairs(Ctx& c)
+{
+  Shared& sh = *c.sh;
+  if (sh.slices.empty() || sh.n_on_pairs < (1ull << 31)) return;
+  sh.slices.clear();
+  sh.pairs_released = true;
+}
+
 void engine_find_loci(Ctx& c, unsigned step)
 {
   if (!c.sh->has_graph) throw StateError("find_loci: no graph");
@@ -835,6 +1119,7 @@ void engine_find_loci(Ctx& c, unsigned step)
   c.sh->n_loci = n_loci;
   c.counters.n_loci = n_loci;
   materialise_offpath(c);
+  release_sliced_pairs(c);
   timer.stop();
   PSI_CUDA(cudaStreamSynchronize(c.stream));
   c.counters.ms_find_loci = timer.ms();
@@ -856,6 +1141,7 @@ void engine_set_loci(Ctx& c, uint64_t n, const uint32_t* node, const uint32_t* o
   c.sh->n_loci = n;
   c.counters.n_loci = n;
   materialise_offpath(c);
+  release_sliced_pairs(c);
 }
 
 void engine_set_option(Ctx& c, const char* name, long long value)
@@ -881,6 +1167,11 @@ void engine_set_option(Ctx& c, const char* name, long long value)
   else if (n == "dindex_max_bytes") {
     if (value < 0) throw ArgError("set_option: dindex_max_bytes must be >= 0 (0 = half of the free device memory)");
     c.opt_dindex_max_bytes = (uint64_t)value;
+  }
+  else if (n == "build_slices") {
+    if (value != 0 && value != 1 && value != 4 && value != 16 && value != 64 && value != 256)
+      throw ArgError("set_option: build_slices is 0 (auto), 1, 4, 16, 64 or 256");
+    c.opt_build_slices = (int)value;     // takes effect at the next set_paths
   }
   else if (n == "build_group_windows") {
     if (value < 0) throw ArgError("set_option: build_group_windows must be >= 0 (0 = from the free device memory)");

@@ -438,6 +438,67 @@ def test_index_built_in_groups_of_paths_is_the_same_index(name):
     assert out[0] == out[1]
 
 
+@pytest.mark.parametrize("slices", [4, 16, 64])
+@pytest.mark.parametrize("name", ["x_k12", "x_k20_d1", "m_k20", "multi_k32", "fuzz_02", "fuzz_08"])
+def test_index_built_in_slices_of_the_kmer_space_is_the_same_index(name, slices):
+    """The sliced build (set_option build_slices; automatic for graphs with more than ~3 G distinct pairs, BASELINE
+    configs[4]) enumerates the path windows once per slice of the k-mer space, keeps the distinct pairs per slice and
+    inserts slice by slice: same entries, k-mers, starting loci and seed sets (all phases, records and dense results,
+    walk mode too) as the one-shot build -- also with groups of paths inside every slice, and after the loci are
+    replaced."""
+    c = CASES[name]
+    g, rp, bases = load_case(c)
+    ps = g.pick_paths(max(c["n_paths"], 6), seed=2)
+    out = []
+    for n_sl, budget in ((1, 0), (slices, 0), (slices, 3000)):
+        ctx = capi.Context(c["k"], 0)
+        ctx.set_option("build_slices", n_sl)
+        ctx.set_option("build_group_windows", budget)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(ps)
+        n_loci = ctx.find_loci()
+        cn = ctx.counters()
+        assert cn["index_build_slices"] == n_sl
+        rec, total = run_chunks(ctx, rp, bases, c["d"], 0)
+        on, _ = run_chunks(ctx, rp, bases, c["d"], 0, capi.ON_PATHS)
+        off, _ = run_chunks(ctx, rp, bases, c["d"], 0, capi.OFF_PATHS)
+        ctx.submit_chunk(rp, bases, 0, c["d"])
+        ctx.seeds_all(capi.ALL | capi.DENSE)
+        dense, extra = ctx.fetch_dense()
+        drec, _ = capi.dense_to_records(dense, extra, rp, c["k"], c["d"] or c["k"])
+        # the loci may be set again (the pairs of a small sliced build are kept): same table
+        node, off_ = ctx.get_loci()
+        ctx.set_loci(node, off_)
+        rec2, _ = run_chunks(ctx, rp, bases, c["d"], 0)
+        out.append((cn["n_path_bases"], cn["n_index_entries"], cn["n_index_kmers"], cn["n_offpath_entries"], n_loci,
+                    util.md5_tuples(capi.canonical(rec)), util.md5_tuples(capi.canonical(on)), util.md5_tuples(capi.canonical(off)),
+                    util.md5_tuples(capi.canonical(drec)), util.md5_tuples(capi.canonical(rec2))))
+        assert out[-1][5] == c["md5"] == out[-1][8] == out[-1][9]
+        ctx.close()
+    assert out[0] == out[1] == out[2]
+    # walk mode over a sliced on-path table
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_option("build_slices", slices)
+    ctx.set_option("offpath_mode", 1)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_paths(ps)
+    ctx.find_loci()
+    rec, _ = run_chunks(ctx, rp, bases, c["d"], 0)
+    assert util.md5_tuples(capi.canonical(rec)) == c["md5"]
+    # a gocc threshold is refused by a sliced build, loudly
+    ctx2 = capi.Context(c["k"], 0)
+    ctx2.set_option("build_slices", slices)
+    ctx2.set_option("gocc_threshold", 3)
+    ctx2.set_graph(g, ids="coord")
+    with pytest.raises(capi.PsiError) as e:
+        ctx2.set_paths(ps)
+    assert e.value.code == capi.ERR_ARG
+    with pytest.raises(capi.PsiError):
+        ctx2.set_option("build_slices", 3)
+    ctx2.close()
+    ctx.close()
+
+
 def test_offpath_budget_falls_back_to_walking():
     """auto mode materialises only when the walks fit the budget; the seed set does not depend on the mode."""
     c = CASES["m_k20"]
