@@ -207,11 +207,17 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _bytes(ptr, n):
+    """n bytes at a char pointer as a numpy copy (any size: ctypes.string_at stops at 2 GiB)."""
+    if n == 0:
+        return np.zeros(0, np.uint8)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(int(n),)).copy()
+
+
 def _np(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype) if dtype != np.uint8 else \
-        np.frombuffer(C.string_at(ptr, n), dtype=np.uint8)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype) if dtype != np.uint8 else _bytes(ptr, n)
 
 
 class Graph:
@@ -227,7 +233,7 @@ class Graph:
         self.row_ptr = np.ctypeslib.as_array(v.row_ptr, shape=(n + 1,)).copy()
         self.col = np.ctypeslib.as_array(v.col, shape=(max(v.n_edges, 1),))[: v.n_edges].copy() \
             if v.n_edges else np.zeros(0, np.uint32)
-        self.seq = np.frombuffer(C.string_at(v.seq, v.n_bases), dtype=np.uint8).copy()
+        self.seq = _bytes(v.seq, v.n_bases)
         self.internal_id = np.ctypeslib.as_array(v.internal_id, shape=(n,)).copy()
         self.coord_id = np.ctypeslib.as_array(v.coord_id, shape=(n,)).copy()
 
@@ -324,7 +330,7 @@ class Reader:
             return None
         n = v.n_reads
         read_ptr = np.ctypeslib.as_array(v.read_ptr, shape=(n + 1,)).copy()
-        bases = np.frombuffer(C.string_at(v.bases, int(read_ptr[-1])), dtype=np.uint8).copy()
+        bases = _bytes(v.bases, int(read_ptr[-1]))
         name_ptr = np.ctypeslib.as_array(v.name_ptr, shape=(n + 1,)).copy()
         names_raw = C.string_at(v.names, int(name_ptr[-1]))
         names = [names_raw[name_ptr[i]:name_ptr[i + 1]].decode() for i in range(n)]

@@ -3,7 +3,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <stdexcept>
+#include <thread>
 
 #ifndef PSI_B200_HOST_ONLY
 #include <cuda_runtime_api.h>
@@ -68,7 +70,7 @@ ChunkReader::ChunkReader(const std::string& path)
   gz_ = gzopen(path.c_str(), "rb");
   if (!gz_) throw std::runtime_error("could not open file '" + path + "'!");
   gzbuffer((gzFile)gz_, 1 << 20);
-  buf_.resize(1 << 20);
+  buf_.resize(4u << 20);
 }
 
 ChunkReader::~ChunkReader()
@@ -76,36 +78,29 @@ ChunkReader::~ChunkReader()
   if (gz_) gzclose((gzFile)gz_);
 }
 
-bool ChunkReader::fill()
+// The next line without consuming it.  Lines are views into buf_: nothing is copied; when a line straddles the end of
+// the buffered data the unread tail moves to the front and the buffer is refilled (and grown for very long lines).
+bool ChunkReader::peek(LineView& lv)
 {
-  if (eof_) return false;
-  int n = gzread((gzFile)gz_, buf_.data(), (unsigned)buf_.size());
-  if (n < 0) throw std::runtime_error("read error in sequence file");
-  buf_pos_ = 0;
-  buf_len_ = (size_t)n;
-  if (n == 0) { eof_ = true; return false; }
-  return true;
-}
-
-bool ChunkReader::getline(std::string& out)
-{
-  out.clear();
-  bool got = false;
-  while (true) {
-    if (buf_pos_ == buf_len_ && !fill()) break;
-    got = true;
+  for (;;) {
     const char* b = buf_.data() + buf_pos_;
-    const char* nl = (const char*)std::memchr(b, '\n', buf_len_ - buf_pos_);
-    if (nl) {
-      out.append(b, nl - b);
-      buf_pos_ += (size_t)(nl - b) + 1;
+    const size_t avail = buf_len_ - buf_pos_;
+    const char* nl = avail ? (const char*)std::memchr(b, '\n', avail) : nullptr;
+    if (nl) { lv.p = b; lv.n = (size_t)(nl - b); line_adv_ = lv.n + 1; break; }
+    if (eof_) {
+      if (!avail) return false;
+      lv.p = b; lv.n = avail; line_adv_ = avail;     // last line without a newline
       break;
     }
-    out.append(b, buf_len_ - buf_pos_);
-    buf_pos_ = buf_len_;
+    if (buf_pos_) { std::memmove(buf_.data(), b, avail); buf_pos_ = 0; buf_len_ = avail; }
+    if (buf_len_ == buf_.size()) buf_.resize(buf_.size() * 2);
+    const int n = gzread((gzFile)gz_, buf_.data() + buf_len_, (unsigned)std::min<size_t>(buf_.size() - buf_len_, 1u << 30));
+    if (n < 0) throw std::runtime_error("read error in sequence file");
+    if (n == 0) eof_ = true;
+    buf_len_ += (size_t)n;
   }
-  if (!out.empty() && out.back() == '\r') out.pop_back();
-  return got;
+  if (lv.n && lv.p[lv.n - 1] == '\r') --lv.n;
+  return true;
 }
 
 // ------------------------------------------------------------ packing --
@@ -129,9 +124,9 @@ inline uint64_t pack8(uint64_t c, uint64_t& bad)
 }
 
 template <class Sink>
-uint64_t pack_bases_impl(const char* bases, uint64_t n_bases, uint64_t* words, Sink&& on_exception)
+uint64_t pack_bases_impl(const char* bases, uint64_t n_bases, uint64_t* words, Sink&& on_exception, uint64_t n_words = ~0ull)
 {
-  const uint64_t n_words = n_bases / 32 + 2;
+  if (n_words == ~0ull) n_words = n_bases / 32 + 2;
   uint64_t n_bad = 0, i = 0;
   for (uint64_t w = 0; w < n_words; ++w) {
     uint64_t word = 0;
@@ -174,6 +169,29 @@ uint64_t pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, std::v
   return pack_bases_impl(bases, n_bases, words, [&](uint64_t p) { exc.push_back(p); });
 }
 
+uint64_t pack_bases_parallel(const char* bases, uint64_t n_bases, uint64_t* words, std::vector<uint64_t>& exc, unsigned max_threads)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  unsigned T = std::min(max_threads, hw ? hw : 1u);
+  const uint64_t per = ((n_bases / std::max(T, 1u)) / 32) * 32;      // whole words per thread
+  if (T < 2 || per < (1u << 20)) return pack_bases(bases, n_bases, words, exc);
+  std::vector<std::vector<uint64_t>> local(T);
+  std::vector<uint64_t> bad(T, 0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      const uint64_t lo = (uint64_t)t * per;
+      const bool last = t + 1 == T;
+      const uint64_t n = last ? n_bases - lo : per;
+      bad[t] = pack_bases_impl(bases + lo, n, words + lo / 32, [&](uint64_t p) { local[t].push_back(lo + p); },
+                               last ? n / 32 + 2 : per / 32);
+    });
+  for (auto& x : th) x.join();
+  uint64_t n_bad = 0;
+  for (unsigned t = 0; t < T; ++t) { n_bad += bad[t]; exc.insert(exc.end(), local[t].begin(), local[t].end()); }
+  return n_bad;
+}
+
 uint64_t ChunkReader::next(uint64_t max_reads, bool packed)
 {
   cur_ ^= 1;            // the previous chunk's buffers stay untouched: its upload may still be in flight
@@ -186,40 +204,42 @@ uint64_t ChunkReader::next(uint64_t max_reads, bool packed)
   s.name_ptr.assign(1, 0);
   staging_.clear();
   first_id_ = consumed_;  // sequence.hpp:1616
-  std::string line, seq, tmp;
   uint64_t n = 0, total = 0;
   bool uniform = true;
   uint64_t len0 = 0;
+  LineView h, t;
   while (max_reads == 0 || n < max_reads) {
-    if (has_pending_) { line.swap(pending_); has_pending_ = false; }
-    else {
-      bool ok;
-      do { ok = getline(line); } while (ok && line.empty());
-      if (!ok) break;
+    bool have = false;
+    while (peek(h)) {                       // blank lines between records are skipped
+      if (h.n) { have = true; break; }
+      consume();
     }
-    if (line[0] != '@' && line[0] != '>') throw std::runtime_error("malformed sequence record");
-    const bool fastq = line[0] == '@';
+    if (!have) break;
+    if (h.p[0] != '@' && h.p[0] != '>') throw std::runtime_error("malformed sequence record");
+    const bool fastq = h.p[0] == '@';
     // name = header up to the first white space (kseq semantics)
     size_t e = 1;
-    while (e < line.size() && line[e] != ' ' && line[e] != '\t') ++e;
-    s.names.append(line, 1, e - 1);
+    while (e < h.n && h.p[e] != ' ' && h.p[e] != '\t') ++e;
+    s.names.append(h.p + 1, e - 1);
     s.name_ptr.push_back(s.names.size());
-    seq.clear();
-    while (getline(tmp)) {
-      if (fastq && !tmp.empty() && tmp[0] == '+') break;
-      if (!fastq && !tmp.empty() && (tmp[0] == '>' || tmp[0] == '@')) { pending_.swap(tmp); has_pending_ = true; break; }
-      seq += tmp;
+    consume();
+    uint64_t seq_len = 0;
+    while (peek(t)) {
+      if (fastq && t.n && t.p[0] == '+') { consume(); break; }
+      if (!fastq && t.n && (t.p[0] == '>' || t.p[0] == '@')) break;       // the next record's header stays unread
+      if (packed) staging_.insert(staging_.end(), t.p, t.p + t.n);
+      else s.bases.append(t.p, t.n);
+      seq_len += t.n;
+      consume();
     }
     if (fastq) {
-      size_t q = 0;
-      while (q < seq.size() && getline(tmp)) q += tmp.size();
+      uint64_t q = 0;
+      while (q < seq_len && peek(t)) { q += t.n; consume(); }
     }
-    if (packed) staging_.insert(staging_.end(), seq.begin(), seq.end());
-    else s.bases.append(seq.data(), seq.size());
-    total += seq.size();
+    total += seq_len;
     s.read_ptr.push_back(total);
-    if (n == 0) len0 = seq.size();
-    else if (seq.size() != len0) uniform = false;
+    if (n == 0) len0 = seq_len;
+    else if (seq_len != len0) uniform = false;
     ++n;
   }
   uniform_len_ = (n && uniform && len0 && len0 <= 0xffffffffull) ? (uint32_t)len0 : 0u;
@@ -227,7 +247,7 @@ uint64_t ChunkReader::next(uint64_t max_reads, bool packed)
     const uint64_t n_words = total / 32 + 2;
     s.words.reserve(n_words * sizeof(uint64_t));
     s.words.resize(n_words * sizeof(uint64_t));
-    pack_bases(staging_.data(), total, reinterpret_cast<uint64_t*>(s.words.data()), s.exc);
+    pack_bases_parallel(staging_.data(), total, reinterpret_cast<uint64_t*>(s.words.data()), s.exc);
   }
   consumed_ += n;
   return n;

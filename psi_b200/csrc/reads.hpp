@@ -40,6 +40,8 @@ class HostBuffer {
 // plain array; the vector form stores all).
 uint64_t pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, uint64_t* exc, uint64_t exc_cap);
 uint64_t pack_bases(const char* bases, uint64_t n_bases, uint64_t* words, std::vector<uint64_t>& exc);
+// the same over several host threads (large chunks; the words and the exception list are identical)
+uint64_t pack_bases_parallel(const char* bases, uint64_t n_bases, uint64_t* words, std::vector<uint64_t>& exc, unsigned max_threads = 8);
 
 class ChunkReader {
  public:
@@ -71,14 +73,14 @@ class ChunkReader {
   };
   Set& set() { return sets_[cur_]; }
   const Set& set() const { return sets_[cur_]; }
-  bool fill();
-  bool getline(std::string& out);
+  // the next line of the input as a view into the read buffer (no copy; valid until the next peek after a consume)
+  struct LineView { const char* p; size_t n; };
+  bool peek(LineView& lv);
+  void consume() { buf_pos_ += line_adv_; line_adv_ = 0; }
   void* gz_ = nullptr;
   std::vector<char> buf_;
-  size_t buf_pos_ = 0, buf_len_ = 0;
+  size_t buf_pos_ = 0, buf_len_ = 0, line_adv_ = 0;
   bool eof_ = false;
-  std::string pending_;  // header line read ahead (FASTA multi-line)
-  bool has_pending_ = false;
   uint64_t consumed_ = 0, first_id_ = 0;
   uint32_t uniform_len_ = 0;
   Set sets_[2];

@@ -12,6 +12,7 @@
 //   - graphs are read from GFA (1 or 2); vg protobuf input is not part of this build;
 //   - all per-chunk times are device times of the CUDA kernels.
 #include <csignal>
+#include <future>
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
@@ -111,11 +112,11 @@ static void find_seeds(TGraph& graph, SeqStreamIn& reads_iss, std::FILE* output_
     log->info("Finding seeds...");
     [[maybe_unused]] auto timer = timer_type("seed-finding");
     auto load = [&](int slot) {
-      log->info("Loading a read chunk...");
       [[maybe_unused]] auto timer = timer_type("load-chunk");
       return readRecords(chunks[slot], reads_iss, params.chunk_size);
     };
     int cur = 0;
+    log->info("Loading a read chunk...");
     bool have = load(cur);
     while (have) {
       auto& chunk = chunks[cur];
@@ -125,18 +126,25 @@ static void find_seeds(TGraph& graph, SeqStreamIn& reads_iss, std::FILE* output_
       log->info("Seeding done in {}.", stats.get_timer("seeding", tid).str());
       log->info("Finding all seeds...");
       finder.seeds_all_begin(seeds, seeds_index);
-      const bool have_next = load(cur ^ 1);
+      // the next chunk is parsed and packed by a second host thread while this one waits for the GPU, expands the
+      // records and writes them (the stream's two buffer sets alternate, so the chunk in flight is not touched)
+      log->info("Loading a read chunk...");
+      auto next_chunk = std::async(std::launch::async, load, cur ^ 1);
       covered.assign(chunk.size(), false);
       const uint64_t first = chunk.rec_offset;
-      finder.seeds_all_wait_records([&](const uint64_t* rec, uint64_t n) {
-        found += n;
-        static_assert(sizeof(std::size_t) == sizeof(uint64_t), "the output format is 4 x size_t");
-        if (n && std::fwrite(rec, 32, n, output_file) != n) throw std::runtime_error("could not write to the output file");
-        for (uint64_t i = 0; i < n; ++i) {
-          const uint64_t r = rec[4 * i + 2] - first;
-          if (!covered[r]) { covered[r] = true; ++covered_reads; }
-        }
-      });
+      try {
+        finder.seeds_all_wait_records([&](const uint64_t* rec, uint64_t n) {
+          found += n;
+          static_assert(sizeof(std::size_t) == sizeof(uint64_t), "the output format is 4 x size_t");
+          if (n && std::fwrite(rec, 32, n, output_file) != n) throw std::runtime_error("could not write to the output file");
+          for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t r = rec[4 * i + 2] - first;
+            if (!covered[r]) { covered[r] = true; ++covered_reads; }
+          }
+        });
+      }
+      catch (...) { next_chunk.wait(); throw; }
+      const bool have_next = next_chunk.get();
       log->info("Found seeds on paths in {}.", stats.get_timer("seeds-on-paths", tid).str());
       log->info("Found seeds off paths in {}.", stats.get_timer("seeds-off-paths", tid).str());
       log->info("Verified distance constraints in {}.", stats.get_timer("query-dindex", tid).str());
