@@ -235,7 +235,7 @@ class Workload:
         self.torch, self.dev, self.rank, self.k, self.read_len, self.n_reads = torch, dev, rank, k, read_len, n_reads
         t0 = time.time()
         self.g = g = build_graph(shape)
-        ps = g.pick_paths(n_paths, seed=1)
+        self.ps = ps = g.pick_paths(n_paths, seed=1)
         self.ctx = ctx = capi.Context(k, dev.index)
         ctx.set_option("offpath_mode", offpath_mode)
         for kv in opts:
@@ -877,11 +877,45 @@ def other_configs(torch, dev, run_async, run_sync, capi):
                              "workload": f"{shape}-shape graph walked from its starting loci for every chunk of {n_reads} x {read_len} bp reads, k={k}"}
             if name == "chr22_150bp":
                 out["distance_index_300_500"] = distance_bench(torch, dev, capi, W.g, 300, 500)
+                out["mem_mode_chr22"] = mem_bench(torch, dev, capi, W)
             W.close()
         except Exception as e:   # an extra line must not take the headline down
             out[name] = {"error": f"{type(e).__name__}: {e}"}
     globals().update(K=k0, READ_LEN=len0)
     return out
+
+
+def mem_bench(torch, dev, capi, W, n_reads=200_000):
+    """MEM mode (SeedFinder::seeds_on_paths(sequence, cb) -> find_mems, SURVEY 8 f3) on the same graph and paths: the
+    suffix table of the path text is built, then one chunk of reads is scanned (hits stay on the device)."""
+    try:
+        import ctypes as C
+        ctx = capi.Context(W.k, dev.index)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_graph(W.g, ids="internal")
+        t0 = time.perf_counter()
+        ctx.build_mem_index(W.ps)
+        build_s = time.perf_counter() - t0
+        L = W.read_len
+        words = W.words_d[0]
+        n_hits = C.c_uint64()
+        times = []
+        for _ in range(3):
+            ctx.submit_chunk_packed_raw(n_reads, n_reads * L, L, words.data_ptr(), 0, W.k, on_device=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctx._ck(capi.lib().psi_b200_find_mems(ctx._h, 0, C.byref(n_hits)))
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sorted(times)[1]
+        res = {"reads_per_s": n_reads / (ms * 1e-3), "ms_per_chunk": ms, "reads": n_reads, "read_len": L, "min_len": W.k, "mems": n_hits.value,
+               "index_build_s": build_s,
+               "workload": f"chr22-shape graph, {len(W.ps.path_ptr) - 1} indexed paths, {n_reads} x {L} bp error-free reads, minimum MEM length {W.k}"}
+        ctx.close()
+        return res
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def distance_bench(torch, dev, capi, g, dmin, dmax, n_pairs=4_000_000):

@@ -1126,3 +1126,30 @@ def test_verify_distance_fuzz_fresh_graphs_vs_oracle(seed):
         ctx.create_distance_index(dmin, dmax)
         assert np.array_equal(ctx.verify_distance(pairs), want), (mode, cap)
         ctx.close()
+
+
+def test_verify_distance_on_a_cyclic_graph_vs_oracle():
+    """The reference's matrix powers count walks, not paths: on a graph with cycles a locus is reached at every distance
+    some walk realises, going round as often as the window allows.  A ring with chords and a self-loop, flat arrays (no
+    GFA: gum's loader sorts topologically); rows, enumeration and the restatement agree on all pairs of loci."""
+    lens = [3, 1, 4, 2, 5, 1, 2]
+    n = len(lens)
+    edges = {0: [1, 3], 1: [2], 2: [3, 2], 3: [4], 4: [5, 0], 5: [6], 6: [0]}      # 2 -> 2 is a self-loop
+    seq_start = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    seq = np.frombuffer(("ACGT" * 8)[:int(seq_start[-1])].encode(), np.uint8)
+    row_ptr = np.concatenate([[0], np.cumsum([len(edges[v]) for v in range(n)])]).astype(np.uint64)
+    col = np.array([u for v in range(n) for u in edges[v]], np.uint32)
+    g = capi.Graph.from_arrays(np.arange(1, n + 1, dtype=np.uint64), seq_start, seq, row_ptr, col, sort=False)
+    og = orc.OGraph.of(g)
+    pairs = np.array([(v, o, u, p) for v in range(n) for o in range(lens[v]) for u in range(n) for p in range(lens[u])], np.uint32)
+    for dmin, dmax in ((1, 1), (2, 9), (17, 40), (60, 61)):
+        want = np.array([orc.verify_distance(og, int(v), int(o), int(u), int(p), dmin, dmax) for v, o, u, p in pairs])
+        assert want.any()
+        for mode, cap in DIST_MODES:
+            ctx = capi.Context(3, 0)
+            ctx.set_graph(g, ids="coord")
+            ctx.set_option("dindex_mode", mode)
+            ctx.set_option("dindex_list_cap", cap)
+            ctx.create_distance_index(dmin, dmax)
+            assert np.array_equal(ctx.verify_distance(pairs), want), (dmin, dmax, mode, cap)
+            ctx.close()
