@@ -699,8 +699,37 @@ def main_sharded(args):
 
     k, L, total, chunk = K, READ_LEN, args.reads_total, args.reads
     t0 = time.time()
-    g = build_graph(args.shape)
-    ps = g.pick_paths(N_PATHS, seed=1)
+    if world == 1:
+        g = build_graph(args.shape)
+        ps = g.pick_paths(N_PATHS, seed=1)
+    else:
+        # ONE host copy of the flattened graph and the picked paths per box: local rank 0 builds them and leaves the
+        # arrays in /dev/shm, every rank maps them read-only (at whole-genome size a private copy per rank, ~50 GB,
+        # would not fit the host's memory eight times)
+        import shutil
+        import types
+        shm = Path("/dev/shm") / f"psi_b200_{args.shape}_{os.environ.get('MASTER_PORT', '0')}"
+        names = ("seq_start", "seq", "row_ptr", "col", "internal_id", "coord_id", "path_ptr", "path_nodes", "path_head", "path_tail")
+        if local == 0:
+            g0 = build_graph(args.shape)
+            ps0 = g0.pick_paths(N_PATHS, seed=1)
+            shutil.rmtree(shm, ignore_errors=True)
+            shm.mkdir(parents=True)
+            for nm, arr in zip(names, (g0.seq_start, g0.seq, g0.row_ptr, g0.col, g0.internal_id, g0.coord_id, ps0.path_ptr, ps0.nodes,
+                                       ps0.head_off, ps0.tail_trim)):
+                np.save(shm / f"{nm}.npy", arr)
+            np.save(shm / "meta.npy", np.array([g0.n_nodes, g0.n_edges, g0.n_bases, g0.n_paths], np.uint64))
+            del g0, ps0
+        dist.barrier()
+        a = {nm: np.load(shm / f"{nm}.npy", mmap_mode="r") for nm in names}
+        meta = np.load(shm / "meta.npy")
+        g = types.SimpleNamespace(n_nodes=int(meta[0]), n_edges=int(meta[1]), n_bases=int(meta[2]), n_paths=int(meta[3]),
+                                  seq_start=a["seq_start"], seq=a["seq"], row_ptr=a["row_ptr"], col=a["col"],
+                                  internal_id=a["internal_id"], coord_id=a["coord_id"])
+        ps = capi.PathSet(path_ptr=a["path_ptr"], nodes=a["path_nodes"], head_off=a["path_head"], tail_trim=a["path_tail"])
+        dist.barrier()
+        if local == 0:
+            shutil.rmtree(shm, ignore_errors=True)      # the mappings keep the pages alive
     t_host = time.time() - t0
     ctx = capi.Context(k, local)
     ctx.set_option("offpath_mode", args.offpath_mode)
