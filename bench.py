@@ -665,8 +665,8 @@ def psikt_drop_in(W, n_reads=2_000_000, chunk=500_000):
         return {"reads_per_s": n_reads / t_find if t_find else None, "seed_finding_s": t_find, "wall_s_with_graph_load_and_index": wall,
                 "reads": n_reads, "chunk": chunk, "seeds_written": n_found, "output_bytes": os.path.getsize(out),
                 "input_bytes": os.path.getsize(fa),
-                "what": "psikt -f reads.fa -l K -n 16 -c CHUNK -o seeds.bin graph.gfa: FASTA parsing + 2-bit packing (one host thread), "
-                        "GPU step, 32-byte records expanded and written, next chunk parsed while the GPU works"}
+                "what": "psikt -f reads.fa -l K -n 16 -c CHUNK -o seeds.bin graph.gfa: FASTA parsing + 2-bit packing of the next chunk "
+                        "on a second host thread while the first one waits for the GPU step, expands the 32-byte records and writes them"}
     finally:
         shutil.rmtree(td, ignore_errors=True)
 

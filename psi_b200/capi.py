@@ -281,7 +281,7 @@ class Graph:
         return PathSet(h)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:     # (module globals are gone at interpreter shutdown)
             lib().psi_b200_graph_free(self._h)
             self._h = None
 
@@ -310,7 +310,7 @@ class PathSet:
         return len(self.path_ptr) - 1
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:     # (module globals are gone at interpreter shutdown)
             lib().psi_b200_pathset_free(self._h)
             self._h = None
 

@@ -172,7 +172,8 @@ struct Shared {
   bool has_dindex = false;         // create_distance_index was given a constructible window
   bool dist_rows = false;          // the rows are materialised (else queries enumerate)
   uint32_t dist_dmin = 0, dist_dmax = 0;
-  DevBuf<uint32_t> dist_row_len;
+  DevBuf<uint32_t> dist_row_len;                              // build time only
+  DevBuf<uint4> dist_packed;                                  // per node {row start lo, hi, row length, label length}
   DevBuf<unsigned long long> dist_row_start, dist_entries;   // entry = node rank << 32 | distance between first characters
   uint64_t n_dist_entries = 0;
 

@@ -218,11 +218,22 @@ __device__ __forceinline__ bool dist_valid(const GraphView& g, const DistQuery& 
   return q.v < g.n_nodes && q.u < g.n_nodes && q.o < __ldg(&g.rec[q.v].seq_len) && q.p < __ldg(&g.rec[q.u].seq_len);
 }
 
+// One 16-byte record per node for the queries: where its row starts, how long it is, and the node's label length (so that
+// a query costs one gather for v and one for u besides its row).
+__global__ void __launch_bounds__(256)
+dist_pack_rows_kernel(GraphView g, const uint32_t* __restrict__ row_len, const unsigned long long* __restrict__ row_start,
+                      uint4* __restrict__ rows)
+{
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= g.n_nodes) return;
+  const unsigned long long st = row_start[v];
+  rows[v] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), row_len[v], g.rec[v].seq_len);
+}
+
 // against the materialised rows: 8 lanes scan row(v)
 __global__ void __launch_bounds__(256)
-dist_query_rows_kernel(GraphView g, const DistQuery* __restrict__ queries, uint64_t n, uint32_t dmin, uint32_t dmax,
-                       const uint32_t* __restrict__ row_len, const unsigned long long* __restrict__ row_start,
-                       const unsigned long long* __restrict__ entries, uint8_t* __restrict__ out)
+dist_query_rows_kernel(const DistQuery* __restrict__ queries, uint64_t n, uint32_t n_nodes, uint32_t dmin, uint32_t dmax,
+                       const uint4* __restrict__ rows, const unsigned long long* __restrict__ entries, uint8_t* __restrict__ out)
 {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t qi = t >> 3;
@@ -231,16 +242,19 @@ dist_query_rows_kernel(GraphView g, const DistQuery* __restrict__ queries, uint6
   if (qi < n) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(queries + qi));
     const DistQuery q{ raw.x, raw.y, raw.z, raw.w };
-    if (dist_valid(g, q)) {
-      if (q.v == q.u) ok = dist_same_node(q, dmin, dmax);
-      else {
-        const long long lo = (long long)dmin + q.o - q.p, hi = (long long)dmax + q.o - q.p;
-        const uint32_t len = __ldg(row_len + q.v);
-        const unsigned long long* row = entries + __ldg(row_start + q.v);
-        for (uint32_t i = sub; i < len; i += 8) {
-          const unsigned long long e = __ldg(row + i);
-          const long long s = (long long)(uint32_t)e;
-          ok = ok || ((uint32_t)(e >> 32) == q.u && s >= lo && s <= hi);
+    if (q.v < n_nodes && q.u < n_nodes) {
+      const uint4 rv = __ldg(rows + q.v);
+      const uint32_t len_u = q.u == q.v ? rv.w : __ldg(&rows[q.u].w);
+      if (q.o < rv.w && q.p < len_u) {          // both loci exist
+        if (q.v == q.u) ok = dist_same_node(q, dmin, dmax);
+        else {
+          const long long lo = (long long)dmin + q.o - q.p, hi = (long long)dmax + q.o - q.p;
+          const unsigned long long* row = entries + (((unsigned long long)rv.y << 32) | rv.x);
+          for (uint32_t i = sub; i < rv.z; i += 8) {
+            const unsigned long long e = __ldg(row + i);
+            const long long s = (long long)(uint32_t)e;
+            ok = ok || ((uint32_t)(e >> 32) == q.u && s >= lo && s <= hi);
+          }
         }
       }
     }
@@ -325,7 +339,7 @@ void engine_create_distance_index(Ctx& c, unsigned dmin, unsigned dmax)
   PSI_CUDA(cudaSetDevice(c.device));
   sh.has_dindex = false;
   sh.dist_rows = false;
-  sh.dist_row_len.release(); sh.dist_row_start.release(); sh.dist_entries.release();
+  sh.dist_row_len.release(); sh.dist_row_start.release(); sh.dist_entries.release(); sh.dist_packed.release();
   sh.n_dist_entries = 0;
   c.counters.n_dindex_entries = 0; c.counters.dindex_bytes = 0; c.counters.dindex_mode = 0; c.counters.ms_dindex_build = 0;
   if (dmin == 0 || dmax < dmin) return;   // "not constructible" (seed_finder.hpp:1198): queries stay unavailable
@@ -417,6 +431,12 @@ void engine_create_distance_index(Ctx& c, unsigned dmin, unsigned dmax)
       throw CudaError("create_distance_index: the two passes disagree on the number of entries");
     }
   }
+  sh.dist_packed.ensure(n);
+  dist_pack_rows_kernel<<<grid_for(n, 256), 256, 0, c.stream>>>(g, sh.dist_row_len.p, sh.dist_row_start.p, reinterpret_cast<uint4*>(sh.dist_packed.p));
+  ++c.counters.launches;
+  PSI_CUDA(cudaGetLastError());
+  PSI_CUDA(cudaStreamSynchronize(c.stream));
+  sh.dist_row_len.release(); sh.dist_row_start.release();
   sh.dist_rows = true;
   sh.n_dist_entries = total;
   float ms = 0;
@@ -424,7 +444,7 @@ void engine_create_distance_index(Ctx& c, unsigned dmin, unsigned dmax)
   c.counters.ms_dindex_build = ms;
   c.counters.dindex_mode = 2;
   c.counters.n_dindex_entries = total;
-  c.counters.dindex_bytes = sh.dist_entries.bytes() + sh.dist_row_len.bytes() + sh.dist_row_start.bytes();
+  c.counters.dindex_bytes = sh.dist_entries.bytes() + sh.dist_packed.bytes();
 }
 
 
@@ -451,8 +471,8 @@ void engine_verify_distance(Ctx& c, uint64_t n, const uint32_t* pairs, uint8_t* 
     d_out = c.dist_out.p;
   }
   if (sh.dist_rows) {
-    dist_query_rows_kernel<<<grid_for(n * 8, 256), 256, 0, c.stream>>>(g, d_q, n, sh.dist_dmin, sh.dist_dmax, sh.dist_row_len.p,
-                                                                       sh.dist_row_start.p, sh.dist_entries.p, d_out);
+    dist_query_rows_kernel<<<grid_for(n * 8, 256), 256, 0, c.stream>>>(d_q, n, sh.n_nodes, sh.dist_dmin, sh.dist_dmax,
+                                                                       reinterpret_cast<const uint4*>(sh.dist_packed.p), sh.dist_entries.p, d_out);
     ++c.counters.launches;
     PSI_CUDA(cudaGetLastError());
   }
