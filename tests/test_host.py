@@ -220,3 +220,62 @@ def test_truncated_reference_paths_file_is_refused(tmp_path):
         with pytest.raises(capi.PsiError) as e:
             g.load_reference_paths(p)
         assert e.value.code == capi.ERR_IO
+
+
+def test_reader_line_views_across_buffer_refills_and_threaded_packing(tmp_path):
+    """The reader parses lines as views into a 4 MB read buffer and packs large chunks over several threads: records
+    that straddle refills, a sequence line longer than the buffer, CRLF line ends, blank lines, multi-line FASTA, FASTQ
+    whose quality line starts with '@' or '+', no newline at the end of the file -- against a plain Python parser; the
+    threaded packer against the single-threaded one."""
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGTN", np.uint8)
+
+    def seq(n):
+        return acgt[rng.choice(5, n, p=[0.2475] * 4 + [0.01])].tobytes()
+    # FASTA: multi-line records of many lengths, one 9 MB line, CRLF here and there, blank lines between records
+    recs = [(b"r%d" % i, seq(int(rng.integers(1, 400)))) for i in range(30000)]
+    recs.insert(777, (b"long", seq(9_000_000)))
+    fa = tmp_path / "big.fa"
+    with open(fa, "wb") as f:
+        for i, (name, s) in enumerate(recs):
+            eol = b"\r\n" if i % 7 == 0 else b"\n"
+            f.write(b">" + name + b" some description" + eol)
+            if name == b"long" or i % 3:
+                f.write(s + eol)
+            else:                                    # wrapped at 60 columns
+                for j in range(0, len(s), 60):
+                    f.write(s[j:j + 60] + eol)
+            if i % 11 == 0:
+                f.write(eol)
+        f.write(b">last\nACGT")                      # no newline at the end
+    recs.append((b"last", b"ACGT"))
+    r = capi.Reader(fa)
+    got_names, got = [], []
+    while True:
+        ch = r.next(5000)
+        if ch is None:
+            break
+        first, rp, bases, names = ch
+        assert first == len(got)
+        got_names += names
+        got += [bases[int(rp[i]):int(rp[i + 1])].tobytes() for i in range(len(rp) - 1)]
+    assert got_names == [n.decode() for n, _ in recs]
+    assert got == [s for _, s in recs]
+    # the same file as packed chunks: words and exceptions equal to packing the characters in one thread
+    r = capi.Reader(fa)
+    at = 0
+    while True:
+        pk = r.next_packed(20000)
+        if pk is None:
+            break
+        n = pk.n_reads
+        flat = np.frombuffer(b"".join(s for _, s in recs[at:at + n]), np.uint8)
+        ref = capi.Packed.pack(pk.read_ptr, flat, at)
+        assert np.array_equal(pk.words, ref.words) and np.array_equal(pk.exc, ref.exc) and pk.first_read_id == at
+        at += n
+    assert at == len(recs)
+    # FASTQ whose quality strings begin with the record markers
+    fq = tmp_path / "q.fastq"
+    fq.write_bytes(b"@a\nACGT\n+a\n@III\n@b x\nGG\n+\n+I\n@c\nT\n+\nI")
+    first, rp, bases, names = capi.Reader(fq).next(0)
+    assert (rp.tolist(), bases.tobytes(), names) == ([0, 4, 6, 7], b"ACGTGGT", ["a", "b", "c"])
