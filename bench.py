@@ -61,6 +61,8 @@ class ClockSampler:
         self.proc = None
         self.gpu = gpu_index
         self.max_mhz = None
+        self.ready = threading.Event()     # nvidia-smi has attached to the driver and delivered its first sample
+        self.t_from = 0.0
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -75,7 +77,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+            self.ready.set()
+
+    def mark(self):
+        """Samples from here on count: nvidia-smi is started early (attaching to the driver takes it a second or two on an
+        8-GPU box, and doing that beside a 3 ms timed loop perturbs the loop), its idle-time samples are dropped."""
+        self.ready.wait(10.0)
+        self.t_from = time.time()
 
     def stop(self):
         if not self.proc:
@@ -88,7 +97,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < self.t_from:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -438,13 +449,15 @@ def main_gpu(args):
 
     n_reads, steps, warmup = args.reads, args.steps, args.warmup
     n_pipes = max(1, args.pipelines)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()        # polls every 100 ms from now on; only the samples taken during the timed loops are kept
     W = Workload(torch, dev, rank, args.shape, K, READ_LEN, n_reads, N_BATCHES, N_PATHS, n_pipes, args.offpath_mode, args.opt)
     ctx, c0 = W.ctx, W.c0
     DENSE = capi.ALL | capi.DENSE
-
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
+    barrier()
     # value: 2-bit chunks resident in HBM -> dense results resident in HBM, n_pipes chunks in flight from one host thread
     ms_val, hits_val, launches_val, kms_val = run_async(W, steps, warmup, n_pipes, "packed", "device", DENSE, False)
     # e2e: the same call sequence with pinned HOST buffers: 2-bit chunk up, dense results down, inside the timed region
