@@ -455,14 +455,21 @@ def main_gpu(args):
     W = Workload(torch, dev, rank, args.shape, K, READ_LEN, n_reads, N_BATCHES, N_PATHS, n_pipes, args.offpath_mode, args.opt)
     ctx, c0 = W.ctx, W.c0
     DENSE = capi.ALL | capi.DENSE
+    # the results' wire format: 5 bytes per seed (PSI_B200_DENSE5) when the graph's loci fit 39 bits, else 6 / 8
+    d5_off_bits, d5 = ctx.dense5_layout()
+    FAST = capi.ALL | (capi.DENSE5 if d5 else capi.DENSE)
+    res_bytes = 5 if d5 else 4 + ctx.dense_off_bytes()
     if rank == 0:
         sampler.mark()
     barrier()
     # value: 2-bit chunks resident in HBM -> dense results resident in HBM, n_pipes chunks in flight from one host thread
-    ms_val, hits_val, launches_val, kms_val = run_async(W, steps, warmup, n_pipes, "packed", "device", DENSE, False)
+    ms_val, hits_val, launches_val, kms_val = run_async(W, steps, warmup, n_pipes, "packed", "device", FAST, False)
     # e2e: the same call sequence with pinned HOST buffers: 2-bit chunk up, dense results down, inside the timed region
-    ms_e2e, hits_e2e, launches_e2e, kms_e2e = run_async(W, steps, warmup, n_pipes, "packed", "host", DENSE, True)
+    ms_e2e, hits_e2e, launches_e2e, kms_e2e = run_async(W, steps, warmup, n_pipes, "packed", "host", FAST, True)
     clocks = sampler.stop() if rank == 0 else None
+    # the same end-to-end loop with round 2's first result format (6 bytes per seed: u32 node id + u16 offset)
+    ms_e2e6, hits_e2e6, _, _ = run_async(W, steps, warmup, n_pipes, "packed", "host", DENSE, True) if d5 else (ms_e2e, hits_e2e, 0, 0)
+    assert hits_e2e6 == hits_e2e
     # beside them: ASCII chunks (the packing then runs inside the fused kernel) and round 1's record formats
     ms_val_ascii, hits_a, _, kms_ascii = run_async(W, steps, warmup, n_pipes, "ascii", "device", DENSE, False)
     ms_val_rec, hits_r, _, kms_rec = run_async(W, steps, warmup, n_pipes, "ascii", "device", capi.ALL, False)
@@ -487,7 +494,7 @@ def main_gpu(args):
                                             "hits_on": acc_one["n_hits_on"]}, hist, device=dev)
 
     barrier()      # every rank copies at the same moment: the figure is one GPU's share of the box's host bandwidth
-    pcie = pcie_ceiling(torch, dev, int(W.words_h[0].numel() * 8), int((4 + ctx.dense_off_bytes()) * W.n_seeds))
+    pcie = pcie_ceiling(torch, dev, int(W.words_h[0].numel() * 8), int(res_bytes * W.n_seeds))
     barrier()
     drop_in = psikt_drop_in(W) if (world == 1 and rank == 0 and not args.no_other_configs) else None
     other = {}
@@ -501,7 +508,7 @@ def main_gpu(args):
         seeds_step, hits_step = acc_one["n_seeds"] / steps, acc_one["n_hits"] / steps
         words_bytes = int(W.words_h[0].numel() * 8)
         ascii_bytes = int(W.ascii_h[0][1].numel() + W.ascii_h[0][0].numel() * 8)
-        off_bytes = ctx.dense_off_bytes()
+        off_bytes = res_bytes - 4
         extra_copy = (n_reads * READ_LEN // K + n_reads + 1) // 256 + 256     # speculative share of the extra list copied with every step
 
         def roof_of(kernel, launch_ms, wall_ms, in_bytes, out_per_seed, traffic_key, what):
@@ -548,7 +555,8 @@ def main_gpu(args):
                        "sharding": "reads sharded by rank, graph + index replicated, NCCL all-reduce of counts only",
                        "formats": "chunk = 2-bit words (psi_b200_packed_chunk, what psi_b200_reader_next_packed hands over; "
                                   f"the reader's packer ran at {W.pack_gbs:.2f} GB/s of characters on one host core here); "
-                                  "results = dense {node id, node offset} per seed (PSI_B200_DENSE)",
+                                  + ("results = 5 bytes per seed: (node id << offset bits | node offset) in 39 bits + the off-path bit "
+                                     "(PSI_B200_DENSE5)" if d5 else "results = dense {node id, node offset} per seed (PSI_B200_DENSE)"),
                        "pipelines": f"{n_pipes} contexts per GPU sharing one resident index, all driven by ONE host thread through "
                                     "psi_b200_seeds_all_async / psi_b200_wait"},
             "seeds_per_s": hits_total / (ms_val * 1e-3), "query_seeds_per_s": seeds_total / (ms_val * 1e-3),
@@ -559,8 +567,12 @@ def main_gpu(args):
                     "fused_kernel_ms": kms_e2e,
                     "pcie": dict(pcie, floor_ms_per_step=max(words_bytes / (pcie["h2d_bidir_gbs"] * 1e6), (4 + off_bytes) * W.n_seeds / (pcie["d2h_bidir_gbs"] * 1e6)),
                                  note="rank 0's link; at N > 1 every rank runs the same copies at the same moment, so this is one GPU's share of the box's host bandwidth"),
-                    "formats": f"up: 2-bit words of the chunk (pinned host memory); down: {4 + off_bytes} bytes per seed (u32 node id, "
-                               f"u{8 * off_bytes} node offset | off-path bit) + the extra list of multi-locus seeds + the step's counters"},
+                    "formats": f"up: 2-bit words of the chunk (pinned host memory); down: {res_bytes} bytes per seed ("
+                               + ("PSI_B200_DENSE5: u32 + u8 planes holding (node id << offset bits | node offset) and the off-path bit"
+                                  if d5 else f"u32 node id, u{8 * off_bytes} node offset | off-path bit")
+                               + ") + the extra list of multi-locus seeds + the step's counters",
+                    "with_6_byte_results": {"value": reads_total / (ms_e2e6 * 1e-3), "ms_per_step": ms_e2e6 / steps,
+                                            "d2h_bytes_per_step": int((4 + ctx.dense_off_bytes()) * W.n_seeds + 16 * extra_copy + 8 * 12)}},
             "roofline": roof,
             "value_ascii_chunks": {"value": reads_total / (ms_val_ascii * 1e-3), "unit": "reads/s", "ms_per_step": ms_val_ascii / steps,
                                    "fused_kernel_ms": kms_ascii,

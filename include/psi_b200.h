@@ -279,6 +279,12 @@ int  psi_b200_submit_chunk_packed(psi_b200_ctx* ctx, const psi_b200_packed_chunk
                                     PCIe, read id / offset implied.  Needs the off-path walks in the index (offpath_mode
                                     0 or 2) and ids below 2^32 - 1; excludes SORTED, NO_RESOLVE, COMPACT */
 
+#define PSI_B200_DENSE5    64u   /* PSI_B200_DENSE in 5 bytes per seed: the locus as one number e = (node id << off_bits) | node
+                                    offset, its low 32 bits in the first plane (u32) and, in a second plane of one byte per
+                                    seed, bits 32..38 of e with the off-path flag in bit 7; no hit = 0xffffffff / 0xff.  For
+                                    graphs whose e stays below 2^39 - 1 (psi_b200_dense5_layout tells, and gives off_bits);
+                                    PSI_B200_ERR_ARG otherwise.  The extra list is the same as PSI_B200_DENSE's */
+
 /* Finds the seeds of the submitted chunk.  The result is the SET of hits
  * (each (read, offset, node, offset) once), resident in device
  * memory; *n_hits is its size (synchronises the stream).  Record order: grouped by blocks of 256
@@ -302,6 +308,7 @@ int  psi_b200_wait(psi_b200_ctx* ctx, uint64_t* n_hits);
  *     ids[s]  (u32)  node id, 0xffffffff = no hit;
  *     offs[s] (u16 when no node label is longer than 32 768 bases, else u32; psi_b200_dense_layout tells) node offset,
  *             top bit set when the hit was found off the indexed paths (seeds_off_paths).
+ * (After a PSI_B200_DENSE5 step the second plane is the one-byte plane described at the flag: off_bytes = 1.)
  * `dense` receives ids[n_seeds] immediately followed by offs[n_seeds]: n_seeds * (4 + off_bytes) bytes; cap_seeds is
  * the number of seeds the buffer has room for.  Seeds whose k-mer occurs at several loci have their further hits in
  * `extra`: 4 x u32 {node_id, node_off, read_id, read_off | off-path << 31} each.  n_hits of the step = dense hits +
@@ -314,6 +321,9 @@ int  psi_b200_fetch_dense(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, ui
 int  psi_b200_fetch_dense_async(psi_b200_ctx* ctx, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra);
 /* Width in bytes (2 or 4) of the node-offset plane for the graph of this context. */
 int  psi_b200_dense_layout(psi_b200_ctx* ctx, unsigned* off_bytes);
+/* PSI_B200_DENSE5: off_bits of the entries (bits of the longest label - 1, fixed when the index is built) and whether
+ * the current index can deliver them. */
+int  psi_b200_dense5_layout(psi_b200_ctx* ctx, unsigned* off_bits, int* available);
 /* Counts of the last completed dense step. */
 int  psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra);
 

@@ -18,7 +18,7 @@ LIB_PATH = _HERE / "libpsi_b200.so"
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_OVERFLOW = -1, -2, -3, -4, -5, -6
-ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE, COMPACT, DENSE = 1, 2, 3, 4, 8, 16, 32
+ON_PATHS, OFF_PATHS, ALL, SORTED, NO_RESOLVE, COMPACT, DENSE, DENSE5 = 1, 2, 3, 4, 8, 16, 32, 64
 NIL32 = 0xFFFFFFFF
 
 # every symbol include/psi_b200.h declares
@@ -28,7 +28,7 @@ SYMBOLS = [
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view", "psi_b200_pathset_load_reference",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
     "psi_b200_reader_next_packed", "psi_b200_pack_bases", "psi_b200_submit_chunk_packed",
-    "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout",
+    "psi_b200_seeds_all_async", "psi_b200_wait", "psi_b200_fetch_dense", "psi_b200_fetch_dense_async", "psi_b200_dense_counts", "psi_b200_dense_layout", "psi_b200_dense5_layout",
     "psi_b200_build_mem_index", "psi_b200_find_mems", "psi_b200_fetch_mems",
     "psi_b200_create_distance_index", "psi_b200_verify_distance",
     "psi_b200_global_error",
@@ -165,6 +165,7 @@ def _bind_device(L, u64p, u32p, vp):
     L.psi_b200_fetch_dense_async.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64]
     L.psi_b200_dense_counts.argtypes = [vp, u64p, u64p]
     L.psi_b200_dense_layout.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.psi_b200_dense5_layout.argtypes = [vp, C.POINTER(C.c_uint), C.POINTER(C.c_int)]
     L.psi_b200_build_mem_index.argtypes = [vp, C.c_uint64, vp, vp, vp, vp]
     L.psi_b200_find_mems.argtypes = [vp, C.c_uint, u64p]
     L.psi_b200_fetch_mems.argtypes = [vp, vp, C.c_uint64, u64p]
@@ -527,6 +528,21 @@ class Context:
         self._ck(lib().psi_b200_fetch_dense(self._h, _ptr(raw), ns, _ptr(extra), ne, C.byref(C.c_uint64()), C.byref(C.c_uint64())))
         return dense_planes(raw, ns, ob), extra
 
+    def dense5_layout(self):
+        """(off_bits, available) of PSI_B200_DENSE5 for the current index."""
+        ob, av = C.c_uint(), C.c_int()
+        self._ck(lib().psi_b200_dense5_layout(self._h, C.byref(ob), C.byref(av)))
+        return ob.value, bool(av.value)
+
+    def fetch_dense5(self):
+        """After seeds_all(flags | DENSE5): the 5-byte planes decoded into the pairs fetch_dense returns
+        (dense (n_seeds, 2) u32 {node id, node offset | off-path << 31}, extra (n_extra, 4) u32)."""
+        ns, ne = self.dense_counts()
+        raw = np.zeros(ns * 5, np.uint8)
+        extra = np.zeros((ne, 4), np.uint32)
+        self._ck(lib().psi_b200_fetch_dense(self._h, _ptr(raw), ns, _ptr(extra), ne, C.byref(C.c_uint64()), C.byref(C.c_uint64())))
+        return dense5_planes(raw, ns, self.dense5_layout()[0]), extra
+
     def fetch_dense_async(self, dense_addr: int, cap_seeds: int, extra_addr: int, cap_extra: int):
         self._ck(lib().psi_b200_fetch_dense_async(self._h, C.c_void_p(dense_addr), cap_seeds, C.c_void_p(extra_addr), cap_extra))
 
@@ -623,6 +639,19 @@ def dense_planes(raw: np.ndarray, n_seeds: int, off_bytes: int) -> np.ndarray:
     else:
         offs = raw[4 * n_seeds: 8 * n_seeds].view(np.uint32)
     return np.column_stack([ids, offs]).astype(np.uint32)
+
+
+def dense5_planes(raw: np.ndarray, n_seeds: int, off_bits: int) -> np.ndarray:
+    """PSI_B200_DENSE5 planes (u32 low words, then one byte per seed) -> (n_seeds, 2) u32 {node id, offset | off-path << 31},
+    NIL32 / 0 for a seed without a hit: the representation dense_planes gives for PSI_B200_DENSE."""
+    lo = raw[:4 * n_seeds].view(np.uint32).astype(np.uint64)
+    hi = raw[4 * n_seeds:5 * n_seeds].astype(np.uint64)
+    nil = (lo == NIL32) & (hi == 0xFF)
+    e = lo | ((hi & np.uint64(0x7F)) << np.uint64(32))
+    out = np.zeros((n_seeds, 2), np.uint32)
+    out[:, 0] = np.where(nil, NIL32, e >> np.uint64(off_bits)).astype(np.uint32)
+    out[:, 1] = np.where(nil, 0, (e & np.uint64((1 << off_bits) - 1)) | ((hi >> np.uint64(7)) << np.uint64(31))).astype(np.uint32)
+    return out
 
 
 def seed_layout(read_ptr, k: int, d: int):

@@ -195,6 +195,15 @@ int psi_b200_dense_layout(psi_b200_ctx* ctx, unsigned* off_bytes)
   })
 }
 
+int psi_b200_dense5_layout(psi_b200_ctx* ctx, unsigned* off_bits, int* available)
+{
+  CTX_GUARD(ctx, {
+    if (!ctx->c->sh->has_graph) throw StateError("dense5_layout: no graph");
+    if (off_bits) *off_bits = ctx->c->sh->code_off_bits;
+    if (available) *available = dense5_available(*ctx->c->sh) ? 1 : 0;
+  })
+}
+
 int psi_b200_dense_counts(psi_b200_ctx* ctx, uint64_t* n_seeds, uint64_t* n_extra)
 {
   CTX_GUARD(ctx, {

@@ -250,7 +250,7 @@ struct Ctx {
   // offsets with the off-path flag in the top bit (u16 or u32); further hits of seeds with several loci are 4 x u32
   // records in `extra`
   bool records_dense = false;
-  uint32_t dense_off_bytes = 4;      // width of the node-offset plane: 2 when no node is longer than 32 768 bases
+  uint32_t dense_off_bytes = 4;      // width of the second plane: 2 when no node is longer than 32 768 bases, 1 for DENSE5
   uint64_t dense_off_plane = 0;      // byte offset of the node-offset plane inside `records`
   DevBuf<uint32_t> extra;
   uint64_t n_dense_seeds = 0, n_extra = 0;
@@ -265,7 +265,7 @@ struct Ctx {
   DevBuf<unsigned long long> dist_counters, dist_big;
   // ---- a step in flight (psi_b200_seeds_all_async .. psi_b200_wait) ----
   bool pending = false;
-  int pending_out_kind = 0;               // 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense
+  int pending_out_kind = 0;               // 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense, 3 = dense, 5 bytes per seed
   unsigned pending_probe_mode = 0;
   uint64_t pending_out_cap_want = 0;      // records: capacity learnt from an overflowed step
   int pending_attempts = 0;

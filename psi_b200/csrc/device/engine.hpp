@@ -23,7 +23,7 @@ void engine_submit_chunk(Ctx& c, uint64_t n_reads, const uint64_t* read_ptr, con
                          uint64_t n_bases, uint64_t first_read_id, unsigned distance, bool on_device);
 void engine_seed_chunk(Ctx& c);   // the seeding kernels of the separate-kernel route (idempotent per chunk)
 void engine_seeds(Ctx& c, unsigned flags);
-// out_kind: 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense per-seed results
+// out_kind: 0 = 4 x u64 records, 1 = 4 x u32 records, 2 = dense per-seed results, 3 = dense results of 5 bytes (DENSE5)
 void engine_seeds_fused(Ctx& c, unsigned probe_mode, int out_kind);
 void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind);
 void engine_seeds_async(Ctx& c, unsigned flags);   // queues the step when the fused route serves it, else runs it synchronously
@@ -105,6 +105,14 @@ inline void ctx_wait(Ctx& c)
     PSI_CUDA(cudaEventSynchronize(c.ev_sync));
   }
   else PSI_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// PSI_B200_DENSE5: the entry (node id << code_off_bits | offset) must stay below the 39-bit "no hit" pattern
+inline bool dense5_available(const Shared& sh)
+{
+  if (!sh.has_table || sh.code_off_bits >= 32) return false;
+  const unsigned __int128 top = ((unsigned __int128)sh.max_node_id + 1) << sh.code_off_bits;
+  return top <= (unsigned __int128)0x7fffffffffull;
 }
 
 inline unsigned grid_for(uint64_t items, unsigned block, unsigned items_per_thread = 1)

@@ -79,12 +79,34 @@ struct FusedOut {
   uint64_t cap;
   uint32_t compact;
   uint32_t* dense_id;           // DENSE: plane of node ids, one per seed (NIL32 = no hit)
-  void* dense_off;              //        plane of node offsets | off-path flag in the top bit: u16 (off16) or u32
-  uint32_t off16;
+  void* dense_off;              //        plane of node offsets | off-path flag in the top bit: u32, u16 or (packed) u8
+  uint32_t off_mode;            // 0: u32 offsets, 1: u16 offsets, 2: DENSE5 -- the 39-bit entry (id << off_bits | offset) split
+                                // into its low 32 bits (dense_id plane) and a byte holding the rest + the off-path flag
   SlowItem* slow_queue;
   uint64_t slow_cap;
   unsigned long long* dc;
 };
+
+// one seed's slot of the dense planes; kind 0 = no hit, 1 = on an indexed path, 2 = off the indexed paths
+__device__ __forceinline__ void st_dense(const FusedOut& out, const GraphView& g, uint32_t s, uint64_t id, uint32_t off, uint32_t kind)
+{
+  if (out.off_mode == 2) {
+    uint32_t lo = NIL32, hi = 0xffu;
+    if (kind) {
+      const uint64_t e = (id << g.code_off_bits) | off;
+      lo = (uint32_t)e;
+      hi = (uint32_t)(e >> 32) | (kind == 2 ? 0x80u : 0u);
+    }
+    out.dense_id[s] = lo;
+    static_cast<uint8_t*>(out.dense_off)[s] = (uint8_t)hi;
+  }
+  else {
+    out.dense_id[s] = kind ? (uint32_t)id : NIL32;
+    const uint32_t v = kind ? off : 0u;
+    if (out.off_mode == 1) static_cast<uint16_t*>(out.dense_off)[s] = (uint16_t)(v | (kind == 2 ? 0x8000u : 0u));
+    else static_cast<uint32_t*>(out.dense_off)[s] = v | (kind == 2 ? 0x80000000u : 0u);
+  }
+}
 
 template <int FMT, int K4, int MIN_CTAS, bool DENSE, bool PACKED>
 __global__ void __launch_bounds__(256, MIN_CTAS)
@@ -370,19 +392,13 @@ seeds_fused_kernel(KmerTable t, GraphView g, FusedChunk ch, uint32_t mode, Fused
     // ---- 5. results ----
     if (DENSE) {
       if (active) {
-        uint32_t vid = NIL32, voff = 0u;                   // also what a queued seed shows until the slow kernel has run
+        uint64_t id = 0, noff = 0;                         // a queued seed shows "no hit" until the slow kernel has run
         if (kind) {
-          uint64_t id, noff;
           decode_code(g, code, id, noff);
-          vid = (uint32_t)id;
-          voff = (uint32_t)noff;
           ++n_hit;
           n_on += kind == 1 ? 1u : 0u;
         }
-        const uint32_t s = seed0 + base + threadIdx.x;
-        out.dense_id[s] = vid;
-        if (out.off16) static_cast<uint16_t*>(out.dense_off)[s] = (uint16_t)(voff | (kind == 2 ? 0x8000u : 0u));
-        else static_cast<uint32_t*>(out.dense_off)[s] = voff | (kind == 2 ? 0x80000000u : 0u);
+        st_dense(out, g, seed0 + base + threadIdx.x, id, (uint32_t)noff, kind);
       }
     }
     else {
@@ -472,11 +488,7 @@ seeds_slow_fused_kernel(KmerTable t, const uint32_t* __restrict__ multi, GraphVi
       else resolve_node(g, __ldg(multi + f.payload + 2 + j), r.node_id, r.node_off);
       const uint32_t kind = single ? (n_on ? 1u : 2u) : (j - from < n_on ? 1u : 2u);
       if (DENSE) {
-        if (j == from) {
-          out.dense_id[it.seed] = (uint32_t)r.node_id;
-          if (out.off16) static_cast<uint16_t*>(out.dense_off)[it.seed] = (uint16_t)((uint32_t)r.node_off | (kind == 2 ? 0x8000u : 0u));
-          else static_cast<uint32_t*>(out.dense_off)[it.seed] = (uint32_t)r.node_off | (kind == 2 ? 0x80000000u : 0u);
-        }
+        if (j == from) st_dense(out, g, it.seed, r.node_id, (uint32_t)r.node_off, kind);
         else {
           if (o < extra_cap)
             asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(extra + 4 * o), "r"((uint32_t)r.node_id), "r"((uint32_t)r.node_off),
@@ -567,7 +579,7 @@ static void fused_enqueue(Ctx& c)
   unsigned long long* dc = c.dev_counters.p;
   const int out_kind = c.pending_out_kind;
   const unsigned probe_mode = c.pending_probe_mode;
-  const bool dense = out_kind == 2;
+  const bool dense = out_kind >= 2;
 
   // Reads per CTA: 256 when that gives at least 4 CTAs per resident slot; fewer when the reads are few or long (d = 1,
   // long reads), but never so few that a CTA has less than 5 batches of seeds (n_seeds_cap is an upper bound).
@@ -618,7 +630,7 @@ static void fused_enqueue(Ctx& c)
   out.compact = out_kind == 1 ? 1u : 0u;
   out.dense_id = reinterpret_cast<uint32_t*>(c.records.p);
   out.dense_off = reinterpret_cast<char*>(c.records.p) + c.dense_off_plane;
-  out.off16 = c.dense_off_bytes == 2 ? 1u : 0u;
+  out.off_mode = c.dense_off_bytes == 1 ? 2u : c.dense_off_bytes == 2 ? 1u : 0u;
   out.slow_queue = c.slow_items.p;
   out.slow_cap = c.slow_items.cap;
   out.dc = dc;
@@ -670,14 +682,14 @@ static void dense_copy_enqueue(Ctx& c)
 // Preconditions (checked by engine_seeds): the index answers every requested phase by itself, records are wanted, unsorted.
 void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind)
 {
-  const bool dense = out_kind == 2;
+  const bool dense = out_kind >= 2;
   if (c.slow_items.cap == 0) c.slow_items.ensure(std::max<uint64_t>(c.n_seeds_cap / 16, 1u << 16));
   c.ev_state[T_PACK] = c.ev_state[T_READ_INDEX] = c.ev_state[T_RESOLVE] = 0;   // no such phases on this route
   c.ev_state[T_OFF] = c.ev_state[T_SORT] = c.ev_state[T_D2H] = 0;
   c.n_dense_seeds = 0;
   if (dense) {
     // two planes in one buffer: 4 bytes of node id per seed, then 2 or 4 bytes of node offset per seed
-    c.dense_off_bytes = c.sh->max_node_len <= 32768u ? 2u : 4u;
+    c.dense_off_bytes = out_kind == 3 ? 1u : c.sh->max_node_len <= 32768u ? 2u : 4u;
     c.dense_off_plane = ((c.n_seeds_cap + 1) * 4 + 255) & ~(uint64_t)255;
     c.records.ensure((c.dense_off_plane + (c.n_seeds_cap + 1) * c.dense_off_bytes + 7) / 8);
     if (c.extra.cap == 0) c.extra.ensure(4 * std::max<uint64_t>(c.n_seeds_cap / 16, 1u << 16));
@@ -701,7 +713,7 @@ void engine_seeds_fused_async(Ctx& c, unsigned probe_mode, int out_kind)
 
 void engine_fetch_dense_async(Ctx& c, void* dense, uint64_t cap_seeds, uint32_t* extra, uint64_t cap_extra)
 {
-  if (!c.pending || c.pending_out_kind != 2) throw StateError("fetch_dense_async: no PSI_B200_DENSE step in flight on this context");
+  if (!c.pending || c.pending_out_kind < 2) throw StateError("fetch_dense_async: no PSI_B200_DENSE step in flight on this context");
   PSI_CUDA(cudaSetDevice(c.device));
   c.pending_dense_dst = dense;
   c.pending_dense_cap = cap_seeds;
@@ -723,7 +735,7 @@ void engine_wait(Ctx& c)
 {
   if (!c.pending) return;
   PSI_CUDA(cudaSetDevice(c.device));
-  const bool dense = c.pending_out_kind == 2;
+  const bool dense = c.pending_out_kind >= 2;
   while (true) {
     ctx_wait(c);
     const uint64_t n_total = c.h_pinned[DC_HITS], n_slow = c.h_pinned[DC_SLOW], n_extra = c.h_pinned[DC_EXTRA];

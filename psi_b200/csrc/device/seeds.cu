@@ -414,8 +414,11 @@ static void engine_seeds_impl(Ctx& c, unsigned flags, bool async)
   const bool sorted = (flags & PSI_B200_SORTED) != 0;
   const bool resolve = !(flags & PSI_B200_NO_RESOLVE);
   const bool compact = (flags & PSI_B200_COMPACT) != 0;
-  const bool dense = (flags & PSI_B200_DENSE) != 0;
+  const bool dense5 = (flags & PSI_B200_DENSE5) != 0;
+  const bool dense = (flags & PSI_B200_DENSE) != 0 || dense5;
   if (dense && (sorted || !resolve || compact)) throw ArgError("seeds_all: PSI_B200_DENSE excludes SORTED, NO_RESOLVE and COMPACT");
+  if (dense5 && !dense5_available(sh))
+    throw ArgError("seeds_all: PSI_B200_DENSE5 needs an index and (node id << offset bits | offset) below 2^39 - 1 (psi_b200_dense5_layout)");
   if ((compact || dense) && resolve) {
     if (sh.max_node_id >= 0xffffffffull) throw ArgError("seeds_all: PSI_B200_COMPACT / PSI_B200_DENSE need node ids below 2^32 - 1");
     if (c.first_read_id + c.n_reads > 0x100000000ull) throw ArgError("seeds_all: PSI_B200_COMPACT / PSI_B200_DENSE need read ids below 2^32");
@@ -427,16 +430,16 @@ static void engine_seeds_impl(Ctx& c, unsigned flags, bool async)
   // the usual case -- the index answers every requested phase, records wanted in emission order -- is ONE kernel
   const bool probe_only = !do_walk && !sorted && resolve;
   if ((c.opt_fused || dense) && do_probe && probe_only) {
-    if (async) engine_seeds_fused_async(c, probe_mode, compact ? 1 : dense ? 2 : 0);
-    else engine_seeds_fused(c, probe_mode, compact ? 1 : dense ? 2 : 0);
+    if (async) engine_seeds_fused_async(c, probe_mode, compact ? 1 : dense5 ? 3 : dense ? 2 : 0);
+    else engine_seeds_fused(c, probe_mode, compact ? 1 : dense5 ? 3 : dense ? 2 : 0);
     return;
   }
   if (dense) {
     // dense results come from the fused kernel only; an index that cannot answer the requested phases hits nothing
     if (do_walk) throw ArgError("seeds_all: PSI_B200_DENSE needs the off-path walks materialised in the index (offpath_mode 0 or 2)");
     if (!sh.has_table) throw StateError("seeds_all: PSI_B200_DENSE needs an index (set_paths / set_loci first)");
-    if (async) engine_seeds_fused_async(c, 0, 2);
-    else engine_seeds_fused(c, 0, 2);
+    if (async) engine_seeds_fused_async(c, 0, dense5 ? 3 : 2);
+    else engine_seeds_fused(c, 0, dense5 ? 3 : 2);
     return;
   }
   engine_seed_chunk(c);

@@ -723,6 +723,19 @@ def test_dense_results_match_reference_golden(name, packed, by_rank):
         assert cnt == len(rec)
         parts.append(rec)
         kinds.append(kd)
+        # the same in 5 bytes per seed (PSI_B200_DENSE5): identical pairs after decoding, identical extra list
+        off_bits, available = ctx.dense5_layout()
+        assert available and (1 << off_bits) >= int((g.seq_start[1:] - g.seq_start[:-1]).max())
+        assert ctx.seeds_all(capi.ALL | capi.DENSE5) == cnt
+        assert ctx.dense_off_bytes() in (2, 4)          # the layout of PSI_B200_DENSE is a property of the graph
+        dense5, extra5 = ctx.fetch_dense5()
+        assert np.array_equal(dense5, dense) and np.array_equal(np.unique(extra5, axis=0), np.unique(extra, axis=0))
+        for flags in (capi.ON_PATHS, capi.OFF_PATHS):
+            ctx.seeds_all(flags | capi.DENSE)
+            d_a, e_a = ctx.fetch_dense()
+            ctx.seeds_all(flags | capi.DENSE5)
+            d_b, e_b = ctx.fetch_dense5()
+            assert np.array_equal(d_a, d_b) and np.array_equal(np.unique(e_a, axis=0), np.unique(e_b, axis=0))
         with pytest.raises(capi.PsiError):
             ctx.fetch()                  # the resident results are dense
         cnt2 = ctx.seeds_all(capi.ALL)
@@ -858,6 +871,28 @@ def test_async_steps_over_forked_contexts_from_one_thread():
     assert ctx.wait() == c["count"]
     for cx in pipes[1:]:
         cx.close()
+    ctx.close()
+
+
+def test_dense5_is_refused_when_the_entries_do_not_fit_39_bits():
+    """PSI_B200_DENSE5 packs (node id << offset bits | offset) into 39 bits: ids beyond that are refused, loudly, and
+    PSI_B200_DENSE still serves them."""
+    c = CASES["x_k12"]
+    g, rp, bases = load_case(c)
+    big = capi.Graph.from_arrays(np.asarray(g.coord_id, np.uint64) + np.uint64(1 << 36), g.seq_start, g.seq, g.row_ptr, g.col,
+                                 np.array([0, len(g.path(0)[1])], np.uint64), g.path(0)[1], sort=False)
+    ctx = capi.Context(c["k"], 0)
+    ctx.set_graph(big, ids="coord")
+    ctx.set_paths(big.pick_paths(2, seed=1))
+    ctx.find_loci()
+    assert ctx.dense5_layout()[1] is False
+    ctx.submit_chunk(rp[:101], bases[:int(rp[100])], 0, c["d"])
+    with pytest.raises(capi.PsiError) as e:
+        ctx.seeds_all(capi.ALL | capi.DENSE5)
+    assert e.value.code == capi.ERR_ARG
+    with pytest.raises(capi.PsiError):
+        ctx.seeds_all(capi.ALL | capi.DENSE)          # ids beyond 32 bits: per-hit records only
+    assert ctx.seeds_all(capi.ALL) > 0
     ctx.close()
 
 
