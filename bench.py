@@ -794,10 +794,11 @@ def main_sharded(args):
         chunks.append((lo + s, e - s, torch.from_numpy(pk.words.view(np.int64)).pin_memory()))
     n_pipes = 3
     pipes = [ctx] + [ctx.fork() for _ in range(n_pipes - 1)]
-    ob = ctx.dense_off_bytes()
+    d5_bits, d5 = ctx.dense5_layout()          # 5-byte results when the graph's loci fit 39 bits, else u32 id + u16 / u32 offset
+    ob = 1 if d5 else ctx.dense_off_bytes()
     dense_h = [torch.empty(chunk * per_read * (4 + ob), dtype=torch.uint8).pin_memory() for _ in pipes]
     extra_h = [torch.empty((chunk * per_read // 8 + 4096, 4), dtype=torch.int32).pin_memory() for _ in pipes]
-    DENSE = capi.ALL | capi.DENSE
+    DENSE = capi.ALL | (capi.DENSE5 if d5 else capi.DENSE)
     stats = {"hits": 0, "seeds_hit": 0, "checked": 0}
     rng = np.random.default_rng(5 + rank)
 
@@ -805,7 +806,8 @@ def main_sharded(args):
         # completeness + soundness of a sample, straight from what arrived in pinned host memory
         ns, ne = pipes[p].dense_counts()
         assert ns == n * per_read, (ns, n, per_read)
-        dense = capi.dense_planes(dense_h[p].numpy()[:ns * (4 + ob)], ns, ob)
+        raw = dense_h[p].numpy()[:ns * (4 + ob)]
+        dense = capi.dense5_planes(raw, ns, d5_bits) if d5 else capi.dense_planes(raw, ns, ob)
         hit = dense[:, 0] != capi.NIL32
         stats["seeds_hit"] += int(hit.sum())
         assert hit.all(), f"{int((~hit).sum())} seeds of error-free reads found nothing"
@@ -873,7 +875,8 @@ def main_sharded(args):
                            "sharding": "contiguous read ranges of equal base count per rank, graph + index replicated, NCCL all-reduce of counts only"},
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "reads/s", "ms_total": ms_e2e,
                         "h2d_bytes_per_step": int(chunks[0][2].numel() * 8) if chunks else 0,
-                        "d2h_bytes_per_step": int(chunk * per_read * (4 + ob))},
+                        "d2h_bytes_per_step": int(chunk * per_read * (4 + ob)),
+                        "result_format": "PSI_B200_DENSE5 (5 bytes per seed)" if d5 else f"PSI_B200_DENSE ({4 + ob} bytes per seed)"},
                 "seeds_per_s": counts["hits"] / ((ms_res or ms_e2e) * 1e-3), "hits": counts["hits"], "query_seeds": counts["seeds"],
                 "verified": f"every seed of every (error-free) read hit; {counts['checked']} sampled records spell their seed in the graph",
                 "index": {"kmers": c0["n_index_kmers"], "entries": c0["n_index_entries"], "bytes": c0["index_bytes"],
@@ -916,9 +919,11 @@ def other_configs(torch, dev, run_async, run_sync, capi):
             globals().update(K=k, READ_LEN=read_len)
             W = Workload(torch, dev, 0, shape, k, read_len, n_reads, 2, N_PATHS, 4, mode)
             if mode == 0:
-                ms, hits, launches, kms = run_async(W, 6, 3, 4, "packed", "device", DENSE, False)
-                ms_e, hits_e, _, _ = run_async(W, 6, 3, 4, "packed", "host", DENSE, True)
-                out[name] = {"value": n_reads * 6 / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms / 6, "fused_kernel_ms": kms,
+                d5 = W.ctx.dense5_layout()[1]
+                fast = capi.ALL | (capi.DENSE5 if d5 else capi.DENSE)
+                ms, hits, launches, kms = run_async(W, 6, 3, 4, "packed", "device", fast, False)
+                ms_e, hits_e, _, _ = run_async(W, 6, 3, 4, "packed", "host", fast, True)
+                out[name] = {"result_bytes_per_seed": 5 if d5 else 4 + W.ctx.dense_off_bytes(), "value": n_reads * 6 / (ms * 1e-3), "unit": "reads/s", "ms_per_step": ms / 6, "fused_kernel_ms": kms,
                              "query_seeds_per_s": W.n_seeds * 6 / (ms * 1e-3), "hits_per_step": hits / 6,
                              "e2e": n_reads * 6 / (ms_e * 1e-3), "index_bytes": W.c0["index_bytes"], "slot_bytes": W.c0["index_slot_bytes"],
                              "starting_loci": W.n_loci, "offpath_entries": W.c0["n_offpath_entries"],
