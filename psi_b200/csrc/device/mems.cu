@@ -258,6 +258,30 @@ find_mems_kernel(GraphView g, MemPaths p, MemIndexView ix, MemChunk ch, uint32_t
     return c;
   };
   while (start + plen < len) {
+    if (plen == 0 && !has_hit) {
+      // A fresh pattern: nothing is reported below minlen characters, and a pattern occurs only if all its prefixes do,
+      // so the first J = min(MEM_PFX, minlen) characters are appended in ONE step when pattern[start : start + J]
+      // occurs -- one bucket of the prefix table instead of J rounds of searches in quarter-of-the-table brackets.  If
+      // it does not occur (or holds a character outside A/C/G/T) the character-by-character scan below finds where.
+      const uint32_t J = minlen < MEM_PFX ? minlen : MEM_PFX;
+      if (J >= 2 && start + J <= len) {
+        uint64_t qn = 0;
+        bool ok = true;
+        for (uint32_t j = 0; j < J && ok; ++j) {
+          const uint32_t c = read_char(start + j);
+          ok = c < 4;
+          qn |= (uint64_t)c << (62 - 2 * j);
+        }
+        if (ok) {
+          const uint64_t x0 = qn >> (64 - 2 * MEM_PFX);
+          const uint64_t blo = __ldg(ix.pstart + x0), bhi = __ldg(ix.pstart + x0 + (1ull << (2 * (MEM_PFX - J))));
+          const uint64_t nlo = mem_lower_bound(ix, blo, bhi, qn, J);
+          const uint64_t step = 1ull << (64 - 2 * J);
+          const uint64_t nhi = (qn + step < qn) ? bhi : mem_lower_bound(ix, nlo, bhi, qn + step, 0);
+          if (nlo < nhi) { q = qn; lo = nlo; hi = nhi; plen = J; continue; }
+        }
+      }
+    }
     if (plen >= minlen) {
       const uint64_t cnt = count_occ();
       if (cnt <= gocc_threshold) {
