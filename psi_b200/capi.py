@@ -355,7 +355,8 @@ class Reader:
             self._h = None
 
     def __del__(self):
-        self.close()
+        if lib is not None:
+            self.close()
 
 
 class Packed:
@@ -431,7 +432,8 @@ class Context:
             self._h = None
 
     def __del__(self):
-        self.close()
+        if lib is not None:     # (module globals are gone at interpreter shutdown)
+            self.close()
 
     def set_stream(self, cuda_stream: int):
         self._ck(lib().psi_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
