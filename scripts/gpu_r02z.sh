@@ -11,6 +11,7 @@ tail -1 $OUT/ncu_launches.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:seeds_fused_kernel -s 8 -c 3 -o $OUT/prof \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-other-configs --pipelines 1 > /dev/null 2> $OUT/ncu_full.err
 tail -1 $OUT/ncu_full.err
+if [ "$2" = "dist" ]; then
 cat > /tmp/dist_prof.py <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -21,5 +22,6 @@ print(bench.distance_bench(torch, torch.device("cuda", 0), capi, g, 300, 500, n_
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:dist_ -c 8 -o $OUT/prof_dist python /tmp/dist_prof.py > $OUT/dist_prof.log 2> $OUT/ncu_dist.err
 tail -1 $OUT/ncu_dist.err
+fi
 bash scripts/gpu_sanitizer2.sh $TAG
 ls -la $OUT

@@ -30,6 +30,9 @@ for slices in (1, 16):
     c = ctx.seeds_all(capi.ALL | capi.DENSE); d, e = ctx.fetch_dense()
     r2, _ = capi.dense_to_records(d, e, rp, case["k"], case["d"], 0)
     assert c == a and np.array_equal(capi.canonical(r2), rec)
+    assert ctx.seeds_all(capi.ALL | capi.DENSE5) == a
+    d5, e5 = ctx.fetch_dense5()
+    assert np.array_equal(d5, d)
     assert ref is None or np.array_equal(ref, rec)
     ref = rec
     ctx.close()

@@ -1188,3 +1188,36 @@ def test_verify_distance_on_a_cyclic_graph_vs_oracle():
             ctx.create_distance_index(dmin, dmax)
             assert np.array_equal(ctx.verify_distance(pairs), want), (dmin, dmax, mode, cap)
             ctx.close()
+
+
+def test_distance_window_with_more_states_than_the_scratch_is_refused_loudly():
+    """A chain of insertion bubbles multiplies the distances at which a node is reached; with a window of thousands of
+    characters a node sees more (node, distance) states than even the global scratch region holds (65 536 per warp).
+    Both modes must say so (PSI_B200_ERR_OVERFLOW) instead of answering from a truncated enumeration -- and a window the
+    scratch does hold still works afterwards on the same context."""
+    import tempfile
+    text = util.random_bubble_gfa(31337, backbone=9000, sites=2500, p_snp=0.0, p_ins=1.0, max_indel=9, multi_allele=0.0)
+    with tempfile.TemporaryDirectory() as td:
+        open(_os.path.join(td, "f.gfa"), "w").write(text)
+        g = capi.Graph.load_gfa(_os.path.join(td, "f.gfa"))
+    og = orc.OGraph.of(g)
+    pairs = np.array([[0, 0, len(g.coord_id) - 1, 0], [1, 0, 2, 0], [0, 0, 40, 0]], np.uint32)
+    ctx = capi.Context(12, 0)
+    ctx.set_graph(g, ids="coord")
+    ctx.set_option("dindex_mode", 2)
+    with pytest.raises(capi.PsiError) as e:
+        ctx.create_distance_index(1, 6000)
+    assert e.value.code == capi.ERR_OVERFLOW
+    with pytest.raises(capi.PsiError):
+        ctx.verify_distance(pairs)            # no index was left behind
+    ctx.set_option("dindex_mode", 1)
+    ctx.create_distance_index(1, 6000)        # nothing is enumerated until a query comes
+    with pytest.raises(capi.PsiError) as e:
+        ctx.verify_distance(np.array([[0, 0, len(g.coord_id) - 1, 0]], np.uint32))
+    assert e.value.code == capi.ERR_OVERFLOW
+    for mode in (2, 1):
+        ctx.set_option("dindex_mode", mode)
+        ctx.create_distance_index(5, 60)
+        want = np.array([orc.verify_distance(og, int(v), int(o), int(u), int(p), 5, 60) for v, o, u, p in pairs])
+        assert np.array_equal(ctx.verify_distance(pairs), want)
+    ctx.close()
