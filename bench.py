@@ -466,7 +466,6 @@ def main_gpu(args):
     ms_val, hits_val, launches_val, kms_val = run_async(W, steps, warmup, n_pipes, "packed", "device", FAST, False)
     # e2e: the same call sequence with pinned HOST buffers: 2-bit chunk up, dense results down, inside the timed region
     ms_e2e, hits_e2e, launches_e2e, kms_e2e = run_async(W, steps, warmup, n_pipes, "packed", "host", FAST, True)
-    clocks = sampler.stop() if rank == 0 else None
     # the same end-to-end loop with round 2's first result format (6 bytes per seed: u32 node id + u16 offset)
     ms_e2e6, hits_e2e6, _, _ = run_async(W, steps, warmup, n_pipes, "packed", "host", DENSE, True) if d5 else (ms_e2e, hits_e2e, 0, 0)
     assert hits_e2e6 == hits_e2e
@@ -481,6 +480,7 @@ def main_gpu(args):
     ms_sep, hits_sep, acc_sep, _ = run_sync(W, steps, warmup, "ascii", capi.ALL)
     ctx.set_option("fused", 1)
     assert hits_sep == hits_val, (hits_sep, hits_val)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over all the timed loops above (value, e2e and the comparison arms)
 
     # per-shard counts and a hits-per-read histogram, reduced with NCCL (the only collective on this path)
     W.submit(0, 0, "packed", "device")
