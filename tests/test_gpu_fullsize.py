@@ -245,3 +245,37 @@ def test_chr22_shape_one_chunk_of_configs2_size(chr22):
     rec, _ = capi.dense_to_records(dense[:m * per_read], extra[extra[:, 2] < m] if len(extra) else extra, rp[:m + 1], k, k, 0)
     assert np.array_equal(sort_rows(rec), rows)
     ctx.close()
+
+
+def test_chr22_shape_sliced_index_build_is_the_one_shot_index(chr22):
+    """The sliced index build (automatic above ~3 G estimated pairs: BASELINE configs[4]) at chr22 size: 16 slices of the
+    k-mer space, paths in groups of a 2^26-window budget inside every slice -- the same number of entries, k-mers,
+    starting loci and off-path entries as the one-shot build, and the same dense results (5-byte and 6-byte planes) and
+    extra list for 300 000 reads, seed for seed."""
+    g, k, n, L = chr22, 20, 300_000, 100
+    rp, bases = synth.reads(g, n, L, 4242)
+    pk = capi.Packed.pack(rp, bases, 0)
+    ps = g.pick_paths(16, seed=1)
+    out = []
+    for slices, budget in ((1, 0), (16, 1 << 26)):
+        ctx = capi.Context(k, 0)
+        ctx.set_option("build_slices", slices)
+        ctx.set_option("build_group_windows", budget)
+        ctx.set_graph(g, ids="coord")
+        ctx.set_paths(ps)
+        n_loci = ctx.find_loci()
+        c = ctx.counters()
+        assert c["index_build_slices"] == slices
+        ctx.submit_chunk_packed(pk, k, with_read_ptr=False)
+        cnt = ctx.seeds_all(capi.ALL | capi.DENSE)
+        dense, extra = ctx.fetch_dense()
+        assert ctx.dense5_layout()[1] and ctx.seeds_all(capi.ALL | capi.DENSE5) == cnt
+        dense5, extra5 = ctx.fetch_dense5()
+        assert np.array_equal(dense5, dense)
+        out.append((c["n_path_bases"], c["n_index_entries"], c["n_index_kmers"], c["n_offpath_entries"], n_loci, cnt, dense,
+                    np.unique(extra, axis=0)))
+        ctx.close()
+    a, b = out
+    assert a[:6] == b[:6], (a[:6], b[:6])
+    assert (a[6][:, 0] != capi.NIL32).all()
+    assert np.array_equal(a[6], b[6]) and np.array_equal(a[7], b[7])
