@@ -67,6 +67,12 @@ typedef struct {
 /* gum::util::load(graph, fname, sort) for GFA1 (S/L/P) and GFA2 (S/E/O)
  * (gum/gfa_utils.hpp:541-554). */
 int  psi_b200_graph_load_gfa(const char* path, int sort, psi_b200_graph** out);
+/* The same for vg's protobuf graph files (`.vg`: libvgio's BGZF / gzip stream of Graph chunks; gum/io_utils.hpp:77-80,
+ * vg_utils.hpp:377-396): nodes, edges and embedded paths of all chunks in file order, mappings in rank order, then the
+ * same node ordering as for GFA.  No protobuf library is involved. */
+int  psi_b200_graph_load_vg(const char* path, int sort, psi_b200_graph** out);
+/* gum::util::load(graph, fname, sort): by file name, `*.vg` is read as vg, anything else as GFA (gum/io_utils.hpp:66-80). */
+int  psi_b200_graph_load(const char* path, int sort, psi_b200_graph** out);
 /* Build from flat arrays (synthetic graphs).  ids[] are external ids; when
  * sort != 0 ranks are re-ordered exactly like the GFA loader would.  Embedded
  * paths: n_paths, path_ptr[n_paths+1], path_nodes = indices into the INPUT

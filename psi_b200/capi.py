@@ -23,7 +23,7 @@ NIL32 = 0xFFFFFFFF
 
 # every symbol include/psi_b200.h declares
 SYMBOLS = [
-    "psi_b200_graph_load_gfa", "psi_b200_graph_from_arrays", "psi_b200_graph_free",
+    "psi_b200_graph_load_gfa", "psi_b200_graph_load_vg", "psi_b200_graph_load", "psi_b200_graph_from_arrays", "psi_b200_graph_free",
     "psi_b200_graph_get_view", "psi_b200_graph_path", "psi_b200_graph_write_gfa",
     "psi_b200_pick_paths", "psi_b200_pathset_free", "psi_b200_pathset_get_view", "psi_b200_pathset_load_reference",
     "psi_b200_reader_open", "psi_b200_reader_next", "psi_b200_reader_close",
@@ -138,6 +138,8 @@ def _bind_host(L):
     u64p, u32p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_void_p
     L.psi_b200_global_error.restype = C.c_char_p
     L.psi_b200_graph_load_gfa.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.psi_b200_graph_load_vg.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.psi_b200_graph_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.psi_b200_graph_from_arrays.argtypes = [C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, vp, vp, C.c_int, C.POINTER(vp)]
     L.psi_b200_graph_free.argtypes = [vp]
     L.psi_b200_graph_free.restype = None
@@ -242,6 +244,19 @@ class Graph:
     def load_gfa(cls, path, sort=True) -> "Graph":
         h = C.c_void_p()
         _check(lib().psi_b200_graph_load_gfa(os.fspath(path).encode(), int(sort), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load(cls, path, sort=True) -> "Graph":
+        """By file name like gum::util::load: *.vg is read as vg (protobuf), anything else as GFA."""
+        h = C.c_void_p()
+        _check(lib().psi_b200_graph_load(os.fspath(path).encode(), int(sort), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load_vg(cls, path, sort=True) -> "Graph":
+        h = C.c_void_p()
+        _check(lib().psi_b200_graph_load_vg(os.fspath(path).encode(), int(sort), C.byref(h)))
         return cls(h)
 
     @classmethod

@@ -59,6 +59,27 @@ int psi_b200_graph_load_gfa(const char* path, int sort, psi_b200_graph** out)
   }
 }
 
+static int load_with(void (*loader)(const std::string&, bool, FlatGraph&), const char* path, int sort, psi_b200_graph** out)
+{
+  if (!path || !out) { g_error = "null argument"; return PSI_B200_ERR_ARG; }
+  *out = nullptr;
+  psi_b200_graph* g = nullptr;
+  try {
+    g = new psi_b200_graph();
+    loader(path, sort != 0, g->g);
+    *out = g;
+    return PSI_B200_OK;
+  }
+  catch (...) {
+    delete g;
+    int rc = translate(g_error);
+    return rc == PSI_B200_ERR_ARG && g_error.find("could not open") != std::string::npos ? PSI_B200_ERR_IO : rc;
+  }
+}
+
+int psi_b200_graph_load_vg(const char* path, int sort, psi_b200_graph** out) { return load_with(load_vg, path, sort, out); }
+int psi_b200_graph_load(const char* path, int sort, psi_b200_graph** out) { return load_with(load_graph_file, path, sort, out); }
+
 int psi_b200_graph_from_arrays(uint64_t n_nodes, const uint64_t* ids, const uint64_t* seq_start, const char* seq,
                                const uint64_t* row_ptr, const uint32_t* col, uint64_t n_paths,
                                const uint64_t* path_ptr, const uint32_t* path_nodes, int sort,

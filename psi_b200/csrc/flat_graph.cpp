@@ -250,6 +250,12 @@ void load_gfa(const std::string& path, bool sort, FlatGraph& out)
   build_flat_graph(std::move(raw), sort, out);
 }
 
+void load_graph_file(const std::string& path, bool sort, FlatGraph& out)
+{
+  if (path.size() > 3 && path.compare(path.size() - 3, 3, ".vg") == 0) load_vg(path, sort, out);
+  else load_gfa(path, sort, out);
+}
+
 void write_gfa1(const FlatGraph& g, const std::string& path)
 {
   std::FILE* f = std::fopen(path.c_str(), "w");

@@ -54,6 +54,10 @@ void build_flat_graph(RawGraph&& raw, bool sort, FlatGraph& out);
 // GFA1 (S/L/P) and GFA2 (S/E/O) reader.  Throws std::runtime_error.
 void load_gfa(const std::string& path, bool sort, FlatGraph& out);
 void write_gfa1(const FlatGraph& g, const std::string& path);
+// vg's protobuf graph files (vg_reader.cpp; no protobuf library involved).  Throws std::runtime_error.
+void load_vg(const std::string& path, bool sort, FlatGraph& out);
+// by file name like gum::util::load (gum/io_utils.hpp:66-80): *.vg -> load_vg, anything else -> load_gfa
+void load_graph_file(const std::string& path, bool sort, FlatGraph& out);
 
 }  // namespace psi_b200
 #endif

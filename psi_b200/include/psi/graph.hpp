@@ -155,13 +155,13 @@ class SeqGraph {
 
 namespace util {
 
-// gum::util::load(graph, fname, sort) for GFA1/GFA2 (gum/gfa_utils.hpp:541-554).
-// vg (protobuf) files are not read by this build; convert with `vg view`.
+// gum::util::load(graph, fname, sort): by file name like gum (gum/io_utils.hpp:66-80) -- `*.vg` is read as vg's protobuf
+// stream (no protobuf library involved), anything else as GFA1 / GFA2 (gum/gfa_utils.hpp:541-554).
 template <typename TSpec>
 inline void load(SeqGraph<TSpec>& graph, const std::string& fname, bool sort = true)
 {
   psi_b200_graph* h = nullptr;
-  if (psi_b200_graph_load_gfa(fname.c_str(), sort ? 1 : 0, &h) != PSI_B200_OK)
+  if (psi_b200_graph_load(fname.c_str(), sort ? 1 : 0, &h) != PSI_B200_OK)
     throw std::runtime_error(psi_b200_global_error());
   graph.reset(h);
 }

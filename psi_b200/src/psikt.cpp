@@ -9,7 +9,7 @@
 // get_seeds -> index_reads -> seeds_all.  What differs, and is logged as such:
 //   - the output is the seed SET (every hit once); the reference's raw stream
 //     repeats hits per covering path / walk and varies from run to run;
-//   - graphs are read from GFA (1 or 2); vg protobuf input is not part of this build;
+//   - graphs are read from GFA (1 or 2) and from vg's protobuf files (.vg), chosen by file name like gum::util::load;
 //   - all per-chunk times are device times of the CUDA kernels.
 #include <csignal>
 #include <future>
@@ -180,11 +180,6 @@ static void startup(const Options& options)
   log->info("- Output file: '{}'", options.output_path);
 
   log->info("Loading input graph from file '{}'...", options.rf_path);
-  if (options.rf_path.size() > 3 && options.rf_path.compare(options.rf_path.size() - 3, 3, ".vg") == 0) {
-    std::string msg = "vg (protobuf) graphs are not read by this build; convert with `vg view` to GFA";
-    log->error(msg);
-    throw std::runtime_error(msg);
-  }
   gum::SeqGraph<gum::Succinct> graph;
   gum::util::load(graph, options.rf_path, true);
   if (gum::util::ids_in_topological_order(graph)) log->info("Input graph node IDs are in topological sort order.");

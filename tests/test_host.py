@@ -279,3 +279,95 @@ def test_reader_line_views_across_buffer_refills_and_threaded_packing(tmp_path):
     fq.write_bytes(b"@a\nACGT\n+a\n@III\n@b x\nGG\n+\n+I\n@c\nT\n+\nI")
     first, rp, bases, names = capi.Reader(fq).next(0)
     assert (rp.tolist(), bases.tobytes(), names) == ([0, 4, 6, 7], b"ACGTGGT", ["a", "b", "c"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# vg protobuf graphs (psi_b200_graph_load_vg / psi_b200_graph_load)
+
+def _pb_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb_field(num, wire, payload):
+    return _pb_varint((num << 3) | wire) + (payload if wire == 0 else _pb_varint(len(payload)) + payload)
+
+
+def _vg_node(seq, nid):
+    return _pb_field(1, 2, seq.encode()) + _pb_field(2, 2, b"n%d" % nid) + _pb_field(3, 0, _pb_varint(nid))
+
+
+def _vg_edge(a, b, from_start=False):
+    e = _pb_field(1, 0, _pb_varint(a)) + _pb_field(2, 0, _pb_varint(b))
+    if from_start:
+        e += _pb_field(3, 0, _pb_varint(1))
+    return e + _pb_field(5, 0, _pb_varint(0))
+
+
+def _vg_mapping(nid, rank):
+    pos = _pb_field(1, 0, _pb_varint(nid)) + _pb_field(2, 0, _pb_varint(0))
+    edit = _pb_field(1, 0, _pb_varint(3)) + _pb_field(2, 0, _pb_varint(3))
+    return _pb_field(1, 2, pos) + _pb_field(2, 2, edit) + _pb_field(5, 0, _pb_varint(rank))
+
+
+def _vg_stream(graphs, tagged=True):
+    out = bytearray()
+    for gmsg in graphs:
+        msgs = ([b"VG"] if tagged else []) + [gmsg]
+        out += _pb_varint(len(msgs))
+        for m in msgs:
+            out += _pb_varint(len(m)) + m
+    return bytes(out)
+
+
+@pytest.mark.parametrize("name", ["tiny", "x"])
+def test_vg_file_loads_the_same_graph_as_its_gfa(name):
+    """The reference's own test graphs exist as .vg and as .gfa: both readers must give the same flattened graph -- ranks,
+    ids, labels, out-edge order, embedded path -- and psi_b200_graph_load chooses by file name like gum::util::load."""
+    a = capi.Graph.load(util.GOLDEN / "inputs" / f"{name}.vg")
+    b = capi.Graph.load_gfa(util.GOLDEN / "inputs" / f"{name}.gfa.gz")
+    for attr in ("seq_start", "seq", "row_ptr", "col", "coord_id", "internal_id"):
+        assert np.array_equal(getattr(a, attr), getattr(b, attr)), attr
+    assert a.n_paths == b.n_paths == 1 and a.path(0)[0] == b.path(0)[0] and np.array_equal(a.path(0)[1], b.path(0)[1])
+    c = capi.Graph.load_vg(util.GOLDEN / "inputs" / f"{name}.vg")
+    assert np.array_equal(c.col, a.col)
+
+
+def test_vg_reader_chunks_untagged_streams_unknown_fields_and_errors(tmp_path):
+    """Hand-encoded vg streams: a graph split over two chunks (edges before their nodes' chunk, a path continued in the
+    second chunk with its mappings out of rank order), with and without type tags, raw and gzip-compressed, with fields
+    this reader does not know; damaged and foreign files are refused."""
+    nodes = {1: "ACGT", 2: "G", 3: "T", 4: "CCA"}
+    chunk1 = b"".join(_pb_field(1, 2, _vg_node(nodes[i], i)) for i in (3, 1)) + _pb_field(2, 2, _vg_edge(1, 2)) + \
+        _pb_field(2, 2, _vg_edge(1, 3)) + _pb_field(3, 2, _pb_field(2, 2, _vg_mapping(2, 2)) + _pb_field(2, 2, _vg_mapping(1, 1)) +
+                                                    _pb_field(1, 2, b"ref")) + _pb_field(9, 0, _pb_varint(77))
+    chunk2 = b"".join(_pb_field(1, 2, _vg_node(nodes[i], i)) for i in (4, 2)) + _pb_field(2, 2, _vg_edge(2, 4)) + \
+        _pb_field(2, 2, _vg_edge(3, 4)) + _pb_field(3, 2, _pb_field(1, 2, b"ref") + _pb_field(2, 2, _vg_mapping(4, 3)) +
+                                                    _pb_field(7, 2, b"ignored"))
+    gfa = tmp_path / "ref.gfa"
+    gfa.write_text("S\t1\tACGT\nS\t2\tG\nS\t3\tT\nS\t4\tCCA\nL\t1\t+\t2\t+\t0M\nL\t1\t+\t3\t+\t0M\nL\t2\t+\t4\t+\t0M\nL\t3\t+\t4\t+\t0M\n"
+                   "P\tref\t1+,2+,4+\t*\n")
+    want = capi.Graph.load_gfa(gfa)
+    for tagged in (True, False):
+        for compress in (False, True):
+            raw = _vg_stream([chunk1, chunk2], tagged)
+            f = tmp_path / f"g_{int(tagged)}{int(compress)}.vg"
+            f.write_bytes(gzip.compress(raw) if compress else raw)
+            g = capi.Graph.load(f)
+            for attr in ("seq_start", "seq", "row_ptr", "col", "coord_id"):
+                assert np.array_equal(getattr(g, attr), getattr(want, attr)), (attr, tagged, compress)
+            assert g.path(0)[0] == "ref" and np.array_equal(g.path(0)[1], want.path(0)[1])
+    raw = _vg_stream([chunk1, chunk2])
+    for bad in (raw[:-3], raw[:40], _vg_stream([chunk1]).replace(b"\x02VG", b"\x03GAM", 1)):
+        f = tmp_path / "bad.vg"
+        f.write_bytes(bad)
+        with pytest.raises(capi.PsiError):
+            capi.Graph.load(f)
+    with pytest.raises(capi.PsiError) as e:
+        capi.Graph.load(tmp_path / "missing.vg")
+    assert e.value.code == capi.ERR_IO

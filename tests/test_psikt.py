@@ -304,3 +304,18 @@ def test_seed_finder_distance_api_matches_the_reference(tmp_path, name):
     assert np.array_equal(out[:ns], want[:ns]), "single queries"
     assert np.array_equal(out[ns:ns + n], want), "bulk query"
     assert np.array_equal(out[ns + n:], want), "index reopened by a second finder"
+
+
+@pytest.mark.gpu
+def test_psikt_reads_a_vg_protobuf_graph(tmp_path):
+    """BASELINE configs[0] names a vg graph: `psikt ... x.vg` (the reference's test/data/small/x.vg, byte for byte) gives
+    the golden seed set of the same graph's GFA -- the .vg reader needs no protobuf library."""
+    c = G["x_k12"]
+    out, log = tmp_path / "seeds.bin", tmp_path / "psi.log"
+    vg = util.GOLDEN / "inputs" / "x.vg"
+    r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", c["k"], "-d", c["d"], "-n", c["n_paths"], "-o", out, "-L", log, "-q", vg])
+    assert r.returncode == 0, r.stderr
+    g = capi.Graph.load(vg)
+    got = capi.canonical(load_psikt_output(out, g))
+    assert len(got) == c["count"] and util.md5_tuples(got) == c["md5"]
+    assert "Input graph node IDs are" in log.read_text()
