@@ -657,7 +657,8 @@ class SeedFinder {
     uint64_t* records = nullptr;   // per-hit records (routes without dense results) / the CLI's 4 x u64 staging
     uint64_t rec_cap = 0;
     // chunk in flight
-    bool pending = false, dense_mode = false, compact = false;
+    bool pending = false, dense_mode = false, compact = false, dense5 = false;
+    unsigned d5_off_bits = 0;
     unsigned flags = 0;
     readsrecord_type seeds;
     ~Pipe()
@@ -804,10 +805,16 @@ class SeedFinder {
     p.compact = ids32;
     // dense per-seed results whenever the index serves them (walk mode and 64-bit ids keep per-hit records)
     if (ids32 && dense_state != 2) {
-      const int rc = psi_b200_seeds_all_async(p.ctx, flags | PSI_B200_DENSE);
+      // 5 bytes per seed when the graph's loci fit 39 bits (PSI_B200_DENSE5), else u32 id + u16 / u32 offset
+      unsigned d5_bits = 0;
+      int d5 = 0;
+      if (psi_b200_dense5_layout(p.ctx, &d5_bits, &d5) != PSI_B200_OK) d5 = 0;
+      const int rc = psi_b200_seeds_all_async(p.ctx, flags | (d5 ? PSI_B200_DENSE5 : PSI_B200_DENSE));
       if (rc == PSI_B200_OK) {
         dense_state = 1;
         p.dense_mode = true;
+        p.dense5 = d5 != 0;
+        p.d5_off_bits = d5_bits;
         uint64_t n_seeds = 0;
         if (seeds.read_len) n_seeds = seeds.n_reads * (seeds.read_len >= seed_len ? (seeds.read_len - seed_len) / seeds.distance + 1 : 0);
         else for (uint64_t r = 0; r < seeds.n_reads; ++r) n_seeds += seeds.seeds_of_read(r);
@@ -869,11 +876,20 @@ class SeedFinder {
       const uint32_t* ids = static_cast<const uint32_t*>(p.dense);
       const uint16_t* off16 = reinterpret_cast<const uint16_t*>(ids + n_seeds);
       const uint32_t* off32 = ids + n_seeds;
+      const uint8_t* hi8 = reinterpret_cast<const uint8_t*>(ids + n_seeds);
+      const uint64_t d5_mask = (1ull << p.d5_off_bits) - 1ull;
       uint64_t s = 0;
       for (uint64_t r = 0; r < seeds.n_reads; ++r) {
         const uint64_t cnt = seeds.read_len ? (seeds.read_len >= seed_len ? (seeds.read_len - seed_len) / seeds.distance + 1 : 0)
                                             : seeds.seeds_of_read(r);
         for (uint64_t j = 0; j < cnt; ++j, ++s) {
+          if (p.dense5) {
+            const uint32_t hi = hi8[s];
+            if (ids[s] == 0xffffffffu && hi == 0xffu) continue;
+            const uint64_t e = (uint64_t)ids[s] | ((uint64_t)(hi & 0x7fu) << 32);
+            emit(e >> p.d5_off_bits, e & d5_mask, seeds.rec_offset + r, j * seeds.distance, (hi >> 7) != 0);
+            continue;
+          }
           if (ids[s] == 0xffffffffu) continue;
           if (dense_off_bytes == 2) emit(ids[s], off16[s] & 0x7fffu, seeds.rec_offset + r, j * seeds.distance, (off16[s] >> 15) != 0);
           else emit(ids[s], off32[s] & 0x7fffffffu, seeds.rec_offset + r, j * seeds.distance, (off32[s] >> 31) != 0);
