@@ -184,6 +184,10 @@ void load_vg(const std::string& path, bool sort, FlatGraph& out)
     if (got < 0) throw std::runtime_error("read error in '" + path + "'");
   }
   Span s{ (const unsigned char*)content.data(), (const unsigned char*)content.data() + content.size() };
+  // libbdsg's serialised HashGraph shares the .vg extension and starts with its magic number (gum/hg_utils.hpp)
+  static const unsigned char HG_MAGIC[4] = { 0x28, 0x4d, 0x4f, 0x38 };
+  if (content.size() >= 4 && std::equal(HG_MAGIC, HG_MAGIC + 4, s.p))
+    throw std::runtime_error("'" + path + "' is a HashGraph file, not a vg protobuf stream: convert it with `vg convert -v` or to GFA");
   Collector c;
   while (!s.empty()) {
     const uint64_t count = varint(s);
