@@ -1,6 +1,8 @@
 // vg_reader.cpp -- reads vg's protobuf graph files (.vg) without libprotobuf / libvgio.
 //
-// Stands behind gum::util::load(graph, "x.vg", sort) (gum/io_utils.hpp:77-80, io_utils_vg.hpp, vg_utils.hpp:377-396):
+// Stands behind the reference CLI's graph loading for .vg input -- parse_vg + gum::util::load(graph, path, loader, true)
+// (reference src/psikt.cpp:238-250) over its minivgio stream reader (vg/stream.hpp:82-123, vg/vg.proto) and gum's vg
+// overloads (gum/io_utils.hpp:77-80, io_utils_vg.hpp, vg_utils.hpp:377-396, chunks merged like merge_vg :436-496):
 // the nodes, edges and embedded paths of all Graph chunks of the file, added in file order, then the same id sort +
 // topological sort as for GFA (build_flat_graph).  A .vg file is libvgio's stream -- BGZF / gzip (or nothing) around
 // groups of `varint count, count x (varint length, message)`, the first message of a group being the type tag "VG" in
