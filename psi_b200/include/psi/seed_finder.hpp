@@ -266,6 +266,21 @@ class SeedFinder {
     return ok;
   }
 
+  /* ---- source compatibility with the reference's lifecycle knobs (seed_finder.hpp:862-874,1066-1081) ----
+   * The reference initialises / finalises Kokkos through these (its distance index runs on Kokkos); nothing here needs
+   * them, they are kept so that code written against the reference compiles unchanged. */
+  static std::atomic_bool& get_kokkos_handling_status() { static std::atomic_bool enabled{ true }; return enabled; }
+  static void set_kokkos_handling_status(bool value = true) { get_kokkos_handling_status().store(value); }
+  void set_as_finaliser() { finaliser = true; }
+  void unset_as_finaliser() { finaliser = false; }
+  bool is_finaliser() const { return finaliser; }
+  // seeds_on_paths skips k-mers with more occurrences in the path text: takes effect when the paths are indexed next
+  void set_gocc_threshold(unsigned int value)
+  {
+    gocc_threshold = value != 0 ? value : UINT_MAX;
+    check(psi_b200_set_option(ctx, "gocc_threshold", value));
+  }
+
   /* ---- accessors ---- */
   const graph_type* get_graph_ptr() const { return graph_ptr; }
   const std::vector<Position<>>& get_starting_loci() const { return starting_loci; }
@@ -958,6 +973,7 @@ class SeedFinder {
   psi_b200_ctx* ctx = nullptr;              // builds and owns the resident graph / index / loci
   psi_b200_pathset* pathset = nullptr;
   bool has_index = false;
+  bool finaliser = true;
   mutable bool loci_dirty = false;
   mutable std::mutex pipes_mutex;
   mutable std::map<std::thread::id, std::unique_ptr<Pipe>> pipes;

@@ -33,7 +33,9 @@ int main(int argc, char** argv)
     std::fclose(f);
   }
 
+  finder_type::set_kokkos_handling_status(false);      // the reference's test does (test_seedfinder.cpp:255)
   finder_type finder(graph, 30);
+  finder.unset_as_finaliser();
   bool threw_without_index = false;
   try { finder.verify_distance((int64_t)ends[0][0], ends[0][1], (int64_t)ends[0][2], ends[0][3]); }
   catch (const std::runtime_error&) { threw_without_index = true; }
