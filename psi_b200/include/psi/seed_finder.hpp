@@ -384,86 +384,91 @@ class SeedFinder {
   // The paths file names the graph it belongs to (node count, base count, a checksum of the labels); a file written
   // for another graph, or a damaged one, is refused (load returns false and the caller rebuilds, as the reference
   // does for a missing piece, seed_finder.hpp:1396-1413).
-  bool serialize_path_index(std::string const& fpath, unsigned int step_size = 1)
+  // the paths alone (reference serialize_path_index_only / load_path_index_only, seed_finder.hpp:1357-1393)
+  bool serialize_path_index_only(std::string const& fpath)
   {
     if (fpath.empty() || !pathset) return false;
-    {
-      [[maybe_unused]] auto timer = stats_ptr->timeit_ts("save-pindex");
-      psi_b200_pathset_view v;
-      if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) return false;
-      std::ofstream ofs(fpath + "_paths.b200", std::ofstream::binary);
-      if (!ofs) return false;
-      const psi_b200_graph_view& gv = graph_ptr->view();
-      const uint64_t hdr[8] = { PATHS_MAGIC, context_, v.n_paths, v.path_ptr[v.n_paths], gv.n_nodes, gv.n_bases, graph_checksum(), 0 };
-      ofs.write(reinterpret_cast<const char*>(hdr), sizeof hdr);
-      ofs.write(reinterpret_cast<const char*>(v.path_ptr), (v.n_paths + 1) * sizeof(uint64_t));
-      // node ranks are stable for a given graph file (the load order is deterministic)
-      ofs.write(reinterpret_cast<const char*>(v.nodes), v.path_ptr[v.n_paths] * sizeof(uint32_t));
-      ofs.write(reinterpret_cast<const char*>(v.head_off), v.n_paths * sizeof(uint32_t));
-      ofs.write(reinterpret_cast<const char*>(v.tail_trim), v.n_paths * sizeof(uint32_t));
-      if (!ofs) return false;
-    }
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("save-pindex");
+    psi_b200_pathset_view v;
+    if (psi_b200_pathset_get_view(pathset, &v) != PSI_B200_OK) return false;
+    std::ofstream ofs(fpath + "_paths.b200", std::ofstream::binary);
+    if (!ofs) return false;
+    const psi_b200_graph_view& gv = graph_ptr->view();
+    const uint64_t hdr[8] = { PATHS_MAGIC, context_, v.n_paths, v.path_ptr[v.n_paths], gv.n_nodes, gv.n_bases, graph_checksum(), 0 };
+    ofs.write(reinterpret_cast<const char*>(hdr), sizeof hdr);
+    ofs.write(reinterpret_cast<const char*>(v.path_ptr), (v.n_paths + 1) * sizeof(uint64_t));
+    // node ranks are stable for a given graph file (the load order is deterministic)
+    ofs.write(reinterpret_cast<const char*>(v.nodes), v.path_ptr[v.n_paths] * sizeof(uint32_t));
+    ofs.write(reinterpret_cast<const char*>(v.head_off), v.n_paths * sizeof(uint32_t));
+    ofs.write(reinterpret_cast<const char*>(v.tail_trim), v.n_paths * sizeof(uint32_t));
+    return (bool)ofs;
+  }
+
+  bool serialize_path_index(std::string const& fpath, unsigned int step_size = 1)
+  {
     // like the reference (seed_finder.hpp:1372-1378): paths, starting loci, distance index
-    return save_starts(fpath, seed_len, step_size) && save_distance_index(fpath);
+    return serialize_path_index_only(fpath) && save_starts(fpath, seed_len, step_size) && save_distance_index(fpath);
+  }
+
+  // `<prefix>_paths.b200` of this build or, failing that, `<prefix>_paths` as the REFERENCE's psikt -I wrote it (coordinate
+  // node ids as an sdsl enc_vector, left / right trims; pathindex.hpp:313-332, path_base.hpp:552-560): the device index is
+  // rebuilt from the paths, the reference's serialised FM-index (`<prefix>`) is not needed.
+  bool load_path_index_only(std::string const& fpath, unsigned int context = 0)
+  {
+    if (fpath.empty()) return false;
+    [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-pindex");
+    std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary | std::ifstream::ate);
+    if (!ifs) return load_reference_paths(fpath, context);
+    const uint64_t file_bytes = (uint64_t)ifs.tellg();
+    ifs.seekg(0);
+    uint64_t hdr[8];
+    ifs.read(reinterpret_cast<char*>(hdr), sizeof hdr);
+    if (!ifs || hdr[0] != PATHS_MAGIC) return false;
+    const psi_b200_graph_view& gv = graph_ptr->view();
+    const uint64_t n_paths = hdr[2], n_entries = hdr[3];
+    // the file must be exactly as long as its header says, and belong to this graph
+    if (n_paths > file_bytes || n_entries > file_bytes) return false;
+    if (file_bytes != sizeof hdr + (n_paths + 1) * 8 + n_entries * 4 + n_paths * 8) return false;
+    if (hdr[4] != gv.n_nodes || hdr[5] != gv.n_bases || hdr[6] != graph_checksum()) return false;
+    std::vector<uint64_t> path_ptr(n_paths + 1);
+    std::vector<uint32_t> nodes(n_entries), head(n_paths), tail(n_paths);
+    ifs.read(reinterpret_cast<char*>(path_ptr.data()), path_ptr.size() * sizeof(uint64_t));
+    ifs.read(reinterpret_cast<char*>(nodes.data()), nodes.size() * sizeof(uint32_t));
+    ifs.read(reinterpret_cast<char*>(head.data()), head.size() * sizeof(uint32_t));
+    ifs.read(reinterpret_cast<char*>(tail.data()), tail.size() * sizeof(uint32_t));
+    if (!ifs || path_ptr.front() != 0 || path_ptr.back() != nodes.size()) return false;
+    for (uint64_t p = 0; p < n_paths; ++p) if (path_ptr[p + 1] < path_ptr[p]) return false;
+    for (uint32_t r : nodes) if (r >= gv.n_nodes) return false;
+    for (uint64_t p = 0; p < n_paths; ++p) {
+      if (path_ptr[p + 1] == path_ptr[p]) { if (head[p] || tail[p]) return false; continue; }
+      const uint32_t first = nodes[path_ptr[p]], last = nodes[path_ptr[p + 1] - 1];
+      if (head[p] > gv.seq_start[first + 1] - gv.seq_start[first]) return false;
+      if (tail[p] > gv.seq_start[last + 1] - gv.seq_start[last]) return false;
+    }
+    context_ = context ? context : (unsigned)hdr[1];
+    reset_pipes();
+    check(psi_b200_set_paths(ctx, n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data()));
+    remember_paths(n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data());
+    has_index = n_paths != 0;
+    return true;
   }
 
   bool load_path_index(std::string const& fpath, unsigned int context = 0, unsigned int step_size = 1,
                        unsigned int dmin = 0, unsigned int dmax = 0)
   {
-    if (fpath.empty()) return false;
-    {
-      [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-pindex");
-      std::ifstream ifs(fpath + "_paths.b200", std::ifstream::binary | std::ifstream::ate);
-      if (!ifs) return load_reference_path_index(fpath, context, step_size, dmin, dmax);
-      const uint64_t file_bytes = (uint64_t)ifs.tellg();
-      ifs.seekg(0);
-      uint64_t hdr[8];
-      ifs.read(reinterpret_cast<char*>(hdr), sizeof hdr);
-      if (!ifs || hdr[0] != PATHS_MAGIC) return false;
-      const psi_b200_graph_view& gv = graph_ptr->view();
-      const uint64_t n_paths = hdr[2], n_entries = hdr[3];
-      // the file must be exactly as long as its header says, and belong to this graph
-      if (n_paths > file_bytes || n_entries > file_bytes) return false;
-      if (file_bytes != sizeof hdr + (n_paths + 1) * 8 + n_entries * 4 + n_paths * 8) return false;
-      if (hdr[4] != gv.n_nodes || hdr[5] != gv.n_bases || hdr[6] != graph_checksum()) return false;
-      std::vector<uint64_t> path_ptr(n_paths + 1);
-      std::vector<uint32_t> nodes(n_entries), head(n_paths), tail(n_paths);
-      ifs.read(reinterpret_cast<char*>(path_ptr.data()), path_ptr.size() * sizeof(uint64_t));
-      ifs.read(reinterpret_cast<char*>(nodes.data()), nodes.size() * sizeof(uint32_t));
-      ifs.read(reinterpret_cast<char*>(head.data()), head.size() * sizeof(uint32_t));
-      ifs.read(reinterpret_cast<char*>(tail.data()), tail.size() * sizeof(uint32_t));
-      if (!ifs || path_ptr.front() != 0 || path_ptr.back() != nodes.size()) return false;
-      for (uint64_t p = 0; p < n_paths; ++p) if (path_ptr[p + 1] < path_ptr[p]) return false;
-      for (uint32_t r : nodes) if (r >= gv.n_nodes) return false;
-      for (uint64_t p = 0; p < n_paths; ++p) {
-        if (path_ptr[p + 1] == path_ptr[p]) { if (head[p] || tail[p]) return false; continue; }
-        const uint32_t first = nodes[path_ptr[p]], last = nodes[path_ptr[p + 1] - 1];
-        if (head[p] > gv.seq_start[first + 1] - gv.seq_start[first]) return false;
-        if (tail[p] > gv.seq_start[last + 1] - gv.seq_start[last]) return false;
-      }
-      context_ = context ? context : (unsigned)hdr[1];
-      reset_pipes();
-      check(psi_b200_set_paths(ctx, n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data()));
-      remember_paths(n_paths, path_ptr.data(), nodes.data(), head.data(), tail.data());
-      has_index = n_paths != 0;
-    }
+    if (!load_path_index_only(fpath, context)) return false;      // seed_finder.hpp:1396-1413
     if (!open_starts(fpath, seed_len, step_size)) {
       add_uncovered_loci(step_size);
       save_starts(fpath, seed_len, step_size);
     }
-    if (!open_distance_index(fpath, dmin, dmax)) {   // seed_finder.hpp:1405-1411
+    if (!open_distance_index(fpath, dmin, dmax)) {
       create_distance_index(dmin, dmax);
       save_distance_index(fpath);
     }
     return true;
   }
 
-  // An index saved by the REFERENCE (psikt -I of cartoonist/psi): `<prefix>_paths` holds its picked paths (coordinate
-  // node ids as an sdsl enc_vector, left / right trims; pathindex.hpp:313-332, path_base.hpp:552-560) and
-  // `<prefix>_loci_e<step>l<k>` its starting loci in the format both builds share.  The device index is rebuilt from
-  // the paths; the reference's serialised FM-index (`<prefix>`) is not needed.
-  bool load_reference_path_index(std::string const& fpath, unsigned int context, unsigned int step_size, unsigned int dmin,
-                                 unsigned int dmax)
+  bool load_reference_paths(std::string const& fpath, unsigned int context)
   {
     psi_b200_pathset* ps = nullptr;
     uint64_t file_context = 0;
@@ -474,14 +479,6 @@ class SeedFinder {
     pathset = ps;
     context_ = (unsigned)file_context;
     index_paths();
-    if (!open_starts(fpath, seed_len, step_size)) {
-      add_uncovered_loci(step_size);
-      save_starts(fpath, seed_len, step_size);
-    }
-    if (!open_distance_index(fpath, dmin, dmax)) {   // seed_finder.hpp:1405-1411
-      create_distance_index(dmin, dmax);
-      save_distance_index(fpath);
-    }
     return true;
   }
 
