@@ -1,9 +1,13 @@
 #!/bin/bash
-# Full pass of a round: parity tests, smoke, bench (with the CPU baseline), the other BASELINE configs, ncu launch list and
-# full capture of the fused kernel.  Usage (under gpurun): bash scripts/gpu_final.sh TAG
-set -u
-TAG=${1:-r01zf}
-bash scripts/gpu_r01t.sh $TAG
-bash scripts/gpu_configs.sh $TAG
-echo "== bench --impl reference"
-timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/$TAG/bench_ref.json 2> gpurun_out/$TAG/bench_ref.err; cut -c1-300 gpurun_out/$TAG/bench_ref.json
+# last pass of the round: full GPU suite, smoke(), the default bench and the reference arm
+TAG=${1:-r02final}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; tail -2 $OUT/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -1 $OUT/bench.err
+timeout 400 python bench.py --impl reference > $OUT/bench_ref.json 2> $OUT/bench_ref.err
+python - <<PY
+import json
+d = json.loads(open("$OUT/bench.json").read().strip().splitlines()[-1])
+r = json.loads(open("$OUT/bench_ref.json").read().strip().splitlines()[-1])
+print("value %.4g e2e %.4g frac %.3f psikt %.3g ref %.4g clocks %s" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["drop_in_psikt"]["reads_per_s"], r["value"], d["clocks"]))
+PY
