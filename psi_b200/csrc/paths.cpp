@@ -82,10 +82,15 @@ namespace {
 
 struct Stream {
   std::ifstream in;
-  explicit Stream(const std::string& f) : in(f, std::ifstream::binary)
+  uint64_t file_bytes = 0;
+  explicit Stream(const std::string& f) : in(f, std::ifstream::binary | std::ifstream::ate)
   {
     if (!in) throw std::runtime_error("could not open file '" + f + "'!");
+    file_bytes = (uint64_t)in.tellg();
+    in.seekg(0);
   }
+  // nothing read from the file may size an allocation beyond what the file itself still holds
+  uint64_t remaining() { const auto p = in.tellg(); return p < 0 ? 0 : file_bytes - (uint64_t)p; }
   uint64_t u64()
   {
     uint64_t v = 0;
@@ -99,7 +104,8 @@ struct Stream {
     const uint64_t h = u64();
     bits = h & ((1ull << 56) - 1);
     width = (unsigned)(h >> 56);
-    if (bits > (1ull << 40)) throw std::runtime_error("reference paths file: implausible vector size");
+    if (bits > (1ull << 40) || ((bits + 63) >> 6) * 8 > remaining())
+      throw std::runtime_error("reference paths file: a vector is longer than the file");
     words.resize((bits + 63) >> 6);
     if (!words.empty()) in.read(reinterpret_cast<char*>(words.data()), words.size() * 8);
     if (!in) throw std::runtime_error("reference paths file: unexpected end of file");
@@ -146,7 +152,9 @@ void enc_vector(Stream& s, std::vector<uint64_t>& out)
   unsigned zw = 0, spw = 0;
   s.int_vector(z, z_bits, zw);
   s.int_vector(sp, sp_bits, spw);
-  if (size > (1ull << 36)) throw std::runtime_error("reference paths file: implausible path length");
+  // every element costs at least one bit of the delta stream (or a sample)
+  if (size > (1ull << 36) || size > z_bits + 64 * (sp_bits / 64 + 1) + 128)
+    throw std::runtime_error("reference paths file: implausible path length");
   out.clear();
   out.reserve(size);
   if (size == 0) return;
