@@ -489,12 +489,14 @@ class SeedFinder {
 
   bool open_starts(const std::string& prefix, unsigned int len, unsigned int step_size)
   {
-    std::ifstream ifs(get_sloci_filepath(prefix, len, step_size), std::ifstream::binary);
+    std::ifstream ifs(get_sloci_filepath(prefix, len, step_size), std::ifstream::binary | std::ifstream::ate);
     if (!ifs) return false;
     [[maybe_unused]] auto timer = stats_ptr->timeit_ts("load-starts");
+    const uint64_t file_bytes = (uint64_t)ifs.tellg();
+    ifs.seekg(0);
     uint64_t n = 0;
     ifs.read(reinterpret_cast<char*>(&n), sizeof n);
-    if (!ifs) return false;
+    if (!ifs || file_bytes < 8 || n != (file_bytes - 8) / 16 || (file_bytes - 8) % 16) return false;   // the count must be the file's
     std::unordered_map<int64_t, int64_t> by_coord;   // external id -> internal id
     const psi_b200_graph_view& v = graph_ptr->view();
     for (uint64_t r = 0; r < v.n_nodes; ++r) by_coord.emplace((int64_t)v.coord_id[r], (int64_t)v.internal_id[r]);
