@@ -457,6 +457,7 @@ void engine_verify_distance(Ctx& c, uint64_t n, const uint32_t* pairs, uint8_t* 
   if (n == 0) return;
   if (!pairs || !out) throw ArgError("verify_distance: null argument");
   if (n >= 0xffffffffull) throw ArgError("verify_distance: more than 2^32 - 1 queries in one call");
+  if (on_device && (reinterpret_cast<uintptr_t>(pairs) & 15u)) throw ArgError("verify_distance: device pairs must be 16-byte aligned");
   PSI_CUDA(cudaSetDevice(c.device));
   nvtxRangePushA("query-dindex");
   struct Pop { ~Pop() { nvtxRangePop(); } } pop_range;
