@@ -101,6 +101,10 @@ def test_mirror_headers_compile_standalone(tmp_path):
     src.write_text('#include "%s"\nint main() { return sizeof(psi::SeedFinder<>) > 0 ? 0 : 1; }\n'
                    % os.fspath(ROOT / "psi_b200/include/psi/seed_finder.hpp"))
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", os.fspath(src)], check=True)
+    # the callers written against the reference's API (find_seeds of the CLI, the reference's distance-index scenario,
+    # the lifecycle knobs) instantiate every method they use: they must compile on a box without a GPU too
+    for caller in ("tests/cpp/seed_finder_driver.cpp", "tests/cpp/distance_driver.cpp", "psi_b200/src/psikt.cpp"):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", os.fspath(ROOT / caller)], check=True)
 
 
 # ------------------------------------------------------------------ GPU --
