@@ -58,6 +58,7 @@ void HostBuffer::reserve(size_t bytes)
 
 void HostBuffer::append(const void* src, size_t bytes)
 {
+  if (bytes == 0) return;      // (an empty line before anything is allocated: memcpy must not see a null pointer)
   if (size_ + bytes > cap_) reserve(size_ + bytes);
   std::memcpy(data_ + size_, src, bytes);
   size_ += bytes;
