@@ -312,11 +312,13 @@ def test_seed_finder_distance_api_matches_the_reference(tmp_path, name):
 
 @pytest.mark.gpu
 def test_psikt_reads_a_vg_protobuf_graph(tmp_path):
-    """BASELINE configs[0] names a vg graph: `psikt ... x.vg` (the reference's test/data/small/x.vg, byte for byte) gives
+    """BASELINE configs[0] names a vg graph: `psikt ... x.vg` (the protobuf stream of the reference's test/data/small/x.vg) gives
     the golden seed set of the same graph's GFA -- the .vg reader needs no protobuf library."""
     c = G["x_k12"]
     out, log = tmp_path / "seeds.bin", tmp_path / "psi.log"
-    vg = util.GOLDEN / "inputs" / "x.vg"
+    import gzip
+    vg = tmp_path / "x.vg"        # the reference's test/data/small/x.vg: its protobuf stream, re-compressed
+    vg.write_bytes(gzip.compress(gzip.decompress((util.GOLDEN / "inputs" / "x_vg_stream.gz").read_bytes())))
     r = run([PSIKT, "-f", util.GOLDEN / c["reads"], "-l", c["k"], "-d", c["d"], "-n", c["n_paths"], "-o", out, "-L", log, "-q", vg])
     assert r.returncode == 0, r.stderr
     g = capi.Graph.load(vg)
